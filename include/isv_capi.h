@@ -1,0 +1,208 @@
+/*
+ * isv_capi.h -- C ABI of the B200-native IS-VINS marginalization + sparsification backend.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: the path is
+ * three argument-less C++ member functions that read/write `Estimator` members
+ * (/root/reference/include/estimator.h:122-154).  Each entry point below cites the reference
+ * code it replaces; the C++ shim in is_vins_b200/host/ (same class / method names as the
+ * reference) packs the members into these PODs, so estimator.cpp keeps its call sites
+ * (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every matrix is COLUMN-MAJOR, i.e. exactly the memory of the Eigen::MatrixXd /
+ *     Eigen::Matrix3d member it mirrors (`m.data()`), unless the field says row-major
+ *     (the ceres `jacobians[i]` blocks are row-major, as ceres demands);
+ *   - pose block  = [px,py,pz,qx,qy,qz,qw]          (src/estimator.cpp:474-487)
+ *     speed-bias  = [v3, ba3, bg3]                   (src/estimator.cpp:489-499)
+ *   - all arithmetic is IEEE FP64 on the GPU; there is NO CPU fallback: every compute entry
+ *     point returns ISV_ERR_CUDA when no sm_100 device is usable;
+ *   - no entry point allocates caller-visible memory, throws, or aborts; device scratch is owned
+ *     by the handle; a handle is not thread-safe (one per host thread and GPU).
+ */
+#ifndef ISV_CAPI_H
+#define ISV_CAPI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISV_ABI_VERSION 1
+
+/* ---- status codes (SURVEY.md 8b "error conventions": the reference has none -- void + assert) */
+typedef enum isv_status {
+  ISV_OK = 0,
+  ISV_ERR_BAD_ARG = 1,
+  ISV_ERR_CUDA = 2,      /* no device / launch failure: loud, never a CPU fallback */
+  ISV_ERR_ALLOC = 3
+} isv_status;
+
+/* per-window status bits written by the kernels (int32 bitmask, 0 == clean) */
+#define ISV_W_NOT_SPD        0x01  /* an LLT met a non-positive pivot (reference: silent NaN)   */
+#define ISV_W_RANK_DEFICIENT 0x02  /* fwd: FullPivHouseholderQR rank < 6 -> eigen path taken    */
+#define ISV_W_NONFINITE      0x04  /* NaN/Inf in an output                                      */
+#define ISV_W_NONUNIT_QUAT   0x08  /* | |q|^2 - 1 | > 1e-9 on an input pose (structured kernel
+                                      assumes the unit quaternions ceres' Plus() guarantees)    */
+#define ISV_W_EIG_NOCONV     0x10  /* Jacobi eigensolver hit its sweep cap                      */
+#define ISV_W_SINGULAR       0x20  /* an LU inverse met a zero pivot                            */
+
+/* ---- configuration: the globals the reference reads inside Marg*  ------ */
+typedef struct isv_config {
+  double alpha;              /* ALPHA, config/euroc_config.yaml:86 ; eigenvalue kept iff > alpha */
+  double proj_sqrt_info[4];  /* ProjectionFactor::sqrt_info 2x2, src/estimator.cpp:35           */
+  double g[3];               /* G, src/parameters.cpp:19,96                                      */
+  double acc_n, gyr_n, acc_w, gyr_w; /* IntegrationBase noise, integration_base.h:21-27          */
+  int vo_size;               /* Vo_SIZE, include/parameters.h:35                                 */
+  int all_buf_size;          /* ALL_BUF_SIZE, include/parameters.h:40                            */
+  int qr_rank_eps_log10;     /* -16: `eps` of src/estimator.cpp:8 used at :1305                  */
+  int reserved;
+} isv_config;
+
+typedef struct isv_handle isv_handle;
+
+/* fills *cfg with config/euroc_config.yaml's values */
+void isv_default_config(isv_config* cfg);
+int isv_abi_version(void);
+/* human-readable name of a status code */
+const char* isv_status_string(isv_status s);
+
+isv_status isv_create(const isv_config* cfg, int device, isv_handle** out);
+void isv_destroy(isv_handle* h);
+/* the CUDA stream every call of this handle is ordered on (cudaStream_t as void*) */
+void* isv_stream(isv_handle* h);
+/* use an external stream (e.g. torch's current stream); 0 restores the handle's own stream */
+isv_status isv_set_stream(isv_handle* h, void* cuda_stream);
+isv_status isv_synchronize(isv_handle* h);
+/* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
+int64_t isv_launch_count(const isv_handle* h);
+
+/* ---- index maps: the bit-exact contract -------------------------------
+ * Each writes (offset, dim) per block into out[2*i], out[2*i+1] and returns the number of blocks.
+ *   init  (src/estimator.cpp:747-758): T0..T_{V-1}, VB_{V-1}, VB_0..VB_{V-2}       -> 2V blocks
+ *   fwd   (src/estimator.cpp:1153-1162): T1, T0, landmark 0..L-1                   -> 2+L blocks
+ *   bwd   (src/estimator.cpp:1358-1366): T_V, VB_V, T_{V-1}, VB_{V-1}              -> 4 blocks  */
+int isv_order_map_init(int vo_size, int32_t* out);
+int isv_order_map_forward(int n_landmarks, int32_t* out);
+int isv_order_map_backward(int vo_size, int32_t* out);
+
+/* ---- record sizes (doubles) ------------------------------------------------------------------ */
+#define ISV_POSE 7
+#define ISV_SB 9
+#define ISV_SE3_REC 48      /* t[3], R[9], sqrt_info[36]            (SE3PriorFactor members)      */
+#define ISV_REL_REC 48      /* delta_t[3], delta_R[9], sqrt_info[36] (RelativePoseFactor members)  */
+#define ISV_VB_REC 90       /* VB[9], sqrt_info[81]                  (Linear9Factor members)       */
+#define ISV_RP_IN_REC 5     /* valid (0/1), sqrt_info[4]  : vioRollPitchEdges[0] if index==0      */
+#define ISV_RP_REC 13       /* R[9], sqrt_info[4]                    (RollPitchFactor members)     */
+#define ISV_PG_REC 89       /* delta_t[3], delta_R[9], sqrt_info[36], covRel[36], distance, covAbs[4]
+                               (CombinedFactors, include/factor/pose_graph_factors.h:6-17)        */
+#define ISV_PREINT_REC 467  /* delta_p[3], delta_q[4] (x,y,z,w), delta_v[3], linearized_ba[3],
+                               linearized_bg[3], sum_dt, jacobian[225], covariance[225]
+                               (IntegrationBase members, integration_base.h:188-203)              */
+#define ISV_LM_COMPONENTS 6 /* x_i, y_i, z_i, x_j, y_j, inv_dep                                    */
+
+/* ---- batched MargForward + MargBackward over independent windows (device pointers) ----------
+ * One "window" = one MARGIN_OLD event = Estimator::MargForward (src/estimator.cpp:1149-1352)
+ * followed by Estimator::MargBackward (:1354-1539).  All pointers are DEVICE pointers, SoA over
+ * windows; landmark observations are component-major and CSR-indexed by lm_offset so that a warp
+ * reads 32 consecutive landmarks of one component in one coalesced 256-byte request.           */
+typedef struct isv_batch_in {
+  int32_t n_windows;
+  int32_t ex_pose_shared;        /* 1: ex_pose is one [7] record for all windows               */
+  const int64_t* lm_offset;      /* [n+1] first landmark of each window in lm_obs               */
+  const double* lm_obs;          /* [6][lm_stride]: pts_i.x, pts_i.y, pts_i.z, pts_j.x, pts_j.y,
+                                    inv_dep  (forwardProjectiontoSparsify[k]->pts_i/pts_j,
+                                    para_Feature[MargPointIdx[k]])                              */
+  int64_t lm_stride;             /* doubles between components (>= lm_offset[n])                */
+  const double* pose_fwd;        /* [n][2][7] para_Pose[0], para_Pose[1]                        */
+  const double* ex_pose;         /* [n][7] or [7]  para_Ex_Pose[0]                              */
+  const double* prior_se3;       /* [n][48]  vioPosePriorEdge            (t, R, sqrt_info)      */
+  const double* prior_rel;       /* [n][48]  vioRelativePoseEdges[1]     (delta_t, delta_R, s)  */
+  const double* prior_rp;        /* [n][5]   vioRollPitchEdges[0] (may be NULL: none valid)     */
+  const double* pose_bwd;        /* [n][2][7] para_Pose[V-1], para_Pose[V]                      */
+  const double* sb_bwd;          /* [n][2][9] para_SpeedBias[V-1], para_SpeedBias[V]            */
+  const double* prior_vb;        /* [n][90]  vioVBPrior                                         */
+  const double* preint;          /* [n][467] backwardIMUtoSparsify->pre_integration             */
+} isv_batch_in;
+
+typedef struct isv_batch_out {
+  double* se3_out;               /* [n][48]  forwardPosePriorEdgeToAdd                          */
+  double* pg_out;                /* [n][89]  CombinedFactors pushed to pose_graph_factors_buf   */
+  double* rel_out;               /* [n][48]  backwardRelativePoseEdgeToAdd                      */
+  double* vb_out;                /* [n][90]  backwardVBEdgeToAdd                                */
+  double* rp_out;                /* [n][13]  rollPitchFactor pushed to vioRollPitchEdges        */
+  int32_t* rank;                 /* [n][2]   fwd: QR rank of Lamda_prior (eigen rank if <6);
+                                             bwd: #eigenvalues > alpha                          */
+  int32_t* status;               /* [n]      ISV_W_* bitmask                                    */
+} isv_batch_out;
+
+#define ISV_RUN_FORWARD  1
+#define ISV_RUN_BACKWARD 2
+#define ISV_RUN_BOTH     3
+
+/* stream-ordered, asynchronous; `which` selects MargForward / MargBackward / both.
+ * Unused inputs/outputs of a skipped half may be NULL.                                          */
+isv_status isv_marg_window_batch(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out,
+                                 int which);
+
+/* same call with HOST pointers in both structs: stages H2D (pinned, chunked, overlapped with
+ * compute), runs the kernels, copies the outputs back and synchronises.  This is what the
+ * e2e number in bench.py times.                                                                 */
+isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in,
+                                      const isv_batch_out* out, int which);
+
+/* ---- single-window convenience wrappers (host pointers, blocking) ----------------------------
+ * These are what the shim's Estimator::MargForward()/MargBackward() call.                       */
+typedef struct isv_fwd_in {
+  int32_t n_landmarks;           /* MargPointIdx.size()                                          */
+  const double* pose0;           /* para_Pose[0]                                                 */
+  const double* pose1;           /* para_Pose[1]                                                 */
+  const double* ex_pose;         /* para_Ex_Pose[0]                                              */
+  const double* inv_dep;         /* [L]    para_Feature[MargPointIdx[k]][0]                      */
+  const double* pts_i;           /* [L][3] forwardProjectiontoSparsify[k]->pts_i                 */
+  const double* pts_j;           /* [L][3] forwardProjectiontoSparsify[k]->pts_j                 */
+  const double* prior_se3;       /* [48]   vioPosePriorEdge                                      */
+  const double* prior_rel;       /* [48]   vioRelativePoseEdges[1]                               */
+  const double* prior_rp;        /* [5] or NULL                                                  */
+} isv_fwd_in;
+
+typedef struct isv_fwd_out {
+  double se3[ISV_SE3_REC];
+  double pg[ISV_PG_REC];
+  int32_t rank;
+  int32_t status;
+} isv_fwd_out;
+
+typedef struct isv_bwd_in {
+  const double* pose_i;          /* para_Pose[V-1]                                               */
+  const double* sb_i;            /* para_SpeedBias[V-1]                                          */
+  const double* pose_j;          /* para_Pose[V]                                                 */
+  const double* sb_j;            /* para_SpeedBias[V]                                            */
+  const double* prior_vb;        /* [90]                                                         */
+  const double* preint;          /* [467]                                                        */
+} isv_bwd_in;
+
+typedef struct isv_bwd_out {
+  double rel[ISV_REL_REC];
+  double vb[ISV_VB_REC];
+  double rp[ISV_RP_REC];
+  int32_t rank;
+  int32_t status;
+} isv_bwd_out;
+
+isv_status isv_marg_forward(isv_handle* h, const isv_fwd_in* in, isv_fwd_out* out);
+isv_status isv_marg_backward(isv_handle* h, const isv_bwd_in* in, isv_bwd_out* out);
+
+/* ---- forensic / literal mode: the dense information matrices -----------------------------------
+ * Builds the reference's dense `Lamda` exactly as the block loops do
+ * (src/estimator.cpp:1168-1238 for forward, :1372-1412 for backward) with the scatter-add kernel,
+ * and the Schur complement `Lamda_prior` (:1286-1288 / :1413-1419).  Host pointers, blocking.
+ * lamda: (12+L)^2 resp. 30^2 doubles, column-major; lamda_prior: 36 resp. 441.  Either may be NULL. */
+isv_status isv_forward_lambda(isv_handle* h, const isv_fwd_in* in, double* lamda, double* lamda_prior);
+isv_status isv_backward_lambda(isv_handle* h, const isv_bwd_in* in, double* lamda, double* lamda_prior,
+                               double* eigenvalues /* [21] ascending, may be NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISV_CAPI_H */

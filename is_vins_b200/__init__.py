@@ -1,0 +1,10 @@
+"""B200-native IS-VINS sliding-window marginalization + sparsification backend.
+
+Product code: the CUDA library `libisv_b200.so` (is_vins_b200/csrc, C ABI in include/isv_capi.h) and
+the thin host mirror in this package.  Nothing here imports `oracle/` (test infrastructure).
+"""
+from . import capi  # noqa: F401
+from .batch import WindowBatch, WindowOutputs, pack_events  # noqa: F401
+from .backend import DeviceBatch, MargBackend  # noqa: F401
+
+__all__ = ["capi", "WindowBatch", "WindowOutputs", "pack_events", "DeviceBatch", "MargBackend"]

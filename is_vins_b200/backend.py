@@ -1,0 +1,140 @@
+"""`MargBackend`: one handle of libisv_b200.so bound to one GPU (include/isv_capi.h).
+
+Mirrors the call sites of the reference's backend (`Estimator::backendOptimization`,
+/root/reference/src/estimator.cpp:1541-1562): `marg_forward` / `marg_backward` for one
+MARGIN_OLD event, and the batched form over independent windows.  All arithmetic happens in the
+CUDA library; there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import capi
+from .batch import WindowBatch, WindowOutputs
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(capi.c_double_p)
+
+
+class DeviceBatch:
+    """A WindowBatch resident in HBM (torch CUDA tensors) plus preallocated outputs."""
+
+    def __init__(self, batch: WindowBatch, device, pinned_src: bool = False):
+        import torch
+        self.torch = torch
+        self.device = torch.device(device)
+        self.n = batch.n
+        self.t: Dict[str, "torch.Tensor"] = {}
+        for f in WindowBatch.FIELDS:
+            a = getattr(batch, f)
+            if a is not None:
+                self.t[f] = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        self.ex_shared = batch.ex_pose.ndim == 1
+        self.n_lm = batch.n_landmarks
+        n = batch.n
+        kw = dict(dtype=torch.float64, device=self.device)
+        self.out = {
+            "se3": torch.empty((n, capi.SE3_REC), **kw), "pg": torch.empty((n, capi.PG_REC), **kw),
+            "rel": torch.empty((n, capi.REL_REC), **kw), "vb": torch.empty((n, capi.VB_REC), **kw),
+            "rp": torch.empty((n, capi.RP_REC), **kw),
+            "rank": torch.zeros((n, 2), dtype=torch.int32, device=self.device),
+            "status": torch.zeros((n,), dtype=torch.int32, device=self.device),
+        }
+
+    def structs(self):
+        t = self.t
+        g = lambda k: t[k].data_ptr() if k in t else None
+        bi = capi.isv_batch_in(self.n, 1 if self.ex_shared else 0, g("lm_offset"), g("lm_obs"), self.n_lm,
+                               g("pose_fwd"), g("ex_pose"), g("prior_se3"), g("prior_rel"), g("prior_rp"),
+                               g("pose_bwd"), g("sb_bwd"), g("prior_vb"), g("preint"))
+        o = self.out
+        bo = capi.isv_batch_out(o["se3"].data_ptr(), o["pg"].data_ptr(), o["rel"].data_ptr(), o["vb"].data_ptr(),
+                                o["rp"].data_ptr(), o["rank"].data_ptr(), o["status"].data_ptr())
+        return bi, bo
+
+    def outputs(self) -> WindowOutputs:
+        o = {k: v.cpu().numpy() for k, v in self.out.items()}
+        return WindowOutputs(o["se3"], o["pg"], o["rel"], o["vb"], o["rp"], o["rank"], o["status"])
+
+
+class MargBackend:
+    def __init__(self, device: int = 0, config: Optional[capi.isv_config] = None):
+        self.lib = capi.load()
+        self.cfg = config if config is not None else capi.default_config()
+        self.h = C.c_void_p()
+        capi.check(self.lib.isv_create(C.byref(self.cfg), int(device), C.byref(self.h)), "isv_create")
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.isv_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def use_torch_stream(self):
+        import torch
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        capi.check(self.lib.isv_set_stream(self.h, C.c_void_p(s)), "isv_set_stream")
+
+    def synchronize(self):
+        capi.check(self.lib.isv_synchronize(self.h), "isv_synchronize")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.isv_launch_count(self.h))
+
+    # ---- batched, device-resident ---------------------------------------------------------------
+    def marg_window_batch(self, dbatch: DeviceBatch, which: int = capi.RUN_BOTH) -> None:
+        """Stream-ordered MargForward+MargBackward over dbatch; results land in dbatch.out."""
+        bi, bo = dbatch.structs()
+        capi.check(self.lib.isv_marg_window_batch(self.h, C.byref(bi), C.byref(bo), which), "isv_marg_window_batch")
+
+    # ---- batched, host pointers (H2D + kernels + D2H inside the call) ---------------------------
+    def marg_window_batch_host(self, batch: WindowBatch, which: int = capi.RUN_BOTH,
+                               out: Optional[WindowOutputs] = None) -> WindowOutputs:
+        n = batch.n
+        if out is None:
+            out = WindowOutputs(np.zeros((n, capi.SE3_REC)), np.zeros((n, capi.PG_REC)), np.zeros((n, capi.REL_REC)),
+                                np.zeros((n, capi.VB_REC)), np.zeros((n, capi.RP_REC)),
+                                np.zeros((n, 2), np.int32), np.zeros((n,), np.int32))
+        bi = capi.isv_batch_in(n, 1 if batch.ex_pose.ndim == 1 else 0, _p(batch.lm_offset), _p(batch.lm_obs),
+                               batch.lm_obs.shape[1], _p(batch.pose_fwd), _p(batch.ex_pose), _p(batch.prior_se3),
+                               _p(batch.prior_rel), _p(batch.prior_rp), _p(batch.pose_bwd), _p(batch.sb_bwd),
+                               _p(batch.prior_vb), _p(batch.preint))
+        bo = capi.isv_batch_out(_p(out.se3), _p(out.pg), _p(out.rel), _p(out.vb), _p(out.rp), _p(out.rank),
+                                _p(out.status))
+        capi.check(self.lib.isv_marg_window_batch_host(self.h, C.byref(bi), C.byref(bo), which),
+                   "isv_marg_window_batch_host")
+        return out
+
+    # ---- one MARGIN_OLD event (what Estimator::MargForward / MargBackward call) -------------------
+    def marg_forward(self, pose0, pose1, ex_pose, inv_dep, pts_i, pts_j, prior_se3, prior_rel, prior_rp=None):
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (pose0, pose1, ex_pose, inv_dep, pts_i, pts_j,
+                                                                 prior_se3, prior_rel)]
+        rp = None if prior_rp is None else np.ascontiguousarray(prior_rp, dtype=np.float64)
+        fi = capi.isv_fwd_in(int(a[3].shape[0]), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), _dp(a[4]), _dp(a[5]),
+                             _dp(a[6]), _dp(a[7]), None if rp is None else _dp(rp))
+        fo = capi.isv_fwd_out()
+        capi.check(self.lib.isv_marg_forward(self.h, C.byref(fi), C.byref(fo)), "isv_marg_forward")
+        return np.array(fo.se3), np.array(fo.pg), int(fo.rank), int(fo.status)
+
+    def marg_backward(self, pose_i, sb_i, pose_j, sb_j, prior_vb, preint):
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (pose_i, sb_i, pose_j, sb_j, prior_vb, preint)]
+        bi = capi.isv_bwd_in(*[_dp(x) for x in a])
+        bo = capi.isv_bwd_out()
+        capi.check(self.lib.isv_marg_backward(self.h, C.byref(bi), C.byref(bo)), "isv_marg_backward")
+        return np.array(bo.rel), np.array(bo.vb), np.array(bo.rp), int(bo.rank), int(bo.status)

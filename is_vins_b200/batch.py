@@ -1,0 +1,187 @@
+"""SoA window batches: the memory layout the C ABI consumes (include/isv_capi.h, isv_batch_in/out).
+
+Plain NumPy on the host; `to_device` moves a batch to torch CUDA tensors (PyTorch is only used for
+device memory and streams).  Matrices inside records are column-major, i.e. the bytes of the
+Eigen member they mirror.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+
+
+def se3_record(t, R, sqrt_info) -> np.ndarray:
+    """SE3PriorFactor / RelativePoseFactor members -> [t3 | R col-major 9 | sqrt_info col-major 36]."""
+    return np.concatenate([np.asarray(t, float).ravel(), np.asarray(R, float).flatten(order="F"),
+                           np.asarray(sqrt_info, float).flatten(order="F")])
+
+
+def vb_record(vb, sqrt_info) -> np.ndarray:
+    return np.concatenate([np.asarray(vb, float).ravel(), np.asarray(sqrt_info, float).flatten(order="F")])
+
+
+def rp_in_record(valid: bool, sqrt_info=None) -> np.ndarray:
+    r = np.zeros(capi.RP_IN_REC)
+    if valid:
+        r[0] = 1.0
+        r[1:5] = np.asarray(sqrt_info, float).flatten(order="F")
+    return r
+
+
+@dataclass
+class WindowBatch:
+    """Inputs of n independent MARGIN_OLD events (MargForward + MargBackward)."""
+    n: int
+    lm_offset: np.ndarray            # int64 [n+1]
+    lm_obs: np.ndarray               # f64 [6, n_lm]  x_i y_i z_i x_j y_j inv_dep
+    pose_fwd: np.ndarray             # [n,2,7]
+    ex_pose: np.ndarray              # [7] (shared) or [n,7]
+    prior_se3: np.ndarray            # [n,48]
+    prior_rel: np.ndarray            # [n,48]
+    prior_rp: Optional[np.ndarray]   # [n,5] or None
+    pose_bwd: np.ndarray             # [n,2,7]
+    sb_bwd: np.ndarray               # [n,2,9]
+    prior_vb: np.ndarray             # [n,90]
+    preint: np.ndarray               # [n,467]
+    imu_raw: Optional[np.ndarray] = None    # [n,K,7] dt,acc,gyr  (input of the pre-integration kernel)
+    imu_init: Optional[np.ndarray] = None   # [n,12]  acc0, gyr0, lin_ba, lin_bg
+
+    FIELDS = ("lm_offset", "lm_obs", "pose_fwd", "ex_pose", "prior_se3", "prior_rel", "prior_rp", "pose_bwd",
+              "sb_bwd", "prior_vb", "preint", "imu_raw", "imu_init")
+
+    @property
+    def n_landmarks(self) -> int:
+        return int(self.lm_offset[-1])
+
+    def input_bytes(self) -> int:
+        return sum(getattr(self, f).nbytes for f in self.FIELDS[:11] if getattr(self, f) is not None)
+
+    def tile(self, reps: int) -> "WindowBatch":
+        """Repeat the batch `reps` times (independent copies of the same windows)."""
+        n = self.n * reps
+        counts = np.tile(np.diff(self.lm_offset), reps)
+        off = np.zeros(n + 1, np.int64)
+        np.cumsum(counts, out=off[1:])
+        t = lambda a: None if a is None else np.ascontiguousarray(np.tile(a, (reps,) + (1,) * (a.ndim - 1)))
+        return WindowBatch(n, off, np.ascontiguousarray(np.tile(self.lm_obs, (1, reps))), t(self.pose_fwd),
+                           self.ex_pose if self.ex_pose.ndim == 1 else t(self.ex_pose), t(self.prior_se3),
+                           t(self.prior_rel), t(self.prior_rp), t(self.pose_bwd), t(self.sb_bwd), t(self.prior_vb),
+                           t(self.preint), t(self.imu_raw), t(self.imu_init))
+
+    def slice(self, lo: int, hi: int) -> "WindowBatch":
+        """Windows [lo, hi) -- the contiguous shard one rank owns."""
+        a, b = int(self.lm_offset[lo]), int(self.lm_offset[hi])
+        s = lambda x: None if x is None else np.ascontiguousarray(x[lo:hi])
+        return WindowBatch(hi - lo, (self.lm_offset[lo:hi + 1] - a).astype(np.int64),
+                           np.ascontiguousarray(self.lm_obs[:, a:b]), s(self.pose_fwd),
+                           self.ex_pose if self.ex_pose.ndim == 1 else s(self.ex_pose), s(self.prior_se3),
+                           s(self.prior_rel), s(self.prior_rp), s(self.pose_bwd), s(self.sb_bwd), s(self.prior_vb),
+                           s(self.preint), s(self.imu_raw), s(self.imu_init))
+
+
+def pack_events(events: Sequence, with_rp: bool = True) -> WindowBatch:
+    """Pack records exposing the reference's member names (``fwd_in``/``bwd_in`` with pose0, pose1,
+    ex_pose, inv_dep, pts_i, pts_j, prior_t, prior_R, prior_sqrt_info, rel_dt, rel_dR, rel_sqrt_info,
+    rp_valid, rp_sqrt_info / pose_i, sb_i, pose_j, sb_j, vb_prior, vb_sqrt_info, pre.pack())."""
+    n = len(events)
+    counts = [int(len(e.fwd_in.inv_dep)) for e in events]
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum(counts, out=off[1:])
+    obs = np.zeros((6, int(off[-1])))
+    pose_fwd = np.zeros((n, 2, 7))
+    prior_se3 = np.zeros((n, capi.SE3_REC))
+    prior_rel = np.zeros((n, capi.REL_REC))
+    prior_rp = np.zeros((n, capi.RP_IN_REC))
+    pose_bwd = np.zeros((n, 2, 7))
+    sb_bwd = np.zeros((n, 2, 9))
+    prior_vb = np.zeros((n, capi.VB_REC))
+    preint = np.zeros((n, capi.PREINT_REC))
+    K = max(int(e.raw_imu.shape[0]) for e in events) if hasattr(events[0], "raw_imu") else 0
+    same_k = K > 0 and all(int(e.raw_imu.shape[0]) == K for e in events)
+    imu_raw = np.zeros((n, K, 7)) if same_k else None
+    imu_init = np.zeros((n, 12)) if same_k else None
+    ex = None
+    for w, e in enumerate(events):
+        f, b = e.fwd_in, e.bwd_in
+        a, c = int(off[w]), int(off[w + 1])
+        obs[0:3, a:c] = np.asarray(f.pts_i, float).T
+        obs[3:5, a:c] = np.asarray(f.pts_j, float).T[0:2]
+        obs[5, a:c] = f.inv_dep
+        pose_fwd[w, 0], pose_fwd[w, 1] = f.pose0, f.pose1
+        ex = np.asarray(f.ex_pose, float) if ex is None else ex
+        prior_se3[w] = se3_record(f.prior_t, f.prior_R, f.prior_sqrt_info)
+        prior_rel[w] = se3_record(f.rel_dt, f.rel_dR, f.rel_sqrt_info)
+        prior_rp[w] = rp_in_record(bool(f.rp_valid), f.rp_sqrt_info)
+        pose_bwd[w, 0], pose_bwd[w, 1] = b.pose_i, b.pose_j
+        sb_bwd[w, 0], sb_bwd[w, 1] = b.sb_i, b.sb_j
+        prior_vb[w] = vb_record(b.vb_prior, b.vb_sqrt_info)
+        preint[w] = b.pre.pack()
+        if same_k:
+            imu_raw[w] = e.raw_imu
+            imu_init[w] = np.concatenate([e.acc0, e.gyr0, b.pre.linearized_ba, b.pre.linearized_bg])
+    return WindowBatch(n, off, obs, pose_fwd, ex, prior_se3, prior_rel, prior_rp if with_rp else None, pose_bwd,
+                       sb_bwd, prior_vb, preint, imu_raw, imu_init)
+
+
+@dataclass
+class WindowOutputs:
+    se3: np.ndarray      # [n,48] forwardPosePriorEdgeToAdd
+    pg: np.ndarray       # [n,89] CombinedFactors
+    rel: np.ndarray      # [n,48] backwardRelativePoseEdgeToAdd
+    vb: np.ndarray       # [n,90] backwardVBEdgeToAdd
+    rp: np.ndarray       # [n,13] rollPitchFactor
+    rank: np.ndarray     # [n,2]
+    status: np.ndarray   # [n]
+
+    # record views (column-major matrices -> numpy row-major arrays)
+    def se3_sqrt_info(self, w):
+        return self.se3[w, 12:48].reshape(6, 6).T
+
+    def se3_t(self, w):
+        return self.se3[w, 0:3]
+
+    def se3_R(self, w):
+        return self.se3[w, 3:12].reshape(3, 3).T
+
+    def pg_dt(self, w):
+        return self.pg[w, 0:3]
+
+    def pg_dR(self, w):
+        return self.pg[w, 3:12].reshape(3, 3).T
+
+    def pg_sqrt_info(self, w):
+        return self.pg[w, 12:48].reshape(6, 6).T
+
+    def pg_covRel(self, w):
+        return self.pg[w, 48:84].reshape(6, 6).T
+
+    def pg_distance(self, w):
+        return self.pg[w, 84]
+
+    def pg_covAbs(self, w):
+        return self.pg[w, 85:89].reshape(2, 2).T
+
+    def rel_dt(self, w):
+        return self.rel[w, 0:3]
+
+    def rel_dR(self, w):
+        return self.rel[w, 3:12].reshape(3, 3).T
+
+    def rel_sqrt_info(self, w):
+        return self.rel[w, 12:48].reshape(6, 6).T
+
+    def vb_VB(self, w):
+        return self.vb[w, 0:9]
+
+    def vb_sqrt_info(self, w):
+        return self.vb[w, 9:90].reshape(9, 9).T
+
+    def rp_R(self, w):
+        return self.rp[w, 0:9].reshape(3, 3).T
+
+    def rp_sqrt_info(self, w):
+        return self.rp[w, 9:13].reshape(2, 2).T

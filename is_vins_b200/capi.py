@@ -1,0 +1,121 @@
+"""ctypes binding of the C ABI in ``include/isv_capi.h`` (libisv_b200.so).
+
+The shared library is the product; this module only loads it and mirrors its PODs.  There is no
+CPU fallback: if the library is missing, or no sm_100 GPU is usable, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libisv_b200.so")
+
+ISV_OK, ISV_ERR_BAD_ARG, ISV_ERR_CUDA, ISV_ERR_ALLOC = 0, 1, 2, 3
+W_NOT_SPD, W_RANK_DEFICIENT, W_NONFINITE, W_NONUNIT_QUAT, W_EIG_NOCONV, W_SINGULAR = 1, 2, 4, 8, 16, 32
+RUN_FORWARD, RUN_BACKWARD, RUN_BOTH = 1, 2, 3
+POSE, SB, SE3_REC, REL_REC, VB_REC, RP_IN_REC, RP_REC, PG_REC, PREINT_REC = 7, 9, 48, 48, 90, 5, 13, 89, 467
+IMU_RAW_REC = 7
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+
+
+class isv_config(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("proj_sqrt_info", C.c_double * 4), ("g", C.c_double * 3),
+                ("acc_n", C.c_double), ("gyr_n", C.c_double), ("acc_w", C.c_double), ("gyr_w", C.c_double),
+                ("vo_size", C.c_int), ("all_buf_size", C.c_int), ("qr_rank_eps_log10", C.c_int),
+                ("reserved", C.c_int)]
+
+
+class isv_batch_in(C.Structure):
+    _fields_ = [("n_windows", C.c_int32), ("ex_pose_shared", C.c_int32), ("lm_offset", C.c_void_p),
+                ("lm_obs", C.c_void_p), ("lm_stride", C.c_int64), ("pose_fwd", C.c_void_p),
+                ("ex_pose", C.c_void_p), ("prior_se3", C.c_void_p), ("prior_rel", C.c_void_p),
+                ("prior_rp", C.c_void_p), ("pose_bwd", C.c_void_p), ("sb_bwd", C.c_void_p),
+                ("prior_vb", C.c_void_p), ("preint", C.c_void_p)]
+
+
+class isv_batch_out(C.Structure):
+    _fields_ = [("se3_out", C.c_void_p), ("pg_out", C.c_void_p), ("rel_out", C.c_void_p),
+                ("vb_out", C.c_void_p), ("rp_out", C.c_void_p), ("rank", C.c_void_p), ("status", C.c_void_p)]
+
+
+class isv_fwd_in(C.Structure):
+    _fields_ = [("n_landmarks", C.c_int32), ("pose0", c_double_p), ("pose1", c_double_p), ("ex_pose", c_double_p),
+                ("inv_dep", c_double_p), ("pts_i", c_double_p), ("pts_j", c_double_p), ("prior_se3", c_double_p),
+                ("prior_rel", c_double_p), ("prior_rp", c_double_p)]
+
+
+class isv_fwd_out(C.Structure):
+    _fields_ = [("se3", C.c_double * SE3_REC), ("pg", C.c_double * PG_REC), ("rank", C.c_int32),
+                ("status", C.c_int32)]
+
+
+class isv_bwd_in(C.Structure):
+    _fields_ = [("pose_i", c_double_p), ("sb_i", c_double_p), ("pose_j", c_double_p), ("sb_j", c_double_p),
+                ("prior_vb", c_double_p), ("preint", c_double_p)]
+
+
+class isv_bwd_out(C.Structure):
+    _fields_ = [("rel", C.c_double * REL_REC), ("vb", C.c_double * VB_REC), ("rp", C.c_double * RP_REC),
+                ("rank", C.c_int32), ("status", C.c_int32)]
+
+
+# every symbol include/isv_capi.h declares: (name, restype, argtypes)
+_H = C.c_void_p
+SYMBOLS = [
+    ("isv_default_config", None, [C.POINTER(isv_config)]),
+    ("isv_abi_version", C.c_int, []),
+    ("isv_status_string", C.c_char_p, [C.c_int]),
+    ("isv_create", C.c_int, [C.POINTER(isv_config), C.c_int, C.POINTER(_H)]),
+    ("isv_destroy", None, [_H]),
+    ("isv_stream", C.c_void_p, [_H]),
+    ("isv_set_stream", C.c_int, [_H, C.c_void_p]),
+    ("isv_synchronize", C.c_int, [_H]),
+    ("isv_launch_count", C.c_int64, [_H]),
+    ("isv_order_map_init", C.c_int, [C.c_int, c_int32_p]),
+    ("isv_order_map_forward", C.c_int, [C.c_int, c_int32_p]),
+    ("isv_order_map_backward", C.c_int, [C.c_int, c_int32_p]),
+    ("isv_marg_window_batch", C.c_int, [_H, C.POINTER(isv_batch_in), C.POINTER(isv_batch_out), C.c_int]),
+    ("isv_marg_window_batch_host", C.c_int, [_H, C.POINTER(isv_batch_in), C.POINTER(isv_batch_out), C.c_int]),
+    ("isv_marg_forward", C.c_int, [_H, C.POINTER(isv_fwd_in), C.POINTER(isv_fwd_out)]),
+    ("isv_marg_backward", C.c_int, [_H, C.POINTER(isv_bwd_in), C.POINTER(isv_bwd_out)]),
+]
+
+_lib: Optional[C.CDLL] = None
+
+
+class IsvError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """dlopen libisv_b200.so (built by ``__graft_entry__.build()`` / ``make -C is_vins_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IsvError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "-- there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)     # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != ISV_OK:
+        name = load().isv_status_string(status).decode()
+        raise IsvError(f"{what or 'isv call'} failed: {name}")
+
+
+def default_config() -> isv_config:
+    cfg = isv_config()
+    load().isv_default_config(C.byref(cfg))
+    return cfg

@@ -1,0 +1,392 @@
+// C ABI of the B200-native IS-VINS marginalization backend (include/isv_capi.h).
+// Host side only: argument checks, device scratch owned by the handle, H2D/D2H staging for the
+// host-pointer entry points, kernel launches.  No CPU fallback anywhere: without a usable sm_100
+// device every compute entry point returns ISV_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "isv_window_kernels.cuh"
+
+using namespace isv;
+
+struct isv_handle {
+  int device;
+  cudaStream_t own_stream;
+  cudaStream_t stream;
+  cudaStream_t copy_stream;
+  isv_config cfg;
+  DevCfg dcfg;
+  int64_t launches;
+  // device mirror of a host batch (grow-only)
+  char* dbuf;
+  size_t dbuf_bytes;
+  char* pinned;
+  size_t pinned_bytes;
+  cudaEvent_t ev[4];
+};
+
+#define ISV_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      fprintf(stderr, "[isv_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return ISV_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+extern "C" {
+
+void isv_default_config(isv_config* c) {
+  if (!c) return;
+  memset(c, 0, sizeof(*c));
+  c->alpha = 0.1;                 // config/euroc_config.yaml:86
+  c->proj_sqrt_info[0] = 460.0;   // yaml:83, src/estimator.cpp:35
+  c->proj_sqrt_info[3] = 460.0;
+  c->g[2] = 9.81007;              // yaml g_norm, src/parameters.cpp:96
+  c->acc_n = 0.22627;             // yaml:57-60
+  c->gyr_n = 0.003988;
+  c->acc_w = 0.001;
+  c->gyr_w = 0.0001;
+  c->vo_size = 8;                 // include/parameters.h:35
+  c->all_buf_size = 18;           // include/parameters.h:40
+  c->qr_rank_eps_log10 = -16;     // src/estimator.cpp:8
+}
+
+int isv_abi_version(void) { return ISV_ABI_VERSION; }
+
+const char* isv_status_string(isv_status s) {
+  switch (s) {
+    case ISV_OK: return "ISV_OK";
+    case ISV_ERR_BAD_ARG: return "ISV_ERR_BAD_ARG";
+    case ISV_ERR_CUDA: return "ISV_ERR_CUDA";
+    case ISV_ERR_ALLOC: return "ISV_ERR_ALLOC";
+  }
+  return "ISV_ERR_UNKNOWN";
+}
+
+isv_status isv_create(const isv_config* cfg, int device, isv_handle** out) {
+  if (!cfg || !out) return ISV_ERR_BAD_ARG;
+  if (cfg->vo_size < 2 || !(cfg->alpha >= 0.0)) return ISV_ERR_BAD_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  ISV_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return ISV_ERR_CUDA;
+  cudaDeviceProp prop;
+  ISV_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    fprintf(stderr, "[isv_b200] device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major,
+            prop.minor);
+    return ISV_ERR_CUDA;
+  }
+  ISV_CUDA(cudaSetDevice(device));
+  isv_handle* h = new (std::nothrow) isv_handle();
+  if (!h) return ISV_ERR_ALLOC;
+  memset(h, 0, sizeof(*h));
+  h->device = device;
+  h->cfg = *cfg;
+  h->dcfg.alpha = cfg->alpha;
+  for (int i = 0; i < 4; ++i) h->dcfg.ps[i] = cfg->proj_sqrt_info[i];
+  for (int i = 0; i < 3; ++i) h->dcfg.g[i] = cfg->g[i];
+  h->dcfg.qr_threshold = pow(10.0, (double)cfg->qr_rank_eps_log10);
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return ISV_ERR_CUDA;
+  }
+  for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
+  h->stream = h->own_stream;
+  cudaFuncSetAttribute(marg_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(kWarpsPerCta * kFwdSmemPerWarp * sizeof(double)));
+  cudaFuncSetAttribute(marg_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(kWarpsPerCta * kBwdSmemPerWarp * sizeof(double)));
+  *out = h;
+  return ISV_OK;
+}
+
+void isv_destroy(isv_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->dbuf) cudaFree(h->dbuf);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  for (int i = 0; i < 4; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  cudaStreamDestroy(h->own_stream);
+  cudaStreamDestroy(h->copy_stream);
+  delete h;
+}
+
+void* isv_stream(isv_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+isv_status isv_set_stream(isv_handle* h, void* s) {
+  if (!h) return ISV_ERR_BAD_ARG;
+  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return ISV_OK;
+}
+
+isv_status isv_synchronize(isv_handle* h) {
+  if (!h) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  ISV_CUDA(cudaStreamSynchronize(h->stream));
+  return ISV_OK;
+}
+
+int64_t isv_launch_count(const isv_handle* h) { return h ? h->launches : 0; }
+
+// ---- index maps -------------------------------------------------------------------------------
+int isv_order_map_init(int V, int32_t* out) {
+  if (V < 2 || !out) return 0;
+  int idx = 0, b = 0;
+  for (int i = 0; i < V; ++i) { out[2 * b] = idx; out[2 * b + 1] = 6; idx += 6; ++b; }
+  out[2 * b] = idx; out[2 * b + 1] = 9; idx += 9; ++b;
+  for (int i = 0; i < V - 1; ++i) { out[2 * b] = idx; out[2 * b + 1] = 9; idx += 9; ++b; }
+  return b;
+}
+
+int isv_order_map_forward(int L, int32_t* out) {
+  if (L < 0 || !out) return 0;
+  out[0] = 0; out[1] = 6; out[2] = 6; out[3] = 6;
+  for (int k = 0; k < L; ++k) { out[4 + 2 * k] = 12 + k; out[5 + 2 * k] = 1; }
+  return 2 + L;
+}
+
+int isv_order_map_backward(int V, int32_t* out) {
+  (void)V;
+  if (!out) return 0;
+  const int32_t m[8] = {0, 6, 6, 9, 15, 6, 21, 9};
+  memcpy(out, m, sizeof(m));
+  return 4;
+}
+
+// ---- batched device entry point ---------------------------------------------------------------
+static isv_status check_batch(const isv_batch_in* in, const isv_batch_out* out, int which) {
+  if (!in || !out || in->n_windows < 0 || (which & ~ISV_RUN_BOTH) || which == 0) return ISV_ERR_BAD_ARG;
+  if (!out->rank) return ISV_ERR_BAD_ARG;
+  if (which & ISV_RUN_FORWARD) {
+    if (!in->lm_offset || !in->pose_fwd || !in->ex_pose || !in->prior_se3 || !in->prior_rel || !out->se3_out ||
+        !out->pg_out)
+      return ISV_ERR_BAD_ARG;
+    if (!in->lm_obs && in->lm_stride != 0) return ISV_ERR_BAD_ARG;
+  }
+  if (which & ISV_RUN_BACKWARD) {
+    if (!in->pose_bwd || !in->sb_bwd || !in->prior_vb || !in->preint || !out->rel_out || !out->vb_out || !out->rp_out)
+      return ISV_ERR_BAD_ARG;
+  }
+  return ISV_OK;
+}
+
+isv_status isv_marg_window_batch(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, int which) {
+  if (!h) return ISV_ERR_BAD_ARG;
+  isv_status st = check_batch(in, out, which);
+  if (st != ISV_OK) return st;
+  const int n = in->n_windows;
+  if (n == 0) return ISV_OK;
+  ISV_CUDA(cudaSetDevice(h->device));
+  if (out->status) ISV_CUDA(cudaMemsetAsync(out->status, 0, sizeof(int32_t) * (size_t)n, h->stream));
+  const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+  if (which & ISV_RUN_FORWARD) {
+    marg_forward_kernel<<<grid, kThreads, kWarpsPerCta * kFwdSmemPerWarp * sizeof(double), h->stream>>>(*in, *out,
+                                                                                                       h->dcfg);
+    ++h->launches;
+  }
+  if (which & ISV_RUN_BACKWARD) {
+    marg_backward_kernel<<<grid, kThreads, kWarpsPerCta * kBwdSmemPerWarp * sizeof(double), h->stream>>>(
+        *in, *out, h->dcfg, h->cfg.vo_size);
+    ++h->launches;
+  }
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+// ---- host-pointer entry point ------------------------------------------------------------------
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static isv_status ensure_dbuf(isv_handle* h, size_t bytes) {
+  if (h->dbuf_bytes >= bytes) return ISV_OK;
+  if (h->dbuf) {
+    ISV_CUDA(cudaStreamSynchronize(h->stream));
+    ISV_CUDA(cudaFree(h->dbuf));
+    h->dbuf = nullptr;
+    h->dbuf_bytes = 0;
+  }
+  size_t cap = bytes + bytes / 4;
+  if (cudaMalloc(&h->dbuf, cap) != cudaSuccess) {
+    cudaGetLastError();
+    return ISV_ERR_ALLOC;
+  }
+  h->dbuf_bytes = cap;
+  return ISV_OK;
+}
+
+isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, int which) {
+  if (!h) return ISV_ERR_BAD_ARG;
+  isv_status st = check_batch(in, out, which);
+  if (st != ISV_OK) return st;
+  const size_t n = (size_t)in->n_windows;
+  if (n == 0) return ISV_OK;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const bool fwd = which & ISV_RUN_FORWARD, bwd = which & ISV_RUN_BACKWARD;
+  const size_t D = sizeof(double);
+  int64_t n_lm = fwd ? in->lm_offset[n] : 0;
+  if (n_lm < 0 || (fwd && in->lm_stride < n_lm)) return ISV_ERR_BAD_ARG;
+  // carve the device mirror
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  size_t o_lmoff = carve(fwd ? (n + 1) * sizeof(int64_t) : 0);
+  size_t o_obs = carve(fwd ? 6 * (size_t)n_lm * D : 0);
+  size_t o_posef = carve(fwd ? n * 14 * D : 0);
+  size_t o_ex = carve(fwd ? (in->ex_pose_shared ? 7 : n * 7) * D : 0);
+  size_t o_pse3 = carve(fwd ? n * ISV_SE3_REC * D : 0);
+  size_t o_prel = carve(fwd ? n * ISV_REL_REC * D : 0);
+  size_t o_prp = carve(fwd && in->prior_rp ? n * ISV_RP_IN_REC * D : 0);
+  size_t o_poseb = carve(bwd ? n * 14 * D : 0);
+  size_t o_sbb = carve(bwd ? n * 18 * D : 0);
+  size_t o_pvb = carve(bwd ? n * ISV_VB_REC * D : 0);
+  size_t o_pre = carve(bwd ? n * ISV_PREINT_REC * D : 0);
+  size_t o_se3 = carve(fwd ? n * ISV_SE3_REC * D : 0);
+  size_t o_pg = carve(fwd ? n * ISV_PG_REC * D : 0);
+  size_t o_rel = carve(bwd ? n * ISV_REL_REC * D : 0);
+  size_t o_vb = carve(bwd ? n * ISV_VB_REC * D : 0);
+  size_t o_rp = carve(bwd ? n * ISV_RP_REC * D : 0);
+  size_t o_rank = carve(n * 2 * sizeof(int32_t));
+  size_t o_stat = carve(n * sizeof(int32_t));
+  st = ensure_dbuf(h, off);
+  if (st != ISV_OK) return st;
+  char* d = h->dbuf;
+  cudaStream_t s = h->stream;
+  isv_batch_in din = *in;
+  isv_batch_out dout;
+  memset(&dout, 0, sizeof(dout));
+  ISV_CUDA(cudaMemsetAsync(d + o_rank, 0, n * 2 * sizeof(int32_t), s));
+  if (fwd) {
+    ISV_CUDA(cudaMemcpyAsync(d + o_lmoff, in->lm_offset, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    for (int c = 0; c < 6 && n_lm > 0; ++c)
+      ISV_CUDA(cudaMemcpyAsync(d + o_obs + (size_t)c * n_lm * D, in->lm_obs + (size_t)c * in->lm_stride,
+                               (size_t)n_lm * D, cudaMemcpyHostToDevice, s));
+    ISV_CUDA(cudaMemcpyAsync(d + o_posef, in->pose_fwd, n * 14 * D, cudaMemcpyHostToDevice, s));
+    ISV_CUDA(cudaMemcpyAsync(d + o_ex, in->ex_pose, (in->ex_pose_shared ? 7 : n * 7) * D, cudaMemcpyHostToDevice, s));
+    ISV_CUDA(cudaMemcpyAsync(d + o_pse3, in->prior_se3, n * ISV_SE3_REC * D, cudaMemcpyHostToDevice, s));
+    ISV_CUDA(cudaMemcpyAsync(d + o_prel, in->prior_rel, n * ISV_REL_REC * D, cudaMemcpyHostToDevice, s));
+    if (in->prior_rp)
+      ISV_CUDA(cudaMemcpyAsync(d + o_prp, in->prior_rp, n * ISV_RP_IN_REC * D, cudaMemcpyHostToDevice, s));
+    din.lm_offset = (const int64_t*)(d + o_lmoff);
+    din.lm_obs = (const double*)(d + o_obs);
+    din.lm_stride = n_lm;
+    din.pose_fwd = (const double*)(d + o_posef);
+    din.ex_pose = (const double*)(d + o_ex);
+    din.prior_se3 = (const double*)(d + o_pse3);
+    din.prior_rel = (const double*)(d + o_prel);
+    din.prior_rp = in->prior_rp ? (const double*)(d + o_prp) : nullptr;
+    dout.se3_out = (double*)(d + o_se3);
+    dout.pg_out = (double*)(d + o_pg);
+  }
+  if (bwd) {
+    ISV_CUDA(cudaMemcpyAsync(d + o_poseb, in->pose_bwd, n * 14 * D, cudaMemcpyHostToDevice, s));
+    ISV_CUDA(cudaMemcpyAsync(d + o_sbb, in->sb_bwd, n * 18 * D, cudaMemcpyHostToDevice, s));
+    ISV_CUDA(cudaMemcpyAsync(d + o_pvb, in->prior_vb, n * ISV_VB_REC * D, cudaMemcpyHostToDevice, s));
+    ISV_CUDA(cudaMemcpyAsync(d + o_pre, in->preint, n * ISV_PREINT_REC * D, cudaMemcpyHostToDevice, s));
+    din.pose_bwd = (const double*)(d + o_poseb);
+    din.sb_bwd = (const double*)(d + o_sbb);
+    din.prior_vb = (const double*)(d + o_pvb);
+    din.preint = (const double*)(d + o_pre);
+    dout.rel_out = (double*)(d + o_rel);
+    dout.vb_out = (double*)(d + o_vb);
+    dout.rp_out = (double*)(d + o_rp);
+  }
+  dout.rank = (int32_t*)(d + o_rank);
+  dout.status = (int32_t*)(d + o_stat);
+  st = isv_marg_window_batch(h, &din, &dout, which);
+  if (st != ISV_OK) return st;
+  if (fwd) {
+    ISV_CUDA(cudaMemcpyAsync(out->se3_out, dout.se3_out, n * ISV_SE3_REC * D, cudaMemcpyDeviceToHost, s));
+    ISV_CUDA(cudaMemcpyAsync(out->pg_out, dout.pg_out, n * ISV_PG_REC * D, cudaMemcpyDeviceToHost, s));
+  }
+  if (bwd) {
+    ISV_CUDA(cudaMemcpyAsync(out->rel_out, dout.rel_out, n * ISV_REL_REC * D, cudaMemcpyDeviceToHost, s));
+    ISV_CUDA(cudaMemcpyAsync(out->vb_out, dout.vb_out, n * ISV_VB_REC * D, cudaMemcpyDeviceToHost, s));
+    ISV_CUDA(cudaMemcpyAsync(out->rp_out, dout.rp_out, n * ISV_RP_REC * D, cudaMemcpyDeviceToHost, s));
+  }
+  ISV_CUDA(cudaMemcpyAsync(out->rank, dout.rank, n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (out->status) ISV_CUDA(cudaMemcpyAsync(out->status, dout.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  ISV_CUDA(cudaStreamSynchronize(s));
+  return ISV_OK;
+}
+
+// ---- single-window wrappers --------------------------------------------------------------------
+isv_status isv_marg_forward(isv_handle* h, const isv_fwd_in* in, isv_fwd_out* out) {
+  if (!h || !in || !out || in->n_landmarks < 0) return ISV_ERR_BAD_ARG;
+  if (!in->pose0 || !in->pose1 || !in->ex_pose || !in->prior_se3 || !in->prior_rel) return ISV_ERR_BAD_ARG;
+  const int L = in->n_landmarks;
+  if (L > 0 && (!in->inv_dep || !in->pts_i || !in->pts_j)) return ISV_ERR_BAD_ARG;
+  double* obs = (double*)malloc(sizeof(double) * 6 * (size_t)(L > 0 ? L : 1));
+  if (!obs) return ISV_ERR_ALLOC;
+  for (int k = 0; k < L; ++k) {
+    obs[k] = in->pts_i[3 * k];
+    obs[L + k] = in->pts_i[3 * k + 1];
+    obs[2 * L + k] = in->pts_i[3 * k + 2];
+    obs[3 * L + k] = in->pts_j[3 * k];
+    obs[4 * L + k] = in->pts_j[3 * k + 1];
+    obs[5 * L + k] = in->inv_dep[k];
+  }
+  int64_t lmoff[2] = {0, L};
+  double posef[14];
+  memcpy(posef, in->pose0, 7 * sizeof(double));
+  memcpy(posef + 7, in->pose1, 7 * sizeof(double));
+  isv_batch_in bi;
+  memset(&bi, 0, sizeof(bi));
+  bi.n_windows = 1;
+  bi.ex_pose_shared = 1;
+  bi.lm_offset = lmoff;
+  bi.lm_obs = obs;
+  bi.lm_stride = L;
+  bi.pose_fwd = posef;
+  bi.ex_pose = in->ex_pose;
+  bi.prior_se3 = in->prior_se3;
+  bi.prior_rel = in->prior_rel;
+  bi.prior_rp = in->prior_rp;
+  int32_t rank[2] = {0, 0};
+  isv_batch_out bo;
+  memset(&bo, 0, sizeof(bo));
+  bo.se3_out = out->se3;
+  bo.pg_out = out->pg;
+  bo.rank = rank;
+  bo.status = &out->status;
+  isv_status st = isv_marg_window_batch_host(h, &bi, &bo, ISV_RUN_FORWARD);
+  free(obs);
+  out->rank = rank[0];
+  return st;
+}
+
+isv_status isv_marg_backward(isv_handle* h, const isv_bwd_in* in, isv_bwd_out* out) {
+  if (!h || !in || !out) return ISV_ERR_BAD_ARG;
+  if (!in->pose_i || !in->sb_i || !in->pose_j || !in->sb_j || !in->prior_vb || !in->preint) return ISV_ERR_BAD_ARG;
+  double poseb[14], sbb[18];
+  memcpy(poseb, in->pose_i, 7 * sizeof(double));
+  memcpy(poseb + 7, in->pose_j, 7 * sizeof(double));
+  memcpy(sbb, in->sb_i, 9 * sizeof(double));
+  memcpy(sbb + 9, in->sb_j, 9 * sizeof(double));
+  isv_batch_in bi;
+  memset(&bi, 0, sizeof(bi));
+  bi.n_windows = 1;
+  bi.pose_bwd = poseb;
+  bi.sb_bwd = sbb;
+  bi.prior_vb = in->prior_vb;
+  bi.preint = in->preint;
+  int32_t rank[2] = {0, 0};
+  isv_batch_out bo;
+  memset(&bo, 0, sizeof(bo));
+  bo.rel_out = out->rel;
+  bo.vb_out = out->vb;
+  bo.rp_out = out->rp;
+  bo.rank = rank;
+  bo.status = &out->status;
+  isv_status st = isv_marg_window_batch_host(h, &bi, &bo, ISV_RUN_BACKWARD);
+  out->rank = rank[1];
+  return st;
+}
+
+}  // extern "C"
