@@ -193,14 +193,12 @@ typedef struct isv_bwd_out {
 isv_status isv_marg_forward(isv_handle* h, const isv_fwd_in* in, isv_fwd_out* out);
 isv_status isv_marg_backward(isv_handle* h, const isv_bwd_in* in, isv_bwd_out* out);
 
-/* ---- forensic / literal mode: the dense information matrices -----------------------------------
- * Builds the reference's dense `Lamda` exactly as the block loops do
- * (src/estimator.cpp:1168-1238 for forward, :1372-1412 for backward) with the scatter-add kernel,
- * and the Schur complement `Lamda_prior` (:1286-1288 / :1413-1419).  Host pointers, blocking.
- * lamda: (12+L)^2 resp. 30^2 doubles, column-major; lamda_prior: 36 resp. 441.  Either may be NULL. */
-isv_status isv_forward_lambda(isv_handle* h, const isv_fwd_in* in, double* lamda, double* lamda_prior);
-isv_status isv_backward_lambda(isv_handle* h, const isv_bwd_in* in, double* lamda, double* lamda_prior,
-                               double* eigenvalues /* [21] ascending, may be NULL */);
+/* ---- unit-test hook: the PSD eigensolver that replaces SelfAdjointEigenSolver on this path -----
+ * (src/estimator.cpp:920,1311,1479).  nb symmetric n x n matrices A (column-major, host) ->
+ * G [nb][n][n] row-major factor rows with  A ~= sum_k g_k g_k^T, g_k mutually orthogonal;
+ * lam [nb][n] = |g_k|^2 (eigenvalues, zero-padded); info [nb][2] = {rows, sweeps}.  n <= 63.      */
+isv_status isv_test_psd_eig(isv_handle* h, int nb, int n, const double* A, double* G, double* lam,
+                            int32_t* info);
 
 #ifdef __cplusplus
 }

@@ -390,3 +390,52 @@ isv_status isv_marg_backward(isv_handle* h, const isv_bwd_in* in, isv_bwd_out* o
 }
 
 }  // extern "C"
+
+// ---- unit-test hook for the warp linear algebra (tests/test_linalg_gpu.py) ---------------------
+namespace isv {
+__global__ void psd_eig_test_kernel(int nb, int n, const double* A, double* G, double* lam, int* info) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (b >= nb) return;
+  double* As = smem + warp * (2 * n * n + 2 * n);
+  double* Gs = As + n * n;
+  double* d = Gs + n * n;
+  for (int i = lane; i < n * n; i += 32) { As[i] = A[(size_t)b * n * n + i]; Gs[i] = 0.0; }
+  __syncwarp();
+  int r = w_pivoted_cholesky_rows(As, n, n, Gs, n, d, lane);
+  int sweeps = (n <= 16) ? w_onesided_jacobi_rows<4>(Gs, n, r, n, d, lane)
+                         : (n <= 32 ? w_onesided_jacobi_rows<2>(Gs, n, r, n, d, lane)
+                                    : w_onesided_jacobi_rows<1>(Gs, n, r, n, d, lane));
+  if (n == 21) {}
+  for (int i = lane; i < n * n; i += 32) G[(size_t)b * n * n + i] = Gs[i];
+  for (int i = lane; i < n; i += 32) lam[(size_t)b * n + i] = i < r ? d[i] : 0.0;
+  if (lane == 0) { info[2 * b] = r; info[2 * b + 1] = sweeps; }
+}
+}  // namespace isv
+
+extern "C" isv_status isv_test_psd_eig(isv_handle* h, int nb, int n, const double* A, double* G, double* lam,
+                                       int32_t* info) {
+  if (!h || nb <= 0 || n < 1 || n > 63 || !A || !G || !lam || !info) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  double *dA, *dG, *dl;
+  int* di;
+  size_t mb = sizeof(double) * (size_t)nb * n * n;
+  ISV_CUDA(cudaMalloc(&dA, mb));
+  ISV_CUDA(cudaMalloc(&dG, mb));
+  ISV_CUDA(cudaMalloc(&dl, sizeof(double) * (size_t)nb * n));
+  ISV_CUDA(cudaMalloc(&di, sizeof(int) * 2 * (size_t)nb));
+  ISV_CUDA(cudaMemcpyAsync(dA, A, mb, cudaMemcpyHostToDevice, h->stream));
+  const int wpc = 2;
+  size_t sm = wpc * (2 * n * n + 2 * n) * sizeof(double);
+  cudaFuncSetAttribute(psd_eig_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  psd_eig_test_kernel<<<(nb + wpc - 1) / wpc, 32 * wpc, sm, h->stream>>>(nb, n, dA, dG, dl, di);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  ISV_CUDA(cudaMemcpyAsync(G, dG, mb, cudaMemcpyDeviceToHost, h->stream));
+  ISV_CUDA(cudaMemcpyAsync(lam, dl, sizeof(double) * (size_t)nb * n, cudaMemcpyDeviceToHost, h->stream));
+  ISV_CUDA(cudaMemcpyAsync(info, di, sizeof(int) * 2 * (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+  ISV_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(dA); cudaFree(dG); cudaFree(dl); cudaFree(di);
+  return ISV_OK;
+}

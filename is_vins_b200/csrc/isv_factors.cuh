@@ -126,12 +126,12 @@ __device__ inline void qleft_qright_br(const Quat& a, const Quat& b, double* M) 
     }
 }
 
-// Unweighted IMU Jacobians in WINDOW column order.  Jfull: 15 x 30 column-major (ld 15), columns
+// Unweighted IMU Jacobians in WINDOW column order.  Jfull: 15 x 30 column-major (ld ldj), columns
 // [col_j_pose .. +6) <- d r / d T_j, [col_j_sb .. +9) <- d r / d VB_j, likewise for i.
 // pre: the 467-double pre-integration record (include/isv_capi.h ISV_PREINT_REC).  res: 15 or null.
 __device__ inline void imu_jacobians(const double* PSi, const double* VBi, const double* PSj, const double* VBj,
-                                     const double* pre, const double* G, double* Jfull, int col_i_pose, int col_i_sb,
-                                     int col_j_pose, int col_j_sb, double* res) {
+                                     const double* pre, const double* G, double* Jfull, int ldj, int col_i_pose,
+                                     int col_i_sb, int col_j_pose, int col_j_sb, double* res) {
   const double* delta_p = pre;
   Quat dq{pre[6], pre[3], pre[4], pre[5]};
   const double* delta_v = pre + 7;
@@ -181,7 +181,7 @@ __device__ inline void imu_jacobians(const double* PSi, const double* VBi, const
   qleft_qright_br(QjinvQi, cq, QLR);
   qleft_br(qmul(QjinvQi, dq), QL1);                       // Q9: uncorrected delta_q
   qleft_br(qmul(qmul(qinv(cq), Qi_inv), Qj), QL2);
-  auto put = [&](int row, int col, double v) { Jfull[row + 15 * col] = v; };
+  auto put = [&](int row, int col, double v) { Jfull[row + ldj * col] = v; };
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) {
       // d / d T_i   (15x6)

@@ -269,4 +269,218 @@ __device__ __forceinline__ int w_jacobi_eig(double* A, int lda, double* V, int l
   return sweep;
 }
 
+// -------------------------------------------------------------------------------------------------
+// PSD eigen-decomposition in factored form: pivoted Cholesky + one-sided (Hestenes) Jacobi.
+//
+// Replaces SelfAdjointEigenSolver on the marginal information matrices of this path
+// (/root/reference/src/estimator.cpp:920, :1311, :1479), which are PSD up to rounding (Schur
+// complements of J^T W J).  Step 1 factors A ~= G^T G with G (r x n) by outer-product Cholesky with
+// diagonal pivoting, stopping at pivots <= n*eps*max_diag (what is dropped is rounding noise many
+// orders below ALPHA; negative rounding-level eigenvalues disappear with it).  Step 2 rotates the
+// ROWS of G until they are mutually orthogonal; then  A = sum_k g_k g_k^T  with eigenvalues
+// lam_k = |g_k|^2 and eigenvectors g_k/|g_k|, so that the reference's
+//     U D^-1 U^T = sum_{lam_k > ALPHA} g_k g_k^T / lam_k^2 .
+// One-sided Jacobi works on r x n (15 x 21 for MargBackward) instead of n x n, needs no eigenvector
+// accumulation, and is accurate to high RELATIVE precision for every kept eigenvalue.
+// -------------------------------------------------------------------------------------------------
+
+// A: n x n symmetric (lower triangle read, ld lda) -- destroyed.  G: receives r rows (row-major,
+// ld ldg >= n).  d: n doubles scratch.  Returns r.
+__device__ __forceinline__ int w_pivoted_cholesky_rows(double* A, int lda, int n, double* G, int ldg, double* d,
+                                                       int lane) {
+  w_symmetrize_from_lower(A, lda, n, lane);
+  double dmax0 = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    double v = A[i + i * lda];
+    d[i] = v;
+    dmax0 = fmax(dmax0, v);
+  }
+  dmax0 = warp_max(dmax0);
+  __syncwarp();
+  const double tol = dmax0 * (double)n * 2.220446049250313e-16;
+  int r = 0;
+  for (; r < n; ++r) {
+    // pivot = largest remaining diagonal (selected indices carry d = -1)
+    double best = -1.0;
+    int bi = 0;
+    for (int i = lane; i < n; i += 32)
+      if (d[i] > best) { best = d[i]; bi = i; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double ob = __shfl_xor_sync(kFullMask, best, o);
+      int oi = __shfl_xor_sync(kFullMask, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (!(best > tol)) break;
+    const double inv = 1.0 / sqrt(best);
+    double* g = G + r * ldg;
+    for (int i = lane; i < n; i += 32) g[i] = (d[i] < 0.0) ? 0.0 : A[i + bi * lda] * inv;
+    __syncwarp();
+    for (int idx = lane; idx < n * n; idx += 32) {
+      int i = idx % n, j = idx / n;
+      A[i + j * lda] = fma(-g[i], g[j], A[i + j * lda]);
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) d[i] = (d[i] < 0.0 || i == bi) ? -1.0 : A[i + i * lda];
+    __syncwarp();
+  }
+  return r;
+}
+
+// Orthogonalise the r rows (length n, row-major, ld ldg) of G by one-sided Jacobi with round-robin
+// ordering; LPP lanes cooperate on one row pair.  lam[k] = |g_k|^2 on return.
+// Returns the number of sweeps used (>= max_sweeps -> not converged).
+template <int LPP>
+__device__ __forceinline__ int w_onesided_jacobi_rows(double* G, int ldg, int r, int n, double* lam, int lane,
+                                                      int max_sweeps = 30, int es = 1) {
+  // element e of row p lives at G[p * ldg + e * es]
+  constexpr int kGroups = 32 / LPP;
+  const int sub = lane % LPP, grp = lane / LPP;
+  const int m = (r + 1) & ~1;
+  const int half = m / 2;
+  const double tol = 2.220446049250313e-16 * sqrt((double)n);
+  int sweep = 0;
+  if (r >= 2) {
+    for (; sweep < max_sweeps; ++sweep) {
+      int rotated = 0;
+      for (int rd = 0; rd < m - 1; ++rd) {
+        for (int kb = 0; kb < half; kb += kGroups) {
+          const int kp = kb + grp;
+          int p = 0, q = 0;
+          bool act = kp < half;
+          if (act) {
+            int a, b;
+            if (kp == 0) { a = m - 1; b = rd; }
+            else { a = rd + kp; if (a >= m - 1) a -= m - 1; b = rd - kp; if (b < 0) b += m - 1; }
+            p = a < b ? a : b;
+            q = a < b ? b : a;
+            act = q < r;
+          }
+          double* gp = G + p * ldg;
+          double* gq = G + q * ldg;
+          double aa = 0.0, bb = 0.0, gg = 0.0;
+          if (act)
+            for (int e = sub; e < n; e += LPP) {
+              double x = gp[e * es], y = gq[e * es];
+              aa = fma(x, x, aa);
+              bb = fma(y, y, bb);
+              gg = fma(x, y, gg);
+            }
+#pragma unroll
+          for (int o = LPP / 2; o > 0; o >>= 1) {
+            aa += __shfl_xor_sync(kFullMask, aa, o);
+            bb += __shfl_xor_sync(kFullMask, bb, o);
+            gg += __shfl_xor_sync(kFullMask, gg, o);
+          }
+          if (act && fabs(gg) > tol * sqrt(aa * bb)) {
+            double zeta = (bb - aa) / (2.0 * gg);
+            double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            double c = 1.0 / sqrt(1.0 + t * t);
+            double s = c * t;
+            for (int e = sub; e < n; e += LPP) {
+              double x = gp[e * es], y = gq[e * es];
+              gp[e * es] = c * x - s * y;
+              gq[e * es] = s * x + c * y;
+            }
+            rotated = 1;
+          }
+        }
+        __syncwarp();
+      }
+      if (!__any_sync(kFullMask, rotated)) break;
+    }
+  }
+  for (int k = lane; k < r; k += 32) {
+    double a = 0.0;
+    for (int e = 0; e < n; ++e) a = fma(G[k * ldg + e * es], G[k * ldg + e * es], a);
+    lam[k] = a;
+  }
+  __syncwarp();
+  return sweep;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Square-root-information marginalisation: Householder QR on the columns [c0, c0+nc) of the stacked
+// whitened Jacobian M (rows x cols, column-major, ld).  On return rows [nc, rows) hold, in the
+// columns outside [c0, c0+nc), a factor Gm with  Gm^T Gm = Lam_rr - Lam_rm Lam_mm^-1 Lam_mr  where
+// Lam = M^T M -- the Schur complement of /root/reference/src/estimator.cpp:1413-1419 (and :808-816)
+// without ever forming Lam or inverting Lam_mm, so no cancellation noise enters the null space.
+// vbuf: rows doubles of scratch.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void w_householder_marginalize(double* M, int ld, int rows, int cols, int c0, int nc,
+                                                          double* vbuf, int lane) {
+  for (int k = 0; k < nc; ++k) {
+    double* ck = M + (size_t)ld * (c0 + k);
+    // reflector for ck[k:rows]
+    double t2 = 0.0;
+    for (int i = k + 1 + lane; i < rows; i += 32) t2 = fma(ck[i], ck[i], t2);
+    t2 = warp_sum(t2);
+    const double x0 = ck[k];
+    __syncwarp();
+    if (t2 > 0.0) {
+      double beta = sqrt(x0 * x0 + t2);
+      if (x0 >= 0.0) beta = -beta;
+      const double inv = 1.0 / (x0 - beta);
+      const double tau = (beta - x0) / beta;
+      for (int i = k + lane; i < rows; i += 32) vbuf[i] = (i == k) ? 1.0 : ck[i] * inv;
+      __syncwarp();
+      // apply (I - tau v v^T) to every other live column: one column per lane
+      for (int j = lane; j < cols; j += 32) {
+        if (j >= c0 && j <= c0 + k) continue;  // eliminated columns (and ck itself, set below)
+        double* cj = M + (size_t)ld * j;
+        double s = 0.0;
+        for (int i = k; i < rows; ++i) s = fma(vbuf[i], cj[i], s);
+        s *= tau;
+        for (int i = k; i < rows; ++i) cj[i] = fma(-s, vbuf[i], cj[i]);
+      }
+      if (lane == 0) ck[k] = beta;
+      for (int i = k + 1 + lane; i < rows; i += 32) ck[i] = 0.0;
+      __syncwarp();
+    }
+  }
+}
+
+// sqrt_info = LLT(cov^-1).matrixL().transpose() computed without forming cov^-1:
+// cov = U1 U1^T with U1 upper triangular (Cholesky started from the last row), then
+// cov^-1 = (U1^-1)^T (U1^-1) and U1^-1 is the unique upper-triangular factor with positive diagonal,
+// i.e. exactly the matrix the reference obtains as  Eigen::LLT(covi.inverse()).matrixL().transpose()
+// (/root/reference/src/estimator.cpp:950,1349,1503,1508,1515).
+// A: N x N SPD in shared memory (upper triangle read, destroyed); out: N x N column-major (global).
+template <int N>
+__device__ __forceinline__ int w_sqrt_info_from_cov(double* A, int ld, double* out, int lane, int& nonfinite) {
+  int bad = 0;
+  for (int j = N - 1; j >= 0; --j) {
+    double d = A[j + j * ld];
+    if (!(d > 0.0)) bad = 1;
+    double r = sqrt(d);
+    __syncwarp();
+    if (lane == 0) A[j + j * ld] = r;
+    for (int i = lane; i < j; i += 32) A[i + j * ld] = A[i + j * ld] / r;
+    __syncwarp();
+    for (int idx = lane; idx < j * j; idx += 32) {
+      int i = idx % j, c = idx / j;
+      if (i <= c) A[i + c * ld] = fma(-A[i + j * ld], A[c + j * ld], A[i + c * ld]);
+    }
+    __syncwarp();
+  }
+  // column `lane` of X = U1^-1 by back substitution, held in registers
+  if (lane < N) {
+    double x[N];
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+      double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = i + 1; k < N; ++k) s = fma(-A[i + k * ld], x[k], s);
+      x[i] = (i <= lane) ? s / A[i + i * ld] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (!isfinite(x[i])) nonfinite = 1;
+      out[i + N * lane] = x[i];
+    }
+  }
+  __syncwarp();
+  return bad;
+}
+
 }  // namespace isv

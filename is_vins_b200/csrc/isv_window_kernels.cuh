@@ -42,7 +42,7 @@ constexpr int kFwdWork = 832;                // staging (16*36) during the loop,
 constexpr int kFwdSmemPerWarp = kFwdConst + kFwdWork;
 // ---- backward ---------------------------------------------------------------------------------
 constexpr int kBwdScratch = 136;
-constexpr int kBwdSmemPerWarp = 450 + 900 + kBwdScratch;
+constexpr int kBwdSmemPerWarp = 750 + 225 + kBwdScratch;
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -347,18 +347,27 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
     w_gemm<false, true>(6, 6, 6, tB, 6, Jr6, 6, tA, 6, 0, lane);      // covi = Jr cov Jr^T
   } else {
     status |= ISV_W_RANK_DEFICIENT;
-    // truncated eigen path (:1311-1331): Wst is destroyed, eigenvectors -> tB(36), cs in wk
-    if (w_jacobi_eig(Wst, 6, tB, 6, 6, wk, lane) >= 30) status |= ISV_W_EIG_NOCONV;
+    // truncated eigen path (:1311-1331), factored form: Lamda_prior = sum_k g_k g_k^T (rows of tB)
+    for (int i = lane; i < 36; i += 32) tB[i] = 0.0;
+    __syncwarp();
+    const int nrow = w_pivoted_cholesky_rows(Wst, 6, 6, tB, 6, wk, lane);
+    if (w_onesided_jacobi_rows<4>(tB, 6, nrow, 6, wk, lane) >= 30) status |= ISV_W_EIG_NOCONV;
     int er = 0;
-    for (int k = 0; k < 6; ++k) er += (Wst[k + 6 * k] > cfg.alpha) ? 1 : 0;
+    for (int k = 0; k < nrow; ++k) er += (wk[k] > cfg.alpha) ? 1 : 0;
     out_rank = er;
-    w_gemm<false, false>(6, 6, 6, Jr6, 6, tB, 6, wk, 6, 0, lane);     // wk = Jr U (all columns)
+    for (int idx = lane; idx < 36; idx += 32) {   // wk+8 = Jr G^T (6 x nrow)
+      int r = idx % 6, k = idx / 6;
+      double acc = 0.0;
+      for (int c = 0; c < 6; ++c) acc = fma(Jr6[r + 6 * c], tB[c + 6 * k], acc);
+      wk[8 + idx] = acc;
+    }
+    __syncwarp();
     for (int idx = lane; idx < 36; idx += 32) {
       int r = idx % 6, c = idx / 6;
       double acc = 0.0;
-      for (int k = 0; k < 6; ++k) {
-        double lamk = Wst[k + 6 * k];
-        if (lamk > cfg.alpha) acc += wk[r + 6 * k] * wk[c + 6 * k] / lamk;
+      for (int k = 0; k < nrow; ++k) {
+        double lamk = wk[k];
+        if (lamk > cfg.alpha) acc += wk[8 + r + 6 * k] * wk[8 + c + 6 * k] / (lamk * lamk);
       }
       tA[idx] = acc;
     }
@@ -377,8 +386,15 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
 }
 
 // =================================================================================================
-// MargBackward
+// MargBackward -- square-root-information form.
+//   M (24 x 30) = [ s_vb on VB_{V-1} ; L^-1 J_imu ]   with  covariance = L L^T   (rows 0-8 / 9-23)
+//   Householder-eliminate the VB_{V-1} columns -> rows 9-23, columns 0-20 = G (15 x 21) with
+//   G^T G = Lamda_prior (:1419);  one-sided Jacobi makes the rows of G orthogonal:
+//   Lamda_prior = sum_k g_k g_k^T, eigenvalues |g_k|^2 (:1479-1497), and for every recovered factor
+//   cov_i = J_i U D^-1 U^T J_i^T = sum_{|g_k|^2 > ALPHA} (J_i g_k)(J_i g_k)^T / |g_k|^4  (:1500-1516).
+// Algebraically identical to the reference's information-form route, without its cancellation.
 // =================================================================================================
+constexpr int kMld = 25;  // odd leading dimension: conflict-free strided row access
 __global__ void __launch_bounds__(kThreads)
 marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size) {
   extern __shared__ double smem[];
@@ -386,10 +402,9 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
   const int warp = threadIdx.x >> 5;
   const int win = blockIdx.x * kWarpsPerCta + warp;
   if (win >= in.n_windows) return;
-  double* W = smem + warp * kBwdSmemPerWarp;  // 15 x 30 (ld 15): IMU Jacobian, whitened in place
-  double* P = W + 450;                        // 15 x 15 covariance -> Cholesky factor
-  double* Lam = W + 450;                      // 30 x 30 (ld 30), overlays P once W is whitened
-  double* sc = W + 1350;                      // scratch: poses [0..31], G[32..34], dinv[40..60], cs[64..]
+  double* M = smem + warp * kBwdSmemPerWarp;  // 24 x 30 (ld 25)
+  double* P = M + 750;                        // 15 x 15 covariance -> Cholesky factor
+  double* sc = M + 975;                       // scratch: poses [0..31], G[32..34], dinv[40..60], lam/vbuf[64..]
   int status = 0, nonfinite = 0;
 
   const double* pose_i = in.pose_bwd + (size_t)win * 14;
@@ -399,23 +414,25 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
   const double* pvb = in.prior_vb + (size_t)win * ISV_VB_REC;
   const double* pre = in.preint + (size_t)win * ISV_PREINT_REC;
 
-  for (int i = lane; i < 450; i += 32) W[i] = 0.0;
+  for (int i = lane; i < 750; i += 32) M[i] = 0.0;
   for (int i = lane; i < 225; i += 32) P[i] = pre[17 + 225 + i];
   if (lane < 7) { sc[lane] = pose_i[lane]; sc[16 + lane] = pose_j[lane]; }
   if (lane >= 7 && lane < 16) { sc[lane] = sb_i[lane - 7]; sc[16 + lane] = sb_j[lane - 7]; }
   if (lane < 3) sc[32 + lane] = cfg.g[lane];
   __syncwarp();
+  // vioVBPrior (Linear9Factor, J = I9 on VB_{V-1}): rows 0-8, columns 21-29 = sqrt_info  (:1372-1380)
+  for (int idx = lane; idx < 81; idx += 32) M[(idx % 9) + kMld * (21 + idx / 9)] = pvb[9 + idx];
   // ---- IMUFactor::Evaluate, tangent twin (imu_factor.h:161-265), columns in OrderMap order -----
   // OrderMap (:1358-1366): T_V@0, VB_V@6, T_{V-1}@15, VB_{V-1}@21
   if (lane == 0) {
     if (nonunit(sc) || nonunit(sc + 16)) status |= ISV_W_NONUNIT_QUAT;
-    imu_jacobians(sc, sc + 7, sc + 16, sc + 23, pre, sc + 32, W, 15, 21, 0, 6, nullptr);
+    imu_jacobians(sc, sc + 7, sc + 16, sc + 23, pre, sc + 32, M + 9, kMld, 15, 21, 0, 6, nullptr);
   }
   __syncwarp();
-  // sqrt_info^T sqrt_info = covariance^-1 (imu_factor.h:181) : P = L L^T, W <- L^-1 W, Lam = W^T W
+  // sqrt_info^T sqrt_info = covariance^-1 (imu_factor.h:181): P = L L^T, rows 9-23 <- L^-1 J
   if (w_chol_lower(P, 15, 15, lane)) status |= ISV_W_NOT_SPD;
   if (lane < 30) {
-    double* col = W + 15 * lane;
+    double* col = M + 9 + kMld * lane;
     for (int i = 0; i < 15; ++i) {
       double s = col[i];
       for (int l = 0; l < i; ++l) s = fma(-P[i + 15 * l], col[l], s);
@@ -423,62 +440,26 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
     }
   }
   __syncwarp();
-  for (int idx = lane; idx < 900; idx += 32) {
-    int i = idx % 30, j = idx / 30;
-    double acc = 0.0;
-    if (i >= j) {
-      for (int l = 0; l < 15; ++l) acc = fma(W[l + 15 * i], W[l + 15 * j], acc);
-    }
-    if (i >= j) Lam[i + 30 * j] = acc;  // Lam overlays P, which is dead once W is whitened
-  }
-  __syncwarp();
-  // vioVBPrior (Linear9Factor, J = I9): Lam[21:30,21:30] += s^T s  (:1372-1380)
-  for (int i = lane; i < 81; i += 32) W[i] = pvb[9 + i];
-  __syncwarp();
-  for (int idx = lane; idx < 81; idx += 32) {
-    int i = idx % 9, j = idx / 9;
-    if (i >= j) {
-      double acc = 0.0;
-      for (int l = 0; l < 9; ++l) acc = fma(W[l + 9 * i], W[l + 9 * j], acc);
-      Lam[(21 + i) + 30 * (21 + j)] += acc;
-    }
-  }
-  __syncwarp();
-  w_symmetrize_from_lower(Lam, 30, 30, lane);
-  // ---- Schur complement over VB_{V-1} (:1413-1419) ---------------------------------------------
-  double* Lmm = Lam + 21 + 30 * 21;
-  if (w_inverse(Lmm, 30, 9, W, lane)) status |= ISV_W_SINGULAR;
-  // T (21x9, in W+200) = Lam_rm * Lmm^-1 ; Lam_prior = Lam_rr - T Lam_rm^T (lower, then mirrored)
-  double* T = W + 200;
-  w_gemm<false, false>(21, 9, 9, Lam + 30 * 21, 30, Lmm, 30, T, 21, 0, lane);
-  for (int idx = lane; idx < 441; idx += 32) {
-    int i = idx % 21, j = idx / 21;
-    if (i >= j) {
-      double acc = 0.0;
-      for (int l = 0; l < 9; ++l) acc = fma(T[i + 21 * l], Lam[j + 30 * (21 + l)], acc);
-      Lam[i + 30 * j] -= acc;
-    }
-  }
-  __syncwarp();
-  w_symmetrize_from_lower(Lam, 30, 21, lane);
-  // ---- truncated eigen-decomposition (:1479-1497) ----------------------------------------------
-  double* V = W;  // 21 x 21 (ld 21)
-  if (w_jacobi_eig(Lam, 30, V, 21, 21, sc + 64, lane) >= 30) status |= ISV_W_EIG_NOCONV;
+  // ---- Schur complement over VB_{V-1} (:1413-1419) as a QR elimination -------------------------
+  w_householder_marginalize(M, kMld, 24, 30, 21, 9, sc + 64, lane);
+  // ---- eigen-decomposition (:1479-1497): orthogonalise the 15 rows of G ------------------------
+  double* G = M + 9;  // row k, element c at G[k + kMld * c]
+  if (w_onesided_jacobi_rows<4>(G, 1, 15, 21, sc + 64, lane, 30, kMld) >= 30) status |= ISV_W_EIG_NOCONV;
   int rank = 0;
   if (lane < 21) {
-    double lamk = Lam[lane + 30 * lane];
+    double lamk = (lane < 15) ? sc[64 + lane] : 0.0;
     int keep = lamk > cfg.alpha;  // strict, Q12
-    sc[40 + lane] = keep ? 1.0 / lamk : 0.0;
+    sc[40 + lane] = keep ? 1.0 / (lamk * lamk) : 0.0;
     rank = keep;
   }
   rank = __popc(__ballot_sync(kFullMask, rank));
   __syncwarp();
   // ---- recovered factors (:1424-1452) and their Jacobian rows (:1456-1477) ---------------------
-  double* Jrel = Lam;        // Ji (36) | Jj (36)
-  double* Jrp = Lam + 72;    // 2 x 6
-  double* JU = Lam + 96;     // up to 9 x 21
-  double* cov = Lam + 288;   // up to 9 x 9
-  double* wk = Lam + 384;    // inverse work (9 x 18)
+  double* T = M + 525;       // dead: R factor columns (225) + P (225) = 450 contiguous doubles
+  double* Jrel = T;          // Ji (36) | Jj (36)
+  double* Jrp = T + 72;      // 2 x 6
+  double* JU = T + 88;       // up to 9 x 15
+  double* cov = T + 224;     // up to 9 x 9
   double* o_rel = out.rel_out + (size_t)win * ISV_REL_REC;
   double* o_vb = out.vb_out + (size_t)win * ISV_VB_REC;
   double* o_rp = out.rp_out + (size_t)win * ISV_RP_REC;
@@ -505,12 +486,12 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
   }
   __syncwarp();
   // relative pose (rows 0-5 of Jr): Jj -> cols 0:6 (T_V), Ji -> cols 15:21 (T_{V-1})
-  for (int idx = lane; idx < 6 * 21; idx += 32) {
+  for (int idx = lane; idx < 6 * 15; idx += 32) {
     int r = idx % 6, k = idx / 6;
     double acc = 0.0;
     for (int c = 0; c < 6; ++c) {
-      acc = fma(Jrel[36 + r + 6 * c], V[c + 21 * k], acc);
-      acc = fma(Jrel[r + 6 * c], V[15 + c + 21 * k], acc);
+      acc = fma(Jrel[36 + r + 6 * c], G[k + kMld * c], acc);
+      acc = fma(Jrel[r + 6 * c], G[k + kMld * (15 + c)], acc);
     }
     JU[idx] = acc;
   }
@@ -518,39 +499,36 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
   for (int idx = lane; idx < 36; idx += 32) {
     int r = idx % 6, c = idx / 6;
     double acc = 0.0;
-    for (int k = 0; k < 21; ++k) acc = fma(JU[r + 6 * k] * dinv[k], JU[c + 6 * k], acc);
+    for (int k = 0; k < 15; ++k) acc = fma(JU[r + 6 * k] * dinv[k], JU[c + 6 * k], acc);
     cov[idx] = acc;
   }
   __syncwarp();
-  if (w_inverse(cov, 6, 6, wk, lane)) status |= ISV_W_SINGULAR;
-  if (chol_store_upper(cov, 6, 6, o_rel + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+  if (w_sqrt_info_from_cov<6>(cov, 6, o_rel + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
   // speed-bias prior (rows 6-14): J = I9 at cols 6:15
   for (int idx = lane; idx < 81; idx += 32) {
     int r = idx % 9, c = idx / 9;
     double acc = 0.0;
-    for (int k = 0; k < 21; ++k) acc = fma(V[6 + r + 21 * k] * dinv[k], V[6 + c + 21 * k], acc);
+    for (int k = 0; k < 15; ++k) acc = fma(G[k + kMld * (6 + r)] * dinv[k], G[k + kMld * (6 + c)], acc);
     cov[idx] = acc;
   }
   __syncwarp();
-  if (w_inverse(cov, 9, 9, wk, lane)) status |= ISV_W_SINGULAR;
-  if (chol_store_upper(cov, 9, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+  if (w_sqrt_info_from_cov<9>(cov, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
   // roll/pitch (rows 15-16): 2x6 at cols 15:21
-  for (int idx = lane; idx < 2 * 21; idx += 32) {
+  for (int idx = lane; idx < 2 * 15; idx += 32) {
     int r = idx % 2, k = idx / 2;
     double acc = 0.0;
-    for (int c = 0; c < 6; ++c) acc = fma(Jrp[r + 2 * c], V[15 + c + 21 * k], acc);
+    for (int c = 0; c < 6; ++c) acc = fma(Jrp[r + 2 * c], G[k + kMld * (15 + c)], acc);
     JU[idx] = acc;
   }
   __syncwarp();
   for (int idx = lane; idx < 4; idx += 32) {
     int r = idx % 2, c = idx / 2;
     double acc = 0.0;
-    for (int k = 0; k < 21; ++k) acc = fma(JU[r + 2 * k] * dinv[k], JU[c + 2 * k], acc);
+    for (int k = 0; k < 15; ++k) acc = fma(JU[r + 2 * k] * dinv[k], JU[c + 2 * k], acc);
     cov[idx] = acc;
   }
   __syncwarp();
-  if (w_inverse(cov, 2, 2, wk, lane)) status |= ISV_W_SINGULAR;
-  if (chol_store_upper(cov, 2, 2, o_rp + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+  if (w_sqrt_info_from_cov<2>(cov, 2, o_rp + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
   if (__any_sync(kFullMask, nonfinite)) status |= ISV_W_NONFINITE;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) status |= __shfl_xor_sync(kFullMask, status, o);

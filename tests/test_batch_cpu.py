@@ -1,0 +1,71 @@
+"""CPU tests of the host-side batch logic, incl. the world_size-2 window sharding over gloo."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from is_vins_b200.batch import WindowBatch
+from tests.helpers import load_batch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _batch():
+    return load_batch(os.path.join(GOLD, "cfg1_L150_ragged.npz"))[0]
+
+
+def test_tile_and_slice_roundtrip():
+    b = _batch()
+    t = b.tile(3)
+    assert t.n == 3 * b.n and t.n_landmarks == 3 * b.n_landmarks
+    for r in range(3):
+        s = t.slice(r * b.n, (r + 1) * b.n)
+        assert np.array_equal(s.lm_offset, b.lm_offset) and np.array_equal(s.lm_obs, b.lm_obs)
+        assert np.array_equal(s.preint, b.preint) and np.array_equal(s.prior_rp, b.prior_rp)
+    s = b.slice(2, 5)  # ragged windows, incl. the empty one (L = 0)
+    assert s.n == 3 and s.lm_offset[0] == 0
+    assert np.array_equal(np.diff(s.lm_offset), np.diff(b.lm_offset)[2:5])
+    a = int(b.lm_offset[2])
+    assert np.array_equal(s.lm_obs, b.lm_obs[:, a:a + s.n_landmarks])
+
+
+def test_alg_bytes_formula():
+    import bench
+    assert bench.alg_bytes(150) == 16312 and bench.alg_bytes(1000) == 63912 and bench.alg_bytes(0, 2) == 5920
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b = _batch()
+    n = b.n
+    lo, hi = rank * n // world, (rank + 1) * n // world   # contiguous block partition
+    shard = b.slice(lo, hi)
+    # the only cross-rank traffic of the path: max-reduce of the timing, sum of counts (untimed)
+    t = torch.tensor([float(rank + 1), float(shard.n), float(shard.n_landmarks)], dtype=torch.float64)
+    mx = t.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sm = t.clone()
+    dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    q.put((rank, lo, hi, float(mx[0]), float(sm[1]), float(sm[2])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_window_sharding_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    b = _batch()
+    assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == b.n     # shards tile [0, n)
+    assert all(r[3] == 2.0 for r in res)                                      # max over ranks
+    assert all(r[4] == b.n and r[5] == b.n_landmarks for r in res)            # nothing lost or duplicated

@@ -53,3 +53,91 @@ def test_host_batch_and_single_window(backend):
                                                       batch.preint[1])
     assert status == 0 and rank == ev.bwd_out.rank
     assert np.array_equal(rel, out.rel[1]) and np.array_equal(vb, out.vb[1]) and np.array_equal(rp, out.rp[1])
+
+
+import os
+
+from tests.helpers import compare_outputs, load_batch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", ["cfg1_L150_ragged.npz", "cfg2_L1000_literal.npz", "bench_windows_L1000.npz",
+                                  "bench_windows_L150.npz"])
+def test_committed_golden_fixtures(backend, name):
+    """cfg1 incl. ragged/empty windows (L = 0, 1, 31, 32, 33, 80); cfg2 = the literal dense oracle at L = 1000."""
+    batch, ref, _ = load_batch(os.path.join(GOLD, name))
+    db = DeviceBatch(batch, "cuda:0")
+    backend.marg_window_batch(db, capi.RUN_BOTH)
+    backend.synchronize()
+    out = db.outputs()
+    errs = compare_outputs(out, ref)
+    assert max(errs.values()) <= TOL, errs
+    assert np.array_equal(out.rank, ref.rank)
+    assert not out.status.any()
+
+
+def test_backward_only_config3(backend):
+    """BASELINE configs[2] maps to MargBackward alone: forward outputs untouched."""
+    batch, ref, _ = load_batch(os.path.join(GOLD, "cfg1_L150_ragged.npz"))
+    db = DeviceBatch(batch, "cuda:0")
+    for k in ("se3", "pg"):
+        db.out[k].fill_(-7.0)
+    backend.marg_window_batch(db, capi.RUN_BACKWARD)
+    backend.synchronize()
+    out = db.outputs()
+    assert max(compare_outputs(out, ref, which=2).values()) <= TOL
+    assert np.all(out.se3 == -7.0) and np.all(out.pg == -7.0)
+    assert np.array_equal(out.rank[:, 1], ref.rank[:, 1])
+
+
+def test_full_size_batch_properties(backend):
+    """BASELINE-size batch (4096 windows x L = 1000): determinism across identical copies, landmark
+    order invariance, clean status, and run-to-run bit reproducibility."""
+    base, ref, _ = load_batch(os.path.join(GOLD, "bench_windows_L1000.npz"))
+    big = base.tile(512)
+    assert big.n == 4096
+    db = DeviceBatch(big, "cuda:0")
+    backend.marg_window_batch(db, capi.RUN_BOTH)
+    backend.synchronize()
+    out = db.outputs()
+    assert not out.status.any()
+    for f in ("se3", "pg", "rel", "vb", "rp"):
+        a = getattr(out, f).reshape(512, base.n, -1)
+        assert np.array_equal(a, np.broadcast_to(a[0], a.shape)), f
+    first = type(out)(out.se3[:8], out.pg[:8], out.rel[:8], out.vb[:8], out.rp[:8], out.rank[:8], out.status[:8])
+    assert max(compare_outputs(first, ref).values()) <= TOL
+    backend.marg_window_batch(db, capi.RUN_BOTH)
+    backend.synchronize()
+    out2 = db.outputs()
+    assert np.array_equal(out.se3, out2.se3) and np.array_equal(out.vb, out2.vb)
+    # permuting the landmarks of every window changes only the summation order
+    rng = np.random.default_rng(0)
+    perm = base.slice(0, base.n)
+    for w in range(perm.n):
+        a, b = int(perm.lm_offset[w]), int(perm.lm_offset[w + 1])
+        p = a + rng.permutation(b - a)
+        perm.lm_obs[:, a:b] = perm.lm_obs[:, p]
+    dp = DeviceBatch(perm, "cuda:0")
+    backend.marg_window_batch(dp, capi.RUN_FORWARD)
+    backend.synchronize()
+    outp = dp.outputs()
+    assert max(compare_outputs(outp, first, which=1).values()) <= 1e-11
+
+
+def test_degenerate_forward_window_is_flagged(backend):
+    """No landmarks, translation-only relative-pose information and P0 == P1: rows/cols 3:6 of
+    Lamda_prior are exactly zero -> FullPivHouseholderQR rank 3 -> the reference's eigen branch
+    (:1311-1331), whose 6x6 `covi.inverse()` is singular (garbage in the reference as well).  The
+    discrete outcome and the flags must be reported."""
+    batch, _, _ = load_batch(os.path.join(GOLD, "cfg1_L150_ragged.npz"))
+    b = batch.slice(3, 4)  # the L = 0 window
+    assert b.n_landmarks == 0
+    b.pose_fwd[0, 1, 0:3] = b.pose_fwd[0, 0, 0:3]
+    s = np.zeros((6, 6))
+    s[0:3, 0:3] = 50.0 * np.eye(3)
+    b.prior_rel[0, 12:48] = s.flatten(order="F")
+    out = backend.marg_window_batch_host(b, capi.RUN_FORWARD)
+    assert int(out.rank[0, 0]) == 3
+    assert out.status[0] & capi.W_RANK_DEFICIENT
+    assert out.status[0] & (capi.W_SINGULAR | capi.W_NOT_SPD | capi.W_NONFINITE)
