@@ -404,9 +404,9 @@ __global__ void psd_eig_test_kernel(int nb, int n, const double* A, double* G, d
   for (int i = lane; i < n * n; i += 32) { As[i] = A[(size_t)b * n * n + i]; Gs[i] = 0.0; }
   __syncwarp();
   int r = w_pivoted_cholesky_rows(As, n, n, Gs, n, d, lane);
-  int sweeps = (n <= 16) ? w_onesided_jacobi_rows<4>(Gs, n, r, n, d, lane)
-                         : (n <= 32 ? w_onesided_jacobi_rows<2>(Gs, n, r, n, d, lane)
-                                    : w_onesided_jacobi_rows<1>(Gs, n, r, n, d, lane));
+  int sweeps = (n <= 8) ? w_onesided_jacobi_rows<4, 2>(Gs, n, r, n, d, lane)
+               : (n <= 24) ? w_onesided_jacobi_rows<4, 6>(Gs, n, r, n, d, lane)
+                           : w_onesided_jacobi_rows<2, 32>(Gs, n, r, n, d, lane);
   if (n == 21) {}
   for (int i = lane; i < n * n; i += 32) G[(size_t)b * n * n + i] = Gs[i];
   for (int i = lane; i < n; i += 32) lam[(size_t)b * n + i] = i < r ? d[i] : 0.0;

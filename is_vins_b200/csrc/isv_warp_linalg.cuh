@@ -327,68 +327,91 @@ __device__ __forceinline__ int w_pivoted_cholesky_rows(double* A, int lda, int n
   return r;
 }
 
-// Orthogonalise the r rows (length n, row-major, ld ldg) of G by one-sided Jacobi with round-robin
-// ordering; LPP lanes cooperate on one row pair.  lam[k] = |g_k|^2 on return.
-// Returns the number of sweeps used (>= max_sweeps -> not converged).
-template <int LPP>
+// Rotation that orthogonalises two rows with squared norms a, b and inner product g:
+//   p' = c p - s q ,  q' = s p + c q ,  tan(2 theta) = 2 g / (b - a), |theta| <= pi/4.
+// cos(2 theta) = |d|/r, r = sqrt(d^2 + 4 g^2), d = b - a;  c = sqrt((1 + cos 2theta)/2),
+// s = sign(d) g / (r c).  Two rsqrt instead of three divisions and two square roots.
+__device__ __forceinline__ void jacobi_cs(double a, double b, double g, double& c, double& s) {
+  const double d = b - a;
+  const double inv_r = rsqrt(fma(d, d, 4.0 * g * g));
+  const double h = fma(0.5 * fabs(d), inv_r, 0.5);  // cos^2(theta) in [1/2, 1]
+  const double inv_c = rsqrt(h);
+  c = h * inv_c;
+  s = (d >= 0.0 ? g : -g) * inv_r * inv_c;
+}
+
+// Orthogonalise the r rows (n elements each; element e of row p at G[p*ldg + e*es]) of G by
+// one-sided Jacobi with round-robin ordering; LPP lanes cooperate on one row pair and keep their
+// NE = ceil(n/LPP) elements of both rows in registers between the inner product and the update.
+// Squared row norms are cached in nrm[] (updated analytically by each rotation, recomputed exactly
+// at the start of every sweep -- the dgesvj strategy).  lam[k] = |g_k|^2 on return (lam may alias
+// nrm).  Returns the number of sweeps used (>= max_sweeps -> not converged).
+template <int LPP, int NE>
 __device__ __forceinline__ int w_onesided_jacobi_rows(double* G, int ldg, int r, int n, double* lam, int lane,
                                                       int max_sweeps = 30, int es = 1) {
-  // element e of row p lives at G[p * ldg + e * es]
   constexpr int kGroups = 32 / LPP;
   const int sub = lane % LPP, grp = lane / LPP;
   const int m = (r + 1) & ~1;
   const int half = m / 2;
-  const double tol = 2.220446049250313e-16 * sqrt((double)n);
+  const double tol2 = 2.220446049250313e-16 * 2.220446049250313e-16 * (double)n;
+  double* nrm = lam;
   int sweep = 0;
-  if (r >= 2) {
-    for (; sweep < max_sweeps; ++sweep) {
-      int rotated = 0;
-      for (int rd = 0; rd < m - 1; ++rd) {
-        for (int kb = 0; kb < half; kb += kGroups) {
-          const int kp = kb + grp;
-          int p = 0, q = 0;
-          bool act = kp < half;
-          if (act) {
-            int a, b;
-            if (kp == 0) { a = m - 1; b = rd; }
-            else { a = rd + kp; if (a >= m - 1) a -= m - 1; b = rd - kp; if (b < 0) b += m - 1; }
-            p = a < b ? a : b;
-            q = a < b ? b : a;
-            act = q < r;
-          }
-          double* gp = G + p * ldg;
-          double* gq = G + q * ldg;
-          double aa = 0.0, bb = 0.0, gg = 0.0;
-          if (act)
-            for (int e = sub; e < n; e += LPP) {
-              double x = gp[e * es], y = gq[e * es];
-              aa = fma(x, x, aa);
-              bb = fma(y, y, bb);
-              gg = fma(x, y, gg);
-            }
-#pragma unroll
-          for (int o = LPP / 2; o > 0; o >>= 1) {
-            aa += __shfl_xor_sync(kFullMask, aa, o);
-            bb += __shfl_xor_sync(kFullMask, bb, o);
-            gg += __shfl_xor_sync(kFullMask, gg, o);
-          }
-          if (act && fabs(gg) > tol * sqrt(aa * bb)) {
-            double zeta = (bb - aa) / (2.0 * gg);
-            double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            double c = 1.0 / sqrt(1.0 + t * t);
-            double s = c * t;
-            for (int e = sub; e < n; e += LPP) {
-              double x = gp[e * es], y = gq[e * es];
-              gp[e * es] = c * x - s * y;
-              gq[e * es] = s * x + c * y;
-            }
-            rotated = 1;
-          }
-        }
-        __syncwarp();
-      }
-      if (!__any_sync(kFullMask, rotated)) break;
+  for (; sweep < max_sweeps && r >= 2; ++sweep) {
+    // exact squared norms
+    for (int k = lane; k < r; k += 32) {
+      double a = 0.0;
+      for (int e = 0; e < n; ++e) a = fma(G[k * ldg + e * es], G[k * ldg + e * es], a);
+      nrm[k] = a;
     }
+    __syncwarp();
+    int rotated = 0;
+    for (int rd = 0; rd < m - 1; ++rd) {
+      for (int kb = 0; kb < half; kb += kGroups) {
+        const int kp = kb + grp;
+        int p = 0, q = 0;
+        bool act = kp < half;
+        if (act) {
+          int a, b;
+          if (kp == 0) { a = m - 1; b = rd; }
+          else { a = rd + kp; if (a >= m - 1) a -= m - 1; b = rd - kp; if (b < 0) b += m - 1; }
+          p = a < b ? a : b;
+          q = a < b ? b : a;
+          act = q < r;
+        }
+        double* gp = G + p * ldg + sub * es;
+        double* gq = G + q * ldg + sub * es;
+        double x[NE], y[NE];
+        double gg = 0.0;
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+          const bool in = act && (sub + i * LPP < n);
+          x[i] = in ? gp[i * LPP * es] : 0.0;
+          y[i] = in ? gq[i * LPP * es] : 0.0;
+          gg = fma(x[i], y[i], gg);
+        }
+#pragma unroll
+        for (int o = LPP / 2; o > 0; o >>= 1) gg += __shfl_xor_sync(kFullMask, gg, o);
+        const double aa = nrm[p], bb = nrm[q];
+        if (act && gg * gg > tol2 * aa * bb) {
+          double c, s;
+          jacobi_cs(aa, bb, gg, c, s);
+#pragma unroll
+          for (int i = 0; i < NE; ++i)
+            if (sub + i * LPP < n) {
+              gp[i * LPP * es] = c * x[i] - s * y[i];
+              gq[i * LPP * es] = s * x[i] + c * y[i];
+            }
+          if (sub == 0) {
+            const double cc = c * c, ss = s * s, csg = 2.0 * c * s * gg;
+            nrm[p] = cc * aa - csg + ss * bb;
+            nrm[q] = ss * aa + csg + cc * bb;
+          }
+          rotated = 1;
+        }
+      }
+      __syncwarp();
+    }
+    if (!__any_sync(kFullMask, rotated)) break;
   }
   for (int k = lane; k < r; k += 32) {
     double a = 0.0;

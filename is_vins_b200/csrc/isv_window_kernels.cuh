@@ -351,7 +351,7 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
     for (int i = lane; i < 36; i += 32) tB[i] = 0.0;
     __syncwarp();
     const int nrow = w_pivoted_cholesky_rows(Wst, 6, 6, tB, 6, wk, lane);
-    if (w_onesided_jacobi_rows<4>(tB, 6, nrow, 6, wk, lane) >= 30) status |= ISV_W_EIG_NOCONV;
+    if (w_onesided_jacobi_rows<4, 2>(tB, 6, nrow, 6, wk, lane) >= 30) status |= ISV_W_EIG_NOCONV;
     int er = 0;
     for (int k = 0; k < nrow; ++k) er += (wk[k] > cfg.alpha) ? 1 : 0;
     out_rank = er;
@@ -444,7 +444,7 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
   w_householder_marginalize(M, kMld, 24, 30, 21, 9, sc + 64, lane);
   // ---- eigen-decomposition (:1479-1497): orthogonalise the 15 rows of G ------------------------
   double* G = M + 9;  // row k, element c at G[k + kMld * c]
-  if (w_onesided_jacobi_rows<4>(G, 1, 15, 21, sc + 64, lane, 30, kMld) >= 30) status |= ISV_W_EIG_NOCONV;
+  if (w_onesided_jacobi_rows<4, 6>(G, 1, 15, 21, sc + 64, lane, 30, kMld) >= 30) status |= ISV_W_EIG_NOCONV;
   int rank = 0;
   if (lane < 21) {
     double lamk = (lane < 15) ? sc[64 + lane] : 0.0;
