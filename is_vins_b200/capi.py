@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libisv_b200.so")
+LIB_PATH = os.environ.get("ISV_B200_LIB", os.path.join(_HERE, "libisv_b200.so"))
 
 ISV_OK, ISV_ERR_BAD_ARG, ISV_ERR_CUDA, ISV_ERR_ALLOC = 0, 1, 2, 3
 W_NOT_SPD, W_RANK_DEFICIENT, W_NONFINITE, W_NONUNIT_QUAT, W_EIG_NOCONV, W_SINGULAR = 1, 2, 4, 8, 16, 32

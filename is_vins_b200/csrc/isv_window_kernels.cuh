@@ -34,6 +34,12 @@ struct DevCfg {
 
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = 32 * kWarpsPerCta;
+#ifndef ISV_FWD_MINB
+#define ISV_FWD_MINB 1
+#endif
+#ifndef ISV_BWD_MINB
+#define ISV_BWD_MINB 4
+#endif
 
 // ---- forward: shared-memory map (doubles, per warp) -----------------------------------------
 constexpr int kXld = 36;                     // staging row stride: conflict-free 64-bit fragment loads
@@ -72,7 +78,7 @@ __device__ __forceinline__ int chol_store_upper(double* M, int ld, int n, double
 // =================================================================================================
 // MargForward
 // =================================================================================================
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, ISV_FWD_MINB)
 marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
@@ -395,7 +401,7 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
 // Algebraically identical to the reference's information-form route, without its cancellation.
 // =================================================================================================
 constexpr int kMld = 25;  // odd leading dimension: conflict-free strided row access
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, ISV_BWD_MINB)
 marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;

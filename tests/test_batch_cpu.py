@@ -34,6 +34,7 @@ def test_tile_and_slice_roundtrip():
 def test_alg_bytes_formula():
     import bench
     assert bench.alg_bytes(150) == 16312 and bench.alg_bytes(1000) == 63912 and bench.alg_bytes(0, 2) == 5920
+    assert bench.alg_bytes(1000, 1, needed_only=True) == 33992
 
 
 def _worker(rank, world, port, q):
