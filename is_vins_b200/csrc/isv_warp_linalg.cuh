@@ -506,4 +506,49 @@ __device__ __forceinline__ int w_sqrt_info_from_cov(double* A, int ld, double* o
   return bad;
 }
 
+// SPD inverse without pivot searches: A = U1 U1^T (reverse-order Cholesky), X = U1^-1 (one column per
+// lane, in registers), A^-1 = X^T X.  A (smem, ld) is overwritten by A^-1; Xs: N*N doubles scratch.
+// Returns 1 when A is not SPD (result then meaningless: the caller falls back to w_inverse).
+template <int N>
+__device__ __forceinline__ int w_spd_inverse(double* A, int ld, double* Xs, int lane) {
+  int bad = 0;
+  for (int j = N - 1; j >= 0; --j) {
+    double d = A[j + j * ld];
+    if (!(d > 0.0)) bad = 1;
+    double r = sqrt(d);
+    __syncwarp();
+    if (lane == 0) A[j + j * ld] = r;
+    for (int i = lane; i < j; i += 32) A[i + j * ld] = A[i + j * ld] / r;
+    __syncwarp();
+    for (int idx = lane; idx < j * j; idx += 32) {
+      int i = idx % j, c = idx / j;
+      if (i <= c) A[i + c * ld] = fma(-A[i + j * ld], A[c + j * ld], A[i + c * ld]);
+    }
+    __syncwarp();
+  }
+  if (lane < N) {
+    double x[N];
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+      double s = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = i + 1; k < N; ++k) s = fma(-A[i + k * ld], x[k], s);
+      x[i] = (i <= lane) ? s / A[i + i * ld] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) Xs[i + N * lane] = x[i];
+  }
+  __syncwarp();
+  for (int idx = lane; idx < N * N; idx += 32) {
+    int i = idx % N, j = idx / N;
+    double acc = 0.0;
+    // (X^T X)[i][j] = sum_k X[k][i] X[k][j], X upper triangular: k <= min(i, j)
+    const int km = i < j ? i : j;
+    for (int k = 0; k <= km; ++k) acc = fma(Xs[k + N * i], Xs[k + N * j], acc);
+    A[i + j * ld] = acc;
+  }
+  __syncwarp();
+  return bad;
+}
+
 }  // namespace isv

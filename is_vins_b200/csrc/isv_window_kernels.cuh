@@ -77,7 +77,15 @@ __device__ __forceinline__ int chol_store_upper(double* M, int ld, int n, double
 
 // =================================================================================================
 // MargForward
+//
+// 9-vector form.  d r/d P1 = -d r/d P0 for a ProjectionFactor (jaco_j.leftCols = -jaco_i.leftCols,
+// projection_factor.cpp:163,173), so each weighted Jacobian row lives in a 9-dimensional space
+//   z = [ T1-rot (3) | T0-rot (3) | pos (3) ] ,   x12 = [ -pos | T1-rot | pos | T0-rot ]   (OrderMap T1@0, T0@6)
+// and the two 12x12 SYRKs collapse to 9x9 ones: rows 0-7 on the FP64 tensor pipe (one DMMA tile per
+// vector per k-step), row 8 as 9 DFMA accumulators per vector.
 // =================================================================================================
+__device__ __forceinline__ int fwd_zmap(int i) { return i < 3 ? 6 + i : (i < 6 ? i - 3 : (i < 9 ? i : i - 6)); }
+
 __global__ void __launch_bounds__(kThreads, ISV_FWD_MINB)
 marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
   extern __shared__ double smem[];
@@ -95,7 +103,7 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
   const double* ex = in.ex_pose + (in.ex_pose_shared ? 0 : (size_t)win * 7);
 
   // ---- per-window constants (projection_factor.cpp:127-147) -----------------------------------
-  // K: [0]ric [9]tic [12]R0 [21]P0 [24]R1 [33]P1 [36]B=ric^T R1^T [45]C=B R0 [54]Ap=C ric
+  // K: [0]ric [9]tic [12]B=ric^T R1^T [21]C=B R0 [30]Ap=C ric [39]tp = ric^T (R1^T (R0 tic + P0 - P1) - tic)
   if (lane == 0) {
     Quat Qi = quat_from_pose(pose0), Qj = quat_from_pose(pose1), qic = quat_from_pose(ex);
     if (nonunit(pose0) || nonunit(pose1) || nonunit(ex)) status |= ISV_W_NONUNIT_QUAT;
@@ -103,19 +111,20 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
     q2R(qic, ric);
     q2R(Qi, R0);
     q2R(Qj, R1);
-    // B = ric^T * R1^T = (R1 * ric)^T
-    mat3_mul(R1, ric, T);
+    mat3_mul(R1, ric, T);  // B = ric^T R1^T = (R1 ric)^T
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) B[3 * r + c] = T[3 * c + r];
     mat3_mul(B, R0, C);
     mat3_mul(C, ric, Ap);
-    for (int i = 0; i < 9; ++i) {
-      K[i] = ric[i]; K[12 + i] = R0[i]; K[24 + i] = R1[i]; K[36 + i] = B[i]; K[45 + i] = C[i]; K[54 + i] = Ap[i];
-    }
-    for (int i = 0; i < 3; ++i) { K[9 + i] = ex[i]; K[21 + i] = pose0[i]; K[33 + i] = pose1[i]; }
+    double a[3], b[3], tp[3];
+    mat3_vec(R0, ex, a);
+    for (int i = 0; i < 3; ++i) a[i] += pose0[i] - pose1[i];
+    mat3_tvec(R1, a, b);
+    for (int i = 0; i < 3; ++i) b[i] -= ex[i];
+    mat3_tvec(ric, b, tp);
+    for (int i = 0; i < 9; ++i) { K[i] = ric[i]; K[12 + i] = B[i]; K[21 + i] = C[i]; K[30 + i] = Ap[i]; }
+    for (int i = 0; i < 3; ++i) { K[9 + i] = ex[i]; K[39 + i] = tp[i]; }
   }
-  // zero the staging buffer once: rows 12..15 stay zero for the whole loop
-  for (int i = lane; i < 16 * kXld; i += 32) X[i] = 0.0;
   __syncwarp();
 
   const long long lm0 = in.lm_offset[win];
@@ -124,121 +133,116 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
   const long long st = in.lm_stride;
   const double s00 = cfg.ps[0], s10 = cfg.ps[1], s01 = cfg.ps[2], s11 = cfg.ps[3];
 
-  // accumulators: tiles (0,0) (1,0) (1,1) of E = sum e e^T and S = sum w w^T
-  double e00a = 0, e00b = 0, e10a = 0, e10b = 0, e11a = 0, e11b = 0;
-  double s00a = 0, s00b = 0, s10a = 0, s10b = 0, s11a = 0, s11b = 0;
+  // accumulators: 8x8 tile of E = sum e e^T and S = sum w w^T (rows 0-7) + row 8 in plain DFMA
+  double te0 = 0, te1 = 0, ts0 = 0, ts1 = 0;
+  double e8[9], w8[9];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) { e8[c] = 0.0; w8[c] = 0.0; }
   const int fm = lane >> 2, fk = lane & 3;
 
+  // software prefetch of the next 32 landmarks
+  double nx = 0, ny = 0, nz = 0, nl = 1;
+  if (lane < L) { nx = ob[lane]; ny = ob[st + lane]; nz = ob[2 * st + lane]; nl = ob[5 * st + lane]; }
   for (int base = 0; base < L; base += 32) {
     const int k = base + lane;
-    double ev[12], wv[12];
+    const double xi = nx, yi = ny, zi = nz, lam = nl;
+    const int kn = k + 32;
+    if (kn < L) { nx = ob[kn]; ny = ob[st + kn]; nz = ob[2 * st + kn]; nl = ob[5 * st + kn]; }
+    double ez[9], wz[9];
     if (k < L) {
-      const double xi = ob[k], yi = ob[st + k], zi = ob[2 * st + k];
-      const double lam = ob[5 * st + k];
-      // pts_camera_i = pts_i / inv_dep ; pts_imu_i = ric*pc + tic ; pts_w = R0*pi + P0
-      const double pc0 = xi / lam, pc1 = yi / lam, pc2 = zi / lam;
-      double pi_[3], pw[3], pj[3], d[3], cj[3];
-      for (int r = 0; r < 3; ++r) pi_[r] = K[3 * r] * pc0 + K[3 * r + 1] * pc1 + K[3 * r + 2] * pc2 + K[9 + r];
-      for (int r = 0; r < 3; ++r)
-        pw[r] = K[12 + 3 * r] * pi_[0] + K[12 + 3 * r + 1] * pi_[1] + K[12 + 3 * r + 2] * pi_[2] + K[21 + r];
-      for (int r = 0; r < 3; ++r) d[r] = pw[r] - K[33 + r];
-      // pts_imu_j = R1^T (pw - P1) ; pts_camera_j = ric^T (pts_imu_j - tic)
-      for (int r = 0; r < 3; ++r) pj[r] = K[24 + r] * d[0] + K[24 + 3 + r] * d[1] + K[24 + 6 + r] * d[2];
-      for (int r = 0; r < 3; ++r) d[r] = pj[r] - K[9 + r];
-      for (int r = 0; r < 3; ++r) cj[r] = K[r] * d[0] + K[3 + r] * d[1] + K[6 + r] * d[2];
+      // pts_camera_i = pts_i / inv_dep ; pts_camera_j = Ap pc + tp (the chain of :137-141 collapsed)
+      const double inv = 1.0 / lam;
+      const double pc0 = xi * inv, pc1 = yi * inv, pc2 = zi * inv;
+      double q[3], cj[3], pi_[3], pj[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        q[r] = K[30 + 3 * r] * pc0 + K[30 + 3 * r + 1] * pc1 + K[30 + 3 * r + 2] * pc2;
+        cj[r] = q[r] + K[39 + r];
+        pi_[r] = K[3 * r] * pc0 + K[3 * r + 1] * pc1 + K[3 * r + 2] * pc2 + K[9 + r];   // pts_imu_i
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) pj[r] = K[3 * r] * cj[0] + K[3 * r + 1] * cj[1] + K[3 * r + 2] * cj[2] + K[9 + r];  // pts_imu_j
       const double iz = 1.0 / cj[2];
       const double rx = -cj[0] * iz * iz, ry = -cj[1] * iz * iz;  // reduce = [iz 0 rx ; 0 iz ry]
       // rB = reduce*B, rC = reduce*C, rT = reduce*ric^T   (2x3 each)
       double rB[6], rC[6], rT[6];
+#pragma unroll
       for (int c = 0; c < 3; ++c) {
-        rB[c] = iz * K[36 + c] + rx * K[36 + 6 + c];
-        rB[3 + c] = iz * K[36 + 3 + c] + ry * K[36 + 6 + c];
-        rC[c] = iz * K[45 + c] + rx * K[45 + 6 + c];
-        rC[3 + c] = iz * K[45 + 3 + c] + ry * K[45 + 6 + c];
-        rT[c] = iz * K[3 * c] + rx * K[3 * c + 2];        // ric^T[0][c] = ric[c][0]
+        rB[c] = iz * K[12 + c] + rx * K[12 + 6 + c];
+        rB[3 + c] = iz * K[12 + 3 + c] + ry * K[12 + 6 + c];
+        rC[c] = iz * K[21 + c] + rx * K[21 + 6 + c];
+        rC[3 + c] = iz * K[21 + 3 + c] + ry * K[21 + 6 + c];
+        rT[c] = iz * K[3 * c] + rx * K[3 * c + 2];
         rT[3 + c] = iz * K[3 * c + 1] + ry * K[3 * c + 2];
       }
-      // unweighted J (2 x 12), column order [T1 (d/dP1, d/dtheta1) | T0 (d/dP0, d/dtheta0)]
-      double J0[12], J1[12];
-      for (int c = 0; c < 3; ++c) {
-        J0[c] = -rB[c];          J1[c] = -rB[3 + c];        // jaco_j left  = ric^T * -Rj^T
-        J0[6 + c] = rB[c];       J1[6 + c] = rB[3 + c];     // jaco_i left  = ric^T * Rj^T
-      }
-      // M*skew(p) row = (M1 p2 - M2 p1, M2 p0 - M0 p2, M0 p1 - M1 p0)
-      J0[3] = rT[1] * pj[2] - rT[2] * pj[1];  J0[4] = rT[2] * pj[0] - rT[0] * pj[2];  J0[5] = rT[0] * pj[1] - rT[1] * pj[0];
-      J1[3] = rT[4] * pj[2] - rT[5] * pj[1];  J1[4] = rT[5] * pj[0] - rT[3] * pj[2];  J1[5] = rT[3] * pj[1] - rT[4] * pj[0];
-      J0[9] = -(rC[1] * pi_[2] - rC[2] * pi_[1]);  J0[10] = -(rC[2] * pi_[0] - rC[0] * pi_[2]);  J0[11] = -(rC[0] * pi_[1] - rC[1] * pi_[0]);
-      J1[9] = -(rC[4] * pi_[2] - rC[5] * pi_[1]);  J1[10] = -(rC[5] * pi_[0] - rC[3] * pi_[2]);  J1[11] = -(rC[3] * pi_[1] - rC[4] * pi_[0]);
-      // jacobian_feature = reduce * Ap * pts_i * -1/(lam^2)
-      double f[3];
-      for (int r = 0; r < 3; ++r) f[r] = K[54 + 3 * r] * xi + K[54 + 3 * r + 1] * yi + K[54 + 3 * r + 2] * zi;
-      const double sc = -1.0 / (lam * lam);
-      const double jl0 = (iz * f[0] + rx * f[2]) * sc, jl1 = (iz * f[1] + ry * f[2]) * sc;
+      // unweighted 2x9 rows: [ T1-rot = rT*skew(pj) | T0-rot = -rC*skew(pi) | pos = rB ]
+      double J0[9], J1[9];
+      J0[0] = rT[1] * pj[2] - rT[2] * pj[1];  J0[1] = rT[2] * pj[0] - rT[0] * pj[2];  J0[2] = rT[0] * pj[1] - rT[1] * pj[0];
+      J1[0] = rT[4] * pj[2] - rT[5] * pj[1];  J1[1] = rT[5] * pj[0] - rT[3] * pj[2];  J1[2] = rT[3] * pj[1] - rT[4] * pj[0];
+      J0[3] = rC[2] * pi_[1] - rC[1] * pi_[2];  J0[4] = rC[0] * pi_[2] - rC[2] * pi_[0];  J0[5] = rC[1] * pi_[0] - rC[0] * pi_[1];
+      J1[3] = rC[5] * pi_[1] - rC[4] * pi_[2];  J1[4] = rC[3] * pi_[2] - rC[5] * pi_[0];  J1[5] = rC[4] * pi_[0] - rC[3] * pi_[1];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { J0[6 + c] = rB[c]; J1[6 + c] = rB[3 + c]; }
+      // jacobian_feature = reduce * Ap * pts_i * -1/lam^2 = -(reduce q)/lam
+      const double jl0 = -(iz * q[0] + rx * q[2]) * inv, jl1 = -(iz * q[1] + ry * q[2]) * inv;
       // weighted by the 2x2 sqrt_info, then rotated into the (u, v) basis of s*jl
       const double g0 = s00 * jl0 + s01 * jl1, g1 = s10 * jl0 + s11 * jl1;
-      double nrm = sqrt(g0 * g0 + g1 * g1);
+      const double n2 = g0 * g0 + g1 * g1;
       double u0 = 1.0, u1 = 0.0;
-      if (nrm > 0.0) { u0 = g0 / nrm; u1 = g1 / nrm; } else { status |= ISV_W_SINGULAR; }
-      // e = (sJ)^T u , w = (sJ)^T v with v = (-u1, u0)
+      if (n2 > 0.0) { const double in_ = rsqrt(n2); u0 = g0 * in_; u1 = g1 * in_; } else { status |= ISV_W_SINGULAR; }
       const double eu0 = u0 * s00 + u1 * s10, eu1 = u0 * s01 + u1 * s11;      // u^T s
       const double ev0 = -u1 * s00 + u0 * s10, ev1 = -u1 * s01 + u0 * s11;    // v^T s
 #pragma unroll
-      for (int c = 0; c < 12; ++c) {
-        ev[c] = eu0 * J0[c] + eu1 * J1[c];
-        wv[c] = ev0 * J0[c] + ev1 * J1[c];
+      for (int c = 0; c < 9; ++c) {
+        ez[c] = eu0 * J0[c] + eu1 * J1[c];
+        wz[c] = ev0 * J0[c] + ev1 * J1[c];
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < 12; ++c) { ev[c] = 0.0; wv[c] = 0.0; }
+      for (int c = 0; c < 9; ++c) { ez[c] = 0.0; wz[c] = 0.0; }
     }
-    // ---- E += e e^T on the FP64 tensor pipe --------------------------------------------------
+    // row 8 of both Gram matrices in registers
 #pragma unroll
-    for (int c = 0; c < 12; ++c) X[c * kXld + lane] = ev[c];
+    for (int c = 0; c < 9; ++c) { e8[c] = fma(ez[8], ez[c], e8[c]); w8[c] = fma(wz[8], wz[c], w8[c]); }
+    // rows 0-7 on the FP64 tensor pipe: stage e (rows 0-7) and w (rows 8-15) together
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { X[c * kXld + lane] = ez[c]; X[(8 + c) * kXld + lane] = wz[c]; }
     __syncwarp();
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
-      const double lo = X[fm * kXld + 4 * s + fk], hi = X[(8 + fm) * kXld + 4 * s + fk];
-      dmma884(e00a, e00b, lo, lo);
-      dmma884(e10a, e10b, hi, lo);
-      dmma884(e11a, e11b, hi, hi);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < 12; ++c) X[c * kXld + lane] = wv[c];
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const double lo = X[fm * kXld + 4 * s + fk], hi = X[(8 + fm) * kXld + 4 * s + fk];
-      dmma884(s00a, s00b, lo, lo);
-      dmma884(s10a, s10b, hi, lo);
-      dmma884(s11a, s11b, hi, hi);
+      const double ae = X[fm * kXld + 4 * s + fk], aw = X[(8 + fm) * kXld + 4 * s + fk];
+      dmma884(te0, te1, ae, ae);
+      dmma884(ts0, ts1, aw, aw);
     }
     __syncwarp();
   }
 
   // ---- tail -------------------------------------------------------------------------------------
-  // work map (doubles): S12[0] E12/H12[144] T16e[288] T16s[544] ; after the unpack:
+  // work map (doubles): S12[0] H12[144] Ze[288] Zs[369] ; then
   // Wst[288] G[432] Jr6[504] sp[540] sr[576] tA[612] tB[684] wk[756]
   double* S12 = X;
   double* H12 = X + 144;
-  double* T16e = X + 288;
-  double* T16s = X + 544;
+  double* Ze = X + 288;   // 9 x 9 Gram matrices (ld 9)
+  double* Zs = X + 369;
   {
     const int r = fm, c = 2 * fk;
-    T16e[r + 16 * c] = e00a;             T16e[r + 16 * (c + 1)] = e00b;
-    T16e[8 + r + 16 * c] = e10a;         T16e[8 + r + 16 * (c + 1)] = e10b;
-    T16e[8 + r + 16 * (8 + c)] = e11a;   T16e[8 + r + 16 * (8 + c + 1)] = e11b;
-    T16s[r + 16 * c] = s00a;             T16s[r + 16 * (c + 1)] = s00b;
-    T16s[8 + r + 16 * c] = s10a;         T16s[8 + r + 16 * (c + 1)] = s10b;
-    T16s[8 + r + 16 * (8 + c)] = s11a;   T16s[8 + r + 16 * (8 + c + 1)] = s11b;
+    Ze[r + 9 * c] = te0;  Ze[r + 9 * (c + 1)] = te1;
+    Zs[r + 9 * c] = ts0;  Zs[r + 9 * (c + 1)] = ts1;
+  }
+#pragma unroll
+  for (int c = 0; c < 9; ++c) { e8[c] = warp_sum(e8[c]); w8[c] = warp_sum(w8[c]); }
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < 9; ++c) { Ze[8 + 9 * c] = e8[c]; Ze[c + 9 * 8] = e8[c]; Zs[8 + 9 * c] = w8[c]; Zs[c + 9 * 8] = w8[c]; }
   }
   __syncwarp();
   for (int idx = lane; idx < 144; idx += 32) {
-    int r = idx % 12, c = idx / 12;
-    int rr = r, cc = c;
-    if (r < 8 && c >= 8) { rr = c; cc = r; }  // tile (0,1) = tile (1,0)^T
-    S12[idx] = T16s[rr + 16 * cc];
-    H12[idx] = T16e[rr + 16 * cc];
+    const int r = idx % 12, c = idx / 12;
+    const int zr = fwd_zmap(r), zc = fwd_zmap(c);
+    const double sg = ((r < 3) != (c < 3)) ? -1.0 : 1.0;
+    S12[idx] = sg * Zs[zr + 9 * zc];
+    H12[idx] = sg * Ze[zr + 9 * zc];
   }
   __syncwarp();
   double* Wst = X + 288;
@@ -253,38 +257,39 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
   const double* prel = in.prior_rel + (size_t)win * ISV_REL_REC;
   double* o_se3 = out.se3_out + (size_t)win * ISV_SE3_REC;
   double* o_pg = out.pg_out + (size_t)win * ISV_PG_REC;
-  // tA <- Jp (36) | tB <- Ji (36), tB+36.. no: use wk for Ji/Jj
   for (int i = lane; i < 36; i += 32) { sp[i] = pse3[12 + i]; sr[i] = prel[12 + i]; }
-  if (lane == 0) {
-    double Rp[9];
-    load_mat3_colmajor(pse3 + 3, Rp);
-    se3prior_jacobian(pose0, pse3, Rp, tA, nullptr);  // vioPosePriorEdge->EvaluateOnlyJacobians(para_Pose[0])
-  } else if (lane == 1) {
-    double dR[9];
-    load_mat3_colmajor(prel + 3, dR);
-    relpose_jacobians(pose0, pose1, prel, dR, wk, wk + 36, nullptr);  // vioRelativePoseEdges[1]
-  } else if (lane == 2) {
-    // pose-graph factor at the current estimate (:1244-1255): tij, Rij, J = [Ji | Jj]
-    Quat Qi = quat_from_pose(pose0), Qj = quat_from_pose(pose1);
-    double dd[3] = {pose1[0] - pose0[0], pose1[1] - pose0[1], pose1[2] - pose0[2]};
-    double tij[3], Rij[9];
-    qrot(qinv(Qi), dd, tij);
-    q2R(qmul(qinv(Qi), Qj), Rij);
-    relpose_jacobians(pose0, pose1, tij, Rij, G, G + 36, nullptr);
-    for (int i = 0; i < 3; ++i) o_pg[i] = tij[i];
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) o_pg[3 + r + 3 * c] = Rij[3 * r + c];
-    o_pg[84] = sqrt(tij[0] * tij[0] + tij[1] * tij[1] + tij[2] * tij[2]);  // distance = delta_t.norm()
-  } else if (lane == 3) {
-    // new SE3PriorFactor(P1, Q1) evaluated at para_Pose[1] (:1291-1297)
-    Quat Q1 = quat_from_pose(pose1);
-    double R1[9];
-    q2R(Q1, R1);
-    double t1[3] = {pose1[0], pose1[1], pose1[2]};
-    se3prior_jacobian(pose1, t1, R1, Jr6, nullptr);
-    for (int i = 0; i < 3; ++i) o_se3[i] = t1[i];
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) o_se3[3 + r + 3 * c] = R1[3 * r + c];
+  // lanes 0/1: the two RelativePoseFactors (vioRelativePoseEdges[1] :1212 ; pose-graph factor :1244-1255)
+  // lanes 2/3: the two SE3PriorFactors    (vioPosePriorEdge :1204 ; new SE3PriorFactor(P1,Q1) :1291-1297)
+  if (lane < 2) {
+    double dt[3], dR[9];
+    if (lane == 0) {
+      for (int i = 0; i < 3; ++i) dt[i] = prel[i];
+      load_mat3_colmajor(prel + 3, dR);
+    } else {
+      Quat Qi = quat_from_pose(pose0), Qj = quat_from_pose(pose1);
+      double dd[3] = {pose1[0] - pose0[0], pose1[1] - pose0[1], pose1[2] - pose0[2]};
+      qrot(qinv(Qi), dd, dt);
+      q2R(qmul(qinv(Qi), Qj), dR);
+      for (int i = 0; i < 3; ++i) o_pg[i] = dt[i];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) o_pg[3 + r + 3 * c] = dR[3 * r + c];
+      o_pg[84] = sqrt(dt[0] * dt[0] + dt[1] * dt[1] + dt[2] * dt[2]);  // distance = delta_t.norm()
+    }
+    double* Jo = lane == 0 ? wk : G;
+    relpose_jacobians(pose0, pose1, dt, dR, Jo, Jo + 36, nullptr);
+  } else if (lane < 4) {
+    double tt[3], Rp[9];
+    const double* ps = lane == 2 ? pose0 : pose1;
+    if (lane == 2) {
+      for (int i = 0; i < 3; ++i) tt[i] = pse3[i];
+      load_mat3_colmajor(pse3 + 3, Rp);
+    } else {
+      q2R(quat_from_pose(pose1), Rp);
+      for (int i = 0; i < 3; ++i) { tt[i] = pose1[i]; o_se3[i] = tt[i]; }
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) o_se3[3 + r + 3 * c] = Rp[3 * r + c];
+    }
+    se3prior_jacobian(ps, tt, Rp, lane == 2 ? tA : Jr6, nullptr);
   } else if (lane == 4) {
     // covAbs = (s^T s)^-1 of vioRollPitchEdges[0] when its index is 0 (:1265-1271)
     double cA[4] = {0, 0, 0, 0};
@@ -321,13 +326,17 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
   // ---- pose-graph relative-pose factor (:1243-1259) -------------------------------------------
   // J = G (6x12, [Ji|Jj]) ; Jpinv = J^T (J J^T)^-1 (full row rank) ; rpOmega = Jpinv^T H12 Jpinv
   w_gemm<false, true>(6, 6, 12, G, 6, G, 6, tA, 6, 0, lane);          // tA = J J^T
-  if (w_inverse(tA, 6, 6, wk, lane)) status |= ISV_W_SINGULAR;
+  if (w_spd_inverse<6>(tA, 6, wk, lane)) status |= ISV_W_SINGULAR;
   w_gemm<true, false>(12, 6, 6, G, 6, tA, 6, tB, 12, 0, lane);        // tB = Jpinv (12x6)
   w_gemm<false, false>(12, 6, 12, H12, 12, tB, 12, wk, 12, 0, lane);  // wk = H12 Jpinv
   w_gemm<true, false>(6, 6, 12, tB, 12, wk, 12, tA, 6, 0, lane);      // tA = rpOmega
   w_copy(Wst, tA, 36, lane);
   if (chol_store_upper(Wst, 6, 6, o_pg + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
-  if (w_inverse(tA, 6, 6, wk, lane)) status |= ISV_W_SINGULAR;        // covRel = rpOmega^-1
+  w_copy(Wst, tA, 36, lane);
+  if (w_spd_inverse<6>(tA, 6, wk, lane)) {                            // covRel = rpOmega^-1
+    w_copy(tA, Wst, 36, lane);
+    if (w_inverse(tA, 6, 6, wk, lane)) status |= ISV_W_SINGULAR;
+  }
   for (int i = lane; i < 36; i += 32) {
     if (!isfinite(tA[i])) nonfinite = 1;
     o_pg[48 + i] = tA[i];
@@ -335,18 +344,37 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
   __syncwarp();
   // ---- Schur complement over T0 (:1286-1288 with the landmarks already eliminated) -------------
   w_copy2d(tA, 6, S12 + 6 + 12 * 6, 12, 6, 6, lane);                  // tA = S[6:12,6:12]
-  if (w_inverse(tA, 6, 6, wk, lane)) status |= ISV_W_SINGULAR;
+  if (w_spd_inverse<6>(tA, 6, wk, lane)) {
+    w_copy2d(tA, 6, S12 + 6 + 12 * 6, 12, 6, 6, lane);
+    if (w_inverse(tA, 6, 6, wk, lane)) status |= ISV_W_SINGULAR;
+  }
   w_gemm<false, false>(6, 6, 6, S12 + 12 * 6, 12, tA, 6, tB, 6, 0, lane);        // tB = S[0:6,6:12] Smm^-1
   w_copy2d(Wst, 6, S12, 12, 6, 6, lane);                                          // Wst = S[0:6,0:6]
   w_gemm<false, true>(6, 6, 6, tB, 6, S12 + 12 * 6, 12, Wst, 6, -1, lane);       // Lamda_prior (6x6)
   // ---- rank decision + recovery of the SE3 prior on T1 (:1304-1349) ---------------------------
+  // Fast path: Lamda_prior^-1 by the SPD route; when ||A||_F ||A^-1||_F < 1e10 every pivot of
+  // Eigen's FullPivHouseholderQR is > 5e-13 of the largest, far above both its early-exit test
+  // (6 eps) and the 1e-16 rank threshold, i.e. qr.rank() == 6 without running the QR.  Otherwise
+  // the QR is restated literally on one lane.
+  w_copy(tA, Wst, 36, lane);
   int rank = 0;
-  if (lane == 0) {
-    for (int i = 0; i < 36; ++i) tB[i] = Wst[i];
-    rank = serial_fullpiv_qr_inverse<6>(tB, tA, cfg.qr_threshold);     // tA = cov = qr.solve(I)
+  {
+    double fa = 0.0, fi = 0.0;
+    for (int i = lane; i < 36; i += 32) fa = fma(tA[i], tA[i], fa);
+    const int bad = w_spd_inverse<6>(tA, 6, wk, lane);
+    for (int i = lane; i < 36; i += 32) fi = fma(tA[i], tA[i], fi);
+    fa = warp_sum(fa);
+    fi = warp_sum(fi);
+    if (!bad && fa * fi < 1e20) rank = 6;
   }
-  rank = __shfl_sync(kFullMask, rank, 0);
-  __syncwarp();
+  if (rank != 6) {
+    if (lane == 0) {
+      for (int i = 0; i < 36; ++i) tB[i] = Wst[i];
+      rank = serial_fullpiv_qr_inverse<6>(tB, tA, cfg.qr_threshold);   // tA = cov = qr.solve(I)
+    }
+    rank = __shfl_sync(kFullMask, rank, 0);
+    __syncwarp();
+  }
   int out_rank = rank;
   if (rank == 6) {
     w_gemm<false, false>(6, 6, 6, Jr6, 6, tA, 6, tB, 6, 0, lane);     // Jr cov
@@ -379,8 +407,8 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
     }
     __syncwarp();
   }
-  if (w_inverse(tA, 6, 6, wk, lane)) status |= ISV_W_SINGULAR;        // covi.inverse()
-  if (chol_store_upper(tA, 6, 6, o_se3 + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+  // sqrt_info = LLT(covi.inverse()).matrixL().transpose()  (:1349)
+  if (w_sqrt_info_from_cov<6>(tA, 6, o_se3 + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD | ISV_W_SINGULAR;
   if (__any_sync(kFullMask, nonfinite)) status |= ISV_W_NONFINITE;
   // merge per-lane status bits
 #pragma unroll
