@@ -476,28 +476,16 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
   __syncwarp();
   // ---- Schur complement over VB_{V-1} (:1413-1419) as a QR elimination -------------------------
   w_householder_marginalize(M, kMld, 24, 30, 21, 9, sc + 64, lane);
-  // ---- eigen-decomposition (:1479-1497): orthogonalise the 15 rows of G ------------------------
-  double* G = M + 9;  // row k, element c at G[k + kMld * c]
-  if (w_onesided_jacobi_rows<4, 6>(G, 1, 15, 21, sc + 64, lane, 30, kMld) >= 30) status |= ISV_W_EIG_NOCONV;
-  int rank = 0;
-  if (lane < 21) {
-    double lamk = (lane < 15) ? sc[64 + lane] : 0.0;
-    int keep = lamk > cfg.alpha;  // strict, Q12
-    sc[40 + lane] = keep ? 1.0 / (lamk * lamk) : 0.0;
-    rank = keep;
-  }
-  rank = __popc(__ballot_sync(kFullMask, rank));
-  __syncwarp();
   // ---- recovered factors (:1424-1452) and their Jacobian rows (:1456-1477) ---------------------
+  double* G = M + 9;         // row k, element c at G[k + kMld * c]
   double* T = M + 525;       // dead: R factor columns (225) + P (225) = 450 contiguous doubles
   double* Jrel = T;          // Ji (36) | Jj (36)
   double* Jrp = T + 72;      // 2 x 6
-  double* JU = T + 88;       // up to 9 x 15
-  double* cov = T + 224;     // up to 9 x 9
+  double* JU = T + 88;       // 17 x 15 (fast path: Y) / up to 9 x 15 (eigen path)
+  double* cov = T + 344;     // up to 9 x 9
   double* o_rel = out.rel_out + (size_t)win * ISV_REL_REC;
   double* o_vb = out.vb_out + (size_t)win * ISV_VB_REC;
   double* o_rp = out.rp_out + (size_t)win * ISV_RP_REC;
-  const double* dinv = sc + 40;
   if (lane == 0) {
     Quat Qi = quat_from_pose(sc), Qj = quat_from_pose(sc + 16);
     double dd[3] = {sc[16] - sc[0], sc[17] - sc[1], sc[18] - sc[2]};
@@ -519,50 +507,175 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
     o_vb[lane - 2] = sc[23 + (lane - 2)];  // Linear9Factor(vb): VB = para_SpeedBias[V]
   }
   __syncwarp();
-  // relative pose (rows 0-5 of Jr): Jj -> cols 0:6 (T_V), Ji -> cols 15:21 (T_{V-1})
-  for (int idx = lane; idx < 6 * 15; idx += 32) {
-    int r = idx % 6, k = idx / 6;
-    double acc = 0.0;
-    for (int c = 0; c < 6; ++c) {
-      acc = fma(Jrel[36 + r + 6 * c], G[k + kMld * c], acc);
-      acc = fma(Jrel[r + 6 * c], G[k + kMld * (15 + c)], acc);
+  // ---- fast path: no eigen-decomposition when every non-zero eigenvalue is provably > ALPHA ----
+  // LQ-factorise G = [L 0] Q (Householder from the right, one ROW per lane in registers) and carry
+  // the 17 rows of the recovered-factor Jacobians Jr (:1456-1464) through the same reflectors:
+  //   Lamda_prior = Q^T [L^T L 0; 0 0] Q ,  pinv = Q^T [(L^T L)^-1 0; 0 0] Q ,
+  //   cov_i = J_i pinv J_i^T = Y_i Y_i^T  with  y_r = L^-T (Jr Q^T)_r[0:15] .
+  // sigma_min(L)^2 >= 1 / ||L^-1||_F^2 is a lower bound of the smallest non-zero eigenvalue; if it
+  // exceeds ALPHA the reference's cut (:1482) keeps exactly these 15 and U D^-1 U^T == pinv.
+  double row[21];
+  if (lane < 15) {
+#pragma unroll
+    for (int c = 0; c < 21; ++c) row[c] = G[lane + kMld * c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 21; ++c) row[c] = 0.0;
+    const int r = lane - 15;
+    if (r < 6) {          // relative pose: Jj -> cols 0:6 (T_V), Ji -> cols 15:21 (T_{V-1})
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { row[c] = Jrel[36 + r + 6 * c]; row[15 + c] = Jrel[r + 6 * c]; }
+    } else if (r < 15) {  // speed-bias prior: I9 at cols 6:15
+#pragma unroll
+      for (int c = 0; c < 9; ++c) row[6 + c] = (c == r - 6) ? 1.0 : 0.0;
+    } else {              // roll/pitch: 2x6 at cols 15:21
+#pragma unroll
+      for (int c = 0; c < 6; ++c) row[15 + c] = Jrp[(r - 15) + 2 * c];
     }
-    JU[idx] = acc;
+  }
+#pragma unroll
+  for (int j = 0; j < 15; ++j) {
+    double t2 = 0.0;
+#pragma unroll
+    for (int c = j + 1; c < 21; ++c) t2 = fma(row[c], row[c], t2);
+    t2 = __shfl_sync(kFullMask, t2, j);
+    const double x0 = __shfl_sync(kFullMask, row[j], j);
+    if (t2 > 0.0) {
+      double beta = sqrt(fma(x0, x0, t2));
+      if (x0 >= 0.0) beta = -beta;
+      const double inv = 1.0 / (x0 - beta);
+      const double tau = (beta - x0) / beta;
+      double v[21];
+      double dot = row[j];
+#pragma unroll
+      for (int c = j + 1; c < 21; ++c) {
+        v[c] = __shfl_sync(kFullMask, row[c], j) * inv;
+        dot = fma(v[c], row[c], dot);
+      }
+      const double sdot = tau * dot;
+      if (lane == j) {
+        row[j] = beta;
+#pragma unroll
+        for (int c = j + 1; c < 21; ++c) row[c] = 0.0;
+      } else {
+        row[j] -= sdot;
+#pragma unroll
+        for (int c = j + 1; c < 21; ++c) row[c] = fma(-sdot, v[c], row[c]);
+      }
+    }
+  }
+  // L (rows of lanes 0-14, lower triangular) -> shared; solve L^T y = rhs for all 32 lanes at once:
+  // lanes 0-14: rhs = e_lane (columns of L^-T, for the eigenvalue bound), lanes 15-31: rhs = (Jr Q^T)_r
+  double* Ls = T + 88;  // 15 x 15 (ld 15) + 15 reciprocal diagonals; overlays JU, which is written later
+  if (lane < 15) {
+#pragma unroll
+    for (int c = 0; c < 15; ++c) Ls[lane + 15 * c] = row[c];
+    Ls[225 + lane] = 1.0 / row[lane];
   }
   __syncwarp();
-  for (int idx = lane; idx < 36; idx += 32) {
-    int r = idx % 6, c = idx / 6;
-    double acc = 0.0;
-    for (int k = 0; k < 15; ++k) acc = fma(JU[r + 6 * k] * dinv[k], JU[c + 6 * k], acc);
-    cov[idx] = acc;
+  double y[15];
+#pragma unroll
+  for (int k = 14; k >= 0; --k) {
+    double sacc = (lane < 15) ? ((lane == k) ? 1.0 : 0.0) : row[k];
+#pragma unroll
+    for (int m2 = k + 1; m2 < 15; ++m2) sacc = fma(-Ls[m2 + 15 * k], y[m2], sacc);
+    y[k] = sacc * Ls[225 + k];
   }
-  __syncwarp();
-  if (w_sqrt_info_from_cov<6>(cov, 6, o_rel + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
-  // speed-bias prior (rows 6-14): J = I9 at cols 6:15
-  for (int idx = lane; idx < 81; idx += 32) {
-    int r = idx % 9, c = idx / 9;
-    double acc = 0.0;
-    for (int k = 0; k < 15; ++k) acc = fma(G[k + kMld * (6 + r)] * dinv[k], G[k + kMld * (6 + c)], acc);
-    cov[idx] = acc;
+  double ninv2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 15; ++k) ninv2 = fma(y[k], y[k], ninv2);
+  ninv2 = (lane < 15) ? ninv2 : 0.0;
+  ninv2 = warp_sum(ninv2);
+  int rank;
+  const bool fast = isfinite(ninv2) && ninv2 > 0.0 && (1.0 / ninv2) > cfg.alpha;
+  if (fast) {
+    rank = 15;
+    __syncwarp();
+    if (lane >= 15) {
+#pragma unroll
+      for (int k = 0; k < 15; ++k) JU[(lane - 15) + 17 * k] = y[k];
+    }
+    __syncwarp();
+    // cov blocks: rel = rows 0-5, vb = rows 6-14, rp = rows 15-16 of Y
+    for (int idx = lane; idx < 36; idx += 32) {
+      int r = idx % 6, c = idx / 6;
+      double acc = 0.0;
+      for (int k = 0; k < 15; ++k) acc = fma(JU[r + 17 * k], JU[c + 17 * k], acc);
+      cov[idx] = acc;
+    }
+    __syncwarp();
+    if (w_sqrt_info_from_cov<6>(cov, 6, o_rel + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+    for (int idx = lane; idx < 81; idx += 32) {
+      int r = idx % 9, c = idx / 9;
+      double acc = 0.0;
+      for (int k = 0; k < 15; ++k) acc = fma(JU[6 + r + 17 * k], JU[6 + c + 17 * k], acc);
+      cov[idx] = acc;
+    }
+    __syncwarp();
+    if (w_sqrt_info_from_cov<9>(cov, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+    for (int idx = lane; idx < 4; idx += 32) {
+      int r = idx % 2, c = idx / 2;
+      double acc = 0.0;
+      for (int k = 0; k < 15; ++k) acc = fma(JU[15 + r + 17 * k], JU[15 + c + 17 * k], acc);
+      cov[idx] = acc;
+    }
+    __syncwarp();
+    if (w_sqrt_info_from_cov<2>(cov, 2, o_rp + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+  } else {
+    // ---- general path: eigen-decomposition (:1479-1497) by one-sided Jacobi on the rows of G ----
+    if (w_onesided_jacobi_rows<4, 6>(G, 1, 15, 21, sc + 64, lane, 30, kMld) >= 30) status |= ISV_W_EIG_NOCONV;
+    int keepf = 0;
+    if (lane < 21) {
+      double lamk = (lane < 15) ? sc[64 + lane] : 0.0;
+      int keep = lamk > cfg.alpha;  // strict, Q12
+      sc[40 + lane] = keep ? 1.0 / (lamk * lamk) : 0.0;
+      keepf = keep;
+    }
+    rank = __popc(__ballot_sync(kFullMask, keepf));
+    __syncwarp();
+    const double* dinv = sc + 40;
+    for (int idx = lane; idx < 6 * 15; idx += 32) {
+      int r = idx % 6, k = idx / 6;
+      double acc = 0.0;
+      for (int c = 0; c < 6; ++c) {
+        acc = fma(Jrel[36 + r + 6 * c], G[k + kMld * c], acc);
+        acc = fma(Jrel[r + 6 * c], G[k + kMld * (15 + c)], acc);
+      }
+      JU[idx] = acc;
+    }
+    __syncwarp();
+    for (int idx = lane; idx < 36; idx += 32) {
+      int r = idx % 6, c = idx / 6;
+      double acc = 0.0;
+      for (int k = 0; k < 15; ++k) acc = fma(JU[r + 6 * k] * dinv[k], JU[c + 6 * k], acc);
+      cov[idx] = acc;
+    }
+    __syncwarp();
+    if (w_sqrt_info_from_cov<6>(cov, 6, o_rel + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+    for (int idx = lane; idx < 81; idx += 32) {
+      int r = idx % 9, c = idx / 9;
+      double acc = 0.0;
+      for (int k = 0; k < 15; ++k) acc = fma(G[k + kMld * (6 + r)] * dinv[k], G[k + kMld * (6 + c)], acc);
+      cov[idx] = acc;
+    }
+    __syncwarp();
+    if (w_sqrt_info_from_cov<9>(cov, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+    for (int idx = lane; idx < 2 * 15; idx += 32) {
+      int r = idx % 2, k = idx / 2;
+      double acc = 0.0;
+      for (int c = 0; c < 6; ++c) acc = fma(Jrp[r + 2 * c], G[k + kMld * (15 + c)], acc);
+      JU[idx] = acc;
+    }
+    __syncwarp();
+    for (int idx = lane; idx < 4; idx += 32) {
+      int r = idx % 2, c = idx / 2;
+      double acc = 0.0;
+      for (int k = 0; k < 15; ++k) acc = fma(JU[r + 2 * k] * dinv[k], JU[c + 2 * k], acc);
+      cov[idx] = acc;
+    }
+    __syncwarp();
+    if (w_sqrt_info_from_cov<2>(cov, 2, o_rp + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
   }
-  __syncwarp();
-  if (w_sqrt_info_from_cov<9>(cov, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
-  // roll/pitch (rows 15-16): 2x6 at cols 15:21
-  for (int idx = lane; idx < 2 * 15; idx += 32) {
-    int r = idx % 2, k = idx / 2;
-    double acc = 0.0;
-    for (int c = 0; c < 6; ++c) acc = fma(Jrp[r + 2 * c], G[k + kMld * (15 + c)], acc);
-    JU[idx] = acc;
-  }
-  __syncwarp();
-  for (int idx = lane; idx < 4; idx += 32) {
-    int r = idx % 2, c = idx / 2;
-    double acc = 0.0;
-    for (int k = 0; k < 15; ++k) acc = fma(JU[r + 2 * k] * dinv[k], JU[c + 2 * k], acc);
-    cov[idx] = acc;
-  }
-  __syncwarp();
-  if (w_sqrt_info_from_cov<2>(cov, 2, o_rp + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
   if (__any_sync(kFullMask, nonfinite)) status |= ISV_W_NONFINITE;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) status |= __shfl_xor_sync(kFullMask, status, o);

@@ -141,3 +141,30 @@ def test_degenerate_forward_window_is_flagged(backend):
     assert int(out.rank[0, 0]) == 3
     assert out.status[0] & capi.W_RANK_DEFICIENT
     assert out.status[0] & (capi.W_SINGULAR | capi.W_NOT_SPD | capi.W_NONFINITE)
+
+
+def test_backward_general_eigen_path_with_truncation():
+    """With ALPHA inside the spectrum of Lamda_prior the LQ fast path must step aside and the
+    one-sided-Jacobi eigen path must reproduce the reference's strict `> ALPHA` cut (:1482)."""
+    from is_vins_b200 import MargBackend
+    from oracle import isv_oracle as O
+    events = _events(1, 4, 60, 3)
+    for ev in events:
+        w = np.sort(ev.bwd_out.eigvals)[-15:]
+        k = int(np.argmax(w[1:] / w[:-1]))
+        alpha = float(np.sqrt(w[k] * w[k + 1]))
+        cfg_o = O.Config(alpha=alpha)
+        ref = O.marg_backward(ev.bwd_in, cfg_o)
+        assert ref.rank == 15 - (k + 1)
+        cfg = capi.default_config()
+        cfg.alpha = alpha
+        be = MargBackend(0, cfg)
+        batch = pack_events([ev])
+        out = be.marg_window_batch_host(batch, capi.RUN_BACKWARD)
+        be.close()
+        assert int(out.rank[0, 1]) == ref.rank
+        from tests.helpers import rel_err
+        assert rel_err(out.rel_sqrt_info(0), ref.rel_sqrt_info) <= 1e-8
+        assert rel_err(out.vb_sqrt_info(0), ref.vb_sqrt_info) <= 1e-8
+        assert rel_err(out.rp_sqrt_info(0), ref.rp_sqrt_info) <= 1e-8
+        assert int(out.status[0]) == 0
