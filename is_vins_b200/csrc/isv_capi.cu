@@ -179,27 +179,31 @@ static isv_status check_batch(const isv_batch_in* in, const isv_batch_out* out, 
   return ISV_OK;
 }
 
-isv_status isv_marg_window_batch(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, int which) {
-  if (!h) return ISV_ERR_BAD_ARG;
-  isv_status st = check_batch(in, out, which);
-  if (st != ISV_OK) return st;
+static isv_status launch_batch(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, int which,
+                               cudaStream_t stream) {
   const int n = in->n_windows;
   if (n == 0) return ISV_OK;
-  ISV_CUDA(cudaSetDevice(h->device));
-  if (out->status) ISV_CUDA(cudaMemsetAsync(out->status, 0, sizeof(int32_t) * (size_t)n, h->stream));
+  if (out->status) ISV_CUDA(cudaMemsetAsync(out->status, 0, sizeof(int32_t) * (size_t)n, stream));
   const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
   if (which & ISV_RUN_FORWARD) {
-    marg_forward_kernel<<<grid, kThreads, kWarpsPerCta * kFwdSmemPerWarp * sizeof(double), h->stream>>>(*in, *out,
-                                                                                                       h->dcfg);
+    marg_forward_kernel<<<grid, kThreads, kWarpsPerCta * kFwdSmemPerWarp * sizeof(double), stream>>>(*in, *out, h->dcfg);
     ++h->launches;
   }
   if (which & ISV_RUN_BACKWARD) {
-    marg_backward_kernel<<<grid, kThreads, kWarpsPerCta * kBwdSmemPerWarp * sizeof(double), h->stream>>>(
-        *in, *out, h->dcfg, h->cfg.vo_size);
+    marg_backward_kernel<<<grid, kThreads, kWarpsPerCta * kBwdSmemPerWarp * sizeof(double), stream>>>(*in, *out, h->dcfg,
+                                                                                                    h->cfg.vo_size);
     ++h->launches;
   }
   ISV_CUDA(cudaGetLastError());
   return ISV_OK;
+}
+
+isv_status isv_marg_window_batch(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, int which) {
+  if (!h) return ISV_ERR_BAD_ARG;
+  isv_status st = check_batch(in, out, which);
+  if (st != ISV_OK) return st;
+  ISV_CUDA(cudaSetDevice(h->device));
+  return launch_batch(h, in, out, which, h->stream);
 }
 
 // ---- host-pointer entry point ------------------------------------------------------------------
@@ -231,88 +235,124 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   ISV_CUDA(cudaSetDevice(h->device));
   const bool fwd = which & ISV_RUN_FORWARD, bwd = which & ISV_RUN_BACKWARD;
   const size_t D = sizeof(double);
-  int64_t n_lm = fwd ? in->lm_offset[n] : 0;
+  const int64_t n_lm = fwd ? in->lm_offset[n] : 0;
   if (n_lm < 0 || (fwd && in->lm_stride < n_lm)) return ISV_ERR_BAD_ARG;
-  // carve the device mirror
+  // carve the device mirror (whole batch; chunks address sub-ranges of it)
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
-  size_t o_lmoff = carve(fwd ? (n + 1) * sizeof(int64_t) : 0);
-  size_t o_obs = carve(fwd ? 6 * (size_t)n_lm * D : 0);
-  size_t o_posef = carve(fwd ? n * 14 * D : 0);
-  size_t o_ex = carve(fwd ? (in->ex_pose_shared ? 7 : n * 7) * D : 0);
-  size_t o_pse3 = carve(fwd ? n * ISV_SE3_REC * D : 0);
-  size_t o_prel = carve(fwd ? n * ISV_REL_REC * D : 0);
-  size_t o_prp = carve(fwd && in->prior_rp ? n * ISV_RP_IN_REC * D : 0);
-  size_t o_poseb = carve(bwd ? n * 14 * D : 0);
-  size_t o_sbb = carve(bwd ? n * 18 * D : 0);
-  size_t o_pvb = carve(bwd ? n * ISV_VB_REC * D : 0);
-  size_t o_pre = carve(bwd ? n * ISV_PREINT_REC * D : 0);
-  size_t o_se3 = carve(fwd ? n * ISV_SE3_REC * D : 0);
-  size_t o_pg = carve(fwd ? n * ISV_PG_REC * D : 0);
-  size_t o_rel = carve(bwd ? n * ISV_REL_REC * D : 0);
-  size_t o_vb = carve(bwd ? n * ISV_VB_REC * D : 0);
-  size_t o_rp = carve(bwd ? n * ISV_RP_REC * D : 0);
-  size_t o_rank = carve(n * 2 * sizeof(int32_t));
-  size_t o_stat = carve(n * sizeof(int32_t));
+  const size_t o_lmoff = carve(fwd ? (n + 1) * sizeof(int64_t) : 0);
+  const size_t o_obs = carve(fwd ? 6 * (size_t)n_lm * D : 0);
+  const size_t o_posef = carve(fwd ? n * 14 * D : 0);
+  const size_t o_ex = carve(fwd ? (in->ex_pose_shared ? 7 : n * 7) * D : 0);
+  const size_t o_pse3 = carve(fwd ? n * ISV_SE3_REC * D : 0);
+  const size_t o_prel = carve(fwd ? n * ISV_REL_REC * D : 0);
+  const size_t o_prp = carve(fwd && in->prior_rp ? n * ISV_RP_IN_REC * D : 0);
+  const size_t o_poseb = carve(bwd ? n * 14 * D : 0);
+  const size_t o_sbb = carve(bwd ? n * 18 * D : 0);
+  const size_t o_pvb = carve(bwd ? n * ISV_VB_REC * D : 0);
+  const size_t o_pre = carve(bwd ? n * ISV_PREINT_REC * D : 0);
+  const size_t o_se3 = carve(fwd ? n * ISV_SE3_REC * D : 0);
+  const size_t o_pg = carve(fwd ? n * ISV_PG_REC * D : 0);
+  const size_t o_rel = carve(bwd ? n * ISV_REL_REC * D : 0);
+  const size_t o_vb = carve(bwd ? n * ISV_VB_REC * D : 0);
+  const size_t o_rp = carve(bwd ? n * ISV_RP_REC * D : 0);
+  const size_t o_rank = carve(n * 2 * sizeof(int32_t));
+  const size_t o_stat = carve(n * sizeof(int32_t));
   st = ensure_dbuf(h, off);
   if (st != ISV_OK) return st;
   char* d = h->dbuf;
-  cudaStream_t s = h->stream;
-  isv_batch_in din = *in;
-  isv_batch_out dout;
-  memset(&dout, 0, sizeof(dout));
-  ISV_CUDA(cudaMemsetAsync(d + o_rank, 0, n * 2 * sizeof(int32_t), s));
+  // Chunked pipeline on two streams: chunk c+1's H2D overlaps chunk c's kernels and D2H (PCIe is
+  // full duplex).  The caller's stream is fenced before and after with events.
+  cudaStream_t ss[2] = {h->own_stream, h->copy_stream};
+  if (h->stream != h->own_stream) {
+    ISV_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    ISV_CUDA(cudaStreamWaitEvent(ss[0], h->ev[0], 0));
+    ISV_CUDA(cudaStreamWaitEvent(ss[1], h->ev[0], 0));
+  } else {
+    ISV_CUDA(cudaEventRecord(h->ev[0], ss[0]));
+    ISV_CUDA(cudaStreamWaitEvent(ss[1], h->ev[0], 0));
+  }
+  ISV_CUDA(cudaMemsetAsync(d + o_rank, 0, n * 2 * sizeof(int32_t), ss[0]));
   if (fwd) {
-    ISV_CUDA(cudaMemcpyAsync(d + o_lmoff, in->lm_offset, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    for (int c = 0; c < 6 && n_lm > 0; ++c)
-      ISV_CUDA(cudaMemcpyAsync(d + o_obs + (size_t)c * n_lm * D, in->lm_obs + (size_t)c * in->lm_stride,
-                               (size_t)n_lm * D, cudaMemcpyHostToDevice, s));
-    ISV_CUDA(cudaMemcpyAsync(d + o_posef, in->pose_fwd, n * 14 * D, cudaMemcpyHostToDevice, s));
-    ISV_CUDA(cudaMemcpyAsync(d + o_ex, in->ex_pose, (in->ex_pose_shared ? 7 : n * 7) * D, cudaMemcpyHostToDevice, s));
-    ISV_CUDA(cudaMemcpyAsync(d + o_pse3, in->prior_se3, n * ISV_SE3_REC * D, cudaMemcpyHostToDevice, s));
-    ISV_CUDA(cudaMemcpyAsync(d + o_prel, in->prior_rel, n * ISV_REL_REC * D, cudaMemcpyHostToDevice, s));
-    if (in->prior_rp)
-      ISV_CUDA(cudaMemcpyAsync(d + o_prp, in->prior_rp, n * ISV_RP_IN_REC * D, cudaMemcpyHostToDevice, s));
-    din.lm_offset = (const int64_t*)(d + o_lmoff);
-    din.lm_obs = (const double*)(d + o_obs);
-    din.lm_stride = n_lm;
-    din.pose_fwd = (const double*)(d + o_posef);
-    din.ex_pose = (const double*)(d + o_ex);
-    din.prior_se3 = (const double*)(d + o_pse3);
-    din.prior_rel = (const double*)(d + o_prel);
-    din.prior_rp = in->prior_rp ? (const double*)(d + o_prp) : nullptr;
-    dout.se3_out = (double*)(d + o_se3);
-    dout.pg_out = (double*)(d + o_pg);
+    ISV_CUDA(cudaMemcpyAsync(d + o_lmoff, in->lm_offset, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ss[0]));
+    ISV_CUDA(cudaMemcpyAsync(d + o_ex, in->ex_pose, (in->ex_pose_shared ? 7 : n * 7) * D, cudaMemcpyHostToDevice, ss[0]));
   }
-  if (bwd) {
-    ISV_CUDA(cudaMemcpyAsync(d + o_poseb, in->pose_bwd, n * 14 * D, cudaMemcpyHostToDevice, s));
-    ISV_CUDA(cudaMemcpyAsync(d + o_sbb, in->sb_bwd, n * 18 * D, cudaMemcpyHostToDevice, s));
-    ISV_CUDA(cudaMemcpyAsync(d + o_pvb, in->prior_vb, n * ISV_VB_REC * D, cudaMemcpyHostToDevice, s));
-    ISV_CUDA(cudaMemcpyAsync(d + o_pre, in->preint, n * ISV_PREINT_REC * D, cudaMemcpyHostToDevice, s));
-    din.pose_bwd = (const double*)(d + o_poseb);
-    din.sb_bwd = (const double*)(d + o_sbb);
-    din.prior_vb = (const double*)(d + o_pvb);
-    din.preint = (const double*)(d + o_pre);
-    dout.rel_out = (double*)(d + o_rel);
-    dout.vb_out = (double*)(d + o_vb);
-    dout.rp_out = (double*)(d + o_rp);
+  ISV_CUDA(cudaEventRecord(h->ev[1], ss[0]));
+  ISV_CUDA(cudaStreamWaitEvent(ss[1], h->ev[1], 0));
+  size_t n_chunks = n / 512;
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > 8) n_chunks = 8;
+  for (size_t c = 0; c < n_chunks; ++c) {
+    const size_t w0 = n * c / n_chunks, w1 = n * (c + 1) / n_chunks, m = w1 - w0;
+    if (m == 0) continue;
+    cudaStream_t s = ss[c & 1];
+    isv_batch_in din;
+    isv_batch_out dout;
+    memset(&din, 0, sizeof(din));
+    memset(&dout, 0, sizeof(dout));
+    din.n_windows = (int32_t)m;
+    din.ex_pose_shared = in->ex_pose_shared;
+    if (fwd) {
+      const int64_t a = in->lm_offset[w0], b = in->lm_offset[w1];
+      // components 3,4 (pts_j) are never read by the information-only marginalization: not copied
+      static const int comps[4] = {0, 1, 2, 5};
+      for (int ci = 0; ci < 4 && b > a; ++ci)
+        ISV_CUDA(cudaMemcpyAsync(d + o_obs + ((size_t)comps[ci] * n_lm + a) * D,
+                                 in->lm_obs + (size_t)comps[ci] * in->lm_stride + a, (size_t)(b - a) * D,
+                                 cudaMemcpyHostToDevice, s));
+      ISV_CUDA(cudaMemcpyAsync(d + o_posef + w0 * 14 * D, in->pose_fwd + w0 * 14, m * 14 * D, cudaMemcpyHostToDevice, s));
+      ISV_CUDA(cudaMemcpyAsync(d + o_pse3 + w0 * ISV_SE3_REC * D, in->prior_se3 + w0 * ISV_SE3_REC, m * ISV_SE3_REC * D,
+                               cudaMemcpyHostToDevice, s));
+      ISV_CUDA(cudaMemcpyAsync(d + o_prel + w0 * ISV_REL_REC * D, in->prior_rel + w0 * ISV_REL_REC, m * ISV_REL_REC * D,
+                               cudaMemcpyHostToDevice, s));
+      if (in->prior_rp)
+        ISV_CUDA(cudaMemcpyAsync(d + o_prp + w0 * ISV_RP_IN_REC * D, in->prior_rp + w0 * ISV_RP_IN_REC,
+                                 m * ISV_RP_IN_REC * D, cudaMemcpyHostToDevice, s));
+      din.lm_offset = (const int64_t*)(d + o_lmoff) + w0;   // absolute offsets into the whole mirror
+      din.lm_obs = (const double*)(d + o_obs);
+      din.lm_stride = n_lm;
+      din.pose_fwd = (const double*)(d + o_posef) + w0 * 14;
+      din.ex_pose = (const double*)(d + o_ex) + (in->ex_pose_shared ? 0 : w0 * 7);
+      din.prior_se3 = (const double*)(d + o_pse3) + w0 * ISV_SE3_REC;
+      din.prior_rel = (const double*)(d + o_prel) + w0 * ISV_REL_REC;
+      din.prior_rp = in->prior_rp ? (const double*)(d + o_prp) + w0 * ISV_RP_IN_REC : nullptr;
+      dout.se3_out = (double*)(d + o_se3) + w0 * ISV_SE3_REC;
+      dout.pg_out = (double*)(d + o_pg) + w0 * ISV_PG_REC;
+    }
+    if (bwd) {
+      ISV_CUDA(cudaMemcpyAsync(d + o_poseb + w0 * 14 * D, in->pose_bwd + w0 * 14, m * 14 * D, cudaMemcpyHostToDevice, s));
+      ISV_CUDA(cudaMemcpyAsync(d + o_sbb + w0 * 18 * D, in->sb_bwd + w0 * 18, m * 18 * D, cudaMemcpyHostToDevice, s));
+      ISV_CUDA(cudaMemcpyAsync(d + o_pvb + w0 * ISV_VB_REC * D, in->prior_vb + w0 * ISV_VB_REC, m * ISV_VB_REC * D,
+                               cudaMemcpyHostToDevice, s));
+      ISV_CUDA(cudaMemcpyAsync(d + o_pre + w0 * ISV_PREINT_REC * D, in->preint + w0 * ISV_PREINT_REC,
+                               m * ISV_PREINT_REC * D, cudaMemcpyHostToDevice, s));
+      din.pose_bwd = (const double*)(d + o_poseb) + w0 * 14;
+      din.sb_bwd = (const double*)(d + o_sbb) + w0 * 18;
+      din.prior_vb = (const double*)(d + o_pvb) + w0 * ISV_VB_REC;
+      din.preint = (const double*)(d + o_pre) + w0 * ISV_PREINT_REC;
+      dout.rel_out = (double*)(d + o_rel) + w0 * ISV_REL_REC;
+      dout.vb_out = (double*)(d + o_vb) + w0 * ISV_VB_REC;
+      dout.rp_out = (double*)(d + o_rp) + w0 * ISV_RP_REC;
+    }
+    dout.rank = (int32_t*)(d + o_rank) + 2 * w0;
+    dout.status = (int32_t*)(d + o_stat) + w0;
+    st = launch_batch(h, &din, &dout, which, s);
+    if (st != ISV_OK) return st;
+    if (fwd) {
+      ISV_CUDA(cudaMemcpyAsync(out->se3_out + w0 * ISV_SE3_REC, dout.se3_out, m * ISV_SE3_REC * D, cudaMemcpyDeviceToHost, s));
+      ISV_CUDA(cudaMemcpyAsync(out->pg_out + w0 * ISV_PG_REC, dout.pg_out, m * ISV_PG_REC * D, cudaMemcpyDeviceToHost, s));
+    }
+    if (bwd) {
+      ISV_CUDA(cudaMemcpyAsync(out->rel_out + w0 * ISV_REL_REC, dout.rel_out, m * ISV_REL_REC * D, cudaMemcpyDeviceToHost, s));
+      ISV_CUDA(cudaMemcpyAsync(out->vb_out + w0 * ISV_VB_REC, dout.vb_out, m * ISV_VB_REC * D, cudaMemcpyDeviceToHost, s));
+      ISV_CUDA(cudaMemcpyAsync(out->rp_out + w0 * ISV_RP_REC, dout.rp_out, m * ISV_RP_REC * D, cudaMemcpyDeviceToHost, s));
+    }
+    ISV_CUDA(cudaMemcpyAsync(out->rank + 2 * w0, dout.rank, m * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (out->status)
+      ISV_CUDA(cudaMemcpyAsync(out->status + w0, dout.status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   }
-  dout.rank = (int32_t*)(d + o_rank);
-  dout.status = (int32_t*)(d + o_stat);
-  st = isv_marg_window_batch(h, &din, &dout, which);
-  if (st != ISV_OK) return st;
-  if (fwd) {
-    ISV_CUDA(cudaMemcpyAsync(out->se3_out, dout.se3_out, n * ISV_SE3_REC * D, cudaMemcpyDeviceToHost, s));
-    ISV_CUDA(cudaMemcpyAsync(out->pg_out, dout.pg_out, n * ISV_PG_REC * D, cudaMemcpyDeviceToHost, s));
-  }
-  if (bwd) {
-    ISV_CUDA(cudaMemcpyAsync(out->rel_out, dout.rel_out, n * ISV_REL_REC * D, cudaMemcpyDeviceToHost, s));
-    ISV_CUDA(cudaMemcpyAsync(out->vb_out, dout.vb_out, n * ISV_VB_REC * D, cudaMemcpyDeviceToHost, s));
-    ISV_CUDA(cudaMemcpyAsync(out->rp_out, dout.rp_out, n * ISV_RP_REC * D, cudaMemcpyDeviceToHost, s));
-  }
-  ISV_CUDA(cudaMemcpyAsync(out->rank, dout.rank, n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  if (out->status) ISV_CUDA(cudaMemcpyAsync(out->status, dout.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  ISV_CUDA(cudaStreamSynchronize(s));
+  ISV_CUDA(cudaStreamSynchronize(ss[0]));
+  ISV_CUDA(cudaStreamSynchronize(ss[1]));
   return ISV_OK;
 }
 
