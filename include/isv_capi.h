@@ -193,6 +193,30 @@ typedef struct isv_bwd_out {
 isv_status isv_marg_forward(isv_handle* h, const isv_fwd_in* in, isv_fwd_out* out);
 isv_status isv_marg_backward(isv_handle* h, const isv_bwd_in* in, isv_bwd_out* out);
 
+/* ---- initFactorGraph sparsification tail (src/estimator.cpp:745-1001) ---------------------------
+ * One-time: the V-1 IMU factors of the initial window -> V-1 RelativePoseFactors
+ * (vioRelativePoseEdges[1..V-1]), the SE3PriorFactor on T_0 (vioPosePriorEdge) and the Linear9Factor
+ * on VB_{V-1} (vioVBPrior).  V = isv_config.vo_size (2..10).  SoA over independent windows.        */
+typedef struct isv_init_in {
+  int32_t n_windows;
+  const double* poses;           /* [n][V][7]     para_Pose[0..V-1]                              */
+  const double* sbs;             /* [n][V][9]     para_SpeedBias[0..V-1]                         */
+  const double* preint;          /* [n][V-1][467] pre_integrations[i+1] (links frame i -> i+1)   */
+} isv_init_in;
+
+typedef struct isv_init_out {
+  double* rel_out;               /* [n][V-1][48]  vioRelativePoseEdges[i+1]                      */
+  double* se3_out;               /* [n][48]       vioPosePriorEdge                               */
+  double* vb_out;                /* [n][90]       vioVBPrior                                     */
+  int32_t* rank;                 /* [n]           #eigenvalues of the 6V+9 marginal > alpha      */
+  int32_t* status;               /* [n]           ISV_W_* bitmask (may be NULL)                  */
+} isv_init_out;
+
+/* device pointers, stream-ordered */
+isv_status isv_init_sparsify_batch(isv_handle* h, const isv_init_in* in, const isv_init_out* out);
+/* host pointers, blocking */
+isv_status isv_init_sparsify_host(isv_handle* h, const isv_init_in* in, const isv_init_out* out);
+
 /* ---- unit-test hook: the PSD eigensolver that replaces SelfAdjointEigenSolver on this path -----
  * (src/estimator.cpp:920,1311,1479).  nb symmetric n x n matrices A (column-major, host) ->
  * G [nb][n][n] row-major factor rows with  A ~= sum_k g_k g_k^T, g_k mutually orthogonal;

@@ -138,3 +138,18 @@ class MargBackend:
         bo = capi.isv_bwd_out()
         capi.check(self.lib.isv_marg_backward(self.h, C.byref(bi), C.byref(bo)), "isv_marg_backward")
         return np.array(bo.rel), np.array(bo.vb), np.array(bo.rp), int(bo.rank), int(bo.status)
+
+    # ---- initFactorGraph sparsification tail (one-time, src/estimator.cpp:745-1001) ---------------
+    def init_sparsify(self, poses, sbs, preint):
+        """poses [n,V,7], sbs [n,V,9], preint [n,V-1,467] (host) -> dict of recovered-factor records."""
+        V = int(self.cfg.vo_size)
+        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, V, 7)
+        n = poses.shape[0]
+        sbs = np.ascontiguousarray(sbs, dtype=np.float64).reshape(n, V, 9)
+        preint = np.ascontiguousarray(preint, dtype=np.float64).reshape(n, V - 1, capi.PREINT_REC)
+        out = {"rel": np.zeros((n, V - 1, capi.REL_REC)), "se3": np.zeros((n, capi.SE3_REC)),
+               "vb": np.zeros((n, capi.VB_REC)), "rank": np.zeros((n,), np.int32), "status": np.zeros((n,), np.int32)}
+        ii = capi.isv_init_in(n, _p(poses), _p(sbs), _p(preint))
+        oo = capi.isv_init_out(_p(out["rel"]), _p(out["se3"]), _p(out["vb"]), _p(out["rank"]), _p(out["status"]))
+        capi.check(self.lib.isv_init_sparsify_host(self.h, C.byref(ii), C.byref(oo)), "isv_init_sparsify_host")
+        return out

@@ -43,6 +43,15 @@ class isv_batch_out(C.Structure):
                 ("vb_out", C.c_void_p), ("rp_out", C.c_void_p), ("rank", C.c_void_p), ("status", C.c_void_p)]
 
 
+class isv_init_in(C.Structure):
+    _fields_ = [("n_windows", C.c_int32), ("poses", C.c_void_p), ("sbs", C.c_void_p), ("preint", C.c_void_p)]
+
+
+class isv_init_out(C.Structure):
+    _fields_ = [("rel_out", C.c_void_p), ("se3_out", C.c_void_p), ("vb_out", C.c_void_p), ("rank", C.c_void_p),
+                ("status", C.c_void_p)]
+
+
 class isv_fwd_in(C.Structure):
     _fields_ = [("n_landmarks", C.c_int32), ("pose0", c_double_p), ("pose1", c_double_p), ("ex_pose", c_double_p),
                 ("inv_dep", c_double_p), ("pts_i", c_double_p), ("pts_j", c_double_p), ("prior_se3", c_double_p),
@@ -83,6 +92,8 @@ SYMBOLS = [
     ("isv_marg_window_batch_host", C.c_int, [_H, C.POINTER(isv_batch_in), C.POINTER(isv_batch_out), C.c_int]),
     ("isv_marg_forward", C.c_int, [_H, C.POINTER(isv_fwd_in), C.POINTER(isv_fwd_out)]),
     ("isv_marg_backward", C.c_int, [_H, C.POINTER(isv_bwd_in), C.POINTER(isv_bwd_out)]),
+    ("isv_init_sparsify_batch", C.c_int, [_H, C.POINTER(isv_init_in), C.POINTER(isv_init_out)]),
+    ("isv_init_sparsify_host", C.c_int, [_H, C.POINTER(isv_init_in), C.POINTER(isv_init_out)]),
     ("isv_test_psd_eig", C.c_int, [_H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int32_p]),
 ]
 

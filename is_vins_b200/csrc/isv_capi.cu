@@ -9,6 +9,7 @@
 #include <cstring>
 #include <new>
 
+#include "isv_init_kernel.cuh"
 #include "isv_window_kernels.cuh"
 
 using namespace isv;
@@ -477,5 +478,58 @@ extern "C" isv_status isv_test_psd_eig(isv_handle* h, int nb, int n, const doubl
   ISV_CUDA(cudaMemcpyAsync(info, di, sizeof(int) * 2 * (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
   ISV_CUDA(cudaStreamSynchronize(h->stream));
   cudaFree(dA); cudaFree(dG); cudaFree(dl); cudaFree(di);
+  return ISV_OK;
+}
+
+// ---- initFactorGraph sparsification tail ------------------------------------------------------------
+extern "C" isv_status isv_init_sparsify_batch(isv_handle* h, const isv_init_in* in, const isv_init_out* out) {
+  if (!h || !in || !out || in->n_windows < 0) return ISV_ERR_BAD_ARG;
+  if (!in->poses || !in->sbs || !in->preint || !out->rel_out || !out->se3_out || !out->vb_out || !out->rank)
+    return ISV_ERR_BAD_ARG;
+  const int V = h->cfg.vo_size;
+  if (V < 2 || V > 10) return ISV_ERR_BAD_ARG;
+  if (in->n_windows == 0) return ISV_OK;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const size_t sm = init_smem_doubles(V) * sizeof(double);
+  ISV_CUDA(cudaFuncSetAttribute(init_sparsify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  init_sparsify_kernel<<<in->n_windows, 32, sm, h->stream>>>(in->n_windows, V, in->poses, in->sbs, in->preint,
+                                                           out->rel_out, out->se3_out, out->vb_out, out->rank,
+                                                           out->status, h->dcfg);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+extern "C" isv_status isv_init_sparsify_host(isv_handle* h, const isv_init_in* in, const isv_init_out* out) {
+  if (!h || !in || !out || in->n_windows < 0) return ISV_ERR_BAD_ARG;
+  if (!in->poses || !in->sbs || !in->preint || !out->rel_out || !out->se3_out || !out->vb_out || !out->rank)
+    return ISV_ERR_BAD_ARG;
+  const size_t n = (size_t)in->n_windows, V = (size_t)h->cfg.vo_size, D = sizeof(double);
+  if (V < 2 || V > 10) return ISV_ERR_BAD_ARG;
+  if (n == 0) return ISV_OK;
+  ISV_CUDA(cudaSetDevice(h->device));
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  const size_t o_p = carve(n * V * 7 * D), o_s = carve(n * V * 9 * D), o_pre = carve(n * (V - 1) * ISV_PREINT_REC * D);
+  const size_t o_rel = carve(n * (V - 1) * ISV_REL_REC * D), o_se3 = carve(n * ISV_SE3_REC * D);
+  const size_t o_vb = carve(n * ISV_VB_REC * D), o_rank = carve(n * 4), o_st = carve(n * 4);
+  isv_status st = ensure_dbuf(h, off);
+  if (st != ISV_OK) return st;
+  char* d = h->dbuf;
+  cudaStream_t s = h->stream;
+  ISV_CUDA(cudaMemcpyAsync(d + o_p, in->poses, n * V * 7 * D, cudaMemcpyHostToDevice, s));
+  ISV_CUDA(cudaMemcpyAsync(d + o_s, in->sbs, n * V * 9 * D, cudaMemcpyHostToDevice, s));
+  ISV_CUDA(cudaMemcpyAsync(d + o_pre, in->preint, n * (V - 1) * ISV_PREINT_REC * D, cudaMemcpyHostToDevice, s));
+  isv_init_in di = {in->n_windows, (const double*)(d + o_p), (const double*)(d + o_s), (const double*)(d + o_pre)};
+  isv_init_out dout = {(double*)(d + o_rel), (double*)(d + o_se3), (double*)(d + o_vb), (int32_t*)(d + o_rank),
+                       (int32_t*)(d + o_st)};
+  st = isv_init_sparsify_batch(h, &di, &dout);
+  if (st != ISV_OK) return st;
+  ISV_CUDA(cudaMemcpyAsync(out->rel_out, dout.rel_out, n * (V - 1) * ISV_REL_REC * D, cudaMemcpyDeviceToHost, s));
+  ISV_CUDA(cudaMemcpyAsync(out->se3_out, dout.se3_out, n * ISV_SE3_REC * D, cudaMemcpyDeviceToHost, s));
+  ISV_CUDA(cudaMemcpyAsync(out->vb_out, dout.vb_out, n * ISV_VB_REC * D, cudaMemcpyDeviceToHost, s));
+  ISV_CUDA(cudaMemcpyAsync(out->rank, dout.rank, n * 4, cudaMemcpyDeviceToHost, s));
+  if (out->status) ISV_CUDA(cudaMemcpyAsync(out->status, dout.status, n * 4, cudaMemcpyDeviceToHost, s));
+  ISV_CUDA(cudaStreamSynchronize(s));
   return ISV_OK;
 }

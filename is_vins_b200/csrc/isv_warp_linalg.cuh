@@ -380,14 +380,19 @@ __device__ __forceinline__ int w_onesided_jacobi_rows(double* G, int ldg, int r,
         }
         double* gp = G + p * ldg + sub * es;
         double* gq = G + q * ldg + sub * es;
-        double x[NE], y[NE];
+        double x[NE > 0 ? NE : 1], y[NE > 0 ? NE : 1];
         double gg = 0.0;
+        if constexpr (NE > 0) {
 #pragma unroll
-        for (int i = 0; i < NE; ++i) {
-          const bool in = act && (sub + i * LPP < n);
-          x[i] = in ? gp[i * LPP * es] : 0.0;
-          y[i] = in ? gq[i * LPP * es] : 0.0;
-          gg = fma(x[i], y[i], gg);
+          for (int i = 0; i < NE; ++i) {
+            const bool in = act && (sub + i * LPP < n);
+            x[i] = in ? gp[i * LPP * es] : 0.0;
+            y[i] = in ? gq[i * LPP * es] : 0.0;
+            gg = fma(x[i], y[i], gg);
+          }
+        } else {  // rows stay in shared memory (long rows: initFactorGraph's 42 x 57 factor)
+          if (act)
+            for (int e = sub; e < n; e += LPP) gg = fma(gp[(e - sub) * es], gq[(e - sub) * es], gg);
         }
 #pragma unroll
         for (int o = LPP / 2; o > 0; o >>= 1) gg += __shfl_xor_sync(kFullMask, gg, o);
@@ -395,12 +400,20 @@ __device__ __forceinline__ int w_onesided_jacobi_rows(double* G, int ldg, int r,
         if (act && gg * gg > tol2 * aa * bb) {
           double c, s;
           jacobi_cs(aa, bb, gg, c, s);
+          if constexpr (NE > 0) {
 #pragma unroll
-          for (int i = 0; i < NE; ++i)
-            if (sub + i * LPP < n) {
-              gp[i * LPP * es] = c * x[i] - s * y[i];
-              gq[i * LPP * es] = s * x[i] + c * y[i];
+            for (int i = 0; i < NE; ++i)
+              if (sub + i * LPP < n) {
+                gp[i * LPP * es] = c * x[i] - s * y[i];
+                gq[i * LPP * es] = s * x[i] + c * y[i];
+              }
+          } else {
+            for (int e = sub; e < n; e += LPP) {
+              const double xv = gp[(e - sub) * es], yv = gq[(e - sub) * es];
+              gp[(e - sub) * es] = c * xv - s * yv;
+              gq[(e - sub) * es] = s * xv + c * yv;
             }
+          }
           if (sub == 0) {
             const double cc = c * c, ss = s * s, csg = 2.0 * c * s * gg;
             nrm[p] = cc * aa - csg + ss * bb;
