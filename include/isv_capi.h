@@ -217,6 +217,23 @@ isv_status isv_init_sparsify_batch(isv_handle* h, const isv_init_in* in, const i
 /* host pointers, blocking */
 isv_status isv_init_sparsify_host(isv_handle* h, const isv_init_in* in, const isv_init_out* out);
 
+/* ---- IMU pre-integration (include/factor/integration_base.h:30-36, :54-158) -----------------------
+ * IntegrationBase(acc_0, gyr_0, linearized_ba, linearized_bg) followed by push_back(dt, acc, gyr) for
+ * every sample: midpoint rule + jacobian / covariance propagation with the handle's noise densities.
+ * preint_out is the 467-double record MargBackward reads (ISV_PREINT_REC).                        */
+typedef struct isv_preint_in {
+  int32_t n;                     /* intervals                                                    */
+  int32_t k_max;                 /* samples stored per interval                                  */
+  const int32_t* k_count;        /* [n] samples used per interval, or NULL = k_max everywhere    */
+  const double* imu_raw;         /* [n][k_max][7] dt, acc[3], gyr[3]   (dt_buf/acc_buf/gyr_buf)  */
+  const double* imu_init;        /* [n][12] acc_0, gyr_0, linearized_ba, linearized_bg           */
+} isv_preint_in;
+
+/* device pointers, stream-ordered */
+isv_status isv_preintegrate_batch(isv_handle* h, const isv_preint_in* in, double* preint_out);
+/* host pointers, blocking */
+isv_status isv_preintegrate_host(isv_handle* h, const isv_preint_in* in, double* preint_out);
+
 /* ---- unit-test hook: the PSD eigensolver that replaces SelfAdjointEigenSolver on this path -----
  * (src/estimator.cpp:920,1311,1479).  nb symmetric n x n matrices A (column-major, host) ->
  * G [nb][n][n] row-major factor rows with  A ~= sum_k g_k g_k^T, g_k mutually orthogonal;

@@ -153,3 +153,15 @@ class MargBackend:
         oo = capi.isv_init_out(_p(out["rel"]), _p(out["se3"]), _p(out["vb"]), _p(out["rank"]), _p(out["status"]))
         capi.check(self.lib.isv_init_sparsify_host(self.h, C.byref(ii), C.byref(oo)), "isv_init_sparsify_host")
         return out
+
+    # ---- IMU pre-integration (include/factor/integration_base.h:30-158) --------------------------
+    def preintegrate(self, imu_raw, imu_init, k_count=None):
+        """imu_raw [n,K,7] (dt, acc, gyr), imu_init [n,12] (acc_0, gyr_0, lin_ba, lin_bg) -> [n,467]."""
+        imu_raw = np.ascontiguousarray(imu_raw, dtype=np.float64)
+        n, K = imu_raw.shape[0], imu_raw.shape[1]
+        imu_init = np.ascontiguousarray(imu_init, dtype=np.float64).reshape(n, 12)
+        kc = None if k_count is None else np.ascontiguousarray(k_count, dtype=np.int32)
+        out = np.zeros((n, capi.PREINT_REC))
+        pi = capi.isv_preint_in(n, K, _p(kc), _p(imu_raw), _p(imu_init))
+        capi.check(self.lib.isv_preintegrate_host(self.h, C.byref(pi), _p(out)), "isv_preintegrate_host")
+        return out

@@ -52,6 +52,11 @@ class isv_init_out(C.Structure):
                 ("status", C.c_void_p)]
 
 
+class isv_preint_in(C.Structure):
+    _fields_ = [("n", C.c_int32), ("k_max", C.c_int32), ("k_count", C.c_void_p), ("imu_raw", C.c_void_p),
+                ("imu_init", C.c_void_p)]
+
+
 class isv_fwd_in(C.Structure):
     _fields_ = [("n_landmarks", C.c_int32), ("pose0", c_double_p), ("pose1", c_double_p), ("ex_pose", c_double_p),
                 ("inv_dep", c_double_p), ("pts_i", c_double_p), ("pts_j", c_double_p), ("prior_se3", c_double_p),
@@ -94,6 +99,8 @@ SYMBOLS = [
     ("isv_marg_backward", C.c_int, [_H, C.POINTER(isv_bwd_in), C.POINTER(isv_bwd_out)]),
     ("isv_init_sparsify_batch", C.c_int, [_H, C.POINTER(isv_init_in), C.POINTER(isv_init_out)]),
     ("isv_init_sparsify_host", C.c_int, [_H, C.POINTER(isv_init_in), C.POINTER(isv_init_out)]),
+    ("isv_preintegrate_batch", C.c_int, [_H, C.POINTER(isv_preint_in), C.c_void_p]),
+    ("isv_preintegrate_host", C.c_int, [_H, C.POINTER(isv_preint_in), C.c_void_p]),
     ("isv_test_psd_eig", C.c_int, [_H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int32_p]),
 ]
 

@@ -10,6 +10,7 @@
 #include <new>
 
 #include "isv_init_kernel.cuh"
+#include "isv_preint_kernel.cuh"
 #include "isv_window_kernels.cuh"
 
 using namespace isv;
@@ -530,6 +531,48 @@ extern "C" isv_status isv_init_sparsify_host(isv_handle* h, const isv_init_in* i
   ISV_CUDA(cudaMemcpyAsync(out->vb_out, dout.vb_out, n * ISV_VB_REC * D, cudaMemcpyDeviceToHost, s));
   ISV_CUDA(cudaMemcpyAsync(out->rank, dout.rank, n * 4, cudaMemcpyDeviceToHost, s));
   if (out->status) ISV_CUDA(cudaMemcpyAsync(out->status, dout.status, n * 4, cudaMemcpyDeviceToHost, s));
+  ISV_CUDA(cudaStreamSynchronize(s));
+  return ISV_OK;
+}
+
+// ---- IMU pre-integration ------------------------------------------------------------------------------
+extern "C" isv_status isv_preintegrate_batch(isv_handle* h, const isv_preint_in* in, double* preint_out) {
+  if (!h || !in || !preint_out || in->n < 0 || in->k_max < 0 || !in->imu_init) return ISV_ERR_BAD_ARG;
+  if (in->k_max > 0 && !in->imu_raw) return ISV_ERR_BAD_ARG;
+  if (in->n == 0) return ISV_OK;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const size_t sm = kWarpsPerCta * kPreSmemPerWarp * sizeof(double);
+  ISV_CUDA(cudaFuncSetAttribute(preintegrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  NoiseCfg nz{h->cfg.acc_n, h->cfg.gyr_n, h->cfg.acc_w, h->cfg.gyr_w};
+  preintegrate_kernel<<<(in->n + kWarpsPerCta - 1) / kWarpsPerCta, kThreads, sm, h->stream>>>(
+      in->n, in->k_max, in->k_count, in->imu_raw, in->imu_init, preint_out, nz);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+extern "C" isv_status isv_preintegrate_host(isv_handle* h, const isv_preint_in* in, double* preint_out) {
+  if (!h || !in || !preint_out || in->n < 0 || in->k_max < 0 || !in->imu_init) return ISV_ERR_BAD_ARG;
+  if (in->k_max > 0 && !in->imu_raw) return ISV_ERR_BAD_ARG;
+  const size_t n = (size_t)in->n, K = (size_t)in->k_max, D = sizeof(double);
+  if (n == 0) return ISV_OK;
+  ISV_CUDA(cudaSetDevice(h->device));
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  const size_t o_raw = carve(n * K * 7 * D), o_init = carve(n * 12 * D), o_k = carve(in->k_count ? n * 4 : 0);
+  const size_t o_out = carve(n * ISV_PREINT_REC * D);
+  isv_status st = ensure_dbuf(h, off);
+  if (st != ISV_OK) return st;
+  char* d = h->dbuf;
+  cudaStream_t s = h->stream;
+  if (K) ISV_CUDA(cudaMemcpyAsync(d + o_raw, in->imu_raw, n * K * 7 * D, cudaMemcpyHostToDevice, s));
+  ISV_CUDA(cudaMemcpyAsync(d + o_init, in->imu_init, n * 12 * D, cudaMemcpyHostToDevice, s));
+  if (in->k_count) ISV_CUDA(cudaMemcpyAsync(d + o_k, in->k_count, n * 4, cudaMemcpyHostToDevice, s));
+  isv_preint_in di = {in->n, in->k_max, in->k_count ? (const int32_t*)(d + o_k) : nullptr, (const double*)(d + o_raw),
+                      (const double*)(d + o_init)};
+  st = isv_preintegrate_batch(h, &di, (double*)(d + o_out));
+  if (st != ISV_OK) return st;
+  ISV_CUDA(cudaMemcpyAsync(preint_out, d + o_out, n * ISV_PREINT_REC * D, cudaMemcpyDeviceToHost, s));
   ISV_CUDA(cudaStreamSynchronize(s));
   return ISV_OK;
 }
