@@ -234,6 +234,91 @@ isv_status isv_preintegrate_batch(isv_handle* h, const isv_preint_in* in, double
 /* host pointers, blocking */
 isv_status isv_preintegrate_host(isv_handle* h, const isv_preint_in* in, double* preint_out);
 
+/* ---- ceres CostFunction::Evaluate contract, batched (SURVEY.md 8a rows 2,3,5,7-10; 8f rank 1) -----
+ * The factors problemSolve() hands to ceres (src/estimator.cpp:1004-1146).  For every factor the
+ * kernels write what `Evaluate(parameters, residuals, jacobians)` writes: residuals = sqrt_info * r
+ * and, per parameter block, jacobians[i] = sqrt_info * d r / d block_i as a ROW-MAJOR
+ * num_residuals x global_size matrix whose 7th pose column is zero (the tangent convention of
+ * PoseLocalParameterization, src/factor/pose_local_parameterization.cpp:3-27).  A NULL output
+ * pointer is ceres' `jacobians == nullptr` / `jacobians[i] == nullptr` for that block.
+ * Parameter blocks are gathered by index; the blocks of many windows may be concatenated.       */
+typedef struct isv_param_blocks {
+  int32_t n_pose, n_speed_bias, n_ex_pose, n_feature;
+  const double* pose;            /* [n_pose][7]        para_Pose        include/estimator.h:122    */
+  const double* speed_bias;      /* [n_speed_bias][9]  para_SpeedBias   :123                       */
+  const double* ex_pose;         /* [n_ex_pose][7]     para_Ex_Pose     :125                       */
+  const double* feature;         /* [n_feature]        para_Feature     :124 (inverse depth)       */
+} isv_param_blocks;
+
+#define ISV_W_BAD_INDEX      0x40  /* a factor referenced a parameter block out of range: skipped  */
+
+/* ProjectionFactor::Evaluate  src/factor/projection_factor.cpp:24-122 ; sqrt_info = isv_config    */
+typedef struct isv_proj_factors {
+  int64_t n;                     /* factors                                                      */
+  int64_t stride;                /* elements between components of idx / obs (>= n)              */
+  const int32_t* idx;            /* [4][stride] imu_i, imu_j, ex pose index, feature_index
+                                    (ProjectionFactor::setIndex, src/estimator.cpp:1081 ; the
+                                    AddResidualBlock argument order :1090)                       */
+  const double* obs;             /* [5][stride] pts_i.x, pts_i.y, pts_i.z, pts_j.x, pts_j.y      */
+  double cauchy_a;               /* 0: no loss.  > 0: ceres::CauchyLoss(a) applied the way ceres'
+                                    Corrector does for rho'' <= 0: r, J scaled by sqrt(rho'(|r|^2))
+                                    (loss_function of :1018 has a = 1)                           */
+} isv_proj_factors;
+typedef struct isv_proj_eval {
+  double* residuals;             /* [n][2]                                                       */
+  double* jac_pose_i;            /* [n][2][7] row-major, or NULL                                 */
+  double* jac_pose_j;            /* [n][2][7] or NULL                                            */
+  double* jac_ex_pose;           /* [n][2][7] or NULL (SetParameterBlockConstant, :1037)         */
+  double* jac_feature;           /* [n][2]    or NULL                                            */
+} isv_proj_eval;
+
+/* IMUFactor::Evaluate  include/factor/imu_factor.h:23-159 (+ integration_base.h:160-186);
+ * sqrt_info = LLT(covariance^-1).matrixL().transpose() is recomputed per call as the reference does */
+#define ISV_IMU_JAC_REC 480      /* 15x7 | 15x9 | 15x7 | 15x9 row-major at offsets 0,105,240,345 */
+typedef struct isv_imu_factors {
+  int32_t n;
+  const int32_t* idx;            /* [n][2] imu_i, imu_j (pose and speed-bias share the frame index) */
+  const double* preint;          /* [n][467] pre_integrations[j] (ISV_PREINT_REC)                */
+} isv_imu_factors;
+typedef struct isv_imu_eval {
+  double* residuals;             /* [n][15]                                                      */
+  double* jacobians;             /* [n][480] or NULL                                             */
+} isv_imu_eval;
+
+/* the recovered / prior factors: RelativePoseFactor (relative_pose_factor.h:27-70), SE3PriorFactor
+ * (se3_prior_factor.h:21-51), Linear9Factor (linear9_factor.h:20-44), RollPitchFactor
+ * (rollpitch_factor.h:26-57), YawFactor (yaw_factor.h:23-49).  Records as in the Marg* outputs.   */
+#define ISV_YAW_REC 4            /* yaw_meas[3], sqrt_info[1]                                    */
+typedef struct isv_small_factors {
+  int32_t n_rel, n_se3, n_vb, n_rp, n_yaw;
+  const int32_t* rel_idx;        /* [n_rel][2] imu_i, imu_j                                      */
+  const double* rel_rec;         /* [n_rel][48]                                                  */
+  const int32_t* se3_idx;        /* [n_se3]                                                      */
+  const double* se3_rec;         /* [n_se3][48]                                                  */
+  const int32_t* vb_idx;         /* [n_vb]  speed-bias block index                               */
+  const double* vb_rec;          /* [n_vb][90]                                                   */
+  const int32_t* rp_idx;         /* [n_rp]                                                       */
+  const double* rp_rec;          /* [n_rp][13]                                                   */
+  const int32_t* yaw_idx;        /* [n_yaw]                                                      */
+  const double* yaw_rec;         /* [n_yaw][4]                                                   */
+  double cauchy_a;               /* as isv_proj_factors.cauchy_a (problemSolve uses a = 1, :1106-1121) */
+} isv_small_factors;
+typedef struct isv_small_eval {
+  double* rel_res;  double* rel_jac;   /* [n_rel][6],  [n_rel][84]  (6x7 | 6x7) or NULL           */
+  double* se3_res;  double* se3_jac;   /* [n_se3][6],  [n_se3][42]                                */
+  double* vb_res;   double* vb_jac;    /* [n_vb][9],   [n_vb][81]                                 */
+  double* rp_res;   double* rp_jac;    /* [n_rp][2],   [n_rp][14]                                 */
+  double* yaw_res;  double* yaw_jac;   /* [n_yaw][1],  [n_yaw][7]                                 */
+} isv_small_eval;
+
+/* device pointers, stream-ordered.  `status` (device int32, may be NULL) receives ISV_W_* bits.   */
+isv_status isv_eval_projection_batch(isv_handle* h, const isv_param_blocks* pb, const isv_proj_factors* f,
+                                     const isv_proj_eval* out, int32_t* status);
+isv_status isv_eval_imu_batch(isv_handle* h, const isv_param_blocks* pb, const isv_imu_factors* f,
+                              const isv_imu_eval* out, int32_t* status);
+isv_status isv_eval_small_batch(isv_handle* h, const isv_param_blocks* pb, const isv_small_factors* f,
+                                const isv_small_eval* out, int32_t* status);
+
 /* ---- unit-test hook: the PSD eigensolver that replaces SelfAdjointEigenSolver on this path -----
  * (src/estimator.cpp:920,1311,1479).  nb symmetric n x n matrices A (column-major, host) ->
  * G [nb][n][n] row-major factor rows with  A ~= sum_k g_k g_k^T, g_k mutually orthogonal;

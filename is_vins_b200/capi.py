@@ -14,6 +14,8 @@ LIB_PATH = os.environ.get("ISV_B200_LIB", os.path.join(_HERE, "libisv_b200.so"))
 
 ISV_OK, ISV_ERR_BAD_ARG, ISV_ERR_CUDA, ISV_ERR_ALLOC = 0, 1, 2, 3
 W_NOT_SPD, W_RANK_DEFICIENT, W_NONFINITE, W_NONUNIT_QUAT, W_EIG_NOCONV, W_SINGULAR = 1, 2, 4, 8, 16, 32
+W_BAD_INDEX = 64
+IMU_JAC_REC, YAW_REC = 480, 4
 RUN_FORWARD, RUN_BACKWARD, RUN_BOTH = 1, 2, 3
 POSE, SB, SE3_REC, REL_REC, VB_REC, RP_IN_REC, RP_REC, PG_REC, PREINT_REC = 7, 9, 48, 48, 90, 5, 13, 89, 467
 IMU_RAW_REC = 7
@@ -78,6 +80,43 @@ class isv_bwd_out(C.Structure):
                 ("rank", C.c_int32), ("status", C.c_int32)]
 
 
+class isv_param_blocks(C.Structure):
+    _fields_ = [("n_pose", C.c_int32), ("n_speed_bias", C.c_int32), ("n_ex_pose", C.c_int32),
+                ("n_feature", C.c_int32), ("pose", C.c_void_p), ("speed_bias", C.c_void_p),
+                ("ex_pose", C.c_void_p), ("feature", C.c_void_p)]
+
+
+class isv_proj_factors(C.Structure):
+    _fields_ = [("n", C.c_int64), ("stride", C.c_int64), ("idx", C.c_void_p), ("obs", C.c_void_p),
+                ("cauchy_a", C.c_double)]
+
+
+class isv_proj_eval(C.Structure):
+    _fields_ = [("residuals", C.c_void_p), ("jac_pose_i", C.c_void_p), ("jac_pose_j", C.c_void_p),
+                ("jac_ex_pose", C.c_void_p), ("jac_feature", C.c_void_p)]
+
+
+class isv_imu_factors(C.Structure):
+    _fields_ = [("n", C.c_int32), ("idx", C.c_void_p), ("preint", C.c_void_p)]
+
+
+class isv_imu_eval(C.Structure):
+    _fields_ = [("residuals", C.c_void_p), ("jacobians", C.c_void_p)]
+
+
+class isv_small_factors(C.Structure):
+    _fields_ = [("n_rel", C.c_int32), ("n_se3", C.c_int32), ("n_vb", C.c_int32), ("n_rp", C.c_int32),
+                ("n_yaw", C.c_int32), ("rel_idx", C.c_void_p), ("rel_rec", C.c_void_p), ("se3_idx", C.c_void_p),
+                ("se3_rec", C.c_void_p), ("vb_idx", C.c_void_p), ("vb_rec", C.c_void_p), ("rp_idx", C.c_void_p),
+                ("rp_rec", C.c_void_p), ("yaw_idx", C.c_void_p), ("yaw_rec", C.c_void_p), ("cauchy_a", C.c_double)]
+
+
+class isv_small_eval(C.Structure):
+    _fields_ = [("rel_res", C.c_void_p), ("rel_jac", C.c_void_p), ("se3_res", C.c_void_p), ("se3_jac", C.c_void_p),
+                ("vb_res", C.c_void_p), ("vb_jac", C.c_void_p), ("rp_res", C.c_void_p), ("rp_jac", C.c_void_p),
+                ("yaw_res", C.c_void_p), ("yaw_jac", C.c_void_p)]
+
+
 # every symbol include/isv_capi.h declares: (name, restype, argtypes)
 _H = C.c_void_p
 SYMBOLS = [
@@ -101,6 +140,12 @@ SYMBOLS = [
     ("isv_init_sparsify_host", C.c_int, [_H, C.POINTER(isv_init_in), C.POINTER(isv_init_out)]),
     ("isv_preintegrate_batch", C.c_int, [_H, C.POINTER(isv_preint_in), C.c_void_p]),
     ("isv_preintegrate_host", C.c_int, [_H, C.POINTER(isv_preint_in), C.c_void_p]),
+    ("isv_eval_projection_batch", C.c_int, [_H, C.POINTER(isv_param_blocks), C.POINTER(isv_proj_factors),
+                                            C.POINTER(isv_proj_eval), C.c_void_p]),
+    ("isv_eval_imu_batch", C.c_int, [_H, C.POINTER(isv_param_blocks), C.POINTER(isv_imu_factors),
+                                     C.POINTER(isv_imu_eval), C.c_void_p]),
+    ("isv_eval_small_batch", C.c_int, [_H, C.POINTER(isv_param_blocks), C.POINTER(isv_small_factors),
+                                       C.POINTER(isv_small_eval), C.c_void_p]),
     ("isv_test_psd_eig", C.c_int, [_H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int32_p]),
 ]
 

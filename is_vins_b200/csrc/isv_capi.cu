@@ -9,6 +9,7 @@
 #include <cstring>
 #include <new>
 
+#include "isv_eval_kernels.cuh"
 #include "isv_init_kernel.cuh"
 #include "isv_preint_kernel.cuh"
 #include "isv_window_kernels.cuh"
@@ -574,5 +575,62 @@ extern "C" isv_status isv_preintegrate_host(isv_handle* h, const isv_preint_in* 
   if (st != ISV_OK) return st;
   ISV_CUDA(cudaMemcpyAsync(preint_out, d + o_out, n * ISV_PREINT_REC * D, cudaMemcpyDeviceToHost, s));
   ISV_CUDA(cudaStreamSynchronize(s));
+  return ISV_OK;
+}
+
+// ---- ceres Evaluate contract, batched -----------------------------------------------------------------
+static bool pb_ok(const isv_param_blocks* pb) {
+  if (!pb || pb->n_pose < 0 || pb->n_speed_bias < 0 || pb->n_ex_pose < 0 || pb->n_feature < 0) return false;
+  if ((pb->n_pose && !pb->pose) || (pb->n_speed_bias && !pb->speed_bias) || (pb->n_ex_pose && !pb->ex_pose) ||
+      (pb->n_feature && !pb->feature))
+    return false;
+  return true;
+}
+
+extern "C" isv_status isv_eval_projection_batch(isv_handle* h, const isv_param_blocks* pb, const isv_proj_factors* f,
+                                                const isv_proj_eval* out, int32_t* status) {
+  if (!h || !pb_ok(pb) || !f || !out || f->n < 0 || f->stride < f->n) return ISV_ERR_BAD_ARG;
+  if (f->n == 0) return ISV_OK;
+  if (!f->idx || !f->obs || !out->residuals || !(f->cauchy_a >= 0.0)) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const long long per_cta = 32LL * kEvalWarps;
+  const long long grid = (f->n + per_cta - 1) / per_cta;
+  if (grid > 0x7fffffffLL) return ISV_ERR_BAD_ARG;
+  eval_projection_kernel<<<(unsigned)grid, kEvalThreads, 0, h->stream>>>(*pb, *f, *out, h->dcfg, status);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+extern "C" isv_status isv_eval_imu_batch(isv_handle* h, const isv_param_blocks* pb, const isv_imu_factors* f,
+                                         const isv_imu_eval* out, int32_t* status) {
+  if (!h || !pb_ok(pb) || !f || !out || f->n < 0) return ISV_ERR_BAD_ARG;
+  if (f->n == 0) return ISV_OK;
+  if (!f->idx || !f->preint || !out->residuals) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const size_t sm = kEvalWarps * kImuEvalSmem * sizeof(double);
+  ISV_CUDA(cudaFuncSetAttribute(eval_imu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  eval_imu_kernel<<<(f->n + kEvalWarps - 1) / kEvalWarps, kEvalThreads, sm, h->stream>>>(*pb, *f, *out, h->dcfg, status);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+extern "C" isv_status isv_eval_small_batch(isv_handle* h, const isv_param_blocks* pb, const isv_small_factors* f,
+                                           const isv_small_eval* out, int32_t* status) {
+  if (!h || !pb_ok(pb) || !f || !out) return ISV_ERR_BAD_ARG;
+  if (f->n_rel < 0 || f->n_se3 < 0 || f->n_vb < 0 || f->n_rp < 0 || f->n_yaw < 0 || !(f->cauchy_a >= 0.0))
+    return ISV_ERR_BAD_ARG;
+  if ((f->n_rel && (!f->rel_idx || !f->rel_rec || !out->rel_res)) || (f->n_se3 && (!f->se3_idx || !f->se3_rec || !out->se3_res)) ||
+      (f->n_vb && (!f->vb_idx || !f->vb_rec || !out->vb_res)) || (f->n_rp && (!f->rp_idx || !f->rp_rec || !out->rp_res)) ||
+      (f->n_yaw && (!f->yaw_idx || !f->yaw_rec || !out->yaw_res)))
+    return ISV_ERR_BAD_ARG;
+  const long long total = (long long)f->n_rel + f->n_se3 + f->n_vb + f->n_rp + f->n_yaw;
+  if (total == 0) return ISV_OK;
+  ISV_CUDA(cudaSetDevice(h->device));
+  eval_small_kernel<<<(unsigned)((total + kEvalThreads - 1) / kEvalThreads), kEvalThreads, 0, h->stream>>>(*pb, *f, *out,
+                                                                                                          status);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
   return ISV_OK;
 }

@@ -16,6 +16,14 @@ namespace isv {
 
 #define ISV_DI __device__ __forceinline__
 
+// the globals the reference reads inside the hot path (isv_config), passed by value to kernels
+struct DevCfg {
+  double alpha;
+  double ps[4];  // ProjectionFactor::sqrt_info, column-major 2x2
+  double g[3];
+  double qr_threshold;
+};
+
 constexpr double kSophusEps = 1e-10;
 constexpr double kSophusEpsSqrt = 1e-5;
 constexpr double kPi = 3.14159265358979323846;

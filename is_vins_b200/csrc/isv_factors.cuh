@@ -90,10 +90,15 @@ __device__ inline void rollpitch_jacobian(const double* PS, const double* Rmeas_
 }
 
 // J: 1x6 ; yaw_meas = Qw.inverse() * UnitX
-__device__ inline void yaw_jacobian(const double* PS, const double* yaw_meas, double* J) {
+__device__ inline void yaw_jacobian(const double* PS, const double* yaw_meas, double* J, double* res = nullptr) {
   Quat ri = qnormalized(quat_from_pose(PS));
   double R[9], S[9], RS[9];
   q2R(ri, R);
+  if (res) {  // residual = (Ri * yaw_meas).y   (yaw_factor.h:31-33)
+    double v[3];
+    qrot(ri, yaw_meas, v);
+    res[0] = v[1];
+  }
   skew3(yaw_meas, S);
   mat3_mul(R, S, RS);
   for (int i = 0; i < 6; ++i) J[i] = 0.0;

@@ -25,13 +25,6 @@
 
 namespace isv {
 
-struct DevCfg {
-  double alpha;
-  double ps[4];  // ProjectionFactor::sqrt_info, column-major 2x2
-  double g[3];
-  double qr_threshold;
-};
-
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = 32 * kWarpsPerCta;
 #ifndef ISV_FWD_MINB

@@ -278,3 +278,132 @@ def make_chain(seed: int, L, rounds: int = 2, cfg: Optional[O.Config] = None, K:
         nrp.setIndex(V - 2)      # pushed with index V-1 (:1516), then shifted by slideWindow
         rps.append(nrp)
     return Chain(cfg, init_in, init_out, events)
+
+
+# ----------------------------------------------------------------------------------------------
+# A whole problemSolve() factor list (src/estimator.cpp:1004-1146): the input of the batched
+# ceres-Evaluate kernels and of the normal-equation builder.
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class WindowProblem:
+    cfg: O.Config
+    poses: np.ndarray            # [N,7]   para_Pose
+    sbs: np.ndarray              # [N,9]   para_SpeedBias
+    ex: np.ndarray               # [1,7]   para_Ex_Pose
+    feat: np.ndarray             # [F]     para_Feature
+    proj_idx: np.ndarray         # int32 [4,P]: imu_i, imu_j, ex index, feature_index
+    proj_obs: np.ndarray         # [5,P]: pts_i.xyz, pts_j.xy
+    imu_idx: np.ndarray          # int32 [N-1,2]
+    imu_pre: List[O.IntegrationBase]
+    rel: List[O.RelativePoseFactor]
+    se3: List[O.SE3PriorFactor]
+    vb: List[O.Linear9Factor]
+    rp: List[O.RollPitchFactor]
+    yaw: List[O.YawFactor]
+
+
+def _rand_sqrt_info(rng, n, scale):
+    a = rng.normal(0, 1.0, (n, n))
+    return O.llt_upper(scale * scale * (a @ a.T + n * np.eye(n)))
+
+
+def make_problem(seed: int, n_features: int = 60, cfg: Optional[O.Config] = None, K: int = 10,
+                 max_track: int = 8) -> WindowProblem:
+    """N = ALL_BUF_SIZE frames, N-1 IMU factors, `n_features` features with start_frame uniform and
+    track length 2..max_track (one ProjectionFactor per later observation, :1062-1092), the prior
+    factor set of :1100-1121 (priors from the oracle's init_sparsify on the first V frames, states
+    then moved so that no residual is zero) plus one YawFactor (a type the path owns, yaw_factor.h)."""
+    cfg = cfg or O.Config()
+    V, N = cfg.vo_size, cfg.all_buf_size
+    rng = np.random.default_rng(seed)
+    frames = make_frames(rng, cfg, N, K=K)
+    expose = ex_pose()
+    init_in = O.InitInput(np.array([f.pose() for f in frames[:V]]), np.array([f.sb() for f in frames[:V]]),
+                          [frames[i + 1].pre for i in range(V - 1)])
+    init_out = O.init_sparsify(init_in, cfg)
+    rel = []
+    for i in range(V - 1):
+        rf = O.RelativePoseFactor(init_out.rel_dt[i], init_out.rel_dR[i])
+        rf.sqrt_info = init_out.rel_sqrt_info[i]
+        rf.setIndex(i, i + 1)
+        rel.append(rf)
+    se3 = O.SE3PriorFactor(init_out.se3_t, R_new=init_out.se3_R)
+    se3.sqrt_info = init_out.se3_sqrt_info
+    se3.setIndex(0)
+    vbp = O.Linear9Factor(init_out.vb)
+    vbp.sqrt_info = init_out.vb_sqrt_info
+    vbp.setIndex(V - 1)
+    rps = []
+    for idx in (2, V - 2):
+        rp = O.RollPitchFactor(frames[idx].Q)
+        rp.sqrt_info = _rand_sqrt_info(rng, 2, 30.0)
+        rp.setIndex(idx)
+        rps.append(rp)
+    yw = O.YawFactor(frames[V - 1].Q)
+    yw.sqrt_info = np.array([[57.0]])
+    yw.index = V - 1
+    # features: truth landmarks from the (unperturbed) host frame, observed with pixel noise
+    qic, tic = O.quat_from_pose(expose), expose[0:3]
+    ric = O.q_to_R(qic)
+    pidx, pobs, feat = [], [], []
+    for f in range(n_features):
+        start = int(rng.integers(0, N - 1))
+        length = int(rng.integers(2, max_track + 1))
+        u, v = rng.uniform(0, IMG_W), rng.uniform(0, IMG_H)
+        pts_i = np.array([(u - CX) / FX, (v - CY) / FY, 1.0])
+        depth = rng.uniform(1.0, 8.0)
+        Ri = O.q_to_R(frames[start].Q)
+        pw = Ri @ (ric @ (pts_i * depth) + tic) + frames[start].P
+        feat.append((1.0 / depth) * (1.0 + rng.normal(0, 0.01)))
+        for j in range(start + 1, min(start + length, N)):
+            Rj = O.q_to_R(frames[j].Q)
+            pj = ric.T @ (Rj.T @ (pw - frames[j].P) - tic)
+            pidx.append((start, j, 0, f))
+            pobs.append((pts_i[0], pts_i[1], pts_i[2], pj[0] / pj[2] + rng.normal(0, 1.0 / 460.0),
+                         pj[1] / pj[2] + rng.normal(0, 1.0 / 460.0)))
+    # post-solve estimates: move every state a little so all residuals are non-trivial
+    for f in frames:
+        f.P = f.P + rng.normal(0, 0.004, 3)
+        f.Q = O.q_normalized(O.q_mul(f.Q, O.SO3.exp(rng.normal(0, 0.001, 3)).q))
+        f.V = f.V + rng.normal(0, 0.01, 3)
+        f.Ba = f.Ba + rng.normal(0, 0.0005, 3)
+        f.Bg = f.Bg + rng.normal(0, 0.00005, 3)
+    return WindowProblem(cfg, np.array([f.pose() for f in frames]), np.array([f.sb() for f in frames]),
+                         expose.reshape(1, 7), np.array(feat), np.array(pidx, dtype=np.int32).T.copy(),
+                         np.array(pobs).T.copy(), np.array([(i, i + 1) for i in range(N - 1)], dtype=np.int32),
+                         [frames[i + 1].pre for i in range(N - 1)], rel, [se3], [vbp], rps, [yw])
+
+
+def cauchy_correct(res: np.ndarray, jacs, a: float):
+    """ceres::CauchyLoss(a) through ceres' Corrector (ceres 2.0.0 internal/ceres/corrector.cc,
+    loss_function.cc; not under /root/reference): rho' = 1/(1+s/a^2), rho'' < 0 always, so the
+    Corrector takes its `rho[2] <= 0` branch: residual and Jacobians are scaled by sqrt(rho')."""
+    if not a or a <= 0:
+        return res, jacs
+    s = float(res @ res)
+    sc = math.sqrt(1.0 / (1.0 + s / (a * a)))
+    return res * sc, [None if j is None else j * sc for j in jacs]
+
+
+def eval_problem_oracle(p: WindowProblem, cauchy_a: float = 0.0):
+    """Every factor's ceres Evaluate output through the oracle: dict name -> (residuals, [jac blocks])."""
+    out = {"proj": [], "imu": [], "rel": [], "se3": [], "vb": [], "rp": [], "yaw": []}
+    s = p.cfg.proj_sqrt_info
+    for k in range(p.proj_idx.shape[1]):
+        i, j, e, f = [int(x) for x in p.proj_idx[:, k]]
+        pf = O.ProjectionFactor(p.proj_obs[0:3, k], np.array([p.proj_obs[3, k], p.proj_obs[4, k], 1.0]), s)
+        r, js = pf.EvaluateCeres([p.poses[i], p.poses[j], p.ex[e], p.feat[f:f + 1]])
+        out["proj"].append(cauchy_correct(r, js, cauchy_a))
+    for k, (i, j) in enumerate(p.imu_idx):
+        out["imu"].append(O.IMUFactor(p.imu_pre[k]).EvaluateCeres([p.poses[i], p.sbs[i], p.poses[j], p.sbs[j]]))
+    for rf in p.rel:
+        out["rel"].append(cauchy_correct(*rf.EvaluateCeres([p.poses[rf.imu_i], p.poses[rf.imu_j]]), cauchy_a))
+    for sf in p.se3:
+        out["se3"].append(cauchy_correct(*sf.EvaluateCeres([p.poses[sf.index]]), cauchy_a))
+    for vf in p.vb:
+        out["vb"].append(cauchy_correct(*vf.EvaluateCeres([p.sbs[vf.index]]), cauchy_a))
+    for rp in p.rp:
+        out["rp"].append(cauchy_correct(*rp.EvaluateCeres([p.poses[rp.index]]), cauchy_a))
+    for yf in p.yaw:
+        out["yaw"].append(cauchy_correct(*yf.EvaluateCeres([p.poses[yf.index]]), cauchy_a))
+    return out
