@@ -319,6 +319,14 @@ isv_status isv_eval_imu_batch(isv_handle* h, const isv_param_blocks* pb, const i
 isv_status isv_eval_small_batch(isv_handle* h, const isv_param_blocks* pb, const isv_small_factors* f,
                                 const isv_small_eval* out, int32_t* status);
 
+/* One problemSolve() iteration: every factor class in one call (any of the three factor sets, with
+ * its output struct, may be NULL).  The projection kernel runs on the handle's stream; the IMU and
+ * prior-factor kernels are forked onto internal streams and joined back, so the call is still
+ * stream-ordered as a whole.  This is what a ceres::EvaluationCallback binds.    */
+isv_status isv_eval_problem(isv_handle* h, const isv_param_blocks* pb, const isv_proj_factors* pf,
+                            const isv_proj_eval* po, const isv_imu_factors* mf, const isv_imu_eval* mo,
+                            const isv_small_factors* sf, const isv_small_eval* so, int32_t* status);
+
 /* ---- unit-test hook: the PSD eigensolver that replaces SelfAdjointEigenSolver on this path -----
  * (src/estimator.cpp:920,1311,1479).  nb symmetric n x n matrices A (column-major, host) ->
  * G [nb][n][n] row-major factor rows with  A ~= sum_k g_k g_k^T, g_k mutually orthogonal;

@@ -146,6 +146,9 @@ SYMBOLS = [
                                      C.POINTER(isv_imu_eval), C.c_void_p]),
     ("isv_eval_small_batch", C.c_int, [_H, C.POINTER(isv_param_blocks), C.POINTER(isv_small_factors),
                                        C.POINTER(isv_small_eval), C.c_void_p]),
+    ("isv_eval_problem", C.c_int, [_H, C.POINTER(isv_param_blocks), C.POINTER(isv_proj_factors),
+                                   C.POINTER(isv_proj_eval), C.POINTER(isv_imu_factors), C.POINTER(isv_imu_eval),
+                                   C.POINTER(isv_small_factors), C.POINTER(isv_small_eval), C.c_void_p]),
     ("isv_test_psd_eig", C.c_int, [_H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int32_p]),
 ]
 

@@ -21,6 +21,8 @@ struct isv_handle {
   cudaStream_t own_stream;
   cudaStream_t stream;
   cudaStream_t copy_stream;
+  cudaStream_t aux[2];   // fork/join side streams of isv_eval_problem
+  cudaEvent_t aux_ev[3];
   isv_config cfg;
   DevCfg dcfg;
   int64_t launches;
@@ -29,6 +31,8 @@ struct isv_handle {
   size_t dbuf_bytes;
   char* pinned;
   size_t pinned_bytes;
+  double* gram;          // [n][42] landmark Gram triangles (forward kernel 1 -> kernel 2), grow-only
+  size_t gram_bytes;
   cudaEvent_t ev[4];
 };
 
@@ -101,8 +105,12 @@ isv_status isv_create(const isv_config* cfg, int device, isv_handle** out) {
     return ISV_ERR_CUDA;
   }
   for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
+  for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
+  for (int i = 0; i < 3; ++i) cudaEventCreateWithFlags(&h->aux_ev[i], cudaEventDisableTiming);
   h->stream = h->own_stream;
-  cudaFuncSetAttribute(marg_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(marg_forward_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(kWarpsPerCta * kAccSmemPerWarp * sizeof(double)));
+  cudaFuncSetAttribute(marg_forward_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kWarpsPerCta * kFwdSmemPerWarp * sizeof(double)));
   cudaFuncSetAttribute(marg_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kWarpsPerCta * kBwdSmemPerWarp * sizeof(double)));
@@ -115,9 +123,14 @@ void isv_destroy(isv_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   if (h->dbuf) cudaFree(h->dbuf);
+  if (h->gram) cudaFree(h->gram);
   if (h->pinned) cudaFreeHost(h->pinned);
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 2; ++i)
+    if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
+  for (int i = 0; i < 3; ++i)
+    if (h->aux_ev[i]) cudaEventDestroy(h->aux_ev[i]);
   cudaStreamDestroy(h->own_stream);
   cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -182,15 +195,20 @@ static isv_status check_batch(const isv_batch_in* in, const isv_batch_out* out, 
   return ISV_OK;
 }
 
+// gram: device scratch [n_windows][42] handed from the landmark kernel to the tail kernel
 static isv_status launch_batch(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, int which,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, double* gram) {
   const int n = in->n_windows;
   if (n == 0) return ISV_OK;
   if (out->status) ISV_CUDA(cudaMemsetAsync(out->status, 0, sizeof(int32_t) * (size_t)n, stream));
   const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
   if (which & ISV_RUN_FORWARD) {
-    marg_forward_kernel<<<grid, kThreads, kWarpsPerCta * kFwdSmemPerWarp * sizeof(double), stream>>>(*in, *out, h->dcfg);
-    ++h->launches;
+    if (!gram) return ISV_ERR_BAD_ARG;
+    marg_forward_accum_kernel<<<grid, kThreads, kWarpsPerCta * kAccSmemPerWarp * sizeof(double), stream>>>(
+        *in, gram, out->status, h->dcfg);
+    marg_forward_tail_kernel<<<grid, kThreads, kWarpsPerCta * kFwdSmemPerWarp * sizeof(double), stream>>>(*in, *out, gram,
+                                                                                                        h->dcfg);
+    h->launches += 2;
   }
   if (which & ISV_RUN_BACKWARD) {
     marg_backward_kernel<<<grid, kThreads, kWarpsPerCta * kBwdSmemPerWarp * sizeof(double), stream>>>(*in, *out, h->dcfg,
@@ -206,7 +224,25 @@ isv_status isv_marg_window_batch(isv_handle* h, const isv_batch_in* in, const is
   isv_status st = check_batch(in, out, which);
   if (st != ISV_OK) return st;
   ISV_CUDA(cudaSetDevice(h->device));
-  return launch_batch(h, in, out, which, h->stream);
+  double* gram = nullptr;
+  if (which & ISV_RUN_FORWARD) {
+    const size_t need = (size_t)in->n_windows * 42 * sizeof(double);
+    if (h->gram_bytes < need) {
+      if (h->gram) {
+        ISV_CUDA(cudaStreamSynchronize(h->stream));
+        ISV_CUDA(cudaFree(h->gram));
+        h->gram = nullptr;
+        h->gram_bytes = 0;
+      }
+      if (cudaMalloc(&h->gram, need + need / 4 + 256) != cudaSuccess) {
+        cudaGetLastError();
+        return ISV_ERR_ALLOC;
+      }
+      h->gram_bytes = need + need / 4 + 256;
+    }
+    gram = h->gram;
+  }
+  return launch_batch(h, in, out, which, h->stream, gram);
 }
 
 // ---- host-pointer entry point ------------------------------------------------------------------
@@ -261,6 +297,7 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   const size_t o_rp = carve(bwd ? n * ISV_RP_REC * D : 0);
   const size_t o_rank = carve(n * 2 * sizeof(int32_t));
   const size_t o_stat = carve(n * sizeof(int32_t));
+  const size_t o_gram = carve(fwd ? n * 42 * D : 0);
   st = ensure_dbuf(h, off);
   if (st != ISV_OK) return st;
   char* d = h->dbuf;
@@ -339,7 +376,7 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     }
     dout.rank = (int32_t*)(d + o_rank) + 2 * w0;
     dout.status = (int32_t*)(d + o_stat) + w0;
-    st = launch_batch(h, &din, &dout, which, s);
+    st = launch_batch(h, &din, &dout, which, s, fwd ? (double*)(d + o_gram) + w0 * 42 : nullptr);
     if (st != ISV_OK) return st;
     if (fwd) {
       ISV_CUDA(cudaMemcpyAsync(out->se3_out + w0 * ISV_SE3_REC, dout.se3_out, m * ISV_SE3_REC * D, cudaMemcpyDeviceToHost, s));
@@ -587,37 +624,35 @@ static bool pb_ok(const isv_param_blocks* pb) {
   return true;
 }
 
-extern "C" isv_status isv_eval_projection_batch(isv_handle* h, const isv_param_blocks* pb, const isv_proj_factors* f,
-                                                const isv_proj_eval* out, int32_t* status) {
+static isv_status eval_projection_on(isv_handle* h, cudaStream_t stream, const isv_param_blocks* pb,
+                                     const isv_proj_factors* f, const isv_proj_eval* out, int32_t* status) {
   if (!h || !pb_ok(pb) || !f || !out || f->n < 0 || f->stride < f->n) return ISV_ERR_BAD_ARG;
   if (f->n == 0) return ISV_OK;
   if (!f->idx || !f->obs || !out->residuals || !(f->cauchy_a >= 0.0)) return ISV_ERR_BAD_ARG;
-  ISV_CUDA(cudaSetDevice(h->device));
   const long long per_cta = 32LL * kEvalWarps;
   const long long grid = (f->n + per_cta - 1) / per_cta;
   if (grid > 0x7fffffffLL) return ISV_ERR_BAD_ARG;
-  eval_projection_kernel<<<(unsigned)grid, kEvalThreads, 0, h->stream>>>(*pb, *f, *out, h->dcfg, status);
+  eval_projection_kernel<<<(unsigned)grid, kEvalThreads, 0, stream>>>(*pb, *f, *out, h->dcfg, status);
   ++h->launches;
   ISV_CUDA(cudaGetLastError());
   return ISV_OK;
 }
 
-extern "C" isv_status isv_eval_imu_batch(isv_handle* h, const isv_param_blocks* pb, const isv_imu_factors* f,
-                                         const isv_imu_eval* out, int32_t* status) {
+static isv_status eval_imu_on(isv_handle* h, cudaStream_t stream, const isv_param_blocks* pb, const isv_imu_factors* f,
+                              const isv_imu_eval* out, int32_t* status) {
   if (!h || !pb_ok(pb) || !f || !out || f->n < 0) return ISV_ERR_BAD_ARG;
   if (f->n == 0) return ISV_OK;
   if (!f->idx || !f->preint || !out->residuals) return ISV_ERR_BAD_ARG;
-  ISV_CUDA(cudaSetDevice(h->device));
   const size_t sm = kEvalWarps * kImuEvalSmem * sizeof(double);
   ISV_CUDA(cudaFuncSetAttribute(eval_imu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  eval_imu_kernel<<<(f->n + kEvalWarps - 1) / kEvalWarps, kEvalThreads, sm, h->stream>>>(*pb, *f, *out, h->dcfg, status);
+  eval_imu_kernel<<<(f->n + kEvalWarps - 1) / kEvalWarps, kEvalThreads, sm, stream>>>(*pb, *f, *out, h->dcfg, status);
   ++h->launches;
   ISV_CUDA(cudaGetLastError());
   return ISV_OK;
 }
 
-extern "C" isv_status isv_eval_small_batch(isv_handle* h, const isv_param_blocks* pb, const isv_small_factors* f,
-                                           const isv_small_eval* out, int32_t* status) {
+static isv_status eval_small_on(isv_handle* h, cudaStream_t stream, const isv_param_blocks* pb,
+                                const isv_small_factors* f, const isv_small_eval* out, int32_t* status) {
   if (!h || !pb_ok(pb) || !f || !out) return ISV_ERR_BAD_ARG;
   if (f->n_rel < 0 || f->n_se3 < 0 || f->n_vb < 0 || f->n_rp < 0 || f->n_yaw < 0 || !(f->cauchy_a >= 0.0))
     return ISV_ERR_BAD_ARG;
@@ -627,10 +662,57 @@ extern "C" isv_status isv_eval_small_batch(isv_handle* h, const isv_param_blocks
     return ISV_ERR_BAD_ARG;
   const long long total = (long long)f->n_rel + f->n_se3 + f->n_vb + f->n_rp + f->n_yaw;
   if (total == 0) return ISV_OK;
-  ISV_CUDA(cudaSetDevice(h->device));
-  eval_small_kernel<<<(unsigned)((total + kEvalThreads - 1) / kEvalThreads), kEvalThreads, 0, h->stream>>>(*pb, *f, *out,
-                                                                                                          status);
+  eval_small_kernel<<<(unsigned)((total + kEvalThreads - 1) / kEvalThreads), kEvalThreads, 0, stream>>>(*pb, *f, *out,
+                                                                                                       status);
   ++h->launches;
   ISV_CUDA(cudaGetLastError());
   return ISV_OK;
+}
+
+extern "C" isv_status isv_eval_projection_batch(isv_handle* h, const isv_param_blocks* pb, const isv_proj_factors* f,
+                                                const isv_proj_eval* out, int32_t* status) {
+  if (!h) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  return eval_projection_on(h, h->stream, pb, f, out, status);
+}
+
+extern "C" isv_status isv_eval_imu_batch(isv_handle* h, const isv_param_blocks* pb, const isv_imu_factors* f,
+                                         const isv_imu_eval* out, int32_t* status) {
+  if (!h) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  return eval_imu_on(h, h->stream, pb, f, out, status);
+}
+
+extern "C" isv_status isv_eval_small_batch(isv_handle* h, const isv_param_blocks* pb, const isv_small_factors* f,
+                                           const isv_small_eval* out, int32_t* status) {
+  if (!h) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  return eval_small_on(h, h->stream, pb, f, out, status);
+}
+
+// All factor classes of one problemSolve() iteration.  The IMU and prior-factor kernels are
+// latency-bound (a few thousand short serial chains): they are forked onto two side streams and
+// overlap the HBM-bound projection kernel, then joined back into the handle's stream.
+extern "C" isv_status isv_eval_problem(isv_handle* h, const isv_param_blocks* pb, const isv_proj_factors* pf,
+                                       const isv_proj_eval* po, const isv_imu_factors* mf, const isv_imu_eval* mo,
+                                       const isv_small_factors* sf, const isv_small_eval* so, int32_t* status) {
+  if (!h || (pf && !po) || (mf && !mo) || (sf && !so)) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const bool fork = (mf && mf->n > 0) || (sf != nullptr);
+  if (fork) {
+    ISV_CUDA(cudaEventRecord(h->aux_ev[0], h->stream));
+    ISV_CUDA(cudaStreamWaitEvent(h->aux[0], h->aux_ev[0], 0));
+    ISV_CUDA(cudaStreamWaitEvent(h->aux[1], h->aux_ev[0], 0));
+  }
+  isv_status st = ISV_OK;
+  if (mf) st = eval_imu_on(h, h->aux[0], pb, mf, mo, status);
+  if (st == ISV_OK && sf) st = eval_small_on(h, h->aux[1], pb, sf, so, status);
+  if (st == ISV_OK && pf) st = eval_projection_on(h, h->stream, pb, pf, po, status);
+  if (fork) {   // always join, also on error, so the streams stay ordered
+    cudaEventRecord(h->aux_ev[1], h->aux[0]);
+    cudaEventRecord(h->aux_ev[2], h->aux[1]);
+    cudaStreamWaitEvent(h->stream, h->aux_ev[1], 0);
+    cudaStreamWaitEvent(h->stream, h->aux_ev[2], 0);
+  }
+  return st;
 }

@@ -50,7 +50,32 @@ ISV_DI void store_rows14(double* stage, int lane, const double* v, double* dst, 
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kEvalThreads)
+// v * skew(p) for a row vector v: [v1 p2 - v2 p1, v2 p0 - v0 p2, v0 p1 - v1 p0]
+ISV_DI void row_skew(const double* v, const double* p, double* o) {
+  o[0] = v[1] * p[2] - v[2] * p[1];
+  o[1] = v[2] * p[0] - v[0] * p[2];
+  o[2] = v[0] * p[1] - v[1] * p[0];
+}
+// o (2x3) = red (2x3) * M (3x3 row-major)  /  red * M^T
+ISV_DI void red_mul(const double* red, const double* M, double* o) {
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[3 * r + c] = red[3 * r] * M[c] + red[3 * r + 1] * M[3 + c] + red[3 * r + 2] * M[6 + c];
+}
+ISV_DI void red_mul_t(const double* red, const double* M, double* o) {
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      o[3 * r + c] = red[3 * r] * M[3 * c] + red[3 * r + 1] * M[3 * c + 1] + red[3 * r + 2] * M[3 * c + 2];
+}
+
+// Register plan: after the common part only the four points (pts_camera_i, pts_imu_i, pts_imu_j,
+// pts_camera_j) and five 2x3 products  red, red*A, red*A*Ri, red*ric^T, red*tmp_r  stay live
+// (A = ric^T Rj^T, tmp_r = A Ri ric); every Jacobian block is a cheap combination of those and is
+// stored as soon as it is formed, so the kernel fits 128 registers -> 4 CTAs (16 warps) per SM.
+__global__ void __launch_bounds__(kEvalThreads, 4)
 eval_projection_kernel(isv_param_blocks pb, isv_proj_factors fs, isv_proj_eval out, DevCfg cfg, int32_t* status) {
   __shared__ double stage_all[kEvalWarps][32 * kStageLd];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -60,125 +85,123 @@ eval_projection_kernel(isv_param_blocks pb, isv_proj_factors fs, isv_proj_eval o
   const long long k = wbase + lane;
   const int nvalid = (int)((fs.n - wbase) < 32 ? (fs.n - wbase) : 32);
   const bool live = k < fs.n;
-  double res[2] = {0.0, 0.0}, Ji[14], Jj[14], Je[14], Jf[2] = {0.0, 0.0};
-#pragma unroll
-  for (int c = 0; c < 14; ++c) { Ji[c] = 0.0; Jj[c] = 0.0; Je[c] = 0.0; }
+  bool ok = false;
+  double pc_i[3], pim_i[3], pim_j[3], pc_j[3], red[6], rA[6], rARi[6], rT[6], rTmp[6];
+  double res0 = 0.0, res1 = 0.0, jf0 = 0.0, jf1 = 0.0;
   if (live) {
     const int ii = fs.idx[k], jj = fs.idx[fs.stride + k], ie = fs.idx[2 * fs.stride + k], iff = fs.idx[3 * fs.stride + k];
-    if (ii < 0 || ii >= pb.n_pose || jj < 0 || jj >= pb.n_pose || ie < 0 || ie >= pb.n_ex_pose || iff < 0 ||
-        iff >= pb.n_feature) {
+    ok = !(ii < 0 || ii >= pb.n_pose || jj < 0 || jj >= pb.n_pose || ie < 0 || ie >= pb.n_ex_pose || iff < 0 ||
+           iff >= pb.n_feature);
+    if (!ok) {
       if (status) atomicOr(status, ISV_W_BAD_INDEX);
     } else {
       const double* PSi = pb.pose + (size_t)ii * 7;
       const double* PSj = pb.pose + (size_t)jj * 7;
       const double* PSe = pb.ex_pose + (size_t)ie * 7;
-      const double Pi[3] = {PSi[0], PSi[1], PSi[2]}, Pj[3] = {PSj[0], PSj[1], PSj[2]}, tic[3] = {PSe[0], PSe[1], PSe[2]};
       const Quat Qi = quat_from_pose(PSi), Qj = quat_from_pose(PSj), qic = quat_from_pose(PSe);
       const double lam = pb.feature[iff];
       const double pts_i[3] = {fs.obs[k], fs.obs[fs.stride + k], fs.obs[2 * fs.stride + k]};
       const double xj = fs.obs[3 * fs.stride + k], yj = fs.obs[4 * fs.stride + k];
       // :38-42
-      const double pc_i[3] = {pts_i[0] / lam, pts_i[1] / lam, pts_i[2] / lam};
-      double pim_i[3], pw[3], d[3], pim_j[3], pc_j[3];
+      double pw[3], d[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) pc_i[a] = pts_i[a] / lam;
       qrot(qic, pc_i, pim_i);
-      for (int a = 0; a < 3; ++a) pim_i[a] += tic[a];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) pim_i[a] += PSe[a];
       qrot(Qi, pim_i, pw);
-      for (int a = 0; a < 3; ++a) d[a] = pw[a] + Pi[a] - Pj[a];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) d[a] = pw[a] + PSi[a] - PSj[a];
       qrot(qinv(Qj), d, pim_j);
-      for (int a = 0; a < 3; ++a) d[a] = pim_j[a] - tic[a];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) d[a] = pim_j[a] - PSe[a];
       qrot(qinv(qic), d, pc_j);
       const double dep_j = pc_j[2];
       const double r0 = pc_j[0] / dep_j - xj, r1 = pc_j[1] / dep_j - yj;     // :48-49
       const double s00 = cfg.ps[0], s10 = cfg.ps[1], s01 = cfg.ps[2], s11 = cfg.ps[3];
-      res[0] = s00 * r0 + s01 * r1;                                          // :52
-      res[1] = s10 * r0 + s11 * r1;
-      const double ls = cauchy_scale(fs.cauchy_a, res[0] * res[0] + res[1] * res[1]);
+      res0 = s00 * r0 + s01 * r1;                                            // :52
+      res1 = s10 * r0 + s11 * r1;
+      const double ls = cauchy_scale(fs.cauchy_a, res0 * res0 + res1 * res1);
+      res0 *= ls;
+      res1 *= ls;
       // reduce = sqrt_info * [1/z 0 -x/z^2 ; 0 1/z -y/z^2]   (:72-75), loss scale folded in
       const double iz = 1.0 / dep_j, iz2 = 1.0 / (dep_j * dep_j);
-      const double u0[3] = {iz, 0.0, -pc_j[0] * iz2}, u1[3] = {0.0, iz, -pc_j[1] * iz2};
-      double red[6];
-      for (int c = 0; c < 3; ++c) {
-        red[c] = ls * (s00 * u0[c] + s01 * u1[c]);
-        red[3 + c] = ls * (s10 * u0[c] + s11 * u1[c]);
-      }
-      res[0] *= ls;
-      res[1] *= ls;
-      double Ri[9], Rj[9], ric[9], A[9], ARi[9], T[9];
-      q2R(Qi, Ri);
-      q2R(Qj, Rj);
-      q2R(qic, ric);
-      mat3_mul(Rj, ric, T);                       // A = ric^T Rj^T = (Rj ric)^T
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) A[3 * r + c] = T[3 * c + r];
-      mat3_mul(A, Ri, ARi);
-      // rA = reduce*A (2x3), rARi = reduce*A*Ri, rT = reduce*ric^T
-      double rA[6], rARi[6], rT[6];
-      for (int r = 0; r < 2; ++r)
-        for (int c = 0; c < 3; ++c) {
-          rA[3 * r + c] = red[3 * r] * A[c] + red[3 * r + 1] * A[3 + c] + red[3 * r + 2] * A[6 + c];
-          rARi[3 * r + c] = red[3 * r] * ARi[c] + red[3 * r + 1] * ARi[3 + c] + red[3 * r + 2] * ARi[6 + c];
-          rT[3 * r + c] = red[3 * r] * ric[3 * c] + red[3 * r + 1] * ric[3 * c + 1] + red[3 * r + 2] * ric[3 * c + 2];
-        }
-      // v * skew(p) (row vector) = [v1 p2 - v2 p1, v2 p0 - v0 p2, v0 p1 - v1 p0]
-      auto row_skew = [](const double* v, const double* p, double* o) {
-        o[0] = v[1] * p[2] - v[2] * p[1];
-        o[1] = v[2] * p[0] - v[0] * p[2];
-        o[2] = v[0] * p[1] - v[1] * p[0];
-      };
-      for (int r = 0; r < 2; ++r) {
-        double t[3];
-        // :80-85  jaco_i = [A | A Ri (-skew(pts_imu_i))]
-        for (int c = 0; c < 3; ++c) Ji[7 * r + c] = rA[3 * r + c];
-        row_skew(rARi + 3 * r, pim_i, t);
-        for (int c = 0; c < 3; ++c) Ji[7 * r + 3 + c] = -t[c];
-        // :93-98  jaco_j = [-A | ric^T skew(pts_imu_j)]
-        for (int c = 0; c < 3; ++c) Jj[7 * r + c] = -rA[3 * r + c];
-        row_skew(rT + 3 * r, pim_j, t);
-        for (int c = 0; c < 3; ++c) Jj[7 * r + 3 + c] = t[c];
-      }
-      if (out.jac_ex_pose) {
-        // :103-111
-        double tmp_r[9], RjtRi[9], M1[9], w1[3], w2[3], a3[3], b3[3];
-        mat3_mul(ARi, ric, tmp_r);
-        mat3_tmul(Rj, Ri, RjtRi);
-        RjtRi[0] -= 1.0; RjtRi[4] -= 1.0; RjtRi[8] -= 1.0;
-        mat3_tmul(ric, RjtRi, M1);                       // ric^T (Rj^T Ri - I)
-        mat3_vec(tmp_r, pc_i, w1);
-        mat3_vec(Ri, tic, a3);
-        for (int a = 0; a < 3; ++a) a3[a] += Pi[a] - Pj[a];
-        mat3_tvec(Rj, a3, b3);
-        for (int a = 0; a < 3; ++a) b3[a] -= tic[a];
-        mat3_tvec(ric, b3, w2);
-        double rTmp[6];
-        for (int r = 0; r < 2; ++r)
-          for (int c = 0; c < 3; ++c)
-            rTmp[3 * r + c] = red[3 * r] * tmp_r[c] + red[3 * r + 1] * tmp_r[3 + c] + red[3 * r + 2] * tmp_r[6 + c];
-        const double ws[3] = {w1[0] + w2[0], w1[1] + w2[1], w1[2] + w2[2]};
-        for (int r = 0; r < 2; ++r) {
-          double t1[3], t2[3];
-          for (int c = 0; c < 3; ++c)
-            Je[7 * r + c] = red[3 * r] * M1[c] + red[3 * r + 1] * M1[3 + c] + red[3 * r + 2] * M1[6 + c];
-          row_skew(rTmp + 3 * r, pc_i, t1);              // (reduce tmp_r) skew(pts_camera_i)
-          row_skew(red + 3 * r, ws, t2);                 // reduce (skew(tmp_r pc_i) + skew(...))
-          for (int c = 0; c < 3; ++c) Je[7 * r + 3 + c] = -t1[c] + t2[c];
-        }
-      }
+      const double u02 = -pc_j[0] * iz2, u12 = -pc_j[1] * iz2;
+      red[0] = ls * s00 * iz;  red[1] = ls * s01 * iz;  red[2] = ls * (s00 * u02 + s01 * u12);
+      red[3] = ls * s10 * iz;  red[4] = ls * s11 * iz;  red[5] = ls * (s10 * u02 + s11 * u12);
       {
-        // :116  reduce * ric^T Rj^T Ri ric * pts_i * -1 / lam^2
-        double tmp_r[9], q[3];
-        mat3_mul(ARi, ric, tmp_r);
-        mat3_vec(tmp_r, pts_i, q);
-        const double sc = -1.0 / (lam * lam);
-        Jf[0] = (red[0] * q[0] + red[1] * q[1] + red[2] * q[2]) * sc;
-        Jf[1] = (red[3] * q[0] + red[4] * q[1] + red[5] * q[2]) * sc;
+        double Ri[9], Rj[9], ric[9], A[9], T[9];
+        q2R(Qj, Rj);
+        q2R(qic, ric);
+        mat3_mul(Rj, ric, T);                       // A = ric^T Rj^T = (Rj ric)^T
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) A[3 * r + c] = T[3 * c + r];
+        red_mul(red, A, rA);
+        red_mul_t(red, ric, rT);
+        q2R(Qi, Ri);
+        mat3_mul(A, Ri, T);                         // A Ri
+        red_mul(red, T, rARi);
+        mat3_mul(T, ric, A);                        // tmp_r = A Ri ric   (:104)
+        red_mul(red, A, rTmp);
       }
+      // :116  reduce * tmp_r * pts_i * -1 / lam^2
+      const double sc = -1.0 / (lam * lam);
+      jf0 = (rTmp[0] * pts_i[0] + rTmp[1] * pts_i[1] + rTmp[2] * pts_i[2]) * sc;
+      jf1 = (rTmp[3] * pts_i[0] + rTmp[4] * pts_i[1] + rTmp[5] * pts_i[2]) * sc;
     }
   }
-  if (live && out.residuals) reinterpret_cast<double2*>(out.residuals)[k] = make_double2(res[0], res[1]);
-  if (live && out.jac_feature) reinterpret_cast<double2*>(out.jac_feature)[k] = make_double2(Jf[0], Jf[1]);
-  if (out.jac_pose_i) store_rows14(stage, lane, Ji, out.jac_pose_i + wbase * 14, nvalid);
-  if (out.jac_pose_j) store_rows14(stage, lane, Jj, out.jac_pose_j + wbase * 14, nvalid);
-  if (out.jac_ex_pose) store_rows14(stage, lane, Je, out.jac_ex_pose + wbase * 14, nvalid);
+  if (live && out.residuals) reinterpret_cast<double2*>(out.residuals)[k] = make_double2(res0, res1);
+  if (live && out.jac_feature) reinterpret_cast<double2*>(out.jac_feature)[k] = make_double2(jf0, jf1);
+  double v[14];
+  if (out.jac_pose_i) {       // :80-85  jaco_i = [A | A Ri (-skew(pts_imu_i))]
+#pragma unroll
+    for (int c = 0; c < 14; ++c) v[c] = 0.0;
+    if (ok) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        double t[3];
+        row_skew(rARi + 3 * r, pim_i, t);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { v[7 * r + c] = rA[3 * r + c]; v[7 * r + 3 + c] = -t[c]; }
+      }
+    }
+    store_rows14(stage, lane, v, out.jac_pose_i + wbase * 14, nvalid);
+  }
+  if (out.jac_pose_j) {       // :93-98  jaco_j = [-A | ric^T skew(pts_imu_j)]
+#pragma unroll
+    for (int c = 0; c < 14; ++c) v[c] = 0.0;
+    if (ok) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        double t[3];
+        row_skew(rT + 3 * r, pim_j, t);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { v[7 * r + c] = -rA[3 * r + c]; v[7 * r + 3 + c] = t[c]; }
+      }
+    }
+    store_rows14(stage, lane, v, out.jac_pose_j + wbase * 14, nvalid);
+  }
+  if (out.jac_ex_pose) {
+    // :103-111  jaco_ex = [ric^T (Rj^T Ri - I) | -tmp_r skew(pc_i) + skew(tmp_r pc_i) + skew(w2)],
+    //   w2 = ric^T (Rj^T (Ri tic + Pi - Pj) - tic).  ric^T (Rj^T Ri - I) = A Ri - ric^T, and because
+    //   pts_imu_j = Rj^T (Ri (ric pc_i + tic) + Pi - Pj):  tmp_r pc_i + w2 = ric^T (pts_imu_j - tic)
+    //   = pts_camera_j, so the two skew terms collapse to skew(pts_camera_j).
+#pragma unroll
+    for (int c = 0; c < 14; ++c) v[c] = 0.0;
+    if (ok) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        double t1[3], t2[3];
+        row_skew(rTmp + 3 * r, pc_i, t1);
+        row_skew(red + 3 * r, pc_j, t2);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { v[7 * r + c] = rARi[3 * r + c] - rT[3 * r + c]; v[7 * r + 3 + c] = t2[c] - t1[c]; }
+      }
+    }
+    store_rows14(stage, lane, v, out.jac_ex_pose + wbase * 14, nvalid);
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -187,7 +210,7 @@ eval_projection_kernel(isv_param_blocks pb, isv_proj_factors fs, isv_proj_eval o
 // -------------------------------------------------------------------------------------------------
 constexpr int kImuEvalSmem = 225 + 225 + 450 + 450 + 16 + 48;
 
-__global__ void __launch_bounds__(kEvalThreads)
+__global__ void __launch_bounds__(kEvalThreads, 4)
 eval_imu_kernel(isv_param_blocks pb, isv_imu_factors fs, isv_imu_eval out, DevCfg cfg, int32_t* status) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -214,7 +237,7 @@ eval_imu_kernel(isv_param_blocks pb, isv_imu_factors fs, isv_imu_eval out, DevCf
   }
   if (lane < 3) sc[32 + lane] = cfg.g[lane];
   __syncwarp();
-  if (lane == 0) imu_jacobians(sc, sc + 7, sc + 16, sc + 23, pre, sc + 32, J, 15, 0, 6, 15, 21, r);
+  imu_jacobians(sc, sc + 7, sc + 16, sc + 23, pre, sc + 32, J, 15, 0, 6, 15, 21, r, lane, 32);
   __syncwarp();
   // sqrt_info = LLT(covariance.inverse()).matrixL().transpose()   (imu_factor.h:44)
   int nonfinite = 0;
@@ -256,7 +279,8 @@ eval_imu_kernel(isv_param_blocks pb, isv_imu_factors fs, isv_imu_eval out, DevCf
 // -------------------------------------------------------------------------------------------------
 // out (rows x 7 row-major) = scale * s (rows x rows col-major) * Jt (rows x 6 col-major, ld rows); 7th col 0
 template <int R>
-ISV_DI void weighted_rows7(const double* s, const double* Jt, double scale, double* o) {
+ISV_DI void weighted_rows7(const double* __restrict__ s, const double* __restrict__ Jt, double scale,
+                           double* __restrict__ o) {
   for (int i = 0; i < R; ++i) {
     for (int c = 0; c < 6; ++c) {
       double acc = 0.0;
@@ -267,7 +291,7 @@ ISV_DI void weighted_rows7(const double* s, const double* Jt, double scale, doub
   }
 }
 template <int R>
-ISV_DI double weighted_res(const double* s, const double* r, double* o) {
+ISV_DI double weighted_res(const double* __restrict__ s, const double* __restrict__ r, double* __restrict__ o) {
   double n2 = 0.0;
   for (int i = 0; i < R; ++i) {
     double acc = 0.0;

@@ -134,9 +134,13 @@ __device__ inline void qleft_qright_br(const Quat& a, const Quat& b, double* M) 
 // Unweighted IMU Jacobians in WINDOW column order.  Jfull: 15 x 30 column-major (ld ldj), columns
 // [col_j_pose .. +6) <- d r / d T_j, [col_j_sb .. +9) <- d r / d VB_j, likewise for i.
 // pre: the 467-double pre-integration record (include/isv_capi.h ISV_PREINT_REC).  res: 15 or null.
+// Cooperative form: called by `nparts` lanes with part = 0..nparts-1; every lane evaluates the short
+// scalar prologue (broadcast loads), the nine 3x3 sub-block positions (r, c) are dealt round-robin
+// and part 0 writes the residual.  part = 0, nparts = 1 is the single-lane form.
 __device__ inline void imu_jacobians(const double* PSi, const double* VBi, const double* PSj, const double* VBj,
-                                     const double* pre, const double* G, double* Jfull, int ldj, int col_i_pose,
-                                     int col_i_sb, int col_j_pose, int col_j_sb, double* res) {
+                                     const double* __restrict__ pre, const double* G, double* Jfull, int ldj,
+                                     int col_i_pose, int col_i_sb, int col_j_pose, int col_j_sb, double* res,
+                                     int part = 0, int nparts = 1) {
   const double* delta_p = pre;
   Quat dq{pre[6], pre[3], pre[4], pre[5]};
   const double* delta_v = pre + 7;
@@ -162,7 +166,7 @@ __device__ inline void imu_jacobians(const double* PSi, const double* VBi, const
   }
   qrot(Qi_inv, a1, v1);
   qrot(Qi_inv, a2, v2);
-  if (res) {
+  if (res && part == 0) {
     Quat e = qmul(qinv(cq), qmul(Qi_inv, Qj));
     double ev[3] = {e.x, e.y, e.z};
     for (int r = 0; r < 3; ++r) {
@@ -187,8 +191,8 @@ __device__ inline void imu_jacobians(const double* PSi, const double* VBi, const
   qleft_br(qmul(QjinvQi, dq), QL1);                       // Q9: uncorrected delta_q
   qleft_br(qmul(qmul(qinv(cq), Qi_inv), Qj), QL2);
   auto put = [&](int row, int col, double v) { Jfull[row + ldj * col] = v; };
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) {
+  for (int rc = part; rc < 9; rc += nparts) {
+      const int r = rc / 3, c = rc - 3 * r;
       // d / d T_i   (15x6)
       put(0 + r, col_i_pose + c, -Ri_inv[3 * r + c]);
       put(0 + r, col_i_pose + 3 + c, S1[3 * r + c]);

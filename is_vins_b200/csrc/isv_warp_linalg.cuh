@@ -17,6 +17,15 @@ namespace isv {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 
+// The window kernels are long straight-line programs executed once per warp: with every routine
+// inlined at every call site they are 170-220 KB of SASS and instruction fetch becomes a limiter
+// (ncu: stall_no_instruction).  -DISV_HEAVY=__noinline__ compiles the heavy routines out of line (one
+// copy per template instantiation); measured on B200 it is 3-5 % SLOWER than full inlining (the
+// run-time loop bounds cost more than the fetches save), so inlining stays the default.
+#ifndef ISV_HEAVY
+#define ISV_HEAVY __forceinline__
+#endif
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
@@ -48,7 +57,7 @@ __device__ __forceinline__ void w_copy2d(double* dst, int ldd, const double* src
 // C (m x n) {=, +=, -=} op(A) (m x k) * op(B) (k x n).   mode: 0 set, 1 add, -1 subtract.
 // TA: A is stored k x m (use A^T);  TB: B is stored n x k (use B^T).
 template <bool TA, bool TB>
-__device__ __forceinline__ void w_gemm(int m, int n, int k, const double* A, int lda, const double* B, int ldb,
+__device__ ISV_HEAVY void w_gemm(int m, int n, int k, const double* A, int lda, const double* B, int ldb,
                                        double* C, int ldc, int mode, int lane) {
   for (int idx = lane; idx < m * n; idx += 32) {
     int i = idx % m, j = idx / m;
@@ -77,7 +86,7 @@ __device__ __forceinline__ void w_symmetrize_from_lower(double* A, int ld, int n
 
 // In-place inverse by Gauss-Jordan with partial (row) pivoting on the augmented matrix [A | I].
 // A: n x n (ld lda) is overwritten by A^-1.  work: n * 2n doubles.  Returns 1 if a zero pivot met.
-__device__ __forceinline__ int w_inverse(double* A, int lda, int n, double* work, int lane) {
+__device__ ISV_HEAVY int w_inverse(double* A, int lda, int n, double* work, int lane) {
   const int n2 = 2 * n;
   // W is n x 2n, column-major, ld = n
   for (int idx = lane; idx < n * n2; idx += 32) {
@@ -129,7 +138,7 @@ __device__ __forceinline__ int w_inverse(double* A, int lda, int n, double* work
 
 // In-place Cholesky A = L L^T reading only the lower triangle (Eigen::LLT semantics);
 // on return the lower triangle holds L (upper triangle untouched).  Returns 1 if not SPD.
-__device__ __forceinline__ int w_chol_lower(double* A, int ld, int n, int lane) {
+__device__ ISV_HEAVY int w_chol_lower(double* A, int ld, int n, int lane) {
   int bad = 0;
   for (int j = 0; j < n; ++j) {
     double d = A[j + j * ld];
@@ -178,7 +187,7 @@ __device__ __forceinline__ void jacobi_pair(int kp, int r, int m, int& p, int& q
   q = a < b ? b : a;
 }
 
-__device__ __forceinline__ int w_jacobi_eig(double* A, int lda, double* V, int ldv, int n, double* cs, int lane,
+__device__ ISV_HEAVY int w_jacobi_eig(double* A, int lda, double* V, int ldv, int n, double* cs, int lane,
                                             int max_sweeps = 30) {
   for (int idx = lane; idx < n * n; idx += 32) {
     int i = idx % n, j = idx / n;
@@ -286,7 +295,7 @@ __device__ __forceinline__ int w_jacobi_eig(double* A, int lda, double* V, int l
 
 // A: n x n symmetric (lower triangle read, ld lda) -- destroyed.  G: receives r rows (row-major,
 // ld ldg >= n).  d: n doubles scratch.  Returns r.
-__device__ __forceinline__ int w_pivoted_cholesky_rows(double* A, int lda, int n, double* G, int ldg, double* d,
+__device__ ISV_HEAVY int w_pivoted_cholesky_rows(double* A, int lda, int n, double* G, int ldg, double* d,
                                                        int lane) {
   w_symmetrize_from_lower(A, lda, n, lane);
   double dmax0 = 0.0;
@@ -347,7 +356,7 @@ __device__ __forceinline__ void jacobi_cs(double a, double b, double g, double& 
 // at the start of every sweep -- the dgesvj strategy).  lam[k] = |g_k|^2 on return (lam may alias
 // nrm).  Returns the number of sweeps used (>= max_sweeps -> not converged).
 template <int LPP, int NE>
-__device__ __forceinline__ int w_onesided_jacobi_rows(double* G, int ldg, int r, int n, double* lam, int lane,
+__device__ ISV_HEAVY int w_onesided_jacobi_rows(double* G, int ldg, int r, int n, double* lam, int lane,
                                                       int max_sweeps = 30, int es = 1) {
   constexpr int kGroups = 32 / LPP;
   const int sub = lane % LPP, grp = lane / LPP;
@@ -443,7 +452,7 @@ __device__ __forceinline__ int w_onesided_jacobi_rows(double* G, int ldg, int r,
 // without ever forming Lam or inverting Lam_mm, so no cancellation noise enters the null space.
 // vbuf: rows doubles of scratch.
 // -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void w_householder_marginalize(double* M, int ld, int rows, int cols, int c0, int nc,
+__device__ ISV_HEAVY void w_householder_marginalize(double* M, int ld, int rows, int cols, int c0, int nc,
                                                           double* vbuf, int lane) {
   for (int k = 0; k < nc; ++k) {
     double* ck = M + (size_t)ld * (c0 + k);
@@ -483,7 +492,7 @@ __device__ __forceinline__ void w_householder_marginalize(double* M, int ld, int
 // (/root/reference/src/estimator.cpp:950,1349,1503,1508,1515).
 // A: N x N SPD in shared memory (upper triangle read, destroyed); out: N x N column-major (global).
 template <int N>
-__device__ __forceinline__ int w_sqrt_info_from_cov(double* A, int ld, double* out, int lane, int& nonfinite) {
+__device__ ISV_HEAVY int w_sqrt_info_from_cov(double* A, int ld, double* out, int lane, int& nonfinite) {
   int bad = 0;
   for (int j = N - 1; j >= 0; --j) {
     double d = A[j + j * ld];
@@ -523,7 +532,7 @@ __device__ __forceinline__ int w_sqrt_info_from_cov(double* A, int ld, double* o
 // lane, in registers), A^-1 = X^T X.  A (smem, ld) is overwritten by A^-1; Xs: N*N doubles scratch.
 // Returns 1 when A is not SPD (result then meaningless: the caller falls back to w_inverse).
 template <int N>
-__device__ __forceinline__ int w_spd_inverse(double* A, int ld, double* Xs, int lane) {
+__device__ ISV_HEAVY int w_spd_inverse(double* A, int ld, double* Xs, int lane) {
   int bad = 0;
   for (int j = N - 1; j >= 0; --j) {
     double d = A[j + j * ld];
@@ -559,6 +568,110 @@ __device__ __forceinline__ int w_spd_inverse(double* A, int ld, double* Xs, int 
     const int km = i < j ? i : j;
     for (int k = 0; k <= km; ++k) acc = fma(Xs[k + N * i], Xs[k + N * j], acc);
     A[i + j * ld] = acc;
+  }
+  __syncwarp();
+  return bad;
+}
+
+// Register-resident form of w_sqrt_info_from_cov (same result: the upper-triangular U1^-1 with
+// cov = U1 U1^T): every lane loads the upper triangle (broadcast LDS), runs the reverse-order
+// Cholesky serially in registers (no barriers, no shuffles; SIMT makes the redundancy free), then
+// lane c < N back-substitutes column c of U1^-1 and stores it.  A is only read.
+template <int N>
+__device__ __forceinline__ int w_sqrt_info_from_cov_regs(const double* A, int ld, double* out, int lane,
+                                                         int& nonfinite) {
+  double u[N][N];   // upper triangle used: u[i][j], i <= j
+  double rinv[N];
+  int bad = 0;
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int i = 0; i <= j; ++i) u[i][j] = A[i + j * ld];
+#pragma unroll
+  for (int j = N - 1; j >= 0; --j) {
+    const double d = u[j][j];
+    if (!(d > 0.0)) bad = 1;
+    const double ri = rsqrt(d);
+    rinv[j] = ri;
+#pragma unroll
+    for (int i = 0; i < j; ++i) u[i][j] *= ri;
+#pragma unroll
+    for (int c = 0; c < j; ++c)
+#pragma unroll
+      for (int i = 0; i <= c; ++i) u[i][c] = fma(-u[i][j], u[c][j], u[i][c]);
+  }
+  // U1 has diagonal sqrt(d_j) = 1 / rinv[j]; column `lane` of X = U1^-1: x_i = (e_i - sum_{k>i} U_ik x_k) rinv_i
+  double x[N];
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double sacc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = i + 1; k < N; ++k) sacc = fma(-u[i][k], x[k], sacc);
+    x[i] = (i <= lane) ? sacc * rinv[i] : 0.0;
+  }
+  if (lane < N) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (!isfinite(x[i])) nonfinite = 1;
+      out[i + N * lane] = x[i];
+    }
+  }
+  __syncwarp();
+  return bad;
+}
+
+// SPD inverse of a small matrix entirely in registers, no shuffles and no barriers inside: EVERY lane
+// loads the lower triangle (broadcast LDS) and runs the same serial LDL^T factorisation (SIMT makes the
+// redundancy free), then lane j < N solves for column j of A^-1 and writes it back.  ~4x fewer warp
+// instructions than the cooperative w_spd_inverse for N = 6, and a much shorter dependent chain.
+// A (smem, ld) is overwritten by A^-1 (full, symmetric).  Returns 1 when A is not SPD.
+template <int N>
+__device__ __forceinline__ int w_spd_inverse_regs(double* A, int ld, int lane) {
+  double l[N][N];   // unit lower factor (strict lower part used), d on the diagonal slot
+  double dinv[N];
+  int bad = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) l[i][j] = A[i + j * ld];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double d = l[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d = fma(-l[j][k] * l[j][k], l[k][k], d);   // l[k][k] holds d_k
+    if (!(d > 0.0)) bad = 1;
+    l[j][j] = d;
+    dinv[j] = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      double v = l[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v = fma(-l[i][k] * l[k][k], l[j][k], v);
+      l[i][j] = v * dinv[j];
+    }
+  }
+  // column `lane` of A^-1:  L y = e ;  z = D^-1 y ;  L^T x = z
+  double x[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double v = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < i; ++k) v = fma(-l[i][k], x[k], v);
+    x[i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] *= dinv[i];
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double v = x[i];
+#pragma unroll
+    for (int k = i + 1; k < N; ++k) v = fma(-l[k][i], x[k], v);
+    x[i] = v;
+  }
+  if (lane < N) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) A[i + lane * ld] = x[i];
   }
   __syncwarp();
   return bad;

@@ -1,7 +1,8 @@
 // The two window kernels of the hot path: one WARP per sliding window, every stage fused, so that
 // only the window's inputs and its recovered factors touch HBM (SURVEY.md 7.2 "KF").
 //
-//   marg_forward_kernel   Estimator::MargForward    /root/reference/src/estimator.cpp:1149-1352
+//   marg_forward_accum_kernel + marg_forward_tail_kernel
+//                         Estimator::MargForward    /root/reference/src/estimator.cpp:1149-1352
 //   marg_backward_kernel  Estimator::MargBackward   /root/reference/src/estimator.cpp:1354-1539
 //
 // MargForward, structured form.  The reference builds the dense (12+L)^2 `Lamda` with the block
@@ -12,9 +13,8 @@
 //     u_k = s*jl_k/|s*jl_k| , v_k _|_ u_k ;  e_k = (sJ_k)^T u_k , w_k = (sJ_k)^T v_k
 //     Lamda[0:12,0:12]            = sum_k e_k e_k^T + w_k w_k^T   (+ prior + rel-pose blocks)
 //     Lamda[0:12,0:12] - B D^-1 B^T = sum_k w_k w_k^T             (Schur over the landmarks)
-// Both sums are SYRKs  X X^T  with X 12 x L: they run on the FP64 tensor pipe
-// (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4), 32 landmarks per warp iteration, staged through
-// shared memory to reach the fragment layout.  Everything after that is 12x12 / 6x6 algebra.
+// Both sums are SYRKs  X X^T  with X 12 x L of rank <= 6: they are accumulated as 6x6 Gram matrices
+// in registers (see "6-vector form" below).  Everything after that is 12x12 / 6x6 algebra.
 #pragma once
 #include "isv_device_math.cuh"
 #include "isv_factors.cuh"
@@ -28,16 +28,18 @@ namespace isv {
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = 32 * kWarpsPerCta;
 #ifndef ISV_FWD_MINB
-#define ISV_FWD_MINB 1
+#define ISV_FWD_MINB 3
+#endif
+#ifndef ISV_FWD_TAIL_MINB
+#define ISV_FWD_TAIL_MINB 4
 #endif
 #ifndef ISV_BWD_MINB
 #define ISV_BWD_MINB 4
 #endif
 
 // ---- forward: shared-memory map (doubles, per warp) -----------------------------------------
-constexpr int kXld = 36;                     // staging row stride: conflict-free 64-bit fragment loads
-constexpr int kFwdConst = 96;                // per-window constants of the landmark phase
-constexpr int kFwdWork = 832;                // staging (16*36) during the loop, tail matrices after it
+constexpr int kFwdConst = 72;                // Psi (12 x 6)
+constexpr int kFwdWork = 832;                // tail matrices
 constexpr int kFwdSmemPerWarp = kFwdConst + kFwdWork;
 // ---- backward ---------------------------------------------------------------------------------
 constexpr int kBwdScratch = 136;
@@ -71,173 +73,214 @@ __device__ __forceinline__ int chol_store_upper(double* M, int ld, int n, double
 // =================================================================================================
 // MargForward
 //
-// 9-vector form.  d r/d P1 = -d r/d P0 for a ProjectionFactor (jaco_j.leftCols = -jaco_i.leftCols,
-// projection_factor.cpp:163,173), so each weighted Jacobian row lives in a 9-dimensional space
-//   z = [ T1-rot (3) | T0-rot (3) | pos (3) ] ,   x12 = [ -pos | T1-rot | pos | T0-rot ]   (OrderMap T1@0, T0@6)
-// and the two 12x12 SYRKs collapse to 9x9 ones: rows 0-7 on the FP64 tensor pipe (one DMMA tile per
-// vector per k-step), row 8 as 9 DFMA accumulators per vector.
+// 6-vector form.  A ProjectionFactor's residual depends on the two poses only through the relative
+// pose T0^-1 T1, so every weighted Jacobian row lives in a 6-dimensional space.  With
+//   D = R0^T R1 ,  F = R1^T R0 ric ,  f = R1^T R0 tic ,  d = R1^T (P0 - P1) ,  tp = ric^T (f + d - tic)
+// and, per landmark (p = pts_i, lam = inv_dep):
+//   w = F p ;  pi^ = w + lam f ;  q~ = ric^T w ;  c~ = q~ + lam tp  (= lam * pts_camera_j) ;
+//   rho = 1 / c~_z ;  (xb, yb) = c~_xy rho ;  Pb = [1 0 -xb ; 0 1 -yb]
+//   u = normalize(s Pb q~)  (direction of s * jacobian_feature, :176-178) , v _|_ u
+//   alpha = ric Pb^T (rho s^T u) ,  beta = ric Pb^T (rho s^T v)
+//   y_e = [ pi^ x alpha ; lam alpha ] ,  y_w = [ pi^ x beta ; lam beta ]                 (6-vectors)
+// the 12-vectors of the 9/12-dimensional forms are  e = Psi y_e , w = Psi y_w  with the per-window
+//   Psi (12x6) = [ 0 -R1 ; -I -skew(d) ; 0 R1 ; D 0 ]     (rows: OrderMap T1@0 [pos, rot], T0@6)
+// so  Lamda[0:12,0:12] = Psi (sum y_e y_e^T + y_w y_w^T) Psi^T  and the landmark Schur complement
+// is  Psi (sum y_w y_w^T) Psi^T.  The two 6x6 Gram matrices (21 + 21 unique entries) are accumulated
+// in registers, one landmark per lane: ~100 DFMA for the chain + 42 for the SYRKs per landmark and
+// no shared-memory staging.  (History: the 9-vector version ran the SYRKs as DMMA.8x8x4 tiles; on
+// B200 DMMA and DFMA share one pipe at the same FLOP rate (tools/fp64_peak.cu), an 8x8 tile wastes
+// 64/21 of the work on a 6x6 symmetric Gram, and the kernel is FP64-pipe bound -- DFMA is 3.4x faster
+// here.  DMMA stays where the tile is full: the dense Schur product of the generic path.)
 // =================================================================================================
-__device__ __forceinline__ int fwd_zmap(int i) { return i < 3 ? 6 + i : (i < 6 ? i - 3 : (i < 9 ? i : i - 6)); }
+// ---- kernel 1: landmark phase.  One warp per window, one landmark per lane and iteration;
+// writes the 21 + 21 lower-triangle entries of the two Gram matrices to gram[win][42].
+constexpr int kAccLd = 33;                         // reduction staging: [21][33] doubles per warp
+constexpr int kAccSmemPerWarp = 24 + 21 * kAccLd;  // constants F f tp ric + staging
 
 __global__ void __launch_bounds__(kThreads, ISV_FWD_MINB)
-marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
+marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* wstatus, DevCfg cfg) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int win = blockIdx.x * kWarpsPerCta + warp;
   if (win >= in.n_windows) return;
-  double* K = smem + warp * kFwdSmemPerWarp;  // constants
-  double* X = K + kFwdConst;                  // staging / tail work
+  double* K = smem + warp * kAccSmemPerWarp;  // [0]F [9]f [12]tp [15]ric
+  double* R = K + 24;                         // reduction staging
   int status = 0;
-  int nonfinite = 0;
 
   const double* pose0 = in.pose_fwd + (size_t)win * 14;
   const double* pose1 = pose0 + 7;
   const double* ex = in.ex_pose + (in.ex_pose_shared ? 0 : (size_t)win * 7);
-
-  // ---- per-window constants (projection_factor.cpp:127-147) -----------------------------------
-  // K: [0]ric [9]tic [12]B=ric^T R1^T [21]C=B R0 [30]Ap=C ric [39]tp = ric^T (R1^T (R0 tic + P0 - P1) - tic)
   if (lane == 0) {
     Quat Qi = quat_from_pose(pose0), Qj = quat_from_pose(pose1), qic = quat_from_pose(ex);
     if (nonunit(pose0) || nonunit(pose1) || nonunit(ex)) status |= ISV_W_NONUNIT_QUAT;
-    double ric[9], R0[9], R1[9], B[9], C[9], Ap[9], T[9];
+    double ric[9], R0[9], R1[9], D[9], F[9], fv[3], dv[3], tp[3], t3[3];
     q2R(qic, ric);
     q2R(Qi, R0);
     q2R(Qj, R1);
-    mat3_mul(R1, ric, T);  // B = ric^T R1^T = (R1 ric)^T
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) B[3 * r + c] = T[3 * c + r];
-    mat3_mul(B, R0, C);
-    mat3_mul(C, ric, Ap);
-    double a[3], b[3], tp[3];
-    mat3_vec(R0, ex, a);
-    for (int i = 0; i < 3; ++i) a[i] += pose0[i] - pose1[i];
-    mat3_tvec(R1, a, b);
-    for (int i = 0; i < 3; ++i) b[i] -= ex[i];
-    mat3_tvec(ric, b, tp);
-    for (int i = 0; i < 9; ++i) { K[i] = ric[i]; K[12 + i] = B[i]; K[21 + i] = C[i]; K[30 + i] = Ap[i]; }
-    for (int i = 0; i < 3; ++i) { K[9 + i] = ex[i]; K[39 + i] = tp[i]; }
+    mat3_tmul(R0, R1, D);          // D = R0^T R1
+    mat3_tmul(D, ric, F);          // F = D^T ric = R1^T R0 ric
+    mat3_tvec(D, ex, fv);          // f = D^T tic
+    for (int i = 0; i < 3; ++i) t3[i] = pose0[i] - pose1[i];
+    mat3_tvec(R1, t3, dv);         // d = R1^T (P0 - P1)
+    for (int i = 0; i < 3; ++i) t3[i] = fv[i] + dv[i] - ex[i];
+    mat3_tvec(ric, t3, tp);
+    for (int i = 0; i < 9; ++i) { K[i] = F[i]; K[15 + i] = ric[i]; }
+    for (int i = 0; i < 3; ++i) { K[9 + i] = fv[i]; K[12 + i] = tp[i]; }
   }
   __syncwarp();
 
   const long long lm0 = in.lm_offset[win];
   const int L = (int)(in.lm_offset[win + 1] - lm0);
-  const double* ob = in.lm_obs + lm0;
+  const double* __restrict__ ob = in.lm_obs + lm0;
   const long long st = in.lm_stride;
   const double s00 = cfg.ps[0], s10 = cfg.ps[1], s01 = cfg.ps[2], s11 = cfg.ps[3];
-
-  // accumulators: 8x8 tile of E = sum e e^T and S = sum w w^T (rows 0-7) + row 8 in plain DFMA
-  double te0 = 0, te1 = 0, ts0 = 0, ts1 = 0;
-  double e8[9], w8[9];
+  // ric is used three times per landmark: keep it in registers; F, f, tp are broadcast LDS
+  double ric[9];
 #pragma unroll
-  for (int c = 0; c < 9; ++c) { e8[c] = 0.0; w8[c] = 0.0; }
-  const int fm = lane >> 2, fk = lane & 3;
+  for (int i = 0; i < 9; ++i) ric[i] = K[15 + i];
 
-  // software prefetch of the next 32 landmarks
-  double nx = 0, ny = 0, nz = 0, nl = 1;
-  if (lane < L) { nx = ob[lane]; ny = ob[st + lane]; nz = ob[2 * st + lane]; nl = ob[5 * st + lane]; }
+  // 21 + 21 accumulators: lower triangles of sum y_e y_e^T and sum y_w y_w^T
+  double ae[21], aw[21];
+#pragma unroll
+  for (int i = 0; i < 21; ++i) { ae[i] = 0.0; aw[i] = 0.0; }
+
+  // software pipeline: the loads of the landmarks two iterations ahead are in flight
+  double nx[2] = {0, 0}, ny[2] = {0, 0}, nz[2] = {0, 0}, nl[2] = {1, 1};
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    const int k = d * 32 + lane;
+    if (k < L) { nx[d] = ob[k]; ny[d] = ob[st + k]; nz[d] = ob[2 * st + k]; nl[d] = ob[5 * st + k]; }
+  }
   for (int base = 0; base < L; base += 32) {
     const int k = base + lane;
-    const double xi = nx, yi = ny, zi = nz, lam = nl;
-    const int kn = k + 32;
-    if (kn < L) { nx = ob[kn]; ny = ob[st + kn]; nz = ob[2 * st + kn]; nl = ob[5 * st + kn]; }
-    double ez[9], wz[9];
+    const double px = nx[0], py = ny[0], pz = nz[0], lam = nl[0];
+    nx[0] = nx[1]; ny[0] = ny[1]; nz[0] = nz[1]; nl[0] = nl[1];
+    const int kn = k + 64;
+    if (kn < L) { nx[1] = ob[kn]; ny[1] = ob[st + kn]; nz[1] = ob[2 * st + kn]; nl[1] = ob[5 * st + kn]; }
     if (k < L) {
-      // pts_camera_i = pts_i / inv_dep ; pts_camera_j = Ap pc + tp (the chain of :137-141 collapsed)
-      const double inv = 1.0 / lam;
-      const double pc0 = xi * inv, pc1 = yi * inv, pc2 = zi * inv;
-      double q[3], cj[3], pi_[3], pj[3];
+      double w[3], ph[3], qt[3];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        q[r] = K[30 + 3 * r] * pc0 + K[30 + 3 * r + 1] * pc1 + K[30 + 3 * r + 2] * pc2;
-        cj[r] = q[r] + K[39 + r];
-        pi_[r] = K[3 * r] * pc0 + K[3 * r + 1] * pc1 + K[3 * r + 2] * pc2 + K[9 + r];   // pts_imu_i
+        w[r] = K[3 * r] * px + K[3 * r + 1] * py + K[3 * r + 2] * pz;
+        ph[r] = fma(lam, K[9 + r], w[r]);
       }
 #pragma unroll
-      for (int r = 0; r < 3; ++r) pj[r] = K[3 * r] * cj[0] + K[3 * r + 1] * cj[1] + K[3 * r + 2] * cj[2] + K[9 + r];  // pts_imu_j
-      const double iz = 1.0 / cj[2];
-      const double rx = -cj[0] * iz * iz, ry = -cj[1] * iz * iz;  // reduce = [iz 0 rx ; 0 iz ry]
-      // rB = reduce*B, rC = reduce*C, rT = reduce*ric^T   (2x3 each)
-      double rB[6], rC[6], rT[6];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        rB[c] = iz * K[12 + c] + rx * K[12 + 6 + c];
-        rB[3 + c] = iz * K[12 + 3 + c] + ry * K[12 + 6 + c];
-        rC[c] = iz * K[21 + c] + rx * K[21 + 6 + c];
-        rC[3 + c] = iz * K[21 + 3 + c] + ry * K[21 + 6 + c];
-        rT[c] = iz * K[3 * c] + rx * K[3 * c + 2];
-        rT[3 + c] = iz * K[3 * c + 1] + ry * K[3 * c + 2];
-      }
-      // unweighted 2x9 rows: [ T1-rot = rT*skew(pj) | T0-rot = -rC*skew(pi) | pos = rB ]
-      double J0[9], J1[9];
-      J0[0] = rT[1] * pj[2] - rT[2] * pj[1];  J0[1] = rT[2] * pj[0] - rT[0] * pj[2];  J0[2] = rT[0] * pj[1] - rT[1] * pj[0];
-      J1[0] = rT[4] * pj[2] - rT[5] * pj[1];  J1[1] = rT[5] * pj[0] - rT[3] * pj[2];  J1[2] = rT[3] * pj[1] - rT[4] * pj[0];
-      J0[3] = rC[2] * pi_[1] - rC[1] * pi_[2];  J0[4] = rC[0] * pi_[2] - rC[2] * pi_[0];  J0[5] = rC[1] * pi_[0] - rC[0] * pi_[1];
-      J1[3] = rC[5] * pi_[1] - rC[4] * pi_[2];  J1[4] = rC[3] * pi_[2] - rC[5] * pi_[0];  J1[5] = rC[4] * pi_[0] - rC[3] * pi_[1];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { J0[6 + c] = rB[c]; J1[6 + c] = rB[3 + c]; }
-      // jacobian_feature = reduce * Ap * pts_i * -1/lam^2 = -(reduce q)/lam
-      const double jl0 = -(iz * q[0] + rx * q[2]) * inv, jl1 = -(iz * q[1] + ry * q[2]) * inv;
-      // weighted by the 2x2 sqrt_info, then rotated into the (u, v) basis of s*jl
-      const double g0 = s00 * jl0 + s01 * jl1, g1 = s10 * jl0 + s11 * jl1;
+      for (int c = 0; c < 3; ++c) qt[c] = ric[c] * w[0] + ric[3 + c] * w[1] + ric[6 + c] * w[2];
+      const double c0 = fma(lam, K[12], qt[0]), c1 = fma(lam, K[13], qt[1]), c2 = fma(lam, K[14], qt[2]);
+      const double rho = 1.0 / c2;
+      const double xb = c0 * rho, yb = c1 * rho;
+      const double pq0 = fma(-xb, qt[2], qt[0]), pq1 = fma(-yb, qt[2], qt[1]);
+      const double g0 = s00 * pq0 + s01 * pq1, g1 = s10 * pq0 + s11 * pq1;
       const double n2 = g0 * g0 + g1 * g1;
-      double u0 = 1.0, u1 = 0.0;
-      if (n2 > 0.0) { const double in_ = rsqrt(n2); u0 = g0 * in_; u1 = g1 * in_; } else { status |= ISV_W_SINGULAR; }
-      const double eu0 = u0 * s00 + u1 * s10, eu1 = u0 * s01 + u1 * s11;      // u^T s
-      const double ev0 = -u1 * s00 + u0 * s10, ev1 = -u1 * s01 + u0 * s11;    // v^T s
+      double u0 = rho, u1 = 0.0;                       // (u, v) pre-scaled by rho
+      if (n2 > 0.0) { const double in_ = rsqrt(n2) * rho; u0 = g0 * in_; u1 = g1 * in_; } else { status |= ISV_W_SINGULAR; }
+      const double a0 = u0 * s00 + u1 * s10, a1 = u0 * s01 + u1 * s11;        // rho s^T u
+      const double b0 = -u1 * s00 + u0 * s10, b1 = -u1 * s01 + u0 * s11;      // rho s^T v
+      double ye[6], yw[6], al[3], be[3];
 #pragma unroll
-      for (int c = 0; c < 9; ++c) {
-        ez[c] = eu0 * J0[c] + eu1 * J1[c];
-        wz[c] = ev0 * J0[c] + ev1 * J1[c];
+      for (int r = 0; r < 3; ++r) {
+        const double n0 = fma(-xb, ric[3 * r + 2], ric[3 * r]), n1 = fma(-yb, ric[3 * r + 2], ric[3 * r + 1]);
+        al[r] = a0 * n0 + a1 * n1;
+        be[r] = b0 * n0 + b1 * n1;
       }
-    } else {
+      ye[0] = ph[1] * al[2] - ph[2] * al[1];  ye[1] = ph[2] * al[0] - ph[0] * al[2];  ye[2] = ph[0] * al[1] - ph[1] * al[0];
+      yw[0] = ph[1] * be[2] - ph[2] * be[1];  yw[1] = ph[2] * be[0] - ph[0] * be[2];  yw[2] = ph[0] * be[1] - ph[1] * be[0];
 #pragma unroll
-      for (int c = 0; c < 9; ++c) { ez[c] = 0.0; wz[c] = 0.0; }
+      for (int r = 0; r < 3; ++r) { ye[3 + r] = lam * al[r]; yw[3 + r] = lam * be[r]; }
+      int t = 0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+          ae[t] = fma(ye[i], ye[j], ae[t]);
+          aw[t] = fma(yw[i], yw[j], aw[t]);
+          ++t;
+        }
     }
-    // row 8 of both Gram matrices in registers
+  }
+  // cross-lane reduction through shared memory: lane l parks its 21 partial sums in column l of a
+  // [21][33] tile, then lane t adds up row t (conflict-free both ways) -- 4x fewer instructions than
+  // 42 shuffle trees.  Fixed summation order: results do not depend on scheduling.
+  double* g = gram + (size_t)win * 42;
 #pragma unroll
-    for (int c = 0; c < 9; ++c) { e8[c] = fma(ez[8], ez[c], e8[c]); w8[c] = fma(wz[8], wz[c], w8[c]); }
-    // rows 0-7 on the FP64 tensor pipe: stage e (rows 0-7) and w (rows 8-15) together
+  for (int half = 0; half < 2; ++half) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { X[c * kXld + lane] = ez[c]; X[(8 + c) * kXld + lane] = wz[c]; }
+    for (int t = 0; t < 21; ++t) R[t * kAccLd + lane] = half ? aw[t] : ae[t];
     __syncwarp();
+    if (lane < 21) {
+      double acc = 0.0;
 #pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const double ae = X[fm * kXld + 4 * s + fk], aw = X[(8 + fm) * kXld + 4 * s + fk];
-      dmma884(te0, te1, ae, ae);
-      dmma884(ts0, ts1, aw, aw);
+      for (int j = 0; j < 32; ++j) acc += R[lane * kAccLd + j];
+      g[half * 21 + lane] = acc;
     }
     __syncwarp();
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) status |= __shfl_xor_sync(kFullMask, status, o);
+  if (lane == 0 && status && wstatus) atomicOr(wstatus + win, status);
+}
 
-  // ---- tail -------------------------------------------------------------------------------------
-  // work map (doubles): S12[0] H12[144] Ze[288] Zs[369] ; then
+// ---- kernel 2: everything after the landmark sums (12x12 / 6x6 algebra), one warp per window ----
+__global__ void __launch_bounds__(kThreads, ISV_FWD_TAIL_MINB)
+marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __restrict__ gram, DevCfg cfg) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int win = blockIdx.x * kWarpsPerCta + warp;
+  if (win >= in.n_windows) return;
+  double* K = smem + warp * kFwdSmemPerWarp;  // Psi (12x6 column-major)
+  double* X = K + kFwdConst;                  // tail work
+  int status = 0;
+  int nonfinite = 0;
+
+  const double* pose0 = in.pose_fwd + (size_t)win * 14;
+  const double* pose1 = pose0 + 7;
+  // work map (doubles): S12[0] H12[144] Ye[288] Ys[324] tmp[360..432) ; then
   // Wst[288] G[432] Jr6[504] sp[540] sr[576] tA[612] tB[684] wk[756]
   double* S12 = X;
   double* H12 = X + 144;
-  double* Ze = X + 288;   // 9 x 9 Gram matrices (ld 9)
-  double* Zs = X + 369;
-  {
-    const int r = fm, c = 2 * fk;
-    Ze[r + 9 * c] = te0;  Ze[r + 9 * (c + 1)] = te1;
-    Zs[r + 9 * c] = ts0;  Zs[r + 9 * (c + 1)] = ts1;
-  }
-#pragma unroll
-  for (int c = 0; c < 9; ++c) { e8[c] = warp_sum(e8[c]); w8[c] = warp_sum(w8[c]); }
-  __syncwarp();
+  double* Ye = X + 288;   // 6 x 6 Gram matrices (ld 6)
+  double* Ys = X + 324;
+  double* Tm = X + 360;   // 12 x 6
   if (lane == 0) {
-#pragma unroll
-    for (int c = 0; c < 9; ++c) { Ze[8 + 9 * c] = e8[c]; Ze[c + 9 * 8] = e8[c]; Zs[8 + 9 * c] = w8[c]; Zs[c + 9 * 8] = w8[c]; }
+    Quat Qi = quat_from_pose(pose0), Qj = quat_from_pose(pose1);
+    double R0[9], R1[9], D[9], dv[3], t3[3];
+    q2R(Qi, R0);
+    q2R(Qj, R1);
+    mat3_tmul(R0, R1, D);
+    for (int i = 0; i < 3; ++i) t3[i] = pose0[i] - pose1[i];
+    mat3_tvec(R1, t3, dv);
+    double* Psi = K;
+    for (int i = 0; i < 72; ++i) Psi[i] = 0.0;
+    double Sd[9];
+    skew3(dv, Sd);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        Psi[r + 12 * (3 + c)] = -R1[3 * r + c];
+        Psi[(3 + r) + 12 * c] = (r == c) ? -1.0 : 0.0;
+        Psi[(3 + r) + 12 * (3 + c)] = -Sd[3 * r + c];
+        Psi[(6 + r) + 12 * (3 + c)] = R1[3 * r + c];
+        Psi[(9 + r) + 12 * c] = D[3 * r + c];
+      }
+  } else if (lane >= 8 && lane < 29) {
+    // unpack the lower triangles: entry t = (i, j), j <= i, row-wise
+    const int t = lane - 8;
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    const int j = t - i * (i + 1) / 2;
+    const double ve = gram[(size_t)win * 42 + t], vw = gram[(size_t)win * 42 + 21 + t];
+    Ye[i + 6 * j] = ve; Ye[j + 6 * i] = ve;
+    Ys[i + 6 * j] = vw; Ys[j + 6 * i] = vw;
   }
   __syncwarp();
-  for (int idx = lane; idx < 144; idx += 32) {
-    const int r = idx % 12, c = idx / 12;
-    const int zr = fwd_zmap(r), zc = fwd_zmap(c);
-    const double sg = ((r < 3) != (c < 3)) ? -1.0 : 1.0;
-    S12[idx] = sg * Zs[zr + 9 * zc];
-    H12[idx] = sg * Ze[zr + 9 * zc];
+  {
+    const double* Psi = K;
+    w_gemm<false, false>(12, 6, 6, Psi, 12, Ys, 6, Tm, 12, 0, lane);
+    w_gemm<false, true>(12, 12, 6, Tm, 12, Psi, 12, S12, 12, 0, lane);   // Schur over the landmarks
+    w_gemm<false, false>(12, 6, 6, Psi, 12, Ye, 6, Tm, 12, 0, lane);
+    w_gemm<false, true>(12, 12, 6, Tm, 12, Psi, 12, H12, 12, 0, lane);   // sum e e^T
   }
-  __syncwarp();
   double* Wst = X + 288;
   double* G = X + 432;
   double* Jr6 = X + 504;
@@ -319,14 +362,14 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
   // ---- pose-graph relative-pose factor (:1243-1259) -------------------------------------------
   // J = G (6x12, [Ji|Jj]) ; Jpinv = J^T (J J^T)^-1 (full row rank) ; rpOmega = Jpinv^T H12 Jpinv
   w_gemm<false, true>(6, 6, 12, G, 6, G, 6, tA, 6, 0, lane);          // tA = J J^T
-  if (w_spd_inverse<6>(tA, 6, wk, lane)) status |= ISV_W_SINGULAR;
+  if (w_spd_inverse_regs<6>(tA, 6, lane)) status |= ISV_W_SINGULAR;
   w_gemm<true, false>(12, 6, 6, G, 6, tA, 6, tB, 12, 0, lane);        // tB = Jpinv (12x6)
   w_gemm<false, false>(12, 6, 12, H12, 12, tB, 12, wk, 12, 0, lane);  // wk = H12 Jpinv
   w_gemm<true, false>(6, 6, 12, tB, 12, wk, 12, tA, 6, 0, lane);      // tA = rpOmega
   w_copy(Wst, tA, 36, lane);
   if (chol_store_upper(Wst, 6, 6, o_pg + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
   w_copy(Wst, tA, 36, lane);
-  if (w_spd_inverse<6>(tA, 6, wk, lane)) {                            // covRel = rpOmega^-1
+  if (w_spd_inverse_regs<6>(tA, 6, lane)) {                            // covRel = rpOmega^-1
     w_copy(tA, Wst, 36, lane);
     if (w_inverse(tA, 6, 6, wk, lane)) status |= ISV_W_SINGULAR;
   }
@@ -337,7 +380,7 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
   __syncwarp();
   // ---- Schur complement over T0 (:1286-1288 with the landmarks already eliminated) -------------
   w_copy2d(tA, 6, S12 + 6 + 12 * 6, 12, 6, 6, lane);                  // tA = S[6:12,6:12]
-  if (w_spd_inverse<6>(tA, 6, wk, lane)) {
+  if (w_spd_inverse_regs<6>(tA, 6, lane)) {
     w_copy2d(tA, 6, S12 + 6 + 12 * 6, 12, 6, 6, lane);
     if (w_inverse(tA, 6, 6, wk, lane)) status |= ISV_W_SINGULAR;
   }
@@ -354,7 +397,7 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
   {
     double fa = 0.0, fi = 0.0;
     for (int i = lane; i < 36; i += 32) fa = fma(tA[i], tA[i], fa);
-    const int bad = w_spd_inverse<6>(tA, 6, wk, lane);
+    const int bad = w_spd_inverse_regs<6>(tA, 6, lane);
     for (int i = lane; i < 36; i += 32) fi = fma(tA[i], tA[i], fi);
     fa = warp_sum(fa);
     fi = warp_sum(fi);
@@ -401,7 +444,7 @@ marg_forward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg) {
     __syncwarp();
   }
   // sqrt_info = LLT(covi.inverse()).matrixL().transpose()  (:1349)
-  if (w_sqrt_info_from_cov<6>(tA, 6, o_se3 + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD | ISV_W_SINGULAR;
+  if (w_sqrt_info_from_cov_regs<6>(tA, 6, o_se3 + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD | ISV_W_SINGULAR;
   if (__any_sync(kFullMask, nonfinite)) status |= ISV_W_NONFINITE;
   // merge per-lane status bits
 #pragma unroll
@@ -597,7 +640,7 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
       cov[idx] = acc;
     }
     __syncwarp();
-    if (w_sqrt_info_from_cov<6>(cov, 6, o_rel + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+    if (w_sqrt_info_from_cov_regs<6>(cov, 6, o_rel + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
     for (int idx = lane; idx < 81; idx += 32) {
       int r = idx % 9, c = idx / 9;
       double acc = 0.0;
@@ -605,7 +648,7 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
       cov[idx] = acc;
     }
     __syncwarp();
-    if (w_sqrt_info_from_cov<9>(cov, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+    if (w_sqrt_info_from_cov_regs<9>(cov, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
     for (int idx = lane; idx < 4; idx += 32) {
       int r = idx % 2, c = idx / 2;
       double acc = 0.0;
@@ -613,7 +656,7 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
       cov[idx] = acc;
     }
     __syncwarp();
-    if (w_sqrt_info_from_cov<2>(cov, 2, o_rp + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+    if (w_sqrt_info_from_cov_regs<2>(cov, 2, o_rp + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
   } else {
     // ---- general path: eigen-decomposition (:1479-1497) by one-sided Jacobi on the rows of G ----
     if (w_onesided_jacobi_rows<4, 6>(G, 1, 15, 21, sc + 64, lane, 30, kMld) >= 30) status |= ISV_W_EIG_NOCONV;
@@ -644,7 +687,7 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
       cov[idx] = acc;
     }
     __syncwarp();
-    if (w_sqrt_info_from_cov<6>(cov, 6, o_rel + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+    if (w_sqrt_info_from_cov_regs<6>(cov, 6, o_rel + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
     for (int idx = lane; idx < 81; idx += 32) {
       int r = idx % 9, c = idx / 9;
       double acc = 0.0;
@@ -652,7 +695,7 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
       cov[idx] = acc;
     }
     __syncwarp();
-    if (w_sqrt_info_from_cov<9>(cov, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+    if (w_sqrt_info_from_cov_regs<9>(cov, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
     for (int idx = lane; idx < 2 * 15; idx += 32) {
       int r = idx % 2, k = idx / 2;
       double acc = 0.0;
@@ -667,7 +710,7 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
       cov[idx] = acc;
     }
     __syncwarp();
-    if (w_sqrt_info_from_cov<2>(cov, 2, o_rp + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+    if (w_sqrt_info_from_cov_regs<2>(cov, 2, o_rp + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
   }
   if (__any_sync(kFullMask, nonfinite)) status |= ISV_W_NONFINITE;
 #pragma unroll

@@ -139,26 +139,33 @@ class DeviceProblem:
         return {k: v.cpu().numpy() for k, v in self.out.items()}
 
 
-def eval_problem(backend, dp: DeviceProblem, cauchy_a: float = 0.0) -> None:
-    """Stream-ordered: the three Evaluate kernels over dp; results land in dp.out, flags in dp.status."""
+def eval_problem(backend, dp: DeviceProblem, cauchy_a: float = 0.0, fused_call: bool = True) -> None:
+    """Stream-ordered: the three Evaluate kernels over dp; results land in dp.out, flags in dp.status.
+    fused_call: one `isv_eval_problem` (IMU / prior kernels overlapped on side streams) instead of the
+    three per-class entry points back to back."""
     lib, h, t = backend.lib, backend.h, dp.t
     pb = dp.param_blocks()
     st = C.c_void_p(dp.status.data_ptr())
+    pf = capi.isv_proj_factors(dp.n_proj, dp.n_proj, t["proj_idx"].data_ptr(), t["proj_obs"].data_ptr(), cauchy_a)
+    po = capi.isv_proj_eval(dp._o("proj_res"), dp._o("proj_ji"), dp._o("proj_jj"), dp._o("proj_je"), dp._o("proj_jf"))
+    mf = capi.isv_imu_factors(dp.n_imu, t["imu_idx"].data_ptr(), t["imu_preint"].data_ptr())
+    mo = capi.isv_imu_eval(dp._o("imu_res"), dp._o("imu_jac"))
+    n = [t[k].shape[0] for k in ("rel_idx", "se3_idx", "vb_idx", "rp_idx", "yaw_idx")]
+    sf = capi.isv_small_factors(*n, t["rel_idx"].data_ptr(), t["rel_rec"].data_ptr(), t["se3_idx"].data_ptr(),
+                                t["se3_rec"].data_ptr(), t["vb_idx"].data_ptr(), t["vb_rec"].data_ptr(),
+                                t["rp_idx"].data_ptr(), t["rp_rec"].data_ptr(), t["yaw_idx"].data_ptr(),
+                                t["yaw_rec"].data_ptr(), cauchy_a)
+    so = capi.isv_small_eval(dp._o("rel_res"), dp._o("rel_jac"), dp._o("se3_res"), dp._o("se3_jac"),
+                             dp._o("vb_res"), dp._o("vb_jac"), dp._o("rp_res"), dp._o("rp_jac"),
+                             dp._o("yaw_res"), dp._o("yaw_jac"))
+    if fused_call:
+        capi.check(lib.isv_eval_problem(h, C.byref(pb), C.byref(pf) if dp.n_proj else None, C.byref(po),
+                                        C.byref(mf) if dp.n_imu else None, C.byref(mo),
+                                        C.byref(sf) if sum(n) else None, C.byref(so), st), "isv_eval_problem")
+        return
     if dp.n_proj:
-        pf = capi.isv_proj_factors(dp.n_proj, dp.n_proj, t["proj_idx"].data_ptr(), t["proj_obs"].data_ptr(), cauchy_a)
-        po = capi.isv_proj_eval(dp._o("proj_res"), dp._o("proj_ji"), dp._o("proj_jj"), dp._o("proj_je"), dp._o("proj_jf"))
         capi.check(lib.isv_eval_projection_batch(h, C.byref(pb), C.byref(pf), C.byref(po), st), "isv_eval_projection_batch")
     if dp.n_imu:
-        mf = capi.isv_imu_factors(dp.n_imu, t["imu_idx"].data_ptr(), t["imu_preint"].data_ptr())
-        mo = capi.isv_imu_eval(dp._o("imu_res"), dp._o("imu_jac"))
         capi.check(lib.isv_eval_imu_batch(h, C.byref(pb), C.byref(mf), C.byref(mo), st), "isv_eval_imu_batch")
-    n = [t[k].shape[0] for k in ("rel_idx", "se3_idx", "vb_idx", "rp_idx", "yaw_idx")]
     if sum(n):
-        sf = capi.isv_small_factors(*n, t["rel_idx"].data_ptr(), t["rel_rec"].data_ptr(), t["se3_idx"].data_ptr(),
-                                    t["se3_rec"].data_ptr(), t["vb_idx"].data_ptr(), t["vb_rec"].data_ptr(),
-                                    t["rp_idx"].data_ptr(), t["rp_rec"].data_ptr(), t["yaw_idx"].data_ptr(),
-                                    t["yaw_rec"].data_ptr(), cauchy_a)
-        so = capi.isv_small_eval(dp._o("rel_res"), dp._o("rel_jac"), dp._o("se3_res"), dp._o("se3_jac"),
-                                 dp._o("vb_res"), dp._o("vb_jac"), dp._o("rp_res"), dp._o("rp_jac"),
-                                 dp._o("yaw_res"), dp._o("yaw_jac"))
         capi.check(lib.isv_eval_small_batch(h, C.byref(pb), C.byref(sf), C.byref(so), st), "isv_eval_small_batch")

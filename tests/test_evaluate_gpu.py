@@ -57,7 +57,7 @@ def test_evaluate_ragged_tiled_and_null_blocks(backend):
     p = sim.make_problem(sim.seed_for(6, 1), n_features=37, max_track=5)
     fp = FactorProblem.from_factors(p).tile(3)
     dp = DeviceProblem(fp, "cuda:0", want_ex_jac=False)
-    eval_problem(backend, dp)
+    eval_problem(backend, dp, fused_call=False)   # the three per-class entry points
     backend.synchronize()
     assert int(dp.status.item()) == 0
     host = dp.host()
