@@ -327,6 +327,78 @@ isv_status isv_eval_problem(isv_handle* h, const isv_param_blocks* pb, const isv
                             const isv_proj_eval* po, const isv_imu_factors* mf, const isv_imu_eval* mo,
                             const isv_small_factors* sf, const isv_small_eval* so, int32_t* status);
 
+/* ---- device-resident factor state of n independent sequences ------------
+ * The members Estimator carries from frame to frame -- vioRelativePoseEdges[1..V-1], vioPosePriorEdge,
+ * vioVBPrior, vioRollPitchEdges (include/estimator.h:137-154) and the pose-graph accumulator
+ * `accumFactor` (src/pose_graph/pose_graph_builder.cpp:157) -- stay in HBM; per frame the host sends
+ * only states and observations.  One call per reference step:
+ *   isv_seq_init         initFactorGraph's sparsification tail + factor installation  :745-1001
+ *   isv_seq_update       factor->update(...) after problemSolve                       :1133-1144
+ *   isv_seq_yaw          double2vector()'s rotation of the two priors                 :520-550
+ *   isv_seq_marginalize  MargForward + MargBackward reading the priors from the state (:1149-1539),
+ *                        CombinedFactors::operator+ / keyframe cut (pose_graph_factors.h:27-51,
+ *                        pose_graph_builder.cpp:157-158,214), slideWindow()'s factor rotation (:1605-1638)
+ * All pointers are DEVICE pointers unless a name says host; calls are stream-ordered.              */
+#define ISV_ACC_REC 119        /* CombinedFactors as a POD record:                                  */
+#define ISV_ACC_COVREL 48      /*   delta_t[3] delta_R[9] sqrt_info[36] | covRel[36]                */
+#define ISV_ACC_DISTANCE 84    /*   distance, length, vio_index, pg_index, ts                       */
+#define ISV_ACC_LENGTH 85
+#define ISV_ACC_VIO_INDEX 86
+#define ISV_ACC_PG_INDEX 87
+#define ISV_ACC_TS 88
+#define ISV_ACC_RI 89          /*   Ri[9] (column-major), ti[3]                                     */
+#define ISV_ACC_TI 98
+#define ISV_ACC_RP_VALID 101   /*   rollPitchFactor != nullptr, its record R[9] sqrt_info[4]        */
+#define ISV_ACC_RP 102
+#define ISV_ACC_COVABS 115     /*   covAbs[4] of the last factor added (operator+ itself drops it)  */
+
+typedef struct isv_seq isv_seq;
+isv_status isv_seq_create(isv_handle* h, int n_sequences, isv_seq** out);
+void isv_seq_destroy(isv_handle* h, isv_seq* s);
+/* rank: device int32 [n] (#eigenvalues > alpha of the init marginal), may be NULL */
+isv_status isv_seq_init(isv_handle* h, isv_seq* s, const isv_init_in* in, int32_t* rank);
+
+typedef struct isv_seq_update_in {
+  const double* old_P;           /* [n][V][3]  Ps[0..V-1] before the solve                          */
+  const double* old_R;           /* [n][V][9]  Rs[0..V-1] before the solve (column-major)           */
+  const double* old_vb;          /* [n][9]     Vs, Bas, Bgs of frame V-1 before the solve           */
+  const double* pose;            /* [n][V][7]  para_Pose[0..V-1] after the solve                    */
+  const double* speed_bias;      /* [n][9]     para_SpeedBias[V-1] after the solve                  */
+} isv_seq_update_in;
+isv_status isv_seq_update(isv_handle* h, isv_seq* s, const isv_seq_update_in* in);
+/* old_R0 [n][9] = Rs[0] before the solve, pose0 [n][7] = para_Pose[0]; rot_diff_out [n][9] or NULL */
+isv_status isv_seq_yaw(isv_handle* h, isv_seq* s, const double* old_R0, const double* pose0, double* rot_diff_out);
+
+typedef struct isv_seq_frame {
+  int32_t ex_pose_shared;
+  const int64_t* lm_offset;      /* as isv_batch_in                                                 */
+  const double* lm_obs;
+  int64_t lm_stride;
+  const double* pose_fwd;        /* [n][2][7]                                                       */
+  const double* ex_pose;
+  const double* pose_bwd;        /* [n][2][7]                                                       */
+  const double* sb_bwd;          /* [n][2][9]                                                       */
+  const double* preint;          /* [n][467]                                                        */
+  const double* ts;              /* [n]    Headers[0]   } CombinedFactors members that do not come  */
+  const double* Ri;              /* [n][9] Rs[0]        } out of the kernels (:1277-1279); all three */
+  const double* ti;              /* [n][3] Ps[0]        } NULL = no pose-graph accumulation          */
+} isv_seq_frame;
+/* kf_out [n][ISV_ACC_REC] receives the accumulated factor of every sequence whose kf_flag [n] is set
+ * (accumFactor->distance > pg_cut_distance; the reference uses 0.1); both may be NULL.             */
+isv_status isv_seq_marginalize(isv_handle* h, isv_seq* s, const isv_seq_frame* f, double pg_cut_distance,
+                               double* kf_out, int32_t* kf_flag);
+
+/* blocking copies of the whole state to / from HOST memory (checkpoint / resume, tests).  Edge-major:
+ * rel [V][n][48] (slot 0 unused), rp [V][n][13] + rp_valid [V][n] (slot = factor index).  `last_*` are
+ * the outputs of the most recent isv_seq_marginalize.  NULL members are skipped.                   */
+typedef struct isv_seq_host {
+  double* rel; double* se3; double* vb; double* rp; int32_t* rp_valid; double* acc; int32_t* pg_count;
+  double* last_se3; double* last_pg; double* last_rel; double* last_vb; double* last_rp;
+  int32_t* last_rank; int32_t* last_status;
+} isv_seq_host;
+isv_status isv_seq_export_host(isv_handle* h, isv_seq* s, const isv_seq_host* out);
+isv_status isv_seq_import_host(isv_handle* h, isv_seq* s, const isv_seq_host* in);
+
 /* ---- unit-test hook: the PSD eigensolver that replaces SelfAdjointEigenSolver on this path -----
  * (src/estimator.cpp:920,1311,1479).  nb symmetric n x n matrices A (column-major, host) ->
  * G [nb][n][n] row-major factor rows with  A ~= sum_k g_k g_k^T, g_k mutually orthogonal;

@@ -7,6 +7,7 @@ from . import capi  # noqa: F401
 from .batch import WindowBatch, WindowOutputs, pack_events  # noqa: F401
 from .backend import DeviceBatch, MargBackend  # noqa: F401
 from .evaluate import DeviceProblem, FactorProblem, eval_problem  # noqa: F401
+from .sequence import SequenceState  # noqa: F401
 
 __all__ = ["capi", "WindowBatch", "WindowOutputs", "pack_events", "DeviceBatch", "MargBackend",
-           "FactorProblem", "DeviceProblem", "eval_problem"]
+           "FactorProblem", "DeviceProblem", "eval_problem", "SequenceState"]

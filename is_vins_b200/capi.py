@@ -16,6 +16,8 @@ ISV_OK, ISV_ERR_BAD_ARG, ISV_ERR_CUDA, ISV_ERR_ALLOC = 0, 1, 2, 3
 W_NOT_SPD, W_RANK_DEFICIENT, W_NONFINITE, W_NONUNIT_QUAT, W_EIG_NOCONV, W_SINGULAR = 1, 2, 4, 8, 16, 32
 W_BAD_INDEX = 64
 IMU_JAC_REC, YAW_REC = 480, 4
+ACC_REC, ACC_COVREL, ACC_DISTANCE, ACC_LENGTH, ACC_VIO_INDEX, ACC_PG_INDEX, ACC_TS = 119, 48, 84, 85, 86, 87, 88
+ACC_RI, ACC_TI, ACC_RP_VALID, ACC_RP, ACC_COVABS = 89, 98, 101, 102, 115
 RUN_FORWARD, RUN_BACKWARD, RUN_BOTH = 1, 2, 3
 POSE, SB, SE3_REC, REL_REC, VB_REC, RP_IN_REC, RP_REC, PG_REC, PREINT_REC = 7, 9, 48, 48, 90, 5, 13, 89, 467
 IMU_RAW_REC = 7
@@ -117,6 +119,23 @@ class isv_small_eval(C.Structure):
                 ("yaw_res", C.c_void_p), ("yaw_jac", C.c_void_p)]
 
 
+class isv_seq_update_in(C.Structure):
+    _fields_ = [("old_P", C.c_void_p), ("old_R", C.c_void_p), ("old_vb", C.c_void_p), ("pose", C.c_void_p),
+                ("speed_bias", C.c_void_p)]
+
+
+class isv_seq_frame(C.Structure):
+    _fields_ = [("ex_pose_shared", C.c_int32), ("lm_offset", C.c_void_p), ("lm_obs", C.c_void_p),
+                ("lm_stride", C.c_int64), ("pose_fwd", C.c_void_p), ("ex_pose", C.c_void_p),
+                ("pose_bwd", C.c_void_p), ("sb_bwd", C.c_void_p), ("preint", C.c_void_p), ("ts", C.c_void_p),
+                ("Ri", C.c_void_p), ("ti", C.c_void_p)]
+
+
+class isv_seq_host(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("rel", "se3", "vb", "rp", "rp_valid", "acc", "pg_count", "last_se3",
+                                          "last_pg", "last_rel", "last_vb", "last_rp", "last_rank", "last_status")]
+
+
 # every symbol include/isv_capi.h declares: (name, restype, argtypes)
 _H = C.c_void_p
 SYMBOLS = [
@@ -149,6 +168,14 @@ SYMBOLS = [
     ("isv_eval_problem", C.c_int, [_H, C.POINTER(isv_param_blocks), C.POINTER(isv_proj_factors),
                                    C.POINTER(isv_proj_eval), C.POINTER(isv_imu_factors), C.POINTER(isv_imu_eval),
                                    C.POINTER(isv_small_factors), C.POINTER(isv_small_eval), C.c_void_p]),
+    ("isv_seq_create", C.c_int, [_H, C.c_int, C.POINTER(C.c_void_p)]),
+    ("isv_seq_destroy", None, [_H, C.c_void_p]),
+    ("isv_seq_init", C.c_int, [_H, C.c_void_p, C.POINTER(isv_init_in), C.c_void_p]),
+    ("isv_seq_update", C.c_int, [_H, C.c_void_p, C.POINTER(isv_seq_update_in)]),
+    ("isv_seq_yaw", C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("isv_seq_marginalize", C.c_int, [_H, C.c_void_p, C.POINTER(isv_seq_frame), C.c_double, C.c_void_p, C.c_void_p]),
+    ("isv_seq_export_host", C.c_int, [_H, C.c_void_p, C.POINTER(isv_seq_host)]),
+    ("isv_seq_import_host", C.c_int, [_H, C.c_void_p, C.POINTER(isv_seq_host)]),
     ("isv_test_psd_eig", C.c_int, [_H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int32_p]),
 ]
 

@@ -12,6 +12,7 @@
 #include "isv_eval_kernels.cuh"
 #include "isv_init_kernel.cuh"
 #include "isv_preint_kernel.cuh"
+#include "isv_seq_kernels.cuh"
 #include "isv_window_kernels.cuh"
 
 using namespace isv;
@@ -715,4 +716,175 @@ extern "C" isv_status isv_eval_problem(isv_handle* h, const isv_param_blocks* pb
     cudaStreamWaitEvent(h->stream, h->aux_ev[2], 0);
   }
   return st;
+}
+
+// ---- device-resident sequence state ---------------------------------------------------------------------
+struct isv_seq {
+  SeqView v;
+  char* slab;
+  size_t bytes;
+  double* rel_init;   // [n][V-1][48] scratch of isv_seq_init
+  double* gram;       // [n][42]
+};
+
+extern "C" isv_status isv_seq_create(isv_handle* h, int n, isv_seq** out) {
+  if (!h || !out || n <= 0) return ISV_ERR_BAD_ARG;
+  *out = nullptr;
+  const int V = h->cfg.vo_size;
+  if (V < 2 || V > 10) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  isv_seq* s = new (std::nothrow) isv_seq();
+  if (!s) return ISV_ERR_ALLOC;
+  memset(s, 0, sizeof(*s));
+  const size_t D = sizeof(double), N = (size_t)n;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  const size_t o_rel = carve(V * N * ISV_REL_REC * D), o_se3 = carve(N * ISV_SE3_REC * D), o_vb = carve(N * ISV_VB_REC * D);
+  const size_t o_rp = carve(V * N * ISV_RP_REC * D), o_rpv = carve(V * N * 4), o_rpin = carve(N * ISV_RP_IN_REC * D);
+  const size_t o_acc = carve(N * ISV_ACC_REC * D), o_cnt = carve(N * 4);
+  const size_t o_se3o = carve(N * ISV_SE3_REC * D), o_pgo = carve(N * ISV_PG_REC * D), o_relo = carve(N * ISV_REL_REC * D);
+  const size_t o_vbo = carve(N * ISV_VB_REC * D), o_rpo = carve(N * ISV_RP_REC * D), o_rank = carve(N * 8), o_st = carve(N * 4);
+  const size_t o_ri = carve(N * (V - 1) * ISV_REL_REC * D), o_gram = carve(N * 42 * D);
+  if (cudaMalloc(&s->slab, off) != cudaSuccess) {
+    cudaGetLastError();
+    delete s;
+    return ISV_ERR_ALLOC;
+  }
+  s->bytes = off;
+  cudaMemsetAsync(s->slab, 0, off, h->stream);
+  char* d = s->slab;
+  s->v = SeqView{n, V, (double*)(d + o_rel), (double*)(d + o_se3), (double*)(d + o_vb), (double*)(d + o_rp),
+                 (int32_t*)(d + o_rpv), (double*)(d + o_rpin), (double*)(d + o_acc), (int32_t*)(d + o_cnt),
+                 (double*)(d + o_se3o), (double*)(d + o_pgo), (double*)(d + o_relo), (double*)(d + o_vbo),
+                 (double*)(d + o_rpo), (int32_t*)(d + o_rank), (int32_t*)(d + o_st)};
+  s->rel_init = (double*)(d + o_ri);
+  s->gram = (double*)(d + o_gram);
+  *out = s;
+  return ISV_OK;
+}
+
+extern "C" void isv_seq_destroy(isv_handle* h, isv_seq* s) {
+  if (!s) return;
+  if (h) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+  }
+  if (s->slab) cudaFree(s->slab);
+  delete s;
+}
+
+extern "C" isv_status isv_seq_init(isv_handle* h, isv_seq* s, const isv_init_in* in, int32_t* rank) {
+  if (!h || !s || !in || in->n_windows != s->v.n) return ISV_ERR_BAD_ARG;
+  isv_init_out o = {s->rel_init, s->v.se3, s->v.vb, rank ? rank : s->v.rank, s->v.status};
+  ISV_CUDA(cudaMemsetAsync(s->v.status, 0, sizeof(int32_t) * (size_t)s->v.n, h->stream));
+  isv_status st = isv_init_sparsify_batch(h, in, &o);
+  if (st != ISV_OK) return st;
+  seq_install_kernel<<<s->v.n, 64, 0, h->stream>>>(s->v, s->rel_init);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+extern "C" isv_status isv_seq_update(isv_handle* h, isv_seq* s, const isv_seq_update_in* in) {
+  if (!h || !s || !in || !in->old_P || !in->old_R || !in->old_vb || !in->pose || !in->speed_bias) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const long long total = (long long)s->v.n * (2 + (s->v.V - 1) + s->v.V);
+  seq_update_kernel<<<(unsigned)((total + 127) / 128), 128, 0, h->stream>>>(s->v, in->old_P, in->old_R, in->old_vb, in->pose,
+                                                                          in->speed_bias);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+extern "C" isv_status isv_seq_yaw(isv_handle* h, isv_seq* s, const double* old_R0, const double* pose0,
+                                  double* rot_diff_out) {
+  if (!h || !s || !old_R0 || !pose0) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  seq_yaw_kernel<<<(s->v.n + 127) / 128, 128, 0, h->stream>>>(s->v, old_R0, pose0, rot_diff_out);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+extern "C" isv_status isv_seq_marginalize(isv_handle* h, isv_seq* s, const isv_seq_frame* f, double pg_cut_distance,
+                                          double* kf_out, int32_t* kf_flag) {
+  if (!h || !s || !f) return ISV_ERR_BAD_ARG;
+  const bool pg = f->ts || f->Ri || f->ti;
+  if (pg && (!f->ts || !f->Ri || !f->ti)) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const SeqView& v = s->v;
+  isv_batch_in bi;
+  memset(&bi, 0, sizeof(bi));
+  bi.n_windows = v.n;
+  bi.ex_pose_shared = f->ex_pose_shared;
+  bi.lm_offset = f->lm_offset;
+  bi.lm_obs = f->lm_obs;
+  bi.lm_stride = f->lm_stride;
+  bi.pose_fwd = f->pose_fwd;
+  bi.ex_pose = f->ex_pose;
+  bi.prior_se3 = v.se3;                                      // vioPosePriorEdge
+  bi.prior_rel = v.rel + (size_t)v.n * ISV_REL_REC;          // vioRelativePoseEdges[1]
+  bi.prior_rp = v.rp_in;                                     // vioRollPitchEdges[0] if its index is 0
+  bi.pose_bwd = f->pose_bwd;
+  bi.sb_bwd = f->sb_bwd;
+  bi.prior_vb = v.vb;                                        // vioVBPrior
+  bi.preint = f->preint;
+  isv_batch_out bo = {v.se3_out, v.pg_out, v.rel_out, v.vb_out, v.rp_out, v.rank, v.status};
+  isv_status st = check_batch(&bi, &bo, ISV_RUN_BOTH);
+  if (st != ISV_OK) return st;
+  st = launch_batch(h, &bi, &bo, ISV_RUN_BOTH, h->stream, s->gram);
+  if (st != ISV_OK) return st;
+  if (pg) {
+    const int wpc = 4;
+    seq_pg_kernel<<<(v.n + wpc - 1) / wpc, 32 * wpc, wpc * kPgSmemPerWarp * sizeof(double), h->stream>>>(
+        v, f->ts, f->Ri, f->ti, pg_cut_distance, kf_out, kf_flag);
+    ++h->launches;
+  }
+  seq_rotate_kernel<<<v.n, 64, 0, h->stream>>>(v);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+static isv_status seq_copy(isv_handle* h, isv_seq* s, const isv_seq_host* x, bool to_host) {
+  if (!h || !s || !x) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const SeqView& v = s->v;
+  const size_t D = sizeof(double), N = (size_t)v.n, V = (size_t)v.V;
+  struct Item { void* host; void* dev; size_t bytes; };
+  const Item items[] = {
+      {x->rel, v.rel, V * N * ISV_REL_REC * D}, {x->se3, v.se3, N * ISV_SE3_REC * D}, {x->vb, v.vb, N * ISV_VB_REC * D},
+      {x->rp, v.rp, V * N * ISV_RP_REC * D}, {x->rp_valid, v.rp_valid, V * N * 4}, {x->acc, v.acc, N * ISV_ACC_REC * D},
+      {x->pg_count, v.pg_count, N * 4}, {x->last_se3, v.se3_out, N * ISV_SE3_REC * D}, {x->last_pg, v.pg_out, N * ISV_PG_REC * D},
+      {x->last_rel, v.rel_out, N * ISV_REL_REC * D}, {x->last_vb, v.vb_out, N * ISV_VB_REC * D},
+      {x->last_rp, v.rp_out, N * ISV_RP_REC * D}, {x->last_rank, v.rank, N * 8}, {x->last_status, v.status, N * 4}};
+  for (const Item& it : items) {
+    if (!it.host) continue;
+    if (to_host) ISV_CUDA(cudaMemcpyAsync(it.host, it.dev, it.bytes, cudaMemcpyDeviceToHost, h->stream));
+    else ISV_CUDA(cudaMemcpyAsync(it.dev, it.host, it.bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (!to_host && x->rp && x->rp_valid) {
+    // rebuild the packed slot-0 record the forward kernel reads
+    // (done on the host side of the copy: valid flag + sqrt_info of slot 0)
+    double* tmp = (double*)malloc(N * ISV_RP_IN_REC * D);
+    if (!tmp) return ISV_ERR_ALLOC;
+    for (size_t q = 0; q < N; ++q) {
+      const int ok = x->rp_valid[q] != 0;
+      tmp[q * ISV_RP_IN_REC] = ok ? 1.0 : 0.0;
+      for (int k = 0; k < 4; ++k) tmp[q * ISV_RP_IN_REC + 1 + k] = ok ? x->rp[q * ISV_RP_REC + 9 + k] : 0.0;
+    }
+    cudaError_t e = cudaMemcpyAsync(v.rp_in, tmp, N * ISV_RP_IN_REC * D, cudaMemcpyHostToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);
+    free(tmp);
+    if (e != cudaSuccess) return ISV_ERR_CUDA;
+  }
+  ISV_CUDA(cudaStreamSynchronize(h->stream));
+  return ISV_OK;
+}
+
+extern "C" isv_status isv_seq_export_host(isv_handle* h, isv_seq* s, const isv_seq_host* out) {
+  return seq_copy(h, s, out, true);
+}
+extern "C" isv_status isv_seq_import_host(isv_handle* h, isv_seq* s, const isv_seq_host* in) {
+  return seq_copy(h, s, in, false);
 }

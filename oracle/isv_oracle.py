@@ -1055,6 +1055,22 @@ class CombinedFactors:
         return self
 
 
+def double2vector_rot_diff(Rs0, pose0) -> np.ndarray:
+    """Estimator::double2vector  src/estimator.cpp:520-546 : the yaw re-anchoring rotation `rot_diff`
+    (Rs[0] = orientation of frame 0 before the solve, pose0 = para_Pose[0] after it).  The caller
+    applies it to the prior factors as :549-550 does:  vioVBPrior->VB.tail<3>() (Q17: the gyro-bias
+    slot) and vioPosePriorEdge->R are pre-multiplied by it."""
+    Rs0 = np.asarray(Rs0, dtype=np.float64)
+    R00 = q_to_R(quat_from_pose(pose0))
+    origin_R0 = R2ypr(Rs0)
+    origin_R00 = R2ypr(R00)
+    y_diff = origin_R0[0] - origin_R00[0]
+    rot_diff = ypr2R(np.array([y_diff, 0.0, 0.0]))
+    if abs(abs(origin_R0[1]) - 90) < 1.0 or abs(abs(origin_R00[1]) - 90) < 1.0:
+        rot_diff = Rs0 @ R00.T
+    return rot_diff
+
+
 # ----------------------------------------------------------------------------------------------
 # Index maps ("OrderMap") -- the bit-exact contract (SURVEY.md 8a row 13)
 # ----------------------------------------------------------------------------------------------

@@ -177,6 +177,12 @@ class MargEvent:
     gyr0: np.ndarray
     fwd_out: Optional[O.ForwardOutput] = None
     bwd_out: Optional[O.BackwardOutput] = None
+    # what the steps around Marg* read (device-resident sequence tests): the states before the solve
+    # (Ps/Rs/Vs/Bas/Bgs) and after it (para_*), the yaw re-anchoring rotation, the pose-graph record
+    upd: Optional[dict] = None
+    rot_diff: Optional[np.ndarray] = None
+    pg_meta: Optional[dict] = None
+    state_after: Optional[dict] = None   # factor members after slideWindow's rotation
 
 
 @dataclass
@@ -188,10 +194,14 @@ class Chain:
 
 
 def _perturb_and_update(rng, frames_win: List[Frame], prior: O.SE3PriorFactor, rels: List[O.RelativePoseFactor],
-                        vbp: O.Linear9Factor, rps: List[O.RollPitchFactor], V: int, scale: float):
+                        vbp: O.Linear9Factor, rps: List[O.RollPitchFactor], V: int, scale: float, rec: Optional[dict] = None):
     """Mimic problemSolve(): states move a little, then factor->update re-centres the
     pseudo-measurements  (src/estimator.cpp:1133-1144)."""
     old = [(f.P.copy(), O.q_to_R(f.Q), f.V.copy(), f.Ba.copy(), f.Bg.copy()) for f in frames_win]
+    if rec is not None:
+        rec["old_P"] = np.array([o[0] for o in old[:V]])
+        rec["old_R"] = np.array([o[1] for o in old[:V]])
+        rec["old_vb"] = np.concatenate([old[V - 1][2], old[V - 1][3], old[V - 1][4]])
     for f in frames_win:
         f.P = f.P + rng.normal(0, 0.003 * scale, 3)
         f.Q = O.q_normalized(O.q_mul(f.Q, O.SO3.exp(rng.normal(0, 0.0005 * scale, 3)).q))
@@ -205,11 +215,21 @@ def _perturb_and_update(rng, frames_win: List[Frame], prior: O.SE3PriorFactor, r
         rels[j].update(old[i][0], old[i][1], old[j][0], old[j][1], frames_win[i].pose(), frames_win[j].pose())
     for rp in rps:
         rp.update(old[rp.index][1], frames_win[rp.index].pose())
+    if rec is not None:
+        rec["new_pose"] = np.array([f.pose() for f in frames_win[:V]])
+        rec["new_sb"] = frames_win[V - 1].sb()
+
+
+def _factor_state(V, prior, rels, vbp, rps):
+    return {"se3": (prior.t.copy(), prior.R.copy(), prior.sqrt_info.copy()),
+            "vb": (vbp.VB.copy(), vbp.sqrt_info.copy()),
+            "rel": {i: (rels[i].delta_t.copy(), rels[i].delta_R.copy(), rels[i].sqrt_info.copy()) for i in range(1, V)},
+            "rp": {rp.index: (rp.R.copy(), rp.sqrt_info.copy()) for rp in rps}}
 
 
 def make_chain(seed: int, L, rounds: int = 2, cfg: Optional[O.Config] = None, K: int = 10,
                max_gap: int = 1, run_oracle: bool = True, perturb: float = 1.0,
-               structured: bool = False) -> Chain:
+               structured: bool = False, with_yaw: bool = False) -> Chain:
     """Run init_sparsify on V frames, then `rounds` MARGIN_OLD events.  L: int or list of ints."""
     cfg = cfg or O.Config()
     V = cfg.vo_size
@@ -237,7 +257,15 @@ def make_chain(seed: int, L, rounds: int = 2, cfg: Optional[O.Config] = None, K:
     events: List[MargEvent] = []
     for r in range(rounds):
         win = frames[r:r + V + 1]
-        _perturb_and_update(rng, win, prior, rels, vbp, rps, V, perturb)
+        upd: dict = {}
+        _perturb_and_update(rng, win, prior, rels, vbp, rps, V, perturb, upd)
+        rot_diff = None
+        if with_yaw:
+            # double2vector (:520-550): the prior factors are rotated by the yaw correction; Marg* then
+            # read para_* (not rotated) and these rotated members (Q17)
+            rot_diff = O.double2vector_rot_diff(upd["old_R"][0], win[0].pose())
+            vbp.VB[6:9] = rot_diff @ vbp.VB[6:9]
+            prior.R = rot_diff @ prior.R
         inv_dep, pts_i, pts_j = make_landmarks(rng, cfg, win[0], win[1], Ls[r], expose)
         rp_valid = bool(rps) and rps[0].index == 0
         fin = O.ForwardInput(win[0].pose(), win[1].pose(), expose, inv_dep, pts_i, pts_j,
@@ -246,7 +274,10 @@ def make_chain(seed: int, L, rounds: int = 2, cfg: Optional[O.Config] = None, K:
                              rp_valid, rps[0].sqrt_info.copy() if rp_valid else None)
         bin_ = O.BackwardInput(win[V - 1].pose(), win[V - 1].sb(), win[V].pose(), win[V].sb(),
                                vbp.VB.copy(), vbp.sqrt_info.copy(), win[V].pre)
-        ev = MargEvent(fin, bin_, win[V].raw, win[V].acc0, win[V].gyr0)
+        ev = MargEvent(fin, bin_, win[V].raw, win[V].acc0, win[V].gyr0, upd=upd, rot_diff=rot_diff)
+        # CombinedFactors members that do not come out of the kernels (:1275-1279)
+        ev.pg_meta = {"ts": float(win[0].t), "Ri": upd["old_R"][0].copy(), "ti": upd["old_P"][0].copy(),
+                      "rp": (rps[0].R.copy(), rps[0].sqrt_info.copy()) if rp_valid else None}
         fo = O.marg_forward(fin, cfg, structured=structured)
         bo = O.marg_backward(bin_, cfg)
         if run_oracle:
@@ -277,6 +308,7 @@ def make_chain(seed: int, L, rounds: int = 2, cfg: Optional[O.Config] = None, K:
         nrp.sqrt_info = bo.rp_sqrt_info
         nrp.setIndex(V - 2)      # pushed with index V-1 (:1516), then shifted by slideWindow
         rps.append(nrp)
+        ev.state_after = _factor_state(V, prior, rels, vbp, rps)
     return Chain(cfg, init_in, init_out, events)
 
 
