@@ -139,6 +139,11 @@ typedef struct isv_batch_out {
 #define ISV_RUN_FORWARD  1
 #define ISV_RUN_BACKWARD 2
 #define ISV_RUN_BOTH     3
+/* profiling aids: the two stages of MargForward on their own.  STAGE1 = landmark phase (Jacobians +
+ * Gram accumulation, leaves its result in the handle's scratch), STAGE2 = the 12x12 / 6x6 tail that
+ * consumes the scratch of the preceding STAGE1 call on the same handle and batch.                */
+#define ISV_RUN_FORWARD_STAGE1 4
+#define ISV_RUN_FORWARD_STAGE2 8
 
 /* stream-ordered, asynchronous; `which` selects MargForward / MargBackward / both.
  * Unused inputs/outputs of a skipped half may be NULL.                                          */

@@ -19,6 +19,7 @@ IMU_JAC_REC, YAW_REC = 480, 4
 ACC_REC, ACC_COVREL, ACC_DISTANCE, ACC_LENGTH, ACC_VIO_INDEX, ACC_PG_INDEX, ACC_TS = 119, 48, 84, 85, 86, 87, 88
 ACC_RI, ACC_TI, ACC_RP_VALID, ACC_RP, ACC_COVABS = 89, 98, 101, 102, 115
 RUN_FORWARD, RUN_BACKWARD, RUN_BOTH = 1, 2, 3
+RUN_FORWARD_STAGE1, RUN_FORWARD_STAGE2 = 4, 8
 POSE, SB, SE3_REC, REL_REC, VB_REC, RP_IN_REC, RP_REC, PG_REC, PREINT_REC = 7, 9, 48, 48, 90, 5, 13, 89, 467
 IMU_RAW_REC = 7
 

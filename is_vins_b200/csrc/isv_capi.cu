@@ -181,9 +181,11 @@ int isv_order_map_backward(int V, int32_t* out) {
 
 // ---- batched device entry point ---------------------------------------------------------------
 static isv_status check_batch(const isv_batch_in* in, const isv_batch_out* out, int which) {
-  if (!in || !out || in->n_windows < 0 || (which & ~ISV_RUN_BOTH) || which == 0) return ISV_ERR_BAD_ARG;
+  if (!in || !out || in->n_windows < 0 || (which & ~(ISV_RUN_BOTH | ISV_RUN_FORWARD_STAGE1 | ISV_RUN_FORWARD_STAGE2)) ||
+      which == 0)
+    return ISV_ERR_BAD_ARG;
   if (!out->rank) return ISV_ERR_BAD_ARG;
-  if (which & ISV_RUN_FORWARD) {
+  if (which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE1 | ISV_RUN_FORWARD_STAGE2)) {
     if (!in->lm_offset || !in->pose_fwd || !in->ex_pose || !in->prior_se3 || !in->prior_rel || !out->se3_out ||
         !out->pg_out)
       return ISV_ERR_BAD_ARG;
@@ -203,13 +205,17 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in, const isv_
   if (n == 0) return ISV_OK;
   if (out->status) ISV_CUDA(cudaMemsetAsync(out->status, 0, sizeof(int32_t) * (size_t)n, stream));
   const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-  if (which & ISV_RUN_FORWARD) {
+  if (which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE1)) {
     if (!gram) return ISV_ERR_BAD_ARG;
     marg_forward_accum_kernel<<<grid, kThreads, kWarpsPerCta * kAccSmemPerWarp * sizeof(double), stream>>>(
         *in, gram, out->status, h->dcfg);
+    ++h->launches;
+  }
+  if (which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE2)) {
+    if (!gram) return ISV_ERR_BAD_ARG;
     marg_forward_tail_kernel<<<grid, kThreads, kWarpsPerCta * kFwdSmemPerWarp * sizeof(double), stream>>>(*in, *out, gram,
                                                                                                         h->dcfg);
-    h->launches += 2;
+    ++h->launches;
   }
   if (which & ISV_RUN_BACKWARD) {
     marg_backward_kernel<<<grid, kThreads, kWarpsPerCta * kBwdSmemPerWarp * sizeof(double), stream>>>(*in, *out, h->dcfg,
@@ -226,7 +232,7 @@ isv_status isv_marg_window_batch(isv_handle* h, const isv_batch_in* in, const is
   if (st != ISV_OK) return st;
   ISV_CUDA(cudaSetDevice(h->device));
   double* gram = nullptr;
-  if (which & ISV_RUN_FORWARD) {
+  if (which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE1 | ISV_RUN_FORWARD_STAGE2)) {
     const size_t need = (size_t)in->n_windows * 42 * sizeof(double);
     if (h->gram_bytes < need) {
       if (h->gram) {
@@ -268,6 +274,7 @@ static isv_status ensure_dbuf(isv_handle* h, size_t bytes) {
 
 isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, int which) {
   if (!h) return ISV_ERR_BAD_ARG;
+  if (which & ~ISV_RUN_BOTH) return ISV_ERR_BAD_ARG;   // the stage flags are device-path profiling aids
   isv_status st = check_batch(in, out, which);
   if (st != ISV_OK) return st;
   const size_t n = (size_t)in->n_windows;
