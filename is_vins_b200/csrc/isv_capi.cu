@@ -32,8 +32,9 @@ struct isv_handle {
   size_t dbuf_bytes;
   char* pinned;
   size_t pinned_bytes;
-  double* gram;          // [n][42] landmark Gram triangles (forward kernel 1 -> kernel 2), grow-only
-  size_t gram_bytes;
+  double* gram;          // [n][42 + kFJ] scratch handed between the kernels of one batch, grow-only:
+  size_t gram_bytes;     //   landmark Gram triangles (forward stage 1 -> 2) and the factor-Jacobian records
+  cudaEvent_t jac_ev[4]; // fork / join of the factor-Jacobian pre-kernel, one pair per launching stream
   cudaEvent_t ev[4];
 };
 
@@ -108,6 +109,7 @@ isv_status isv_create(const isv_config* cfg, int device, isv_handle** out) {
   for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
   for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
   for (int i = 0; i < 3; ++i) cudaEventCreateWithFlags(&h->aux_ev[i], cudaEventDisableTiming);
+  for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&h->jac_ev[i], cudaEventDisableTiming);
   h->stream = h->own_stream;
   cudaFuncSetAttribute(marg_forward_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kWarpsPerCta * kAccSmemPerWarp * sizeof(double)));
@@ -132,6 +134,8 @@ void isv_destroy(isv_handle* h) {
     if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
   for (int i = 0; i < 3; ++i)
     if (h->aux_ev[i]) cudaEventDestroy(h->aux_ev[i]);
+  for (int i = 0; i < 4; ++i)
+    if (h->jac_ev[i]) cudaEventDestroy(h->jac_ev[i]);
   cudaStreamDestroy(h->own_stream);
   cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -198,30 +202,56 @@ static isv_status check_batch(const isv_batch_in* in, const isv_batch_out* out, 
   return ISV_OK;
 }
 
-// gram: device scratch [n_windows][42] handed from the landmark kernel to the tail kernel
+// scratch: device memory [n_windows][kScratchPerWindow]: the landmark Gram triangles (42) handed from the
+// landmark kernel to the tail kernel, then the factor-Jacobian records (kFJ) of marg_factor_jac_kernel
+constexpr size_t kScratchPerWindow = 42 + kFJ;
+
 static isv_status launch_batch(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, int which,
-                               cudaStream_t stream, double* gram) {
+                               cudaStream_t stream, double* scratch) {
   const int n = in->n_windows;
   if (n == 0) return ISV_OK;
+  if (!scratch) return ISV_ERR_BAD_ARG;
+  double* gram = scratch;
+  double* fj = scratch + (size_t)n * 42;
+  const bool stage1 = which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE1);
+  const bool stage2 = which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE2);
+  const bool bwd = which & ISV_RUN_BACKWARD;
   if (out->status) ISV_CUDA(cudaMemsetAsync(out->status, 0, sizeof(int32_t) * (size_t)n, stream));
   const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-  if (which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE1)) {
-    if (!gram) return ISV_ERR_BAD_ARG;
+  // MargForward and MargBackward are independent: when both run, the backward chain (factor
+  // Jacobians -> marg_backward_kernel) is forked onto a side stream so that its latency-bound CTAs share
+  // the SMs with the FP64-bound landmark kernel, and joined back at the end.
+  const bool fork = bwd && (stage1 || stage2);
+  const int slot = (stream == h->copy_stream) ? 1 : 0;
+  cudaStream_t bs = fork ? h->aux[slot] : stream;
+  if (fork) {
+    ISV_CUDA(cudaEventRecord(h->jac_ev[2 * slot], stream));
+    ISV_CUDA(cudaStreamWaitEvent(bs, h->jac_ev[2 * slot], 0));
+  }
+  if (bwd) {
+    // the IMU Jacobian record is sparse: zero-fill it, the kernel writes the non-zero blocks
+    ISV_CUDA(cudaMemset2DAsync(fj + kFJ_IMU, kFJ * sizeof(double), 0, 450 * sizeof(double), (size_t)n, bs));
+    marg_factor_jac_kernel<<<dim3((n + 127) / 128, 3), 128, 0, bs>>>(*in, *out, fj, h->dcfg, 4);
+    marg_backward_kernel<<<grid, kThreads, kWarpsPerCta * kBwdSmemPerWarp * sizeof(double), bs>>>(*in, *out, fj, h->dcfg,
+                                                                                                 h->cfg.vo_size);
+    h->launches += 2;
+    if (fork) ISV_CUDA(cudaEventRecord(h->jac_ev[2 * slot + 1], bs));
+  }
+  if (stage2) {
+    marg_factor_jac_kernel<<<dim3((n + 127) / 128, 4), 128, 0, stream>>>(*in, *out, fj, h->dcfg, 0);
+    ++h->launches;
+  }
+  if (stage1) {
     marg_forward_accum_kernel<<<grid, kThreads, kWarpsPerCta * kAccSmemPerWarp * sizeof(double), stream>>>(
         *in, gram, out->status, h->dcfg);
     ++h->launches;
   }
-  if (which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE2)) {
-    if (!gram) return ISV_ERR_BAD_ARG;
+  if (stage2) {
     marg_forward_tail_kernel<<<grid, kThreads, kWarpsPerCta * kFwdSmemPerWarp * sizeof(double), stream>>>(*in, *out, gram,
-                                                                                                        h->dcfg);
+                                                                                                        fj, h->dcfg);
     ++h->launches;
   }
-  if (which & ISV_RUN_BACKWARD) {
-    marg_backward_kernel<<<grid, kThreads, kWarpsPerCta * kBwdSmemPerWarp * sizeof(double), stream>>>(*in, *out, h->dcfg,
-                                                                                                    h->cfg.vo_size);
-    ++h->launches;
-  }
+  if (fork) ISV_CUDA(cudaStreamWaitEvent(stream, h->jac_ev[2 * slot + 1], 0));
   ISV_CUDA(cudaGetLastError());
   return ISV_OK;
 }
@@ -232,8 +262,8 @@ isv_status isv_marg_window_batch(isv_handle* h, const isv_batch_in* in, const is
   if (st != ISV_OK) return st;
   ISV_CUDA(cudaSetDevice(h->device));
   double* gram = nullptr;
-  if (which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE1 | ISV_RUN_FORWARD_STAGE2)) {
-    const size_t need = (size_t)in->n_windows * 42 * sizeof(double);
+  {
+    const size_t need = (size_t)in->n_windows * kScratchPerWindow * sizeof(double);
     if (h->gram_bytes < need) {
       if (h->gram) {
         ISV_CUDA(cudaStreamSynchronize(h->stream));
@@ -305,7 +335,7 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   const size_t o_rp = carve(bwd ? n * ISV_RP_REC * D : 0);
   const size_t o_rank = carve(n * 2 * sizeof(int32_t));
   const size_t o_stat = carve(n * sizeof(int32_t));
-  const size_t o_gram = carve(fwd ? n * 42 * D : 0);
+  const size_t o_gram = carve(n * kScratchPerWindow * D);   // per-chunk slices: [w0 * kScratchPerWindow ...)
   st = ensure_dbuf(h, off);
   if (st != ISV_OK) return st;
   char* d = h->dbuf;
@@ -384,7 +414,7 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     }
     dout.rank = (int32_t*)(d + o_rank) + 2 * w0;
     dout.status = (int32_t*)(d + o_stat) + w0;
-    st = launch_batch(h, &din, &dout, which, s, fwd ? (double*)(d + o_gram) + w0 * 42 : nullptr);
+    st = launch_batch(h, &din, &dout, which, s, (double*)(d + o_gram) + w0 * kScratchPerWindow);
     if (st != ISV_OK) return st;
     if (fwd) {
       ISV_CUDA(cudaMemcpyAsync(out->se3_out + w0 * ISV_SE3_REC, dout.se3_out, m * ISV_SE3_REC * D, cudaMemcpyDeviceToHost, s));
@@ -751,7 +781,7 @@ extern "C" isv_status isv_seq_create(isv_handle* h, int n, isv_seq** out) {
   const size_t o_acc = carve(N * ISV_ACC_REC * D), o_cnt = carve(N * 4);
   const size_t o_se3o = carve(N * ISV_SE3_REC * D), o_pgo = carve(N * ISV_PG_REC * D), o_relo = carve(N * ISV_REL_REC * D);
   const size_t o_vbo = carve(N * ISV_VB_REC * D), o_rpo = carve(N * ISV_RP_REC * D), o_rank = carve(N * 8), o_st = carve(N * 4);
-  const size_t o_ri = carve(N * (V - 1) * ISV_REL_REC * D), o_gram = carve(N * 42 * D);
+  const size_t o_ri = carve(N * (V - 1) * ISV_REL_REC * D), o_gram = carve(N * kScratchPerWindow * D);
   if (cudaMalloc(&s->slab, off) != cudaSuccess) {
     cudaGetLastError();
     delete s;

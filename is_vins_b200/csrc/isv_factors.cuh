@@ -131,7 +131,7 @@ __device__ inline void qleft_qright_br(const Quat& a, const Quat& b, double* M) 
     }
 }
 
-// Unweighted IMU Jacobians in WINDOW column order.  Jfull: 15 x 30 column-major (ld ldj), columns
+// Unweighted IMU Jacobians in WINDOW column order.  Jfull: 15 x 30, column-major (ld ldj) by default, columns
 // [col_j_pose .. +6) <- d r / d T_j, [col_j_sb .. +9) <- d r / d VB_j, likewise for i.
 // pre: the 467-double pre-integration record (include/isv_capi.h ISV_PREINT_REC).  res: 15 or null.
 // Cooperative form: called by `nparts` lanes with part = 0..nparts-1; every lane evaluates the short
@@ -140,7 +140,7 @@ __device__ inline void qleft_qright_br(const Quat& a, const Quat& b, double* M) 
 __device__ inline void imu_jacobians(const double* PSi, const double* VBi, const double* PSj, const double* VBj,
                                      const double* __restrict__ pre, const double* G, double* Jfull, int ldj,
                                      int col_i_pose, int col_i_sb, int col_j_pose, int col_j_sb, double* res,
-                                     int part = 0, int nparts = 1) {
+                                     int part = 0, int nparts = 1, int row_stride = 1) {
   const double* delta_p = pre;
   Quat dq{pre[6], pre[3], pre[4], pre[5]};
   const double* delta_v = pre + 7;
@@ -190,7 +190,8 @@ __device__ inline void imu_jacobians(const double* PSi, const double* VBi, const
   qleft_qright_br(QjinvQi, cq, QLR);
   qleft_br(qmul(QjinvQi, dq), QL1);                       // Q9: uncorrected delta_q
   qleft_br(qmul(qmul(qinv(cq), Qi_inv), Qj), QL2);
-  auto put = [&](int row, int col, double v) { Jfull[row + ldj * col] = v; };
+  // element (row, col) at Jfull[row * row_stride + col * ldj]: (1, ld) = column-major, (ld, 1) = row-major
+  auto put = [&](int row, int col, double v) { Jfull[row * row_stride + ldj * col] = v; };
   for (int rc = part; rc < 9; rc += nparts) {
       const int r = rc / 3, c = rc - 3 * r;
       // d / d T_i   (15x6)

@@ -42,8 +42,7 @@ constexpr int kFwdConst = 72;                // Psi (12 x 6)
 constexpr int kFwdWork = 832;                // tail matrices
 constexpr int kFwdSmemPerWarp = kFwdConst + kFwdWork;
 // ---- backward ---------------------------------------------------------------------------------
-constexpr int kBwdScratch = 136;
-constexpr int kBwdSmemPerWarp = 750 + 225 + kBwdScratch;
+constexpr int kBwdSmemPerWarp = 240 + 24 + 315 + 425 + 48;   // Lc | hv | Gs | T | sc (isv_window_kernels.cuh)
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -68,6 +67,148 @@ __device__ __forceinline__ int chol_store_upper(double* M, int ld, int n, double
   }
   __syncwarp();
   return bad;
+}
+
+// =================================================================================================
+// Factor-Jacobian pre-kernel.  Everything in Marg* that is ONE short scalar chain per window -- the
+// tangent twins of the prior / recovered factors and of the IMU factor (SO(3) log / Jr^-1 with their
+// transcendental calls), the records that are pure functions of the poses -- is evaluated here with
+// one THREAD per window instead of one lane of a warp per window, and handed to the window kernels
+// through a [n][kFJ] scratch.  Inside the warp-per-window kernels the same work kept 31 lanes idle for
+// ~1.5-1.8 k instructions of a latency-bound chain.  Measured alternatives that were slower: the IMU factor split 9 ways over threads
+// (redundant strided header loads), a coalesced warp-per-window IMU kernel (45 us), __launch_bounds__
+// for more resident CTAs (spills).
+//   tasks 0-3 (forward):  Wst (12x12) = [ sp [0 | Jp] ; sr [Jj | Ji] ]  (:1203-1238),
+//       G (6x12) = [Ji | Jj] of the pose-graph RelativePoseFactor (:1244-1255), Jr6 of the new
+//       SE3PriorFactor (:1291-1297); writes pg_out[0:12), [84], [85:89) and se3_out[0:12)
+//   tasks 4-6 (backward): IMU Jacobian 15x30 row-major in OrderMap column order (:1382-1412),
+//       [Ji | Jj] of the new RelativePoseFactor (:1424-1433), J of the RollPitchFactor (:1445-1447);
+//       writes rel_out[0:12), rp_out[0:9), vb_out[0:9)
+// =================================================================================================
+constexpr int kFJ_W = 0, kFJ_G = 144, kFJ_JR6 = 216, kFJ_IMU = 252, kFJ_REL = 702, kFJ_RP = 774, kFJ = 786;
+
+constexpr int kJacTasks = 7;   // blockIdx.y: one short chain per (window, factor)
+
+__global__ void __launch_bounds__(128)
+marg_factor_jac_kernel(isv_batch_in in, isv_batch_out out, double* __restrict__ fj, DevCfg cfg, int task0) {
+  const int win = blockIdx.x * blockDim.x + threadIdx.x;
+  if (win >= in.n_windows) return;
+  const int task = task0 + blockIdx.y;   // forward launch: task0 = 0, gridDim.y = 4; backward: task0 = 4, gridDim.y = 3
+  double* F = fj + (size_t)win * kFJ;
+  if (task < 4) {
+    const double* pose0 = in.pose_fwd + (size_t)win * 14;
+    const double* pose1 = pose0 + 7;
+    const double* pse3 = in.prior_se3 + (size_t)win * ISV_SE3_REC;
+    const double* prel = in.prior_rel + (size_t)win * ISV_REL_REC;
+    double* o_se3 = out.se3_out + (size_t)win * ISV_SE3_REC;
+    double* o_pg = out.pg_out + (size_t)win * ISV_PG_REC;
+    double* W = F + kFJ_W;
+    if (task == 0) {
+      // vioRelativePoseEdges[1]: rows 6-11 = sr * [Jj | Ji]   (OrderMap: T1@0, T0@6)
+      // (a thread per window reads its record with a 384-byte stride: load every value exactly once)
+      double Ja[36], Jb[36], dt[3], dR[9], sr[36];
+#pragma unroll
+      for (int i = 0; i < 36; ++i) sr[i] = prel[12 + i];
+      for (int i = 0; i < 3; ++i) dt[i] = prel[i];
+      load_mat3_colmajor(prel + 3, dR);
+      relpose_jacobians(pose0, pose1, dt, dR, Ja, Jb, nullptr);
+#pragma unroll
+      for (int c = 0; c < 12; ++c) {
+        const double* Jc = (c < 6) ? (Jb + 6 * c) : (Ja + 6 * (c - 6));
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          double acc = 0.0;
+#pragma unroll
+          for (int l = 0; l < 6; ++l) acc = fma(sr[r + 6 * l], Jc[l], acc);
+          W[6 + r + 12 * c] = acc;
+        }
+      }
+    } else if (task == 1) {
+      // vioPosePriorEdge: rows 0-5 = sp * [0 | Jp]
+      double Ja[36], tt[3], Rp[9], sp[36];
+#pragma unroll
+      for (int i = 0; i < 36; ++i) sp[i] = pse3[12 + i];
+      for (int i = 0; i < 3; ++i) tt[i] = pse3[i];
+      load_mat3_colmajor(pse3 + 3, Rp);
+      se3prior_jacobian(pose0, tt, Rp, Ja, nullptr);
+#pragma unroll
+      for (int c = 0; c < 12; ++c)
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          double acc = 0.0;
+          if (c >= 6) {
+#pragma unroll
+            for (int l = 0; l < 6; ++l) acc = fma(sp[r + 6 * l], Ja[l + 6 * (c - 6)], acc);
+          }
+          W[r + 12 * c] = acc;
+        }
+    } else if (task == 2) {
+      // pose-graph RelativePoseFactor(T0 -> T1) at the current estimate
+      double dt[3], dR[9];
+      Quat Qi = quat_from_pose(pose0), Qj = quat_from_pose(pose1);
+      double dd[3] = {pose1[0] - pose0[0], pose1[1] - pose0[1], pose1[2] - pose0[2]};
+      qrot(qinv(Qi), dd, dt);
+      q2R(qmul(qinv(Qi), Qj), dR);
+      for (int i = 0; i < 3; ++i) o_pg[i] = dt[i];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) o_pg[3 + r + 3 * c] = dR[3 * r + c];
+      o_pg[84] = sqrt(dt[0] * dt[0] + dt[1] * dt[1] + dt[2] * dt[2]);  // distance = delta_t.norm()
+      relpose_jacobians(pose0, pose1, dt, dR, F + kFJ_G, F + kFJ_G + 36, nullptr);
+    } else {
+      // new SE3PriorFactor(P1, Q1)
+      double tt[3], Rp[9];
+      q2R(quat_from_pose(pose1), Rp);
+      for (int i = 0; i < 3; ++i) { tt[i] = pose1[i]; o_se3[i] = tt[i]; }
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) o_se3[3 + r + 3 * c] = Rp[3 * r + c];
+      se3prior_jacobian(pose1, tt, Rp, F + kFJ_JR6, nullptr);
+      // covAbs = (s^T s)^-1 of vioRollPitchEdges[0] when its index is 0 (:1265-1271)
+      double cA[4] = {0, 0, 0, 0};
+      if (in.prior_rp) {
+        const double* rp = in.prior_rp + (size_t)win * ISV_RP_IN_REC;
+        if (rp[0] != 0.0) {
+          double a = rp[1], b = rp[2], c = rp[3], d = rp[4];  // col-major s = [a c; b d]
+          double m00 = a * a + b * b, m01 = a * c + b * d, m11 = c * c + d * d;
+          double det = m00 * m11 - m01 * m01;
+          cA[0] = m11 / det; cA[1] = -m01 / det; cA[2] = -m01 / det; cA[3] = m00 / det;
+        }
+      }
+      for (int i = 0; i < 4; ++i) o_pg[85 + i] = cA[i];
+    }
+  } else {
+    const double* pose_i = in.pose_bwd + (size_t)win * 14;
+    const double* pose_j = pose_i + 7;
+    const double* sb_i = in.sb_bwd + (size_t)win * 18;
+    const double* sb_j = sb_i + 9;
+    if (task == 4) {
+      // IMUFactor::Evaluate, tangent twin (imu_factor.h:161-265); OrderMap (:1358-1366):
+      // T_V@0, VB_V@6, T_{V-1}@15, VB_{V-1}@21.  The record was zero-filled by the launcher.
+      const double* pre = in.preint + (size_t)win * ISV_PREINT_REC;
+      if ((nonunit(pose_i) || nonunit(pose_j)) && out.status) atomicOr(out.status + win, ISV_W_NONUNIT_QUAT);
+      imu_jacobians(pose_i, sb_i, pose_j, sb_j, pre, cfg.g, F + kFJ_IMU, 1, 15, 21, 0, 6, nullptr, 0, 1, 30);
+    } else if (task == 5) {
+      double* o_rel = out.rel_out + (size_t)win * ISV_REL_REC;
+      Quat Qi = quat_from_pose(pose_i), Qj = quat_from_pose(pose_j);
+      double dd[3] = {pose_j[0] - pose_i[0], pose_j[1] - pose_i[1], pose_j[2] - pose_i[2]};
+      double tij[3], Rij[9];
+      qrot(qinv(Qi), dd, tij);
+      q2R(qmul(qinv(Qi), Qj), Rij);
+      relpose_jacobians(pose_i, pose_j, tij, Rij, F + kFJ_REL, F + kFJ_REL + 36, nullptr);
+      for (int i = 0; i < 3; ++i) o_rel[i] = tij[i];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) o_rel[3 + r + 3 * c] = Rij[3 * r + c];
+    } else {
+      // RollPitchFactor(Qw) with Qw = Q_{V-1}: member R = Qw.toRotationMatrix()
+      double* o_vb = out.vb_out + (size_t)win * ISV_VB_REC;
+      double* o_rp = out.rp_out + (size_t)win * ISV_RP_REC;
+      double Rm[9];
+      q2R(quat_from_pose(pose_i), Rm);
+      rollpitch_jacobian(pose_i, Rm, F + kFJ_RP, nullptr);
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) o_rp[r + 3 * c] = Rm[3 * r + c];
+      for (int i = 0; i < 9; ++i) o_vb[i] = sb_j[i];   // Linear9Factor(vb): VB = para_SpeedBias[V]
+    }
+  }
 }
 
 // =================================================================================================
@@ -223,7 +364,8 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
 
 // ---- kernel 2: everything after the landmark sums (12x12 / 6x6 algebra), one warp per window ----
 __global__ void __launch_bounds__(kThreads, ISV_FWD_TAIL_MINB)
-marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __restrict__ gram, DevCfg cfg) {
+marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __restrict__ gram,
+                         const double* __restrict__ fj, DevCfg cfg) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -237,7 +379,7 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
   const double* pose0 = in.pose_fwd + (size_t)win * 14;
   const double* pose1 = pose0 + 7;
   // work map (doubles): S12[0] H12[144] Ye[288] Ys[324] tmp[360..432) ; then
-  // Wst[288] G[432] Jr6[504] sp[540] sr[576] tA[612] tB[684] wk[756]
+  // Wst[288] G[432] Jr6[504] tA[612] tB[684] wk[756]
   double* S12 = X;
   double* H12 = X + 144;
   double* Ye = X + 288;   // 6 x 6 Gram matrices (ld 6)
@@ -284,75 +426,16 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
   double* Wst = X + 288;
   double* G = X + 432;
   double* Jr6 = X + 504;
-  double* sp = X + 540;
-  double* sr = X + 576;
   double* tA = X + 612;
   double* tB = X + 684;
   double* wk = X + 756;
-  const double* pse3 = in.prior_se3 + (size_t)win * ISV_SE3_REC;
-  const double* prel = in.prior_rel + (size_t)win * ISV_REL_REC;
   double* o_se3 = out.se3_out + (size_t)win * ISV_SE3_REC;
   double* o_pg = out.pg_out + (size_t)win * ISV_PG_REC;
-  for (int i = lane; i < 36; i += 32) { sp[i] = pse3[12 + i]; sr[i] = prel[12 + i]; }
-  // lanes 0/1: the two RelativePoseFactors (vioRelativePoseEdges[1] :1212 ; pose-graph factor :1244-1255)
-  // lanes 2/3: the two SE3PriorFactors    (vioPosePriorEdge :1204 ; new SE3PriorFactor(P1,Q1) :1291-1297)
-  if (lane < 2) {
-    double dt[3], dR[9];
-    if (lane == 0) {
-      for (int i = 0; i < 3; ++i) dt[i] = prel[i];
-      load_mat3_colmajor(prel + 3, dR);
-    } else {
-      Quat Qi = quat_from_pose(pose0), Qj = quat_from_pose(pose1);
-      double dd[3] = {pose1[0] - pose0[0], pose1[1] - pose0[1], pose1[2] - pose0[2]};
-      qrot(qinv(Qi), dd, dt);
-      q2R(qmul(qinv(Qi), Qj), dR);
-      for (int i = 0; i < 3; ++i) o_pg[i] = dt[i];
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) o_pg[3 + r + 3 * c] = dR[3 * r + c];
-      o_pg[84] = sqrt(dt[0] * dt[0] + dt[1] * dt[1] + dt[2] * dt[2]);  // distance = delta_t.norm()
-    }
-    double* Jo = lane == 0 ? wk : G;
-    relpose_jacobians(pose0, pose1, dt, dR, Jo, Jo + 36, nullptr);
-  } else if (lane < 4) {
-    double tt[3], Rp[9];
-    const double* ps = lane == 2 ? pose0 : pose1;
-    if (lane == 2) {
-      for (int i = 0; i < 3; ++i) tt[i] = pse3[i];
-      load_mat3_colmajor(pse3 + 3, Rp);
-    } else {
-      q2R(quat_from_pose(pose1), Rp);
-      for (int i = 0; i < 3; ++i) { tt[i] = pose1[i]; o_se3[i] = tt[i]; }
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) o_se3[3 + r + 3 * c] = Rp[3 * r + c];
-    }
-    se3prior_jacobian(ps, tt, Rp, lane == 2 ? tA : Jr6, nullptr);
-  } else if (lane == 4) {
-    // covAbs = (s^T s)^-1 of vioRollPitchEdges[0] when its index is 0 (:1265-1271)
-    double cA[4] = {0, 0, 0, 0};
-    if (in.prior_rp) {
-      const double* rp = in.prior_rp + (size_t)win * ISV_RP_IN_REC;
-      if (rp[0] != 0.0) {
-        double a = rp[1], b = rp[2], c = rp[3], d = rp[4];  // col-major s = [a c; b d]
-        double m00 = a * a + b * b, m01 = a * c + b * d, m11 = c * c + d * d;
-        double det = m00 * m11 - m01 * m01;
-        cA[0] = m11 / det; cA[1] = -m01 / det; cA[2] = -m01 / det; cA[3] = m00 / det;
-      }
-    }
-    for (int i = 0; i < 4; ++i) o_pg[85 + i] = cA[i];
-  }
-  __syncwarp();
-  // Wst (12x12): rows 0-5 = sp * [0 | Jp], rows 6-11 = sr * [Jj | Ji]   (OrderMap: T1@0, T0@6)
-  for (int idx = lane; idx < 144; idx += 32) {
-    int r = idx % 12, c = idx / 12;
-    double acc = 0.0;
-    if (r < 6) {
-      if (c >= 6)
-        for (int l = 0; l < 6; ++l) acc = fma(sp[r + 6 * l], tA[l + 6 * (c - 6)], acc);
-    } else {
-      const double* Jb = (c < 6) ? (wk + 36 + 6 * c) : (wk + 6 * (c - 6));
-      for (int l = 0; l < 6; ++l) acc = fma(sr[(r - 6) + 6 * l], Jb[l], acc);
-    }
-    Wst[idx] = acc;
+  // Wst (12x12: rows 0-5 = sp [0 | Jp], rows 6-11 = sr [Jj | Ji]), G (6x12) and Jr6 (6x6) come from
+  // marg_factor_jac_kernel; they are contiguous in the scratch in the order of the work map
+  {
+    const double* F = fj + (size_t)win * kFJ;
+    for (int i = lane; i < 252; i += 32) Wst[i] = F[i];
   }
   __syncwarp();
   // S12 += Wst^T Wst ; H12 = E12 + S12  (= Lamda[0:12,0:12], :1243)
@@ -464,83 +547,124 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
 //   cov_i = J_i U D^-1 U^T J_i^T = sum_{|g_k|^2 > ALPHA} (J_i g_k)(J_i g_k)^T / |g_k|^4  (:1500-1516).
 // Algebraically identical to the reference's information-form route, without its cancellation.
 // =================================================================================================
-constexpr int kMld = 25;  // odd leading dimension: conflict-free strided row access
+// Column-per-lane formulation: lane c < 30 owns column c of M in REGISTERS from its creation to the
+// end of the elimination (rows 9-23: 15 doubles; lanes 21-29 also the 9 prior rows).  Only the
+// Cholesky columns of the covariance and the current Householder vector travel through shared memory
+// (broadcast loads), so the elimination costs one LDS + two DFMA per element instead of four LDS, one
+// STS and two DFMA.  The prior's sqrt_info is upper triangular (LLT(...).matrixL().transpose()), so
+// reflector k only touches row k and the 15 IMU rows.
+constexpr int kGld = 21;  // G rows in shared memory: element (k, c) at Gs[k * 21 + c]
+constexpr int kBwdLc = 0, kBwdHv = 240, kBwdGs = 264, kBwdT = 579;
 __global__ void __launch_bounds__(kThreads, ISV_BWD_MINB)
-marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size) {
+marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restrict__ fj, DevCfg cfg, int vo_size) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int win = blockIdx.x * kWarpsPerCta + warp;
   if (win >= in.n_windows) return;
-  double* M = smem + warp * kBwdSmemPerWarp;  // 24 x 30 (ld 25)
-  double* P = M + 750;                        // 15 x 15 covariance -> Cholesky factor
-  double* sc = M + 975;                       // scratch: poses [0..31], G[32..34], dinv[40..60], lam/vbuf[64..]
+  double* S = smem + warp * kBwdSmemPerWarp;
+  double* Lc = S + kBwdLc;     // Cholesky factor of the covariance, column k at Lc[15 k + i]; [225..240) = 1 / L_kk
+  double* hv = S + kBwdHv;     // current Householder vector (15) + tau
+  double* Gs = S + kBwdGs;     // 15 x 21
+  double* T = S + kBwdT;       // Jrel (72) | Jrp (16) | JU / Ls (256) | cov (81)
+  double* sc = T + 425;        // scratch of the general path: dinv[0..21), lam[24..)
   int status = 0, nonfinite = 0;
 
-  const double* pose_i = in.pose_bwd + (size_t)win * 14;
-  const double* pose_j = pose_i + 7;
-  const double* sb_i = in.sb_bwd + (size_t)win * 18;
-  const double* sb_j = sb_i + 9;
   const double* pvb = in.prior_vb + (size_t)win * ISV_VB_REC;
   const double* pre = in.preint + (size_t)win * ISV_PREINT_REC;
-
-  for (int i = lane; i < 750; i += 32) M[i] = 0.0;
-  for (int i = lane; i < 225; i += 32) P[i] = pre[17 + 225 + i];
-  if (lane < 7) { sc[lane] = pose_i[lane]; sc[16 + lane] = pose_j[lane]; }
-  if (lane >= 7 && lane < 16) { sc[lane] = sb_i[lane - 7]; sc[16 + lane] = sb_j[lane - 7]; }
-  if (lane < 3) sc[32 + lane] = cfg.g[lane];
-  __syncwarp();
-  // vioVBPrior (Linear9Factor, J = I9 on VB_{V-1}): rows 0-8, columns 21-29 = sqrt_info  (:1372-1380)
-  for (int idx = lane; idx < 81; idx += 32) M[(idx % 9) + kMld * (21 + idx / 9)] = pvb[9 + idx];
-  // ---- IMUFactor::Evaluate, tangent twin (imu_factor.h:161-265), columns in OrderMap order -----
-  // OrderMap (:1358-1366): T_V@0, VB_V@6, T_{V-1}@15, VB_{V-1}@21
-  if (lane == 0) {
-    if (nonunit(sc) || nonunit(sc + 16)) status |= ISV_W_NONUNIT_QUAT;
-    imu_jacobians(sc, sc + 7, sc + 16, sc + 23, pre, sc + 32, M + 9, kMld, 15, 21, 0, 6, nullptr);
-  }
-  __syncwarp();
-  // sqrt_info^T sqrt_info = covariance^-1 (imu_factor.h:181): P = L L^T, rows 9-23 <- L^-1 J
-  if (w_chol_lower(P, 15, 15, lane)) status |= ISV_W_NOT_SPD;
-  if (lane < 30) {
-    double* col = M + 9 + kMld * lane;
-    for (int i = 0; i < 15; ++i) {
-      double s = col[i];
-      for (int l = 0; l < i; ++l) s = fma(-P[i + 15 * l], col[l], s);
-      col[i] = s / P[i + 15 * i];
-    }
-  }
-  __syncwarp();
-  // ---- Schur complement over VB_{V-1} (:1413-1419) as a QR elimination -------------------------
-  w_householder_marginalize(M, kMld, 24, 30, 21, 9, sc + 64, lane);
-  // ---- recovered factors (:1424-1452) and their Jacobian rows (:1456-1477) ---------------------
-  double* G = M + 9;         // row k, element c at G[k + kMld * c]
-  double* T = M + 525;       // dead: R factor columns (225) + P (225) = 450 contiguous doubles
+  const double* F = fj + (size_t)win * kFJ;
+  double* o_rel = out.rel_out + (size_t)win * ISV_REL_REC;
+  double* o_vb = out.vb_out + (size_t)win * ISV_VB_REC;
+  double* o_rp = out.rp_out + (size_t)win * ISV_RP_REC;
   double* Jrel = T;          // Ji (36) | Jj (36)
   double* Jrp = T + 72;      // 2 x 6
   double* JU = T + 88;       // 17 x 15 (fast path: Y) / up to 9 x 15 (eigen path)
   double* cov = T + 344;     // up to 9 x 9
-  double* o_rel = out.rel_out + (size_t)win * ISV_REL_REC;
-  double* o_vb = out.vb_out + (size_t)win * ISV_VB_REC;
-  double* o_rp = out.rp_out + (size_t)win * ISV_RP_REC;
-  if (lane == 0) {
-    Quat Qi = quat_from_pose(sc), Qj = quat_from_pose(sc + 16);
-    double dd[3] = {sc[16] - sc[0], sc[17] - sc[1], sc[18] - sc[2]};
-    double tij[3], Rij[9];
-    qrot(qinv(Qi), dd, tij);
-    q2R(qmul(qinv(Qi), Qj), Rij);
-    relpose_jacobians(sc, sc + 16, tij, Rij, Jrel, Jrel + 36, nullptr);
-    for (int i = 0; i < 3; ++i) o_rel[i] = tij[i];
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) o_rel[3 + r + 3 * c] = Rij[3 * r + c];
-  } else if (lane == 1) {
-    // RollPitchFactor(Qw) with Qw = Q_{V-1}: member R = Qw.toRotationMatrix()
-    double Rm[9];
-    q2R(quat_from_pose(sc), Rm);
-    rollpitch_jacobian(sc, Rm, Jrp, nullptr);
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) o_rp[r + 3 * c] = Rm[3 * r + c];
-  } else if (lane >= 2 && lane < 11) {
-    o_vb[lane - 2] = sc[23 + (lane - 2)];  // Linear9Factor(vb): VB = para_SpeedBias[V]
+  for (int i = lane; i < 84; i += 32) T[i] = F[kFJ_REL + i];
+
+  // ---- covariance = L L^T, one column per lane in registers (right-looking) ------------------------
+  {
+    const int j = lane < 15 ? lane : 14;
+    double a[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) a[i] = pre[17 + 225 + i + 15 * j];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+      if (lane == k) {
+        const double d = a[k];
+        if (!(d > 0.0)) status |= ISV_W_NOT_SPD;
+        const double ri = rsqrt(d);
+        Lc[225 + k] = ri;
+#pragma unroll
+        for (int i = k; i < 15; ++i) Lc[15 * k + i] = (i == k) ? d * ri : a[i] * ri;
+      }
+      __syncwarp();
+      if (lane > k && lane < 15) {
+        const double ljk = Lc[15 * k + j];
+#pragma unroll
+        for (int i = k + 1; i < 15; ++i) a[i] = fma(-Lc[15 * k + i], ljk, a[i]);   // rows < j are dead weight
+      }
+    }
+    __syncwarp();
+  }
+  // ---- my column: IMU rows (unweighted Jacobian from marg_factor_jac_kernel, row-major 15 x 30:
+  //      coalesced) and, for the VB_{V-1} columns, the prior rows (sqrt_info column, :1372-1380) -----
+  const int c = lane < 30 ? lane : 29;
+  double col[15], pr[9];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) col[i] = F[kFJ_IMU + 30 * i + c];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) pr[i] = (lane >= 21 && lane < 30) ? pvb[9 + i + 9 * (lane - 21)] : 0.0;
+
+  // ---- sqrt_info^T sqrt_info = covariance^-1 (imu_factor.h:181): col <- L^-1 col ------------------
+#pragma unroll
+  for (int i = 0; i < 15; ++i) {
+    double sacc = col[i];
+#pragma unroll
+    for (int l = 0; l < i; ++l) sacc = fma(-Lc[15 * l + i], col[l], sacc);
+    col[i] = sacc * Lc[225 + i];
+  }
+  // ---- Schur complement over VB_{V-1} (:1413-1419) as a QR elimination of columns 21..29 -----------
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    if (lane == 21 + k) {
+      double t2 = 0.0;
+#pragma unroll
+      for (int i = 0; i < 15; ++i) t2 = fma(col[i], col[i], t2);
+      const double x0 = pr[k];
+      double tau = 0.0;
+      if (t2 > 0.0) {
+        double beta = sqrt(fma(x0, x0, t2));
+        if (x0 >= 0.0) beta = -beta;
+        const double inv = 1.0 / (x0 - beta);
+        tau = (beta - x0) / beta;
+#pragma unroll
+        for (int i = 0; i < 15; ++i) hv[i] = col[i] * inv;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 15; ++i) hv[i] = 0.0;
+      }
+      hv[15] = tau;
+    }
+    __syncwarp();
+    {
+      // apply (I - tau v v^T), v = [1 (row k) ; hv (IMU rows)], to every live column other than 21+k
+      const double tau = hv[15];
+      double dot = (lane > 21 + k && lane < 30) ? pr[k] : 0.0;   // row k is zero outside the VB columns
+#pragma unroll
+      for (int i = 0; i < 15; ++i) dot = fma(hv[i], col[i], dot);
+      const double sd = tau * dot;
+      if (lane < 21 || lane > 21 + k) {
+#pragma unroll
+        for (int i = 0; i < 15; ++i) col[i] = fma(-sd, hv[i], col[i]);
+      }
+    }
+    __syncwarp();
+  }
+  // rows 9-23 of columns 0..20 are G (15 x 21) with G^T G = Lamda_prior: transpose to one row per lane
+  if (lane < 21) {
+#pragma unroll
+    for (int i = 0; i < 15; ++i) Gs[i * kGld + lane] = col[i];
   }
   __syncwarp();
   // ---- fast path: no eigen-decomposition when every non-zero eigenvalue is provably > ALPHA ----
@@ -553,20 +677,20 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
   double row[21];
   if (lane < 15) {
 #pragma unroll
-    for (int c = 0; c < 21; ++c) row[c] = G[lane + kMld * c];
+    for (int cc = 0; cc < 21; ++cc) row[cc] = Gs[lane * kGld + cc];
   } else {
 #pragma unroll
-    for (int c = 0; c < 21; ++c) row[c] = 0.0;
+    for (int cc = 0; cc < 21; ++cc) row[cc] = 0.0;
     const int r = lane - 15;
     if (r < 6) {          // relative pose: Jj -> cols 0:6 (T_V), Ji -> cols 15:21 (T_{V-1})
 #pragma unroll
-      for (int c = 0; c < 6; ++c) { row[c] = Jrel[36 + r + 6 * c]; row[15 + c] = Jrel[r + 6 * c]; }
+      for (int cc = 0; cc < 6; ++cc) { row[cc] = Jrel[36 + r + 6 * cc]; row[15 + cc] = Jrel[r + 6 * cc]; }
     } else if (r < 15) {  // speed-bias prior: I9 at cols 6:15
 #pragma unroll
-      for (int c = 0; c < 9; ++c) row[6 + c] = (c == r - 6) ? 1.0 : 0.0;
+      for (int cc = 0; cc < 9; ++cc) row[6 + cc] = (cc == r - 6) ? 1.0 : 0.0;
     } else {              // roll/pitch: 2x6 at cols 15:21
 #pragma unroll
-      for (int c = 0; c < 6; ++c) row[15 + c] = Jrp[(r - 15) + 2 * c];
+      for (int cc = 0; cc < 6; ++cc) row[15 + cc] = Jrp[(r - 15) + 2 * cc];
     }
   }
 #pragma unroll
@@ -648,7 +772,7 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
       cov[idx] = acc;
     }
     __syncwarp();
-    if (w_sqrt_info_from_cov_regs<9>(cov, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+    if (w_sqrt_info_from_cov<9>(cov, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
     for (int idx = lane; idx < 4; idx += 32) {
       int r = idx % 2, c = idx / 2;
       double acc = 0.0;
@@ -659,23 +783,23 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
     if (w_sqrt_info_from_cov_regs<2>(cov, 2, o_rp + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
   } else {
     // ---- general path: eigen-decomposition (:1479-1497) by one-sided Jacobi on the rows of G ----
-    if (w_onesided_jacobi_rows<4, 6>(G, 1, 15, 21, sc + 64, lane, 30, kMld) >= 30) status |= ISV_W_EIG_NOCONV;
+    if (w_onesided_jacobi_rows<4, 6>(Gs, kGld, 15, 21, sc + 24, lane, 30, 1) >= 30) status |= ISV_W_EIG_NOCONV;
     int keepf = 0;
     if (lane < 21) {
-      double lamk = (lane < 15) ? sc[64 + lane] : 0.0;
+      double lamk = (lane < 15) ? sc[24 + lane] : 0.0;
       int keep = lamk > cfg.alpha;  // strict, Q12
-      sc[40 + lane] = keep ? 1.0 / (lamk * lamk) : 0.0;
+      sc[lane] = keep ? 1.0 / (lamk * lamk) : 0.0;
       keepf = keep;
     }
     rank = __popc(__ballot_sync(kFullMask, keepf));
     __syncwarp();
-    const double* dinv = sc + 40;
+    const double* dinv = sc;
     for (int idx = lane; idx < 6 * 15; idx += 32) {
       int r = idx % 6, k = idx / 6;
       double acc = 0.0;
       for (int c = 0; c < 6; ++c) {
-        acc = fma(Jrel[36 + r + 6 * c], G[k + kMld * c], acc);
-        acc = fma(Jrel[r + 6 * c], G[k + kMld * (15 + c)], acc);
+        acc = fma(Jrel[36 + r + 6 * c], Gs[k * kGld + c], acc);
+        acc = fma(Jrel[r + 6 * c], Gs[k * kGld + 15 + c], acc);
       }
       JU[idx] = acc;
     }
@@ -691,15 +815,15 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int vo_size
     for (int idx = lane; idx < 81; idx += 32) {
       int r = idx % 9, c = idx / 9;
       double acc = 0.0;
-      for (int k = 0; k < 15; ++k) acc = fma(G[k + kMld * (6 + r)] * dinv[k], G[k + kMld * (6 + c)], acc);
+      for (int k = 0; k < 15; ++k) acc = fma(Gs[k * kGld + 6 + r] * dinv[k], Gs[k * kGld + 6 + c], acc);
       cov[idx] = acc;
     }
     __syncwarp();
-    if (w_sqrt_info_from_cov_regs<9>(cov, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+    if (w_sqrt_info_from_cov<9>(cov, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
     for (int idx = lane; idx < 2 * 15; idx += 32) {
       int r = idx % 2, k = idx / 2;
       double acc = 0.0;
-      for (int c = 0; c < 6; ++c) acc = fma(Jrp[r + 2 * c], G[k + kMld * (15 + c)], acc);
+      for (int c = 0; c < 6; ++c) acc = fma(Jrp[r + 2 * c], Gs[k * kGld + 15 + c], acc);
       JU[idx] = acc;
     }
     __syncwarp();
