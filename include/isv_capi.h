@@ -144,6 +144,10 @@ typedef struct isv_batch_out {
  * consumes the scratch of the preceding STAGE1 call on the same handle and batch.                */
 #define ISV_RUN_FORWARD_STAGE1 4
 #define ISV_RUN_FORWARD_STAGE2 8
+/* likewise: the factor-Jacobian launches alone (thread per window and factor; they feed STAGE2 and the
+ * backward kernel through the handle's scratch), and the backward kernel alone                    */
+#define ISV_RUN_FACTOR_JAC 16
+#define ISV_RUN_BACKWARD_STAGE2 32
 
 /* stream-ordered, asynchronous; `which` selects MargForward / MargBackward / both.
  * Unused inputs/outputs of a skipped half may be NULL.                                          */
@@ -403,6 +407,55 @@ typedef struct isv_seq_host {
 } isv_seq_host;
 isv_status isv_seq_export_host(isv_handle* h, isv_seq* s, const isv_seq_host* out);
 isv_status isv_seq_import_host(isv_handle* h, isv_seq* s, const isv_seq_host* in);
+
+/* ---- generic marginalization: the engine behind a VINS-Mono style `MarginalizationInfo` ------------
+ * (addResidualBlockInfo / preMarginalize / marginalize / getParameterBlocks).  IS-VINS deleted that class
+ * (SURVEY.md section 0), so this follows VINS-Mono's published `MarginalizationInfo::marginalize`
+ * (vins_estimator/src/factor/marginalization_factor.cpp): A = sum J^T J, b = sum J^T r over every residual
+ * block ("ThreadsConstructA"), Schur complement with the eigen-thresholded pseudo-inverse of A_mm,
+ * eigen-decomposition of the reduced system, linearized_jacobians = S^1/2 V^T, linearized_residuals =
+ * S^-1/2 V^T b.  Parity is unpinned by the reference.
+ * Inputs are EVALUATED residual blocks: `values` holds what CostFunction::Evaluate (+ loss correction)
+ * wrote -- e.g. the output buffers of isv_eval_problem -- and the tables say where each block lives and
+ * which tangent position it maps to.  Tangent layout per problem: [ m_dense | m_diag | n_keep ], pos =
+ * their sum; the m_diag marginalized blocks must be scalars that no residual block couples with each
+ * other (inverse depths), m_dense <= 32.  All pointers are DEVICE pointers.                          */
+typedef struct isv_ne_block {
+  int64_t jac_offset;            /* first element of the Jacobian block in `values` (row-major)       */
+  int32_t row_stride;            /* doubles between rows (global size: 7 for a pose block)            */
+  int32_t local_size;            /* tangent columns used (6 for a pose block), <= 9                   */
+  int32_t pos;                   /* position of the block in the tangent vector                       */
+  int32_t reserved;
+} isv_ne_block;
+typedef struct isv_ne_factor {
+  int64_t res_offset;            /* first residual in `values`                                        */
+  int32_t n_res;                 /* <= 15                                                             */
+  int32_t n_blocks;              /* <= 4 (constant parameter blocks are simply not listed)            */
+  int32_t first_block;           /* index into the block table                                        */
+  int32_t problem;               /* which problem of the batch                                        */
+} isv_ne_factor;
+typedef struct isv_marg_generic_in {
+  int32_t n_problems, pos, m_dense, m_diag;
+  int64_t n_factors;
+  const isv_ne_factor* factors;
+  const isv_ne_block* blocks;
+  const double* values;
+  double eps;                    /* 1e-8 in VINS-Mono                                                 */
+} isv_marg_generic_in;
+typedef struct isv_marg_generic_out {
+  double* A;                     /* [n_problems][pos][pos] column-major; scratch on return            */
+  double* b;                     /* [n_problems][pos]                                                 */
+  double* A_red;                 /* [n_problems][n][n]  A_rr - A_rm A_mm^+ A_mr  (n = n_keep)         */
+  double* b_red;                 /* [n_problems][n]                                                   */
+  double* linearized_jacobians;  /* [n_problems][n][n] column-major, rows in ascending eigenvalue order */
+  double* linearized_residuals;  /* [n_problems][n]                                                   */
+  int32_t* rank;                 /* [n_problems] eigenvalues of the reduced system > eps              */
+  int32_t* status;               /* [n_problems] ISV_W_* (may be NULL)                                */
+} isv_marg_generic_out;
+/* stage 1 only: zero A, b and scatter-add every residual block (the normal equations of the problem) */
+isv_status isv_build_normal_equations(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out);
+/* stage 1 + Schur complement + eigen-decomposition */
+isv_status isv_marginalize_generic(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out);
 
 /* ---- unit-test hook: the PSD eigensolver that replaces SelfAdjointEigenSolver on this path -----
  * (src/estimator.cpp:920,1311,1479).  nb symmetric n x n matrices A (column-major, host) ->

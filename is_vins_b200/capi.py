@@ -19,7 +19,7 @@ IMU_JAC_REC, YAW_REC = 480, 4
 ACC_REC, ACC_COVREL, ACC_DISTANCE, ACC_LENGTH, ACC_VIO_INDEX, ACC_PG_INDEX, ACC_TS = 119, 48, 84, 85, 86, 87, 88
 ACC_RI, ACC_TI, ACC_RP_VALID, ACC_RP, ACC_COVABS = 89, 98, 101, 102, 115
 RUN_FORWARD, RUN_BACKWARD, RUN_BOTH = 1, 2, 3
-RUN_FORWARD_STAGE1, RUN_FORWARD_STAGE2 = 4, 8
+RUN_FORWARD_STAGE1, RUN_FORWARD_STAGE2, RUN_FACTOR_JAC, RUN_BACKWARD_STAGE2 = 4, 8, 16, 32
 POSE, SB, SE3_REC, REL_REC, VB_REC, RP_IN_REC, RP_REC, PG_REC, PREINT_REC = 7, 9, 48, 48, 90, 5, 13, 89, 467
 IMU_RAW_REC = 7
 
@@ -177,6 +177,8 @@ SYMBOLS = [
     ("isv_seq_marginalize", C.c_int, [_H, C.c_void_p, C.POINTER(isv_seq_frame), C.c_double, C.c_void_p, C.c_void_p]),
     ("isv_seq_export_host", C.c_int, [_H, C.c_void_p, C.POINTER(isv_seq_host)]),
     ("isv_seq_import_host", C.c_int, [_H, C.c_void_p, C.POINTER(isv_seq_host)]),
+    ("isv_build_normal_equations", C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    ("isv_marginalize_generic", C.c_int, [_H, C.c_void_p, C.c_void_p]),
     ("isv_test_psd_eig", C.c_int, [_H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int32_p]),
 ]
 

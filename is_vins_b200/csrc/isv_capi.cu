@@ -11,6 +11,7 @@
 
 #include "isv_eval_kernels.cuh"
 #include "isv_init_kernel.cuh"
+#include "isv_marg_generic.cuh"
 #include "isv_preint_kernel.cuh"
 #include "isv_seq_kernels.cuh"
 #include "isv_window_kernels.cuh"
@@ -185,17 +186,16 @@ int isv_order_map_backward(int V, int32_t* out) {
 
 // ---- batched device entry point ---------------------------------------------------------------
 static isv_status check_batch(const isv_batch_in* in, const isv_batch_out* out, int which) {
-  if (!in || !out || in->n_windows < 0 || (which & ~(ISV_RUN_BOTH | ISV_RUN_FORWARD_STAGE1 | ISV_RUN_FORWARD_STAGE2)) ||
-      which == 0)
-    return ISV_ERR_BAD_ARG;
+  constexpr int kAll = ISV_RUN_BOTH | ISV_RUN_FORWARD_STAGE1 | ISV_RUN_FORWARD_STAGE2 | ISV_RUN_FACTOR_JAC | ISV_RUN_BACKWARD_STAGE2;
+  if (!in || !out || in->n_windows < 0 || (which & ~kAll) || which == 0) return ISV_ERR_BAD_ARG;
   if (!out->rank) return ISV_ERR_BAD_ARG;
-  if (which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE1 | ISV_RUN_FORWARD_STAGE2)) {
+  if (which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE1 | ISV_RUN_FORWARD_STAGE2 | ISV_RUN_FACTOR_JAC)) {
     if (!in->lm_offset || !in->pose_fwd || !in->ex_pose || !in->prior_se3 || !in->prior_rel || !out->se3_out ||
         !out->pg_out)
       return ISV_ERR_BAD_ARG;
     if (!in->lm_obs && in->lm_stride != 0) return ISV_ERR_BAD_ARG;
   }
-  if (which & ISV_RUN_BACKWARD) {
+  if (which & (ISV_RUN_BACKWARD | ISV_RUN_BACKWARD_STAGE2 | ISV_RUN_FACTOR_JAC)) {
     if (!in->pose_bwd || !in->sb_bwd || !in->prior_vb || !in->preint || !out->rel_out || !out->vb_out || !out->rp_out)
       return ISV_ERR_BAD_ARG;
   }
@@ -215,29 +215,34 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in, const isv_
   double* fj = scratch + (size_t)n * 42;
   const bool stage1 = which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE1);
   const bool stage2 = which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE2);
-  const bool bwd = which & ISV_RUN_BACKWARD;
+  const bool jac_fwd = which & (ISV_RUN_FORWARD | ISV_RUN_FACTOR_JAC);
+  const bool jac_bwd = which & (ISV_RUN_BACKWARD | ISV_RUN_FACTOR_JAC);
+  const bool bwd = which & (ISV_RUN_BACKWARD | ISV_RUN_BACKWARD_STAGE2);
   if (out->status) ISV_CUDA(cudaMemsetAsync(out->status, 0, sizeof(int32_t) * (size_t)n, stream));
   const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
   // MargForward and MargBackward are independent: when both run, the backward chain (factor
   // Jacobians -> marg_backward_kernel) is forked onto a side stream so that its latency-bound CTAs share
   // the SMs with the FP64-bound landmark kernel, and joined back at the end.
-  const bool fork = bwd && (stage1 || stage2);
+  const bool fork = (which & ISV_RUN_BACKWARD) && (which & ISV_RUN_FORWARD);
   const int slot = (stream == h->copy_stream) ? 1 : 0;
   cudaStream_t bs = fork ? h->aux[slot] : stream;
   if (fork) {
     ISV_CUDA(cudaEventRecord(h->jac_ev[2 * slot], stream));
     ISV_CUDA(cudaStreamWaitEvent(bs, h->jac_ev[2 * slot], 0));
   }
-  if (bwd) {
+  if (jac_bwd) {
     // the IMU Jacobian record is sparse: zero-fill it, the kernel writes the non-zero blocks
     ISV_CUDA(cudaMemset2DAsync(fj + kFJ_IMU, kFJ * sizeof(double), 0, 450 * sizeof(double), (size_t)n, bs));
     marg_factor_jac_kernel<<<dim3((n + 127) / 128, 3), 128, 0, bs>>>(*in, *out, fj, h->dcfg, 4);
+    ++h->launches;
+  }
+  if (bwd) {
     marg_backward_kernel<<<grid, kThreads, kWarpsPerCta * kBwdSmemPerWarp * sizeof(double), bs>>>(*in, *out, fj, h->dcfg,
                                                                                                  h->cfg.vo_size);
-    h->launches += 2;
-    if (fork) ISV_CUDA(cudaEventRecord(h->jac_ev[2 * slot + 1], bs));
+    ++h->launches;
   }
-  if (stage2) {
+  if (fork) ISV_CUDA(cudaEventRecord(h->jac_ev[2 * slot + 1], bs));
+  if (jac_fwd) {
     marg_factor_jac_kernel<<<dim3((n + 127) / 128, 4), 128, 0, stream>>>(*in, *out, fj, h->dcfg, 0);
     ++h->launches;
   }
@@ -924,4 +929,67 @@ extern "C" isv_status isv_seq_export_host(isv_handle* h, isv_seq* s, const isv_s
 }
 extern "C" isv_status isv_seq_import_host(isv_handle* h, isv_seq* s, const isv_seq_host* in) {
   return seq_copy(h, s, in, false);
+}
+
+// ---- generic marginalization (MarginalizationInfo engine) ---------------------------------------------------
+static isv_status marg_generic_check(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out,
+                                     bool full) {
+  if (!h || !in || !out) return ISV_ERR_BAD_ARG;
+  if (in->n_problems < 1 || in->pos < 1 || in->m_dense < 0 || in->m_diag < 0 || in->m_dense > kMgMaxDense) return ISV_ERR_BAD_ARG;
+  if (in->m_dense + in->m_diag >= in->pos || in->n_factors < 0 || !(in->eps >= 0.0)) return ISV_ERR_BAD_ARG;
+  if (in->n_factors > 0 && (!in->factors || !in->blocks || !in->values)) return ISV_ERR_BAD_ARG;
+  if (!out->A || !out->b) return ISV_ERR_BAD_ARG;
+  if (full && (!out->A_red || !out->b_red || !out->linearized_jacobians || !out->linearized_residuals || !out->rank))
+    return ISV_ERR_BAD_ARG;
+  return ISV_OK;
+}
+
+extern "C" isv_status isv_build_normal_equations(isv_handle* h, const isv_marg_generic_in* in,
+                                                 const isv_marg_generic_out* out) {
+  isv_status st = marg_generic_check(h, in, out, false);
+  if (st != ISV_OK) return st;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const size_t np = (size_t)in->n_problems, pos = (size_t)in->pos;
+  ISV_CUDA(cudaMemsetAsync(out->A, 0, np * pos * pos * sizeof(double), h->stream));
+  ISV_CUDA(cudaMemsetAsync(out->b, 0, np * pos * sizeof(double), h->stream));
+  if (out->status) ISV_CUDA(cudaMemsetAsync(out->status, 0, np * sizeof(int32_t), h->stream));
+  if (in->n_factors > 0) {
+    const long long grid = (in->n_factors + kNeWarps - 1) / kNeWarps;
+    if (grid > 0x7fffffffLL) return ISV_ERR_BAD_ARG;
+    ne_build_kernel<<<(unsigned)grid, 32 * kNeWarps, kNeWarps * kNeSmemPerWarp * sizeof(double), h->stream>>>(
+        *in, out->A, out->b, out->status);
+    ++h->launches;
+  }
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+extern "C" isv_status isv_marginalize_generic(isv_handle* h, const isv_marg_generic_in* in,
+                                              const isv_marg_generic_out* out) {
+  isv_status st = marg_generic_check(h, in, out, true);
+  if (st != ISV_OK) return st;
+  st = isv_build_normal_equations(h, in, out);
+  if (st != ISV_OK) return st;
+  const size_t n = (size_t)(in->pos - in->m_dense - in->m_diag);
+  // factor rows of the reduced system (n x n per problem): handle-owned scratch
+  const size_t need = (size_t)in->n_problems * n * n * sizeof(double);
+  if (h->gram_bytes < need) {
+    if (h->gram) {
+      ISV_CUDA(cudaStreamSynchronize(h->stream));
+      ISV_CUDA(cudaFree(h->gram));
+      h->gram = nullptr;
+      h->gram_bytes = 0;
+    }
+    if (cudaMalloc(&h->gram, need + 256) != cudaSuccess) {
+      cudaGetLastError();
+      return ISV_ERR_ALLOC;
+    }
+    h->gram_bytes = need + 256;
+  }
+  const size_t sm = (2 * kMgMaxDense * kMgMaxDense + 6 * 16 + 32) * sizeof(double);
+  ISV_CUDA(cudaFuncSetAttribute(marg_schur_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  marg_schur_eig_kernel<<<in->n_problems, kMgThreads, sm, h->stream>>>(*in, *out, h->gram);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
 }

@@ -1,0 +1,352 @@
+// Generic marginalization engine behind the `MarginalizationInfo` facade the north_star names
+// (addResidualBlockInfo / preMarginalize / marginalize / getParameterBlocks).  IS-VINS itself deleted
+// VINS-Mono's marginalization_factor.{h,cpp}, so this follows the PUBLISHED
+// VINS-Mono algorithm (HKUST-Aerial-Robotics/VINS-Mono, vins_estimator/src/factor/
+// marginalization_factor.cpp, `MarginalizationInfo::marginalize`): parity is unpinned by the reference.
+//
+//   ne_build_kernel        ThreadsConstructA: A += J_i^T J_j , b += J_i^T r over all residual blocks,
+//                          scattered by parameter-block position -- one warp per residual block, its
+//                          Jacobians staged in shared memory, one FP64 atomic per (entry, factor)
+//   marg_schur_eig_kernel  A_rr - A_rm A_mm^+ A_mr ,  b_rr - A_rm A_mm^+ b_mm ,  eigen-decomposition of
+//                          the reduced system, linearized_jacobians = S^1/2 V^T , residuals = S^-1/2 V^T b
+//                          -- one CTA per problem.
+// Layout of the tangent vector: [ m_dense | m_diag | n_keep ].  `m_diag` marginalized blocks are
+// scalars that no residual block couples with each other (inverse depths: every ProjectionFactor
+// touches exactly one), so that part of A_mm is diagonal and its elimination is the dense product
+//   C -= X D^-1 X^T ,  X = A[R, diag]   (R = dense-marginalized + kept rows)
+// which runs on the FP64 tensor cores (mma.sync.m8n8k4.f64 -> DMMA.8x8x4) with full 8x8 tiles: the one
+// place on this path where the tensor pipe beats DFMA (isv_window_kernels.cuh explains why the 6x6
+// landmark Grams do not).  The remaining m_dense x m_dense block (pose + speed-bias of the oldest
+// frame, <= 32) gets VINS-Mono's eigen-thresholded pseudo-inverse.  Block-wise pseudo-inversion
+// equals the joint one of VINS-Mono whenever A_mm has no eigenvalue <= eps; a scalar pivot or dense
+// eigenvalue <= eps raises ISV_W_RANK_DEFICIENT.
+#pragma once
+#include "isv_device_math.cuh"
+#include "isv_warp_linalg.cuh"
+#include "isv_window_kernels.cuh"   // dmma884
+
+#include "../../include/isv_capi.h"
+
+namespace isv {
+
+constexpr int kNeMaxRes = 15, kNeMaxCols = 36, kNeWarps = 4;
+constexpr int kNeSmemPerWarp = kNeMaxRes * kNeMaxCols + 16 + 8;
+
+__global__ void __launch_bounds__(32 * kNeWarps)
+ne_build_kernel(isv_marg_generic_in in, double* __restrict__ A, double* __restrict__ b, int32_t* status) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long f = (long long)blockIdx.x * kNeWarps + warp;
+  if (f >= in.n_factors) return;
+  double* J = smem + warp * kNeSmemPerWarp;   // n_res x total columns, row-major, ld = kNeMaxCols
+  double* r = J + kNeMaxRes * kNeMaxCols;
+  int* meta = reinterpret_cast<int*>(r + 16);  // per block: column offset in J, pos, local size (4 blocks)
+  const isv_ne_factor fa = in.factors[f];
+  const int nres = fa.n_res, nb = fa.n_blocks;
+  bool ok = nres >= 1 && nres <= kNeMaxRes && nb >= 1 && nb <= 4 && fa.problem >= 0 && fa.problem < in.n_problems;
+  int tot = 0;
+  if (ok) {
+    for (int k = 0; k < nb; ++k) {
+      const isv_ne_block bl = in.blocks[fa.first_block + k];
+      if (bl.local_size < 1 || bl.local_size > 9 || bl.pos < 0 || bl.pos + bl.local_size > in.pos) ok = false;
+      if (lane == 0) { meta[3 * k] = tot; meta[3 * k + 1] = bl.pos; meta[3 * k + 2] = bl.local_size; }
+      tot += bl.local_size;
+    }
+  }
+  if (!ok || tot > kNeMaxCols) {
+    if (lane == 0 && status) atomicOr(status, ISV_W_BAD_INDEX);
+    return;
+  }
+  for (int i = lane; i < nres; i += 32) r[i] = in.values[fa.res_offset + i];
+  for (int k = 0; k < nb; ++k) {
+    const isv_ne_block bl = in.blocks[fa.first_block + k];
+    int c0 = 0;
+    for (int kk = 0; kk < k; ++kk) c0 += in.blocks[fa.first_block + kk].local_size;
+    for (int idx = lane; idx < nres * bl.local_size; idx += 32) {
+      const int row = idx / bl.local_size, col = idx - row * bl.local_size;
+      J[row * kNeMaxCols + c0 + col] = in.values[bl.jac_offset + (long long)row * bl.row_stride + col];
+    }
+  }
+  __syncwarp();
+  double* Ap = A + (size_t)fa.problem * in.pos * in.pos;
+  double* bp = b + (size_t)fa.problem * in.pos;
+  // every (a, c) column pair of the staged Jacobian: A[pos(a), pos(c)] += J[:,a] . J[:,c]
+  for (int idx = lane; idx < tot * tot; idx += 32) {
+    const int a = idx / tot, c = idx - a * tot;
+    double acc = 0.0;
+    for (int l = 0; l < nres; ++l) acc = fma(J[l * kNeMaxCols + a], J[l * kNeMaxCols + c], acc);
+    int pa = 0, pc = 0;
+    for (int k = 0; k < nb; ++k) {
+      if (a >= meta[3 * k] && a < meta[3 * k] + meta[3 * k + 2]) pa = meta[3 * k + 1] + a - meta[3 * k];
+      if (c >= meta[3 * k] && c < meta[3 * k] + meta[3 * k + 2]) pc = meta[3 * k + 1] + c - meta[3 * k];
+    }
+    if (acc != 0.0) atomicAdd(Ap + pa + (size_t)in.pos * pc, acc);
+  }
+  for (int a = lane; a < tot; a += 32) {
+    double acc = 0.0;
+    for (int l = 0; l < nres; ++l) acc = fma(J[l * kNeMaxCols + a], r[l], acc);
+    int pa = 0;
+    for (int k = 0; k < nb; ++k)
+      if (a >= meta[3 * k] && a < meta[3 * k] + meta[3 * k + 2]) pa = meta[3 * k + 1] + a - meta[3 * k];
+    if (acc != 0.0) atomicAdd(bp + pa, acc);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+constexpr int kMgThreads = 256;
+constexpr int kMgMaxDense = 32;
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+
+// smem (doubles): P[32*32] V[32*32] cs[6*16] red[32] + ints
+__global__ void __launch_bounds__(kMgThreads)
+marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* __restrict__ Gbuf) {
+  extern __shared__ double smem[];
+  double* P = smem;                       // m_dense x m_dense
+  double* V = P + kMgMaxDense * kMgMaxDense;
+  double* cs = V + kMgMaxDense * kMgMaxDense;
+  double* red = cs + 6 * 16;              // 32
+  __shared__ int s_status;
+  if (threadIdx.x == 0) s_status = 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kMgThreads / 32;
+  const int prob = blockIdx.x;
+  const int pos = in.pos, md = in.m_dense, mg = in.m_diag, m = md + mg, n = pos - m, nr = md + n;
+  double* A = out.A + (size_t)prob * pos * pos;
+  double* b = out.b + (size_t)prob * pos;
+  double* Ar = out.A_red + (size_t)prob * n * n;
+  double* br = out.b_red + (size_t)prob * n;
+  double* G = Gbuf + (size_t)prob * n * n;   // rows of the factor, row-major
+  const double eps = in.eps;
+  int status = 0;
+  auto R = [&](int i) { return i < md ? i : i + mg; };   // compact index -> position in A
+
+  // ---- phase A: eliminate the diagonal (scalar) marginalized blocks:  C -= X D^-1 X^T  on DMMA ----
+  if (mg > 0) {
+    const int nt = (nr + 7) / 8;
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int t = warp; t < nt * nt; t += nw) {
+      const int ti = t / nt, tj = t - ti * nt;
+      if (tj < ti) continue;               // symmetric: upper tiles, mirrored below
+      const int ra = 8 * ti + fr, rb = 8 * tj + fr;
+      const double* rowa = (ra < nr) ? A + R(ra) : nullptr;   // A[R(ra) + pos * l]
+      const double* rowb = (rb < nr) ? A + R(rb) : nullptr;
+      double d0 = 0.0, d1 = 0.0;
+      for (int k0 = 0; k0 < mg; k0 += 4) {
+        const int l = k0 + fk;
+        double a = 0.0, bb = 0.0;
+        if (l < mg) {
+          const size_t col = (size_t)pos * (md + l);
+          const double d = A[(md + l) + col];
+          const double di = d > eps ? 1.0 / d : 0.0;
+          if (rowa) a = rowa[col] * di;
+          if (rowb) bb = rowb[col];
+        }
+        dmma884(d0, d1, a, bb);
+      }
+      // D fragment: row = lane / 4, cols = 2 (lane % 4) + {0, 1}
+      const int i = 8 * ti + fr, j0 = 8 * tj + 2 * fk;
+      // tiles are disjoint in (i, j): the entries written here are only read as INPUT in columns
+      // md..m-1, which are never written, so the in-place update is race-free
+      if (i < nr && j0 < nr) {
+        A[R(i) + (size_t)pos * R(j0)] -= d0;
+        if (ti != tj) A[R(j0) + (size_t)pos * R(i)] -= d0;
+      }
+      if (i < nr && j0 + 1 < nr) {
+        A[R(i) + (size_t)pos * R(j0 + 1)] -= d1;
+        if (ti != tj) A[R(j0 + 1) + (size_t)pos * R(i)] -= d1;
+      }
+    }
+    // b_R -= X D^-1 b_diag ; flag unusable pivots
+    for (int i = tid; i < nr; i += kMgThreads) {
+      double acc = 0.0;
+      for (int l = 0; l < mg; ++l) {
+        const size_t col = (size_t)pos * (md + l);
+        const double d = A[(md + l) + col];
+        if (d > eps) acc = fma(A[R(i) + col] / d, b[md + l], acc);
+      }
+      b[R(i)] -= acc;
+    }
+    for (int l = tid; l < mg; l += kMgThreads)
+      if (!(A[(md + l) + (size_t)pos * (md + l)] > eps)) status |= ISV_W_RANK_DEFICIENT;
+  }
+  __syncthreads();
+  // ---- phase B: dense marginalized block: Amm = (P + P^T)/2, eigen-thresholded pseudo-inverse ---------
+  for (int idx = tid; idx < md * md; idx += kMgThreads) {
+    const int i = idx % md, j = idx / md;
+    P[i + md * j] = 0.5 * (A[i + (size_t)pos * j] + A[j + (size_t)pos * i]);
+  }
+  __syncthreads();
+  if (warp == 0 && md > 0) {
+    if (w_jacobi_eig(P, md, V, md, md, cs, lane) >= 30) status |= ISV_W_EIG_NOCONV;
+    // pinv = V diag(lam > eps ? 1/lam : 0) V^T  -> back into P (cs reused for the inverted spectrum)
+    for (int k = lane; k < md; k += 32) {
+      const double lam = P[k + md * k];
+      if (!(lam > eps)) status |= ISV_W_RANK_DEFICIENT;
+      cs[k] = lam > eps ? 1.0 / lam : 0.0;
+    }
+    __syncwarp();
+    for (int idx = lane; idx < md * md; idx += 32) {
+      const int i = idx % md, j = idx / md;
+      double acc = 0.0;
+      for (int k = 0; k < md; ++k) acc = fma(V[i + md * k] * cs[k], V[j + md * k], acc);
+      P[idx] = acc;
+    }
+  }
+  __syncthreads();
+  // A_red = A_rr - A_rm pinv A_mr ;  b_red = b_rr - A_rm pinv b_mm      (r = kept, m = dense marginalized)
+  for (int idx = tid; idx < n * md; idx += kMgThreads) {   // T = A_rm pinv  (n x md) into G scratch
+    const int i = idx % n, k = idx / n;
+    double acc = 0.0;
+    for (int l = 0; l < md; ++l) acc = fma(A[(m + i) + (size_t)pos * l], P[l + md * k], acc);
+    G[idx] = acc;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * n; idx += kMgThreads) {
+    const int i = idx % n, j = idx / n;
+    double acc = A[(m + i) + (size_t)pos * (m + j)];
+    for (int k = 0; k < md; ++k) acc = fma(-G[i + n * k], A[k + (size_t)pos * (m + j)], acc);
+    Ar[idx] = acc;
+  }
+  for (int i = tid; i < n; i += kMgThreads) {
+    double acc = b[m + i];
+    for (int k = 0; k < md; ++k) acc = fma(-G[i + n * k], b[k], acc);
+    br[i] = acc;
+  }
+  __syncthreads();
+  // ---- phase C: A_red ~= G^T G by outer-product Cholesky with diagonal pivoting (A_red is PSD up to
+  //      rounding; what is dropped is below n * eps_mach * max diagonal).  Works on a copy in A's kept block.
+  double* W = A;   // reuse the first n*n doubles of this problem's A as the work copy (A is consumed)
+  for (int idx = tid; idx < n * n; idx += kMgThreads) {
+    const int i = idx % n, j = idx / n;
+    W[idx] = 0.5 * (Ar[i + (size_t)n * j] + Ar[j + (size_t)n * i]);
+  }
+  __syncthreads();
+  double dmax0 = 0.0;
+  for (int i = tid; i < n; i += kMgThreads) dmax0 = fmax(dmax0, W[i + (size_t)n * i]);
+  dmax0 = warp_max(dmax0);
+  if (lane == 0) red[warp] = dmax0;
+  __syncthreads();
+  dmax0 = 0.0;
+  for (int w = 0; w < nw; ++w) dmax0 = fmax(dmax0, red[w]);
+  const double stop = (double)n * 2.220446049250313e-16 * dmax0;
+  int rank = 0;
+  for (int k = 0; k < n; ++k) {
+    // pivot = arg max of the remaining diagonal
+    double best = -1.0;
+    int bi = -1;
+    for (int i = tid; i < n; i += kMgThreads) {
+      const double d = W[i + (size_t)n * i];
+      if (d > best) { best = d; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(kFullMask, best, o);
+      const int oi = __shfl_xor_sync(kFullMask, bi, o);
+      if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { red[warp] = best; reinterpret_cast<int*>(red + 16)[warp] = bi; }
+    __syncthreads();
+    best = -1.0; bi = -1;
+    for (int w = 0; w < nw; ++w) {
+      const double ob = red[w];
+      const int oi = reinterpret_cast<int*>(red + 16)[w];
+      if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
+    }
+    if (!(best > stop) || bi < 0) break;
+    const double ri = rsqrt(best);
+    double* g = G + (size_t)rank * n;
+    for (int j = tid; j < n; j += kMgThreads) g[j] = W[bi + (size_t)n * j] * ri;
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += kMgThreads) {
+      const int i = idx % n, j = idx / n;
+      W[idx] = fma(-g[i], g[j], W[idx]);
+    }
+    __syncthreads();
+    if (tid == 0) W[bi + (size_t)n * bi] = 0.0;   // exactly eliminated
+    ++rank;
+    __syncthreads();
+  }
+  // ---- phase D: one-sided Jacobi on the rows of G (rank x n): afterwards A_red = sum_k g_k g_k^T with
+  //      mutually orthogonal g_k, eigenvalues |g_k|^2 ----------------------------------------------------
+  {
+    const int mm = (rank + 1) & ~1, half = mm / 2;
+    const double tol = 2.220446049250313e-16 * sqrt((double)n);
+    for (int sweep = 0; sweep < 40 && rank >= 2; ++sweep) {
+      int rotated = 0;
+      for (int rr = 0; rr < mm - 1; ++rr) {
+        for (int kp = warp; kp < half; kp += nw) {
+          int p, q;
+          jacobi_pair(kp, rr, mm, p, q);
+          if (q >= rank) continue;
+          double* gp = G + (size_t)p * n;
+          double* gq = G + (size_t)q * n;
+          double a = 0.0, bq = 0.0, gm = 0.0;
+          for (int j = lane; j < n; j += 32) {
+            const double x = gp[j], y = gq[j];
+            a = fma(x, x, a); bq = fma(y, y, bq); gm = fma(x, y, gm);
+          }
+          a = warp_sum(a); bq = warp_sum(bq); gm = warp_sum(gm);
+          if (fabs(gm) > tol * sqrt(a * bq) && gm != 0.0) {
+            double c, s;
+            jacobi_cs(a, bq, gm, c, s);
+            for (int j = lane; j < n; j += 32) {
+              const double x = gp[j], y = gq[j];
+              gp[j] = c * x - s * y;
+              gq[j] = s * x + c * y;
+            }
+            rotated = 1;
+          }
+        }
+        __syncthreads();
+      }
+      if (!__syncthreads_or(rotated)) break;
+      if (sweep == 39) status |= ISV_W_EIG_NOCONV;
+    }
+  }
+  // ---- phase E: outputs, rows in ascending eigenvalue order (Eigen's convention): n - kept zero rows
+  //      first, then sqrt(lam_k) v_k^T = g_k^T ; residual_k = g_k . b_red / lam_k -------------------------
+  double* LJ = out.linearized_jacobians + (size_t)prob * n * n;   // column-major n x n
+  double* LR = out.linearized_residuals + (size_t)prob * n;
+  for (int idx = tid; idx < n * n; idx += kMgThreads) LJ[idx] = 0.0;
+  for (int i = tid; i < n; i += kMgThreads) LR[i] = 0.0;
+  __syncthreads();
+  // lam_k and g_k.b per row (warp per row), staged in W[0..2n)
+  for (int k = warp; k < rank; k += nw) {
+    const double* g = G + (size_t)k * n;
+    double l2 = 0.0, gb = 0.0;
+    for (int j = lane; j < n; j += 32) { l2 = fma(g[j], g[j], l2); gb = fma(g[j], br[j], gb); }
+    l2 = warp_sum(l2); gb = warp_sum(gb);
+    if (lane == 0) { W[k] = l2; W[n + k] = gb; }
+  }
+  __syncthreads();
+  int kept = 0;
+  for (int k = 0; k < rank; ++k) kept += (W[k] > eps) ? 1 : 0;
+  for (int k = warp; k < rank; k += nw) {
+    const double lam = W[k];
+    if (!(lam > eps)) continue;
+    int below = 0;   // kept eigenvalues smaller than this one (ties by index)
+    for (int t = 0; t < rank; ++t) {
+      const double lt = W[t];
+      if (lt > eps && (lt < lam || (lt == lam && t < k))) ++below;
+    }
+    const int row = (n - kept) + below;
+    const double* g = G + (size_t)k * n;
+    for (int j = lane; j < n; j += 32) LJ[row + (size_t)n * j] = g[j];
+    if (lane == 0) LR[row] = W[n + k] / lam;
+  }
+  if (tid == 0) out.rank[prob] = kept;
+  if (status) atomicOr(&s_status, status);
+  __syncthreads();
+  if (tid == 0 && out.status && s_status) atomicOr(out.status + prob, s_status);
+}
+
+}  // namespace isv

@@ -1,0 +1,203 @@
+"""`MarginalizationInfo`: the VINS-Mono marginalization API the north_star names
+(addResidualBlockInfo / preMarginalize / marginalize / getParameterBlocks), on the GPU engine
+(include/isv_capi.h `isv_eval_problem` + `isv_marginalize_generic`).  IS-VINS deleted this class
+(SURVEY.md section 0): the semantics follow VINS-Mono's published marginalization_factor.cpp, with one
+documented difference -- parameter blocks are ordered by first appearance (VINS-Mono iterates an
+`unordered_map` keyed by address, i.e. implementation-defined order): marginalized blocks of size > 1,
+then marginalized scalar blocks (inverse depths), then the kept blocks.  `parameter_block_idx` reports
+the resulting positions, so the mapping is exact and reproducible.
+
+Parameter blocks are named by (family, index): ("pose", i), ("speed_bias", i), ("ex_pose", e),
+("feature", f) -- the `para_Pose[i]` ... arrays of the estimator.  No arithmetic happens on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import capi
+from .evaluate import DeviceProblem, FactorProblem, eval_problem, rel_record, rp_record, vb_record, yaw_record
+
+Key = Tuple[str, int]
+GLOBAL_SIZE = {"pose": 7, "speed_bias": 9, "ex_pose": 7, "feature": 1}
+LOCAL_SIZE = {"pose": 6, "speed_bias": 9, "ex_pose": 6, "feature": 1}     # MarginalizationInfo::localSize
+# per factor kind: parameter families in ceres argument order, residual size, (offset, row stride) of each
+# Jacobian block inside the kind's Evaluate output record
+KINDS = {
+    "projection": (("pose", "pose", "ex_pose", "feature"), 2, None),
+    "imu": (("pose", "speed_bias", "pose", "speed_bias"), 15, ((0, 7), (105, 9), (240, 7), (345, 9))),
+    "rel": (("pose", "pose"), 6, ((0, 7), (42, 7))),
+    "se3": (("pose",), 6, ((0, 7),)),
+    "vb": (("speed_bias",), 9, ((0, 9),)),
+    "rp": (("pose",), 2, ((0, 7),)),
+    "yaw": (("pose",), 1, ((0, 7),)),
+}
+
+
+class ResidualBlockInfo:
+    """cost function (by kind + its members), the parameter blocks it touches and the drop set."""
+
+    def __init__(self, kind: str, parameter_blocks: Sequence[Key], drop_set: Sequence[int] = (), **members):
+        fam = KINDS[kind][0]
+        assert len(parameter_blocks) == len(fam) and all(k[0] == f for k, f in zip(parameter_blocks, fam)), \
+            f"{kind} takes parameter blocks {fam}"
+        self.kind, self.parameter_blocks, self.drop_set, self.members = kind, list(parameter_blocks), list(drop_set), members
+
+
+class isv_ne_block(C.Structure):
+    _fields_ = [("jac_offset", C.c_int64), ("row_stride", C.c_int32), ("local_size", C.c_int32), ("pos", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class isv_ne_factor(C.Structure):
+    _fields_ = [("res_offset", C.c_int64), ("n_res", C.c_int32), ("n_blocks", C.c_int32), ("first_block", C.c_int32),
+                ("problem", C.c_int32)]
+
+
+class MarginalizationInfo:
+    def __init__(self, backend, eps: float = 1e-8, cauchy_a: float = 1.0, constant: Sequence[Key] = ()):
+        """cauchy_a: CauchyLoss scale of every non-IMU residual block (VINS passes `loss_function` to the
+        projection and prior blocks and NULL to the IMU block); 0 disables.  constant: parameter blocks
+        ceres holds constant (SetParameterBlockConstant) -- they get no column."""
+        self.be, self.eps, self.cauchy_a, self.constant = backend, float(eps), float(cauchy_a), set(constant)
+        self.factors: List[ResidualBlockInfo] = []
+        self.parameter_block_size: Dict[Key, int] = {}
+        self.parameter_block_idx: Dict[Key, int] = {}
+        self._drop: List[Key] = []
+        self.m = self.n = 0
+        self._dp: Optional[DeviceProblem] = None
+
+    # ---- VINS-Mono API ------------------------------------------------------------------------------
+    def addResidualBlockInfo(self, info: ResidualBlockInfo) -> None:
+        self.factors.append(info)
+        for k in info.parameter_blocks:
+            self.parameter_block_size[k] = GLOBAL_SIZE[k[0]]
+        for i in info.drop_set:
+            k = info.parameter_blocks[i]
+            if k not in self._drop:
+                self._drop.append(k)
+
+    def preMarginalize(self, para: Dict[str, np.ndarray]) -> None:
+        """Evaluate every residual block at the current parameter values (GPU, isv_eval_problem)."""
+        by = {k: [f for f in self.factors if f.kind == k] for k in KINDS}
+        self._by = by
+        P = len(by["projection"])
+        pidx = np.zeros((4, P), np.int32)
+        pobs = np.zeros((5, P))
+        for c, f in enumerate(by["projection"]):
+            pidx[:, c] = [k[1] for k in f.parameter_blocks]
+            pobs[0:3, c], pobs[3:5, c] = f.members["pts_i"], np.asarray(f.members["pts_j"])[0:2]
+        i32 = lambda rows, shape: np.asarray(rows, np.int32).reshape(shape)
+        f64 = lambda rows, w: np.asarray(rows, float).reshape(-1, w)
+        M = lambda f: f.members
+        fp = FactorProblem(
+            np.ascontiguousarray(para["pose"], float), np.ascontiguousarray(para["speed_bias"], float),
+            np.ascontiguousarray(para["ex_pose"], float).reshape(-1, 7), np.ascontiguousarray(para["feature"], float),
+            pidx, pobs,
+            i32([(f.parameter_blocks[0][1], f.parameter_blocks[2][1]) for f in by["imu"]], (-1, 2)),
+            f64([M(f)["preint"] for f in by["imu"]], capi.PREINT_REC),
+            i32([(f.parameter_blocks[0][1], f.parameter_blocks[1][1]) for f in by["rel"]], (-1, 2)),
+            f64([rel_record(M(f)["delta_t"], M(f)["delta_R"], M(f)["sqrt_info"]) for f in by["rel"]], capi.REL_REC),
+            i32([f.parameter_blocks[0][1] for f in by["se3"]], (-1,)),
+            f64([rel_record(M(f)["t"], M(f)["R"], M(f)["sqrt_info"]) for f in by["se3"]], capi.SE3_REC),
+            i32([f.parameter_blocks[0][1] for f in by["vb"]], (-1,)),
+            f64([vb_record(M(f)["VB"], M(f)["sqrt_info"]) for f in by["vb"]], capi.VB_REC),
+            i32([f.parameter_blocks[0][1] for f in by["rp"]], (-1,)),
+            f64([rp_record(M(f)["R"], M(f)["sqrt_info"]) for f in by["rp"]], capi.RP_REC),
+            i32([f.parameter_blocks[0][1] for f in by["yaw"]], (-1,)),
+            f64([yaw_record(M(f)["yaw_meas"], M(f)["sqrt_info"]) for f in by["yaw"]], capi.YAW_REC))
+        for f in by["imu"]:
+            assert f.parameter_blocks[0][1] == f.parameter_blocks[1][1] and f.parameter_blocks[2][1] == f.parameter_blocks[3][1]
+        self._dp = DeviceProblem(fp, f"cuda:{self.be.device}")
+        eval_problem(self.be, self._dp, self.cauchy_a)
+
+    def marginalize(self) -> None:
+        import torch
+        assert self._dp is not None, "call preMarginalize first"
+        dp, by = self._dp, self._by
+        # ---- ordering (see module docstring) -> parameter_block_idx, m, n --------------------------------
+        order: List[Key] = [k for k in self._drop if LOCAL_SIZE[k[0]] > 1 and k not in self.constant]
+        m_dense = sum(LOCAL_SIZE[k[0]] for k in order)
+        diag = [k for k in self._drop if LOCAL_SIZE[k[0]] == 1 and k not in self.constant]
+        order += diag
+        seen = set(order)
+        for f in self.factors:
+            for k in f.parameter_blocks:
+                if k not in seen and k not in self.constant:
+                    seen.add(k)
+                    order.append(k)
+        pos = 0
+        self.parameter_block_idx = {}
+        for k in order:
+            self.parameter_block_idx[k] = pos
+            pos += LOCAL_SIZE[k[0]]
+        self.m, self.n = m_dense + len(diag), pos - m_dense - len(diag)
+        # ---- one `values` array: the Evaluate outputs, concatenated ---------------------------------------
+        names = ["proj_res", "proj_ji", "proj_jj", "proj_je", "proj_jf", "imu_res", "imu_jac", "rel_res", "rel_jac",
+                 "se3_res", "se3_jac", "vb_res", "vb_jac", "rp_res", "rp_jac", "yaw_res", "yaw_jac"]
+        base, off = {}, 0
+        for nm in names:
+            base[nm] = off
+            off += dp.out[nm].numel()
+        values = torch.cat([dp.out[nm].reshape(-1) for nm in names])
+        facs, blks = [], []
+        for c, f in enumerate(by["projection"]):
+            first = len(blks)
+            for nm, k, w in (("proj_ji", f.parameter_blocks[0], 14), ("proj_jj", f.parameter_blocks[1], 14),
+                             ("proj_je", f.parameter_blocks[2], 14), ("proj_jf", f.parameter_blocks[3], 2)):
+                if k in self.constant:
+                    continue
+                gs = GLOBAL_SIZE[k[0]]
+                blks.append((base[nm] + w * c, gs, LOCAL_SIZE[k[0]], self.parameter_block_idx[k]))
+            facs.append((base["proj_res"] + 2 * c, 2, len(blks) - first, first))
+        for kind in ("imu", "rel", "se3", "vb", "rp", "yaw"):
+            fam, nres, layout = KINDS[kind]
+            width = dp.out[kind + "_jac"].shape[1] if dp.out[kind + "_jac"].ndim == 2 else 0
+            for c, f in enumerate(by[kind]):
+                first = len(blks)
+                for k, (o, stride) in zip(f.parameter_blocks, layout):
+                    if k in self.constant:
+                        continue
+                    blks.append((base[kind + "_jac"] + width * c + o, stride, LOCAL_SIZE[k[0]], self.parameter_block_idx[k]))
+                facs.append((base[kind + "_res"] + nres * c, nres, len(blks) - first, first))
+        fa = (isv_ne_factor * len(facs))(*[isv_ne_factor(r, nr, nb, fb, 0) for r, nr, nb, fb in facs])
+        ba = (isv_ne_block * len(blks))(*[isv_ne_block(j, st, ls, p, 0) for j, st, ls, p in blks])
+        dev = dp.device
+        d_f = torch.frombuffer(bytearray(bytes(fa)), dtype=torch.uint8).to(dev)
+        d_b = torch.frombuffer(bytearray(bytes(ba)), dtype=torch.uint8).to(dev)
+        n = self.n
+        z = lambda *s: torch.zeros(s, dtype=torch.float64, device=dev)
+        o = {"A": z(pos, pos), "b": z(pos), "A_red": z(n, n), "b_red": z(n), "J": z(n, n), "r": z(n),
+             "rank": torch.zeros((1,), dtype=torch.int32, device=dev), "status": torch.zeros((1,), dtype=torch.int32, device=dev)}
+
+        class _In(C.Structure):
+            _fields_ = [("n_problems", C.c_int32), ("pos", C.c_int32), ("m_dense", C.c_int32), ("m_diag", C.c_int32),
+                        ("n_factors", C.c_int64), ("factors", C.c_void_p), ("blocks", C.c_void_p), ("values", C.c_void_p),
+                        ("eps", C.c_double)]
+
+        class _Out(C.Structure):
+            _fields_ = [(k, C.c_void_p) for k in ("A", "b", "A_red", "b_red", "linearized_jacobians",
+                                                  "linearized_residuals", "rank", "status")]
+        gi = _In(1, pos, m_dense, len(diag), len(facs), d_f.data_ptr(), d_b.data_ptr(), values.data_ptr(), self.eps)
+        go = _Out(o["A"].data_ptr(), o["b"].data_ptr(), o["A_red"].data_ptr(), o["b_red"].data_ptr(), o["J"].data_ptr(),
+                  o["r"].data_ptr(), o["rank"].data_ptr(), o["status"].data_ptr())
+        lib = self.be.lib
+        lib.isv_marginalize_generic.restype = C.c_int
+        lib.isv_marginalize_generic.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        capi.check(lib.isv_marginalize_generic(self.be.h, C.byref(gi), C.byref(go)), "isv_marginalize_generic")
+        self.be.synchronize()
+        # column-major (Eigen) -> numpy
+        self.A_red = o["A_red"].cpu().numpy().reshape(n, n).T.copy()
+        self.b_red = o["b_red"].cpu().numpy()
+        self.linearized_jacobians = o["J"].cpu().numpy().reshape(n, n).T.copy()
+        self.linearized_residuals = o["r"].cpu().numpy()
+        self.rank = int(o["rank"].item())
+        self.status = int(o["status"].item()) | int(dp.status.item())
+        self.pos = pos
+
+    def getParameterBlocks(self) -> List[Tuple[Key, int, int]]:
+        """kept blocks in order: (key, global size, position in the reduced tangent vector = idx - m)"""
+        keep = [(k, self.parameter_block_size[k], i - self.m) for k, i in self.parameter_block_idx.items() if i >= self.m]
+        return sorted(keep, key=lambda t: t[2])

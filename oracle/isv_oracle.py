@@ -1458,3 +1458,65 @@ def init_sparsify(inp: InitInput, cfg: Config) -> InitOutput:
     return InitOutput(Lamda, Lamda_prior, w, rank,
                       np.array([r.delta_t for r in rels]), np.array([r.delta_R for r in rels]),
                       np.array([r.sqrt_info for r in rels]), se3.t, se3.R, se3.sqrt_info, vbf.VB, vbf.sqrt_info, kld)
+
+
+# ----------------------------------------------------------------------------------------------
+# VINS-Mono MarginalizationInfo::marginalize (HKUST-Aerial-Robotics/VINS-Mono,
+# vins_estimator/src/factor/marginalization_factor.cpp) -- NOT under /root/reference: IS-VINS deleted
+# the class.  Restated from the published algorithm as the checker of the generic
+# facade (north_star's MarginalizationInfo API); parity unpinned.
+# ----------------------------------------------------------------------------------------------
+def vins_mono_marginalize(factors, pos: int, m: int, eps: float = 1e-8):
+    """factors: list of (residual (k,), [(tangent position, J (k x local_size)), ...]) already evaluated
+    and loss-corrected (ResidualBlockInfo::Evaluate).  Returns dict(A, b, A_red, b_red,
+    linearized_jacobians, linearized_residuals, rank).  Literal: dense A, JOINT eigen-thresholded
+    pseudo-inverse of Amm = (A_mm + A_mm^T)/2, eigen-decomposition of the reduced system."""
+    A = np.zeros((pos, pos))
+    b = np.zeros(pos)
+    for r, blocks in factors:                               # ThreadsConstructA
+        for i, (pi, Ji) in enumerate(blocks):
+            for j, (pj, Jj) in enumerate(blocks):
+                if j < i:
+                    continue
+                blk = Ji.T @ Jj
+                A[pi:pi + Ji.shape[1], pj:pj + Jj.shape[1]] += blk
+                if j != i:
+                    A[pj:pj + Jj.shape[1], pi:pi + Ji.shape[1]] += blk.T
+            b[pi:pi + Ji.shape[1]] += Ji.T @ r
+    n = pos - m
+    Amm = 0.5 * (A[:m, :m] + A[:m, :m].T)
+    w, V = np.linalg.eigh(Amm)
+    winv = np.where(w > eps, 1.0 / np.where(w > eps, w, 1.0), 0.0)
+    Amm_inv = (V * winv) @ V.T
+    bmm, Amr, Arm, Arr, brr = b[:m], A[:m, m:], A[m:, :m], A[m:, m:], b[m:]
+    A_red = Arr - Arm @ Amm_inv @ Amr
+    b_red = brr - Arm @ Amm_inv @ bmm
+    w2, V2 = np.linalg.eigh(0.5 * (A_red + A_red.T))
+    S = np.where(w2 > eps, w2, 0.0)
+    S_inv = np.where(w2 > eps, 1.0 / np.where(w2 > eps, w2, 1.0), 0.0)
+    lin_J = np.sqrt(S)[:, None] * V2.T
+    lin_r = np.sqrt(S_inv) * (V2.T @ b_red)
+    return {"A": A, "b": b, "A_red": A_red, "b_red": b_red, "linearized_jacobians": lin_J,
+            "linearized_residuals": lin_r, "rank": int(np.sum(w2 > eps)), "min_eig_Amm": float(w.min())}
+
+
+def schur_complement_longdouble(A, b, m: int):
+    """Adjudicator for the generic marginalization: A_rr - A_rm A_mm^-1 A_mr and b_r - A_rm A_mm^-1 b_m in
+    80-bit extended precision (np.longdouble, eps ~ 1e-19) by a Cholesky solve; valid when A_mm is positive
+    definite (then the eigen-thresholded pseudo-inverse is the inverse).  Returned as float64."""
+    Al = np.asarray(A, dtype=np.longdouble)
+    bl = np.asarray(b, dtype=np.longdouble)
+    Amm = (Al[:m, :m] + Al[:m, :m].T) / np.longdouble(2)
+    L = np.zeros((m, m), dtype=np.longdouble)
+    for j in range(m):
+        d = Amm[j, j] - L[j, :j] @ L[j, :j]
+        L[j, j] = np.sqrt(d)
+        if j + 1 < m:
+            L[j + 1:, j] = (Amm[j + 1:, j] - L[j + 1:, :j] @ L[j, :j]) / L[j, j]
+    rhs = np.concatenate([Al[:m, m:], bl[:m, None]], axis=1)
+    Y = np.zeros_like(rhs)
+    for i in range(m):                       # L Y = rhs
+        Y[i] = (rhs[i] - L[i, :i] @ Y[:i]) / L[i, i]
+    S = Al[m:, m:] - Y[:, :-1].T @ Y[:, :-1]
+    s = bl[m:] - Y[:, :-1].T @ Y[:, -1]
+    return np.asarray(S, dtype=np.float64), np.asarray(s, dtype=np.float64)

@@ -340,7 +340,7 @@ def _rand_sqrt_info(rng, n, scale):
 
 
 def make_problem(seed: int, n_features: int = 60, cfg: Optional[O.Config] = None, K: int = 10,
-                 max_track: int = 8) -> WindowProblem:
+                 max_track: int = 8, host0: float = 0.0) -> WindowProblem:
     """N = ALL_BUF_SIZE frames, N-1 IMU factors, `n_features` features with start_frame uniform and
     track length 2..max_track (one ProjectionFactor per later observation, :1062-1092), the prior
     factor set of :1100-1121 (priors from the oracle's init_sparsify on the first V frames, states
@@ -380,6 +380,8 @@ def make_problem(seed: int, n_features: int = 60, cfg: Optional[O.Config] = None
     pidx, pobs, feat = [], [], []
     for f in range(n_features):
         start = int(rng.integers(0, N - 1))
+        if host0 > 0.0 and rng.random() < host0:     # fraction of features hosted in the oldest frame
+            start = 0
         length = int(rng.integers(2, max_track + 1))
         u, v = rng.uniform(0, IMG_W), rng.uniform(0, IMG_H)
         pts_i = np.array([(u - CX) / FX, (v - CY) / FY, 1.0])
