@@ -272,6 +272,17 @@ typedef struct isv_proj_factors {
   double cauchy_a;               /* 0: no loss.  > 0: ceres::CauchyLoss(a) applied the way ceres'
                                     Corrector does for rho'' <= 0: r, J scaled by sqrt(rho'(|r|^2))
                                     (loss_function of :1018 has a = 1)                           */
+  /* ProjectionTdFactor (online time-offset estimation; north_star / BASELINE configs[3]).  ABSENT from
+   * the reference (only `para_Td` and the per-observation velocity / td fields
+   * exist, include/estimator.h:126, include/feature_tracker/feature_manager.h:24-39): follows VINS-Mono's
+   * published projection_td_factor.cpp, parity unpinned.  td_obs == NULL -> plain ProjectionFactor.  */
+  const double* td_obs;          /* [8][stride] velocity_i.x, velocity_i.y, velocity_j.x, velocity_j.y,
+                                    td_i, td_j, row_i - ROW/2, row_j - ROW/2                      */
+  const double* td;              /* [n_td] para_Td[.][0]                                          */
+  const int32_t* td_idx;         /* [n] index into td, or NULL = 0                                */
+  int32_t n_td;
+  int32_t reserved;
+  double tr_over_row;            /* TR / ROW (rolling-shutter read-out per image row), 0 = global shutter */
 } isv_proj_factors;
 typedef struct isv_proj_eval {
   double* residuals;             /* [n][2]                                                       */
@@ -279,6 +290,7 @@ typedef struct isv_proj_eval {
   double* jac_pose_j;            /* [n][2][7] or NULL                                            */
   double* jac_ex_pose;           /* [n][2][7] or NULL (SetParameterBlockConstant, :1037)         */
   double* jac_feature;           /* [n][2]    or NULL                                            */
+  double* jac_td;                /* [n][2]    or NULL (ProjectionTdFactor's 5th block)            */
 } isv_proj_eval;
 
 /* IMUFactor::Evaluate  include/factor/imu_factor.h:23-159 (+ integration_base.h:160-186);

@@ -91,12 +91,13 @@ class isv_param_blocks(C.Structure):
 
 class isv_proj_factors(C.Structure):
     _fields_ = [("n", C.c_int64), ("stride", C.c_int64), ("idx", C.c_void_p), ("obs", C.c_void_p),
-                ("cauchy_a", C.c_double)]
+                ("cauchy_a", C.c_double), ("td_obs", C.c_void_p), ("td", C.c_void_p), ("td_idx", C.c_void_p),
+                ("n_td", C.c_int32), ("reserved", C.c_int32), ("tr_over_row", C.c_double)]
 
 
 class isv_proj_eval(C.Structure):
     _fields_ = [("residuals", C.c_void_p), ("jac_pose_i", C.c_void_p), ("jac_pose_j", C.c_void_p),
-                ("jac_ex_pose", C.c_void_p), ("jac_feature", C.c_void_p)]
+                ("jac_ex_pose", C.c_void_p), ("jac_feature", C.c_void_p), ("jac_td", C.c_void_p)]
 
 
 class isv_imu_factors(C.Structure):

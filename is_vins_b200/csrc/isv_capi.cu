@@ -675,7 +675,12 @@ static isv_status eval_projection_on(isv_handle* h, cudaStream_t stream, const i
   const long long per_cta = 32LL * kEvalWarps;
   const long long grid = (f->n + per_cta - 1) / per_cta;
   if (grid > 0x7fffffffLL) return ISV_ERR_BAD_ARG;
-  eval_projection_kernel<<<(unsigned)grid, kEvalThreads, 0, stream>>>(*pb, *f, *out, h->dcfg, status);
+  if (f->td_obs) {
+    if (!f->td || f->n_td < 1) return ISV_ERR_BAD_ARG;
+    eval_projection_kernel<true><<<(unsigned)grid, kEvalThreads, 0, stream>>>(*pb, *f, *out, h->dcfg, status);
+  } else {
+    eval_projection_kernel<false><<<(unsigned)grid, kEvalThreads, 0, stream>>>(*pb, *f, *out, h->dcfg, status);
+  }
   ++h->launches;
   ISV_CUDA(cudaGetLastError());
   return ISV_OK;

@@ -75,6 +75,9 @@ ISV_DI void red_mul_t(const double* red, const double* M, double* o) {
 // pts_camera_j) and five 2x3 products  red, red*A, red*A*Ri, red*ric^T, red*tmp_r  stay live
 // (A = ric^T Rj^T, tmp_r = A Ri ric); every Jacobian block is a cheap combination of those and is
 // stored as soon as it is formed, so the kernel fits 128 registers -> 4 CTAs (16 warps) per SM.
+// HAS_TD: ProjectionTdFactor (5th block, shifted observations); compiled separately so that the plain
+// ProjectionFactor path keeps its register budget.
+template <bool HAS_TD>
 __global__ void __launch_bounds__(kEvalThreads, 4)
 eval_projection_kernel(isv_param_blocks pb, isv_proj_factors fs, isv_proj_eval out, DevCfg cfg, int32_t* status) {
   __shared__ double stage_all[kEvalWarps][32 * kStageLd];
@@ -87,7 +90,7 @@ eval_projection_kernel(isv_param_blocks pb, isv_proj_factors fs, isv_proj_eval o
   const bool live = k < fs.n;
   bool ok = false;
   double pc_i[3], pim_i[3], pim_j[3], pc_j[3], red[6], rA[6], rARi[6], rT[6], rTmp[6];
-  double res0 = 0.0, res1 = 0.0, jf0 = 0.0, jf1 = 0.0;
+  double res0 = 0.0, res1 = 0.0, jf0 = 0.0, jf1 = 0.0, jt0 = 0.0, jt1 = 0.0;
   if (live) {
     const int ii = fs.idx[k], jj = fs.idx[fs.stride + k], ie = fs.idx[2 * fs.stride + k], iff = fs.idx[3 * fs.stride + k];
     ok = !(ii < 0 || ii >= pb.n_pose || jj < 0 || jj >= pb.n_pose || ie < 0 || ie >= pb.n_ex_pose || iff < 0 ||
@@ -100,8 +103,25 @@ eval_projection_kernel(isv_param_blocks pb, isv_proj_factors fs, isv_proj_eval o
       const double* PSe = pb.ex_pose + (size_t)ie * 7;
       const Quat Qi = quat_from_pose(PSi), Qj = quat_from_pose(PSj), qic = quat_from_pose(PSe);
       const double lam = pb.feature[iff];
-      const double pts_i[3] = {fs.obs[k], fs.obs[fs.stride + k], fs.obs[2 * fs.stride + k]};
-      const double xj = fs.obs[3 * fs.stride + k], yj = fs.obs[4 * fs.stride + k];
+      double pts_i[3] = {fs.obs[k], fs.obs[fs.stride + k], fs.obs[2 * fs.stride + k]};
+      double xj = fs.obs[3 * fs.stride + k], yj = fs.obs[4 * fs.stride + k];
+      double vix = 0.0, viy = 0.0, vjx = 0.0, vjy = 0.0;
+      if (HAS_TD) {
+        // ProjectionTdFactor: pts_td = pts - (td - td_obs + TR / ROW * row) * velocity   (velocity.z = 0)
+        const int it = fs.td_idx ? fs.td_idx[k] : 0;
+        if (it < 0 || it >= fs.n_td) {
+          ok = false;
+          if (status) atomicOr(status, ISV_W_BAD_INDEX);
+        } else {
+          const double td = fs.td[it];
+          vix = fs.td_obs[k]; viy = fs.td_obs[fs.stride + k];
+          vjx = fs.td_obs[2 * fs.stride + k]; vjy = fs.td_obs[3 * fs.stride + k];
+          const double di = td - fs.td_obs[4 * fs.stride + k] + fs.tr_over_row * fs.td_obs[6 * fs.stride + k];
+          const double dj = td - fs.td_obs[5 * fs.stride + k] + fs.tr_over_row * fs.td_obs[7 * fs.stride + k];
+          pts_i[0] -= di * vix; pts_i[1] -= di * viy;
+          xj -= dj * vjx; yj -= dj * vjy;
+        }
+      }
       // :38-42
       double pw[3], d[3];
 #pragma unroll
@@ -150,10 +170,16 @@ eval_projection_kernel(isv_param_blocks pb, isv_proj_factors fs, isv_proj_eval o
       const double sc = -1.0 / (lam * lam);
       jf0 = (rTmp[0] * pts_i[0] + rTmp[1] * pts_i[1] + rTmp[2] * pts_i[2]) * sc;
       jf1 = (rTmp[3] * pts_i[0] + rTmp[4] * pts_i[1] + rTmp[5] * pts_i[2]) * sc;
+      // jacobian_td = reduce * tmp_r * velocity_i / inv_dep * -1 + sqrt_info * velocity_j.head(2)
+      if (HAS_TD) {
+        jt0 = -(rTmp[0] * vix + rTmp[1] * viy) / lam + ls * (s00 * vjx + s01 * vjy);
+        jt1 = -(rTmp[3] * vix + rTmp[4] * viy) / lam + ls * (s10 * vjx + s11 * vjy);
+      }
     }
   }
   if (live && out.residuals) reinterpret_cast<double2*>(out.residuals)[k] = make_double2(res0, res1);
   if (live && out.jac_feature) reinterpret_cast<double2*>(out.jac_feature)[k] = make_double2(jf0, jf1);
+  if (HAS_TD && live && out.jac_td) reinterpret_cast<double2*>(out.jac_td)[k] = make_double2(jt0, jt1);
   double v[14];
   if (out.jac_pose_i) {       // :80-85  jaco_i = [A | A Ri (-skew(pts_imu_i))]
 #pragma unroll

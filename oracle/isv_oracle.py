@@ -767,6 +767,50 @@ class ProjectionFactor:
         return float(r @ r)
 
 
+class ProjectionTdFactor(ProjectionFactor):
+    """VINS-Mono vins_estimator/src/factor/projection_td_factor.cpp (ABSENT from /root/reference, SURVEY.md
+    section 0; restated from the published algorithm for BASELINE configs[3] -- parity unpinned):
+    observations are shifted by the time offset td along their image velocity,
+        pts_td = pts - (td - td_obs + TR / ROW * row) * velocity ,  velocity.z = 0 ,
+    then the ProjectionFactor chain; 5th parameter block td (1) with
+        jacobian_td = reduce * ric^T Rj^T Ri ric * velocity_i / inv_dep * -1 + sqrt_info * velocity_j.head(2)."""
+
+    def __init__(self, pts_i, pts_j, velocity_i, velocity_j, td_i, td_j, row_i, row_j, sqrt_info, tr_over_row=0.0):
+        super().__init__(pts_i, pts_j, sqrt_info)
+        self.obs_i = np.array(pts_i, dtype=np.float64)
+        self.obs_j = np.array(pts_j, dtype=np.float64)
+        self.velocity_i = np.array([velocity_i[0], velocity_i[1], 0.0])
+        self.velocity_j = np.array([velocity_j[0], velocity_j[1], 0.0])
+        self.td_i, self.td_j, self.row_i, self.row_j = float(td_i), float(td_j), float(row_i), float(row_j)
+        self.tr_over_row = float(tr_over_row)
+
+    def EvaluateCeres(self, parameters, want=(True, True, True, True, True)):
+        td = float(parameters[4][0])
+        self.pts_i = self.obs_i - (td - self.td_i + self.tr_over_row * self.row_i) * self.velocity_i
+        self.pts_j = self.obs_j - (td - self.td_j + self.tr_over_row * self.row_j) * self.velocity_j
+        r, reduce, ji, jj, jex, jf = self._common(parameters[0], parameters[1], parameters[2], parameters[3][0])
+        res = self.sqrt_info @ r
+        red = self.sqrt_info @ reduce
+        out = []
+        for j, w in zip((ji, jj, jex), want[:3]):
+            if not w:
+                out.append(None)
+                continue
+            full = np.zeros((2, 7))
+            full[:, :6] = red @ j
+            out.append(full)
+        out.append((red @ jf).reshape(2, 1) if want[3] else None)
+        if want[4]:
+            Ri, Rj = q_to_R(quat_from_pose(parameters[0])), q_to_R(quat_from_pose(parameters[1]))
+            ric = q_to_R(quat_from_pose(parameters[2]))
+            inv_dep = float(parameters[3][0])
+            jtd = red @ ric.T @ Rj.T @ Ri @ ric @ self.velocity_i / inv_dep * -1.0 + self.sqrt_info @ self.velocity_j[0:2]
+            out.append(jtd.reshape(2, 1))
+        else:
+            out.append(None)
+        return res, out
+
+
 # ----------------------------------------------------------------------------------------------
 # include/factor/relative_pose_factor.h
 # ----------------------------------------------------------------------------------------------

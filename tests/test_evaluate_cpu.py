@@ -81,3 +81,19 @@ def test_factor_problem_pack_and_tile():
                           np.array([[2 * 18], [2 * 18], [2], [2 * len(fp.feature)]]) * np.ones((1, P), np.int64))
     assert np.array_equal(t.imu_idx[-1], fp.imu_idx[-1] + 2 * 18)
     assert np.array_equal(t.vb_idx, fp.vb_idx[0] + 18 * np.arange(3))
+
+
+def test_projection_td_twin_matches_finite_differences():
+    """ProjectionTdFactor (VINS-Mono, absent from the reference): analytic blocks incl. d r / d td vs FD."""
+    p = sim.make_problem(sim.seed_for(6, 11), n_features=6)
+    rng = np.random.default_rng(5)
+    k = 2
+    i, j, e, f = [int(x) for x in p.proj_idx[:, k]]
+    pf = O.ProjectionTdFactor(p.proj_obs[0:3, k], np.array([p.proj_obs[3, k], p.proj_obs[4, k], 1.0]),
+                              rng.normal(0, 0.3, 2), rng.normal(0, 0.3, 2), 0.004, -0.003, 57.0, -120.0,
+                              p.cfg.proj_sqrt_info, tr_over_row=0.03 / 480)
+    params = [p.poses[i], p.poses[j], p.ex[e], p.feat[f:f + 1], np.array([0.011])]
+    r, js = pf.EvaluateCeres(params)
+    fd = _fd_blocks(lambda q: pf.EvaluateCeres(q, want=(False,) * 5)[0], params, (6, 6, 6, 1, 1))
+    for a, b in zip(js, fd):
+        assert np.allclose(np.asarray(a)[:, :b.shape[1]], b, rtol=2e-5, atol=2e-4 * np.abs(b).max())

@@ -81,3 +81,48 @@ def test_evaluate_flags_bad_index(backend):
     eval_problem(backend, dp)
     backend.synchronize()
     assert int(dp.status.item()) & capi.W_BAD_INDEX
+
+
+def test_projection_td_factor_matches_oracle(backend):
+    """ProjectionTdFactor through isv_eval_projection_batch (td_obs != NULL): 5 blocks incl. jac_td."""
+    import ctypes as C
+    import torch
+    from oracle import isv_oracle as O
+    p = sim.make_problem(sim.seed_for(6, 12), n_features=45)
+    rng = np.random.default_rng(12)
+    P = p.proj_idx.shape[1]
+    tdo = np.zeros((8, P))
+    tdo[0:4] = rng.normal(0, 0.4, (4, P))
+    tdo[4:6] = rng.normal(0, 0.005, (2, P))
+    tdo[6:8] = rng.uniform(-240, 240, (2, P))
+    td = np.array([0.013, -0.02])
+    td_idx = rng.integers(0, 2, P).astype(np.int32)
+    tr = 0.033 / 480
+    dev = "cuda:0"
+    t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt)
+    d = {"pose": t(p.poses), "sb": t(p.sbs), "ex": t(p.ex), "feat": t(p.feat), "idx": t(p.proj_idx, torch.int32),
+         "obs": t(p.proj_obs), "tdo": t(tdo), "td": t(td), "tdi": t(td_idx, torch.int32)}
+    o = {k: torch.zeros((P, w), dtype=torch.float64, device=dev) for k, w in
+         (("res", 2), ("ji", 14), ("jj", 14), ("je", 14), ("jf", 2), ("jt", 2))}
+    st = torch.zeros((1,), dtype=torch.int32, device=dev)
+    pb = capi.isv_param_blocks(len(p.poses), len(p.sbs), 1, len(p.feat), d["pose"].data_ptr(), d["sb"].data_ptr(),
+                               d["ex"].data_ptr(), d["feat"].data_ptr())
+    pf = capi.isv_proj_factors(P, P, d["idx"].data_ptr(), d["obs"].data_ptr(), 1.0, d["tdo"].data_ptr(),
+                               d["td"].data_ptr(), d["tdi"].data_ptr(), 2, 0, tr)
+    po = capi.isv_proj_eval(*[o[k].data_ptr() for k in ("res", "ji", "jj", "je", "jf", "jt")])
+    capi.check(backend.lib.isv_eval_projection_batch(backend.h, C.byref(pb), C.byref(pf), C.byref(po),
+                                                     C.c_void_p(st.data_ptr())), "isv_eval_projection_batch")
+    backend.synchronize()
+    assert int(st.item()) == 0
+    h = {k: v.cpu().numpy() for k, v in o.items()}
+    worst = 0.0
+    for k in range(P):
+        i, j, e, f = [int(x) for x in p.proj_idx[:, k]]
+        fac = O.ProjectionTdFactor(p.proj_obs[0:3, k], np.array([p.proj_obs[3, k], p.proj_obs[4, k], 1.0]), tdo[0:2, k],
+                                   tdo[2:4, k], tdo[4, k], tdo[5, k], tdo[6, k], tdo[7, k], p.cfg.proj_sqrt_info, tr)
+        r, js = fac.EvaluateCeres([p.poses[i], p.poses[j], p.ex[e], p.feat[f:f + 1], td[td_idx[k]:td_idx[k] + 1]])
+        r, js = sim.cauchy_correct(r, js, 1.0)
+        worst = max(worst, rel_err(h["res"][k], r))
+        for name, jb in zip(("ji", "jj", "je", "jf", "jt"), js):
+            worst = max(worst, rel_err(h[name][k], np.asarray(jb).ravel()))
+    assert worst <= TOL, worst
