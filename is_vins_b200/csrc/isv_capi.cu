@@ -23,7 +23,7 @@ struct isv_handle {
   cudaStream_t own_stream;
   cudaStream_t stream;
   cudaStream_t copy_stream;
-  cudaStream_t aux[2];   // fork/join side streams of isv_eval_problem
+  cudaStream_t aux[4];   // fork/join side streams: [0..1] isv_eval_problem and the backward chain (per slot), [2..3] forward factor Jacobians
   cudaEvent_t aux_ev[3];
   isv_config cfg;
   DevCfg dcfg;
@@ -35,7 +35,7 @@ struct isv_handle {
   size_t pinned_bytes;
   double* gram;          // [n][42 + kFJ] scratch handed between the kernels of one batch, grow-only:
   size_t gram_bytes;     //   landmark Gram triangles (forward stage 1 -> 2) and the factor-Jacobian records
-  cudaEvent_t jac_ev[4]; // fork / join of the factor-Jacobian pre-kernel, one pair per launching stream
+  cudaEvent_t jac_ev[6]; // fork / join events of launch_batch, three per launching stream
   cudaEvent_t ev[4];
 };
 
@@ -108,9 +108,9 @@ isv_status isv_create(const isv_config* cfg, int device, isv_handle** out) {
     return ISV_ERR_CUDA;
   }
   for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
-  for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
+  for (int i = 0; i < 4; ++i) cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
   for (int i = 0; i < 3; ++i) cudaEventCreateWithFlags(&h->aux_ev[i], cudaEventDisableTiming);
-  for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&h->jac_ev[i], cudaEventDisableTiming);
+  for (int i = 0; i < 6; ++i) cudaEventCreateWithFlags(&h->jac_ev[i], cudaEventDisableTiming);
   h->stream = h->own_stream;
   cudaFuncSetAttribute(marg_forward_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kWarpsPerCta * kAccSmemPerWarp * sizeof(double)));
@@ -131,11 +131,11 @@ void isv_destroy(isv_handle* h) {
   if (h->pinned) cudaFreeHost(h->pinned);
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 4; ++i)
     if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
   for (int i = 0; i < 3; ++i)
     if (h->aux_ev[i]) cudaEventDestroy(h->aux_ev[i]);
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 6; ++i)
     if (h->jac_ev[i]) cudaEventDestroy(h->jac_ev[i]);
   cudaStreamDestroy(h->own_stream);
   cudaStreamDestroy(h->copy_stream);
@@ -220,15 +220,24 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in, const isv_
   const bool bwd = which & (ISV_RUN_BACKWARD | ISV_RUN_BACKWARD_STAGE2);
   if (out->status) ISV_CUDA(cudaMemsetAsync(out->status, 0, sizeof(int32_t) * (size_t)n, stream));
   const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-  // MargForward and MargBackward are independent: when both run, the backward chain (factor
-  // Jacobians -> marg_backward_kernel) is forked onto a side stream so that its latency-bound CTAs share
-  // the SMs with the FP64-bound landmark kernel, and joined back at the end.
-  const bool fork = (which & ISV_RUN_BACKWARD) && (which & ISV_RUN_FORWARD);
+  // Three independent chains: [landmark kernel] on the caller's stream, [forward factor Jacobians] and
+  // [backward factor Jacobians -> marg_backward_kernel] on side streams.  The factor-Jacobian launches are
+  // pure latency (one thread per window and factor, ~1.5 % issue utilisation): started together with the
+  // FP64-bound landmark kernel they hide behind it; the tail kernel joins the forward Jacobians, the end of
+  // the call joins the backward chain.
+  const bool fork_b = (which & ISV_RUN_BACKWARD) && (which & ISV_RUN_FORWARD);
+  const bool fork_f = jac_fwd && stage1;
   const int slot = (stream == h->copy_stream) ? 1 : 0;
-  cudaStream_t bs = fork ? h->aux[slot] : stream;
-  if (fork) {
-    ISV_CUDA(cudaEventRecord(h->jac_ev[2 * slot], stream));
-    ISV_CUDA(cudaStreamWaitEvent(bs, h->jac_ev[2 * slot], 0));
+  cudaEvent_t* ev = h->jac_ev + 3 * slot;   // [0] fork point, [1] backward chain done, [2] forward Jacobians done
+  cudaStream_t bs = fork_b ? h->aux[slot] : stream;
+  cudaStream_t fs = fork_f ? h->aux[2 + slot] : stream;
+  if (fork_b || fork_f) ISV_CUDA(cudaEventRecord(ev[0], stream));
+  if (fork_b) ISV_CUDA(cudaStreamWaitEvent(bs, ev[0], 0));
+  if (fork_f) ISV_CUDA(cudaStreamWaitEvent(fs, ev[0], 0));
+  if (jac_fwd) {
+    marg_factor_jac_kernel<<<dim3((n + 127) / 128, 4), 128, 0, fs>>>(*in, *out, fj, h->dcfg, 0);
+    ++h->launches;
+    if (fork_f) ISV_CUDA(cudaEventRecord(ev[2], fs));
   }
   if (jac_bwd) {
     // the IMU Jacobian record is sparse: zero-fill it, the kernel writes the non-zero blocks
@@ -236,27 +245,24 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in, const isv_
     marg_factor_jac_kernel<<<dim3((n + 127) / 128, 3), 128, 0, bs>>>(*in, *out, fj, h->dcfg, 4);
     ++h->launches;
   }
-  if (bwd) {
-    marg_backward_kernel<<<grid, kThreads, kWarpsPerCta * kBwdSmemPerWarp * sizeof(double), bs>>>(*in, *out, fj, h->dcfg,
-                                                                                                 h->cfg.vo_size);
-    ++h->launches;
-  }
-  if (fork) ISV_CUDA(cudaEventRecord(h->jac_ev[2 * slot + 1], bs));
-  if (jac_fwd) {
-    marg_factor_jac_kernel<<<dim3((n + 127) / 128, 4), 128, 0, stream>>>(*in, *out, fj, h->dcfg, 0);
-    ++h->launches;
-  }
   if (stage1) {
     marg_forward_accum_kernel<<<grid, kThreads, kWarpsPerCta * kAccSmemPerWarp * sizeof(double), stream>>>(
         *in, gram, out->status, h->dcfg);
     ++h->launches;
   }
+  if (bwd) {
+    marg_backward_kernel<<<grid, kThreads, kWarpsPerCta * kBwdSmemPerWarp * sizeof(double), bs>>>(*in, *out, fj, h->dcfg,
+                                                                                                 h->cfg.vo_size);
+    ++h->launches;
+  }
+  if (fork_b) ISV_CUDA(cudaEventRecord(ev[1], bs));
+  if (fork_f) ISV_CUDA(cudaStreamWaitEvent(stream, ev[2], 0));
   if (stage2) {
     marg_forward_tail_kernel<<<grid, kThreads, kWarpsPerCta * kFwdSmemPerWarp * sizeof(double), stream>>>(*in, *out, gram,
                                                                                                         fj, h->dcfg);
     ++h->launches;
   }
-  if (fork) ISV_CUDA(cudaStreamWaitEvent(stream, h->jac_ev[2 * slot + 1], 0));
+  if (fork_b) ISV_CUDA(cudaStreamWaitEvent(stream, ev[1], 0));
   ISV_CUDA(cudaGetLastError());
   return ISV_OK;
 }
