@@ -74,6 +74,14 @@ class FactorProblem:
             i32([f.index for f in p.rp], (-1,)), f64([rp_record(f.R, f.sqrt_info) for f in p.rp], capi.RP_REC),
             i32([f.index for f in p.yaw], (-1,)), f64([yaw_record(f.yaw_meas, f.sqrt_info) for f in p.yaw], capi.YAW_REC))
 
+    @classmethod
+    def load(cls, path: str) -> "FactorProblem":
+        """From an .npz holding the fields of this class (tests/golden/problem_*.npz)."""
+        z = np.load(path)
+        return cls(*[z[k] for k in ("pose", "speed_bias", "ex_pose", "feature", "proj_idx", "proj_obs", "imu_idx",
+                                    "imu_preint", "rel_idx", "rel_rec", "se3_idx", "se3_rec", "vb_idx", "vb_rec",
+                                    "rp_idx", "rp_rec", "yaw_idx", "yaw_rec")])
+
     def tile(self, reps: int) -> "FactorProblem":
         """`reps` independent copies (parameter blocks concatenated, indices offset)."""
         n_pose, n_sb, n_ex, n_feat = len(self.pose), len(self.speed_bias), len(self.ex_pose), len(self.feature)

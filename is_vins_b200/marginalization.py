@@ -113,7 +113,7 @@ class MarginalizationInfo:
         self._dp = DeviceProblem(fp, f"cuda:{self.be.device}")
         eval_problem(self.be, self._dp, self.cauchy_a)
 
-    def marginalize(self) -> None:
+    def marginalize(self, keep_tables: bool = False) -> None:
         import torch
         assert self._dp is not None, "call preMarginalize first"
         dp, by = self._dp, self._by
@@ -188,6 +188,9 @@ class MarginalizationInfo:
         lib.isv_marginalize_generic.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         capi.check(lib.isv_marginalize_generic(self.be.h, C.byref(gi), C.byref(go)), "isv_marginalize_generic")
         self.be.synchronize()
+        if keep_tables:   # for tools/bench_marg_generic.py: the device tables of this problem
+            self._gi, self._go = gi, go
+            self._tables = {"factors_bytes": bytes(fa), "d_f": d_f, "d_b": d_b, "values": values, "out": o}
         # column-major (Eigen) -> numpy
         self.A_red = o["A_red"].cpu().numpy().reshape(n, n).T.copy()
         self.b_red = o["b_red"].cpu().numpy()

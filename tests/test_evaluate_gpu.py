@@ -126,3 +126,22 @@ def test_projection_td_factor_matches_oracle(backend):
         for name, jb in zip(("ji", "jj", "je", "jf", "jt"), js):
             worst = max(worst, rel_err(h[name][k], np.asarray(jb).ravel()))
     assert worst <= TOL, worst
+
+
+@pytest.mark.parametrize("name", ["problem_F60.npz", "problem_F300_host0.npz"])
+def test_committed_problem_fixtures(backend, name):
+    """tests/golden/problem_*.npz: the oracle's Evaluate outputs committed with the inputs."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+    z = np.load(path)
+    dp = DeviceProblem(FactorProblem.load(path), "cuda:0")
+    eval_problem(backend, dp, 1.0)
+    backend.synchronize()
+    assert int(dp.status.item()) == 0
+    h = dp.host()
+    n = z["ref_proj_res"].shape[0]
+    for k in ("proj_res", "proj_ji", "proj_jj", "proj_je", "proj_jf"):
+        assert rel_err(h[k][:n], z["ref_" + k]) <= TOL, k
+    # the IMU factor carries no loss function (problemSolve passes NULL): cauchy_a must not touch it
+    assert rel_err(h["imu_res"], z["ref_imu_res"]) <= TOL
+    assert rel_err(h["imu_jac"], z["ref_imu_jac"]) <= TOL

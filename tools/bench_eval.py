@@ -2,7 +2,7 @@
 """Roofline of the batched ceres-Evaluate kernels (isv_eval_*_batch): factors evaluated / s and
 achieved HBM GB/s (algorithmic bytes / CUDA-event time) against MEASURED_PEAKS.json.
 
-    python tools/bench_eval.py [--windows 256] [--features 1000] [--steps 20] [--no-ex-jac]
+    python tools/bench_eval.py [--windows 256] [--steps 20] [--no-ex-jac]
 
 Algorithmic bytes per ProjectionFactor: in 4*4 (indices) + 5*8 (observation) = 56 B,
 out 8*(2 + 14 + 14 [+ 14] + 2) = 256 B (368 B with the extrinsic block); the gathered parameter blocks
@@ -22,17 +22,14 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--windows", type=int, default=256)
-    ap.add_argument("--features", type=int, default=1000)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--no-ex-jac", action="store_true")
     ap.add_argument("--cauchy", type=float, default=1.0)
     args = ap.parse_args()
     import torch
     from is_vins_b200 import DeviceProblem, FactorProblem, MargBackend, eval_problem
-    from oracle import sim   # synthetic problem generator only (test infrastructure); nothing timed uses it
-
-    p = sim.make_problem(sim.seed_for(6, 100), n_features=args.features)
-    fp = FactorProblem.from_factors(p).tile(args.windows)
+    # committed synthetic problemSolve() factor list (tests/golden/make_problem_golden.py, seed 20266100)
+    fp = FactorProblem.load(os.path.join(ROOT, "tests", "golden", "problem_F1000.npz")).tile(args.windows)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     be = MargBackend(0)
@@ -74,7 +71,7 @@ def main():
     ach = alg / (ms_proj * 1e-3) / 1e9
     print(json.dumps({
         "metric": "factors_evaluated_per_s", "value": (P + ni) / (ms_all * 1e-3), "unit": "factors/s",
-        "config": {"workload": f"problemSolve() factor list, {args.windows} windows x {args.features} features "
+        "config": {"workload": f"problemSolve() factor list, {args.windows} windows x 1000 features "
                                f"({P} ProjectionFactors, {ni} IMUFactors), Cauchy a={args.cauchy}, "
                                f"ex-pose block {'constant' if args.no_ex_jac else 'evaluated'}",
                    "l2": "inputs_larger_than_l2"},
