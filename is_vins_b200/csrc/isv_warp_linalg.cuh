@@ -620,6 +620,62 @@ __device__ __forceinline__ int w_sqrt_info_from_cov_regs(const double* A, int ld
   return bad;
 }
 
+// Several small SPD matrices turned into their sqrt-information factors AT ONCE, one column per lane:
+// lane (group g, column c) owns column c of its group's covariance A_g (N_g x N_g, column-major, ld N_g)
+// in registers; the reverse-order Cholesky A = U1 U1^T runs right-looking with the finished column
+// broadcast through the group's scratch Us (N*N + N doubles), then every lane back-substitutes its own
+// column of U1^-1 (the matrix w_sqrt_info_from_cov produces) and stores it.  The groups share one
+// instruction stream, so three matrices cost what the largest one costs.  All 32 lanes must call it;
+// `active` = this lane owns a column.  NMAX >= every N.
+template <int NMAX>
+__device__ __forceinline__ int w_sqrt_info_multi(const double* A, int N, int c, bool active, double* Us, double* out,
+                                                 int& nonfinite) {
+  double a[NMAX];
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) a[i] = (active && i <= c) ? A[i + N * c] : 0.0;
+  int bad = 0;
+#pragma unroll
+  for (int j = NMAX - 1; j >= 0; --j) {
+    if (active && c == j) {
+      const double d = a[j];
+      if (!(d > 0.0)) bad = 1;
+      const double ri = rsqrt(d);
+      Us[N * N + j] = ri;
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i)
+        if (i < j) Us[j * N + i] = a[i] * ri;
+    }
+    __syncwarp();
+    if (active && c < j && j < N) {
+      const double ucj = Us[j * N + c];
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i)
+        if (i <= c) a[i] = fma(-Us[j * N + i], ucj, a[i]);
+    }
+  }
+  __syncwarp();
+  // column c of X = U1^-1 : x_i = ((i == c) - sum_{i < k <= c} U1[i][k] x_k) / U1[i][i]
+  double x[NMAX];
+#pragma unroll
+  for (int i = NMAX - 1; i >= 0; --i) {
+    double sacc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = i + 1; k < NMAX; ++k)
+      if (active && k <= c) sacc = fma(-Us[k * N + i], x[k], sacc);
+    x[i] = (active && i <= c) ? sacc * Us[N * N + i] : 0.0;
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i)
+      if (i < N) {
+        if (!isfinite(x[i])) nonfinite = 1;
+        out[i + N * c] = x[i];
+      }
+  }
+  __syncwarp();
+  return bad;
+}
+
 // SPD inverse of a small matrix entirely in registers, no shuffles and no barriers inside: EVERY lane
 // loads the lower triangle (broadcast LDS) and runs the same serial LDL^T factorisation (SIMT makes the
 // redundancy free), then lane j < N solves for column j of A^-1 and writes it back.  ~4x fewer warp

@@ -42,7 +42,7 @@ constexpr int kFwdConst = 72;                // Psi (12 x 6)
 constexpr int kFwdWork = 832;                // tail matrices
 constexpr int kFwdSmemPerWarp = kFwdConst + kFwdWork;
 // ---- backward ---------------------------------------------------------------------------------
-constexpr int kBwdSmemPerWarp = 240 + 24 + 315 + 425 + 48;   // Lc | hv | Gs | T | sc (isv_window_kernels.cuh)
+constexpr int kBwdSmemPerWarp = 240 + 24 + 315 + 472 + 48;   // Lc | hv | Gs | T | sc (isv_window_kernels.cuh)
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -566,8 +566,8 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
   double* Lc = S + kBwdLc;     // Cholesky factor of the covariance, column k at Lc[15 k + i]; [225..240) = 1 / L_kk
   double* hv = S + kBwdHv;     // current Householder vector (15) + tau
   double* Gs = S + kBwdGs;     // 15 x 21
-  double* T = S + kBwdT;       // Jrel (72) | Jrp (16) | JU / Ls (256) | cov (81)
-  double* sc = T + 425;        // scratch of the general path: dinv[0..21), lam[24..)
+  double* T = S + kBwdT;       // Jrel (72) | Jrp (16) | JU / Ls (256) | cov 9x9, 6x6, 2x2 (128)
+  double* sc = T + 472;        // scratch of the general path: dinv[0..21), lam[24..)
   int status = 0, nonfinite = 0;
 
   const double* pvb = in.prior_vb + (size_t)win * ISV_VB_REC;
@@ -756,31 +756,34 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
       for (int k = 0; k < 15; ++k) JU[(lane - 15) + 17 * k] = y[k];
     }
     __syncwarp();
-    // cov blocks: rel = rows 0-5, vb = rows 6-14, rp = rows 15-16 of Y
-    for (int idx = lane; idx < 36; idx += 32) {
-      int r = idx % 6, c = idx / 6;
+    // cov blocks: rel = rows 0-5, vb = rows 6-14, rp = rows 15-16 of Y ; cov_i = Y_i Y_i^T
+    double* cov6 = cov + 81;
+    double* cov2 = cov + 117;
+    for (int idx = lane; idx < 121; idx += 32) {
+      int r0, n, e;
+      double* dst;
+      if (idx < 81) { r0 = 6; n = 9; e = idx; dst = cov; }
+      else if (idx < 117) { r0 = 0; n = 6; e = idx - 81; dst = cov6; }
+      else { r0 = 15; n = 2; e = idx - 117; dst = cov2; }
+      const int r = e % n, c = e / n;
       double acc = 0.0;
-      for (int k = 0; k < 15; ++k) acc = fma(JU[r + 17 * k], JU[c + 17 * k], acc);
-      cov[idx] = acc;
+#pragma unroll
+      for (int k = 0; k < 15; ++k) acc = fma(JU[r0 + r + 17 * k], JU[r0 + c + 17 * k], acc);
+      dst[e] = acc;
     }
     __syncwarp();
-    if (w_sqrt_info_from_cov_regs<6>(cov, 6, o_rel + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
-    for (int idx = lane; idx < 81; idx += 32) {
-      int r = idx % 9, c = idx / 9;
-      double acc = 0.0;
-      for (int k = 0; k < 15; ++k) acc = fma(JU[6 + r + 17 * k], JU[6 + c + 17 * k], acc);
-      cov[idx] = acc;
+    {
+      // the three sqrt-information factors at once: lanes 0-8 vb (9x9), 9-14 rel (6x6), 15-16 rp (2x2);
+      // the per-group scratch overlays JU, which is dead from here on
+      const bool act = lane < 17;
+      const int grp = lane < 9 ? 0 : (lane < 15 ? 1 : 2);
+      const int N = grp == 0 ? 9 : (grp == 1 ? 6 : 2);
+      const int c = grp == 0 ? lane : (grp == 1 ? lane - 9 : lane - 15);
+      const double* Ag = grp == 0 ? cov : (grp == 1 ? cov6 : cov2);
+      double* Usg = JU + (grp == 0 ? 0 : (grp == 1 ? 90 : 132));
+      double* og = grp == 0 ? o_vb + 9 : (grp == 1 ? o_rel + 12 : o_rp + 9);
+      if (w_sqrt_info_multi<9>(Ag, N, c, act, Usg, og, nonfinite)) status |= ISV_W_NOT_SPD;
     }
-    __syncwarp();
-    if (w_sqrt_info_from_cov<9>(cov, 9, o_vb + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
-    for (int idx = lane; idx < 4; idx += 32) {
-      int r = idx % 2, c = idx / 2;
-      double acc = 0.0;
-      for (int k = 0; k < 15; ++k) acc = fma(JU[15 + r + 17 * k], JU[15 + c + 17 * k], acc);
-      cov[idx] = acc;
-    }
-    __syncwarp();
-    if (w_sqrt_info_from_cov_regs<2>(cov, 2, o_rp + 9, lane, nonfinite)) status |= ISV_W_NOT_SPD;
   } else {
     // ---- general path: eigen-decomposition (:1479-1497) by one-sided Jacobi on the rows of G ----
     if (w_onesided_jacobi_rows<4, 6>(Gs, kGld, 15, 21, sc + 24, lane, 30, 1) >= 30) status |= ISV_W_EIG_NOCONV;
