@@ -468,6 +468,10 @@ typedef struct isv_marg_generic_out {
 isv_status isv_build_normal_equations(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out);
 /* stage 1 + Schur complement + eigen-decomposition */
 isv_status isv_marginalize_generic(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out);
+/* stage 1 + Schur complement only (A_red, b_red; rank = -1; linearized_* untouched and may be NULL).  With
+ * every feature in the diagonal block and m_dense = 0 this is the reduced camera system that ceres'
+ * DENSE_SCHUR forms inside problemSolve() (src/estimator.cpp:1124) -- SURVEY.md 8f rank 1.           */
+isv_status isv_reduced_system(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out);
 
 /* ---- unit-test hook: the PSD eigensolver that replaces SelfAdjointEigenSolver on this path -----
  * (src/estimator.cpp:920,1311,1479).  nb symmetric n x n matrices A (column-major, host) ->

@@ -975,8 +975,26 @@ extern "C" isv_status isv_build_normal_equations(isv_handle* h, const isv_marg_g
   return ISV_OK;
 }
 
+static isv_status marginalize_generic_impl(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out,
+                                           int schur_only);
+
 extern "C" isv_status isv_marginalize_generic(isv_handle* h, const isv_marg_generic_in* in,
                                               const isv_marg_generic_out* out) {
+  return marginalize_generic_impl(h, in, out, 0);
+}
+
+// normal equations + Schur complement only: with every feature in the diagonal block and m_dense = 0 this
+// is the reduced camera system ceres' DENSE_SCHUR solves (src/estimator.cpp:1124), built on the GPU
+extern "C" isv_status isv_reduced_system(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out) {
+  if (!out || !out->A_red || !out->b_red || !out->rank) return ISV_ERR_BAD_ARG;
+  isv_marg_generic_out o = *out;
+  if (!o.linearized_jacobians) o.linearized_jacobians = o.A_red;   // not written in this mode
+  if (!o.linearized_residuals) o.linearized_residuals = o.b_red;
+  return marginalize_generic_impl(h, in, &o, 1);
+}
+
+static isv_status marginalize_generic_impl(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out,
+                                           int schur_only) {
   isv_status st = marg_generic_check(h, in, out, true);
   if (st != ISV_OK) return st;
   st = isv_build_normal_equations(h, in, out);
@@ -999,7 +1017,7 @@ extern "C" isv_status isv_marginalize_generic(isv_handle* h, const isv_marg_gene
   }
   const size_t sm = (2 * kMgMaxDense * kMgMaxDense + 6 * 16 + 32) * sizeof(double);
   ISV_CUDA(cudaFuncSetAttribute(marg_schur_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  marg_schur_eig_kernel<<<in->n_problems, kMgThreads, sm, h->stream>>>(*in, *out, h->gram);
+  marg_schur_eig_kernel<<<in->n_problems, kMgThreads, sm, h->stream>>>(*in, *out, h->gram, schur_only);
   ++h->launches;
   ISV_CUDA(cudaGetLastError());
   return ISV_OK;

@@ -109,7 +109,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 // smem (doubles): P[32*32] V[32*32] cs[6*16] red[32] + ints
 __global__ void __launch_bounds__(kMgThreads)
-marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* __restrict__ Gbuf) {
+marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* __restrict__ Gbuf, int schur_only) {
   extern __shared__ double smem[];
   double* P = smem;                       // m_dense x m_dense
   double* V = P + kMgMaxDense * kMgMaxDense;
@@ -222,6 +222,13 @@ marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* 
     br[i] = acc;
   }
   __syncthreads();
+  if (schur_only) {   // reduced system only (DENSE_SCHUR's reduced camera system): no eigen-decomposition
+    if (tid == 0) out.rank[prob] = -1;
+    if (status) atomicOr(&s_status, status);
+    __syncthreads();
+    if (tid == 0 && out.status && s_status) atomicOr(out.status + prob, s_status);
+    return;
+  }
   // ---- phase C: A_red ~= G^T G by outer-product Cholesky with diagonal pivoting (A_red is PSD up to
   //      rounding; what is dropped is below n * eps_mach * max diagonal).  Works on a copy in A's kept block.
   double* W = A;   // reuse the first n*n doubles of this problem's A as the work copy (A is consumed)

@@ -113,7 +113,9 @@ class MarginalizationInfo:
         self._dp = DeviceProblem(fp, f"cuda:{self.be.device}")
         eval_problem(self.be, self._dp, self.cauchy_a)
 
-    def marginalize(self, keep_tables: bool = False) -> None:
+    def marginalize(self, keep_tables: bool = False, schur_only: bool = False) -> None:
+        """schur_only: stop after the Schur complement (A_red, b_red) -- with every feature dropped and no dense
+        block this is the reduced camera system of DENSE_SCHUR (`isv_reduced_system`)."""
         import torch
         assert self._dp is not None, "call preMarginalize first"
         dp, by = self._dp, self._by
@@ -184,9 +186,8 @@ class MarginalizationInfo:
         go = _Out(o["A"].data_ptr(), o["b"].data_ptr(), o["A_red"].data_ptr(), o["b_red"].data_ptr(), o["J"].data_ptr(),
                   o["r"].data_ptr(), o["rank"].data_ptr(), o["status"].data_ptr())
         lib = self.be.lib
-        lib.isv_marginalize_generic.restype = C.c_int
-        lib.isv_marginalize_generic.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        capi.check(lib.isv_marginalize_generic(self.be.h, C.byref(gi), C.byref(go)), "isv_marginalize_generic")
+        fn = lib.isv_reduced_system if schur_only else lib.isv_marginalize_generic
+        capi.check(fn(self.be.h, C.byref(gi), C.byref(go)), "isv_marginalize_generic")
         self.be.synchronize()
         if keep_tables:   # for tools/bench_marg_generic.py: the device tables of this problem
             self._gi, self._go = gi, go

@@ -102,3 +102,52 @@ def test_marginalization_info_matches_vins_mono_oracle(backend, cauchy_a, ex_con
     keep = mi.getParameterBlocks()
     assert keep[0][2] == 0 and all(b[2] > a[2] for a, b in zip(keep, keep[1:]))
     assert sum(LOCAL_SIZE[k[0][0]] for k in keep) == mi.n
+
+
+def test_reduced_camera_system_of_a_whole_window(backend):
+    """SURVEY 8f rank 1, second half: the reduced camera system DENSE_SCHUR forms inside problemSolve()
+    (src/estimator.cpp:1004-1124) built on the GPU: every factor of the 18-frame window, every feature
+    eliminated (diagonal block, DMMA Schur product), no dense block, no eigen-decomposition."""
+    p = sim.make_problem(sim.seed_for(9, 7), n_features=90, max_track=8)
+    const = {("ex_pose", 0)}
+    mi = MarginalizationInfo(backend, eps=1e-8, cauchy_a=1.0, constant=list(const))
+    ofac = []
+    s = p.cfg.proj_sqrt_info
+    for k in range(p.proj_idx.shape[1]):
+        i, j, e, f = [int(x) for x in p.proj_idx[:, k]]
+        keys = [("pose", i), ("pose", j), ("ex_pose", e), ("feature", f)]
+        pts_i, pts_j = p.proj_obs[0:3, k], np.array([p.proj_obs[3, k], p.proj_obs[4, k], 1.0])
+        mi.addResidualBlockInfo(ResidualBlockInfo("projection", keys, drop_set=[3], pts_i=pts_i, pts_j=pts_j))
+        r, js = O.ProjectionFactor(pts_i, pts_j, s).EvaluateCeres([p.poses[i], p.poses[j], p.ex[e], p.feat[f:f + 1]])
+        ofac.append(sim.cauchy_correct(r, js, 1.0) + (keys,))
+    for k, (i, j) in enumerate(p.imu_idx):
+        keys = [("pose", int(i)), ("speed_bias", int(i)), ("pose", int(j)), ("speed_bias", int(j))]
+        mi.addResidualBlockInfo(ResidualBlockInfo("imu", keys, preint=p.imu_pre[k].pack()))
+        ofac.append(O.IMUFactor(p.imu_pre[k]).EvaluateCeres([p.poses[i], p.sbs[i], p.poses[j], p.sbs[j]]) + (keys,))
+    for rf in p.rel:
+        keys = [("pose", rf.imu_i), ("pose", rf.imu_j)]
+        mi.addResidualBlockInfo(ResidualBlockInfo("rel", keys, delta_t=rf.delta_t, delta_R=rf.delta_R, sqrt_info=rf.sqrt_info))
+        ofac.append(sim.cauchy_correct(*rf.EvaluateCeres([p.poses[rf.imu_i], p.poses[rf.imu_j]]), 1.0) + (keys,))
+    sf, vf = p.se3[0], p.vb[0]
+    mi.addResidualBlockInfo(ResidualBlockInfo("se3", [("pose", sf.index)], t=sf.t, R=sf.R, sqrt_info=sf.sqrt_info))
+    ofac.append(sim.cauchy_correct(*sf.EvaluateCeres([p.poses[sf.index]]), 1.0) + ([("pose", sf.index)],))
+    mi.addResidualBlockInfo(ResidualBlockInfo("vb", [("speed_bias", vf.index)], VB=vf.VB, sqrt_info=vf.sqrt_info))
+    ofac.append(sim.cauchy_correct(*vf.EvaluateCeres([p.sbs[vf.index]]), 1.0) + ([("speed_bias", vf.index)],))
+    for rp in p.rp:
+        mi.addResidualBlockInfo(ResidualBlockInfo("rp", [("pose", rp.index)], R=rp.R, sqrt_info=rp.sqrt_info))
+        ofac.append(sim.cauchy_correct(*rp.EvaluateCeres([p.poses[rp.index]]), 1.0) + ([("pose", rp.index)],))
+    mi.preMarginalize({"pose": p.poses, "speed_bias": p.sbs, "ex_pose": p.ex, "feature": p.feat})
+    mi.marginalize(schur_only=True)
+    assert mi.status == 0, hex(mi.status)
+    idx = mi.parameter_block_idx
+    n_feat = sum(1 for k in idx if k[0] == "feature")
+    assert mi.m == n_feat and mi.n == 18 * 15 and sorted(v for k, v in idx.items() if k[0] == "feature") == list(range(n_feat))
+    facs = [(r, [(idx[k], np.asarray(j)[:, :LOCAL_SIZE[k[0]]]) for k, j in zip(keys, js) if k not in const])
+            for r, js, keys in ofac]
+    ref = O.vins_mono_marginalize(facs, mi.pos, mi.m, eps=1e-8)
+    S_hp, s_hp = O.schur_complement_longdouble(ref["A"], ref["b"], mi.m)
+    e_ref, e_gpu = rel_err(ref["A_red"], S_hp), rel_err(mi.A_red, S_hp)
+    print(f"reduced camera system vs 80-bit truth: literal FP64 {e_ref:.2e}, CUDA {e_gpu:.2e}")
+    assert e_gpu <= max(1e-9, 2.0 * e_ref)
+    assert rel_err(mi.b_red, s_hp) <= max(1e-9, 2.0 * rel_err(ref["b_red"], s_hp))
+    assert np.array_equal(mi.A_red != 0, mi.A_red.T != 0)      # symmetric fill pattern
