@@ -25,7 +25,10 @@
 
 namespace isv {
 
-constexpr int kWarpsPerCta = 4;
+#ifndef ISV_WARPS_PER_CTA
+#define ISV_WARPS_PER_CTA 4
+#endif
+constexpr int kWarpsPerCta = ISV_WARPS_PER_CTA;
 constexpr int kThreads = 32 * kWarpsPerCta;
 #ifndef ISV_FWD_MINB
 #define ISV_FWD_MINB 3
