@@ -1017,7 +1017,12 @@ static isv_status marginalize_generic_impl(isv_handle* h, const isv_marg_generic
   }
   const size_t sm = (2 * kMgMaxDense * kMgMaxDense + 6 * 16 + 32) * sizeof(double);
   ISV_CUDA(cudaFuncSetAttribute(marg_schur_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  marg_schur_eig_kernel<<<in->n_problems, kMgThreads, sm, h->stream>>>(*in, *out, h->gram, schur_only);
+  if (in->m_diag > 0) {
+    const int nt = (in->pos - in->m_diag + kSdTile - 1) / kSdTile;
+    schur_diag_dmma_kernel<<<dim3(nt * (nt + 1) / 2, in->n_problems), kSdThreads, 0, h->stream>>>(*in, *out);
+    ++h->launches;
+  }
+  marg_schur_eig_kernel<<<in->n_problems, kMgThreads, sm, h->stream>>>(*in, *out, h->gram, schur_only, 1);
   ++h->launches;
   ISV_CUDA(cudaGetLastError());
   return ISV_OK;

@@ -93,6 +93,125 @@ ne_build_kernel(isv_marg_generic_in in, double* __restrict__ A, double* __restri
 }
 
 // -------------------------------------------------------------------------------------------------
+// Phase A as its own kernel: the Schur complement over the diagonal (inverse-depth) block,
+//     C[R, R] -= X D^-1 X^T ,   b[R] -= X D^-1 b_diag ,   X = A[R, diag]  (nr x m_diag)
+// as a tiled SYRK on the FP64 tensor cores.
+// One CTA (4 warps) per 64 x 64 tile of the upper triangle
+// of C and per problem; the K loop runs over the landmarks in slabs of 16 staged in shared memory
+// (coalesced: for a fixed landmark the rows of X are contiguous in the column-major A); every warp owns a
+// 32 x 32 patch = 4 x 4 DMMA.8x8x4 tiles (32 accumulator registers), 16 DMMA per 8 fragment loads; several
+// CTAs per SM hide the slab loads of one behind the DMMAs of the others.  The
+// slab leading dimension 68 makes the 64-bit fragment loads bank-conflict free (k * 68 mod 16 = 0,4,8,12).
+// -------------------------------------------------------------------------------------------------
+constexpr int kSdTile = 64, kSdSlab = 16, kSdLd = 68, kSdThreads = 128;
+
+__global__ void __launch_bounds__(kSdThreads)
+schur_diag_dmma_kernel(isv_marg_generic_in in, isv_marg_generic_out out) {
+  __shared__ double Xa[kSdSlab * kSdLd];   // rows of tile ti, scaled by 1/d_l
+  __shared__ double Xb[kSdSlab * kSdLd];   // rows of tile tj
+  __shared__ double dinv_s[kSdSlab], bd_s[kSdSlab];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int prob = blockIdx.y;
+  const int pos = in.pos, md = in.m_dense, mg = in.m_diag, m = md + mg, nr = pos - mg;
+  const int nt = (nr + kSdTile - 1) / kSdTile;
+  // blockIdx.x enumerates the upper-triangular tile pairs (ti <= tj)
+  int ti = 0, rem = blockIdx.x;
+  while (rem >= nt - ti) { rem -= nt - ti; ++ti; }
+  const int tj = ti + rem;
+  double* A = out.A + (size_t)prob * pos * pos;
+  double* b = out.b + (size_t)prob * pos;
+  const double eps = in.eps;
+  auto R = [&](int i) { return i < md ? i : i + mg; };
+  const int fr = lane >> 2, fk = lane & 3;
+  const int wi = (warp >> 1) * 32, wj = (warp & 1) * 32;   // this warp's 32 x 32 patch inside the tile
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc[a][c][0] = 0.0; acc[a][c][1] = 0.0; }
+  double bacc = 0.0;
+  // register double-buffering: the 16 global loads of slab s+1 (8 per operand and thread, all independent)
+  // are issued before the DMMAs of slab s and parked in shared memory after them
+  constexpr int kPer = kSdSlab * kSdTile / kSdThreads;   // 8
+  double va[kPer], vb[kPer], dv = 0.0, bv = 0.0;
+  auto fetch = [&](int l0) {
+#pragma unroll
+    for (int it = 0; it < kPer; ++it) {
+      const int idx = tid + it * kSdThreads;
+      const int k = idx / kSdTile, r = idx - k * kSdTile;
+      const int l = l0 + k;
+      const int ia = kSdTile * ti + r, ib = kSdTile * tj + r;
+      va[it] = 0.0;
+      vb[it] = 0.0;
+      if (l < mg) {
+        const size_t col = (size_t)pos * (md + l);
+        if (ia < nr) va[it] = A[R(ia) + col];
+        if (ib < nr) vb[it] = A[R(ib) + col];
+      }
+    }
+    if (tid < kSdSlab) {
+      const int l = l0 + tid;
+      dv = 0.0;
+      bv = 0.0;
+      if (l < mg) { dv = A[(md + l) + (size_t)pos * (md + l)]; bv = b[md + l]; }
+    }
+  };
+  fetch(0);
+  for (int l0 = 0; l0 < mg; l0 += kSdSlab) {
+    if (tid < kSdSlab) {
+      dinv_s[tid] = dv > eps ? 1.0 / dv : 0.0;
+      bd_s[tid] = bv;
+      if (l0 + tid < mg && !(dv > eps) && blockIdx.x == 0 && out.status) atomicOr(out.status + prob, ISV_W_RANK_DEFICIENT);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kPer; ++it) {
+      const int idx = tid + it * kSdThreads;
+      const int k = idx / kSdTile, r = idx - k * kSdTile;
+      Xa[k * kSdLd + r] = va[it] * dinv_s[k];
+      Xb[k * kSdLd + r] = vb[it];
+    }
+    __syncthreads();
+    if (l0 + kSdSlab < mg) fetch(l0 + kSdSlab);
+#pragma unroll
+    for (int ks = 0; ks < kSdSlab / 4; ++ks) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) af[a] = Xa[(4 * ks + fk) * kSdLd + wi + 8 * a + fr];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bf[c] = Xb[(4 * ks + fk) * kSdLd + wj + 8 * c + fr];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dmma884(acc[a][c][0], acc[a][c][1], af[a], bf[c]);
+    }
+    if (ti == tj && tid < kSdTile) {   // b[R] -= X D^-1 b_diag for the rows of this (diagonal) tile
+#pragma unroll
+      for (int k = 0; k < kSdSlab; ++k) bacc = fma(Xa[k * kSdLd + tid], bd_s[k], bacc);
+    }
+    __syncthreads();
+  }
+  // epilogue: D fragment = (row lane / 4, cols 2 (lane % 4) + {0, 1}) of every 8 x 8 tile
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = kSdTile * ti + wi + 8 * a + fr, j = kSdTile * tj + wj + 8 * c + 2 * fk + e;
+        if (i < nr && j < nr) {
+          A[R(i) + (size_t)pos * R(j)] -= acc[a][c][e];
+          if (ti != tj) A[R(j) + (size_t)pos * R(i)] -= acc[a][c][e];
+        }
+      }
+  if (ti == tj && tid < kSdTile) {
+    const int i = kSdTile * ti + tid;
+    if (i < nr) b[R(i)] -= bacc;
+  }
+  (void)m;
+}
+
+// -------------------------------------------------------------------------------------------------
 constexpr int kMgThreads = 256;
 constexpr int kMgMaxDense = 32;
 
@@ -109,7 +228,8 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 // smem (doubles): P[32*32] V[32*32] cs[6*16] red[32] + ints
 __global__ void __launch_bounds__(kMgThreads)
-marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* __restrict__ Gbuf, int schur_only) {
+marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* __restrict__ Gbuf, int schur_only,
+                      int phase_a_done) {
   extern __shared__ double smem[];
   double* P = smem;                       // m_dense x m_dense
   double* V = P + kMgMaxDense * kMgMaxDense;
@@ -130,7 +250,7 @@ marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* 
   auto R = [&](int i) { return i < md ? i : i + mg; };   // compact index -> position in A
 
   // ---- phase A: eliminate the diagonal (scalar) marginalized blocks:  C -= X D^-1 X^T  on DMMA ----
-  if (mg > 0) {
+  if (mg > 0 && !phase_a_done) {   // in-kernel variant (one CTA per problem, fragments straight from L2)
     const int nt = (nr + 7) / 8;
     const int fr = lane >> 2, fk = lane & 3;
     for (int t = warp; t < nt * nt; t += nw) {
