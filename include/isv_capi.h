@@ -473,6 +473,35 @@ isv_status isv_marginalize_generic(isv_handle* h, const isv_marg_generic_in* in,
  * DENSE_SCHUR forms inside problemSolve() (src/estimator.cpp:1124) -- SURVEY.md 8f rank 1.           */
 isv_status isv_reduced_system(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out);
 
+/* The whole MarginalizationInfo::preMarginalize + marginalize step from HOST memory, blocking: H2D of the
+ * parameter blocks and factor lists, `Evaluate` of every residual block on the GPU (isv_eval_*), the block
+ * tables built from the per-family tangent positions, isv_marginalize_generic (or isv_reduced_system when
+ * schur_only != 0), D2H of the results.  This is what the C++ `MarginalizationInfo` of
+ * is_vins_b200/host/isv_marginalization_info.hpp calls.  All pointers are HOST pointers; the factor
+ * structs are the ones of the isv_eval_* family.  pos_* give the tangent position of every parameter block
+ * in the layout [m_dense | m_diag | keep] or -1 for a block ceres holds constant / that no factor uses.   */
+typedef struct isv_marg_host_in {
+  isv_param_blocks pb;
+  isv_proj_factors proj;
+  isv_imu_factors imu;
+  isv_small_factors small_factors;
+  const int32_t* pos_pose;
+  const int32_t* pos_speed_bias;
+  const int32_t* pos_ex_pose;
+  const int32_t* pos_feature;
+  int32_t pos, m_dense, m_diag, schur_only;
+  double eps;
+} isv_marg_host_in;
+typedef struct isv_marg_host_out {
+  double* A_red;                 /* [n][n] column-major, n = pos - m_dense - m_diag                    */
+  double* b_red;                 /* [n]                                                                */
+  double* linearized_jacobians;  /* [n][n] column-major (untouched when schur_only)                    */
+  double* linearized_residuals;  /* [n]                                                                */
+  int32_t rank;
+  int32_t status;
+} isv_marg_host_out;
+isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in* in, isv_marg_host_out* out);
+
 /* ---- unit-test hook: the PSD eigensolver that replaces SelfAdjointEigenSolver on this path -----
  * (src/estimator.cpp:920,1311,1479).  nb symmetric n x n matrices A (column-major, host) ->
  * G [nb][n][n] row-major factor rows with  A ~= sum_k g_k g_k^T, g_k mutually orthogonal;

@@ -181,6 +181,7 @@ SYMBOLS = [
     ("isv_build_normal_equations", C.c_int, [_H, C.c_void_p, C.c_void_p]),
     ("isv_marginalize_generic", C.c_int, [_H, C.c_void_p, C.c_void_p]),
     ("isv_reduced_system", C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    ("isv_marginalize_host", C.c_int, [_H, C.c_void_p, C.c_void_p]),
     ("isv_test_psd_eig", C.c_int, [_H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int32_p]),
 ]
 

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "isv_eval_kernels.cuh"
 #include "isv_init_kernel.cuh"
@@ -1025,5 +1026,184 @@ static isv_status marginalize_generic_impl(isv_handle* h, const isv_marg_generic
   marg_schur_eig_kernel<<<in->n_problems, kMgThreads, sm, h->stream>>>(*in, *out, h->gram, schur_only, 1);
   ++h->launches;
   ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+// ---- MarginalizationInfo::preMarginalize + marginalize from host memory ---------------------------------------
+extern "C" isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in* in, isv_marg_host_out* out) {
+  if (!h || !in || !out || !pb_ok(&in->pb)) return ISV_ERR_BAD_ARG;
+  const isv_param_blocks& pb = in->pb;
+  const isv_proj_factors& pf = in->proj;
+  const isv_imu_factors& mf = in->imu;
+  const isv_small_factors& sf = in->small_factors;
+  if (pf.n < 0 || mf.n < 0 || sf.n_rel < 0 || sf.n_se3 < 0 || sf.n_vb < 0 || sf.n_rp < 0 || sf.n_yaw < 0) return ISV_ERR_BAD_ARG;
+  if (pf.td_obs) return ISV_ERR_BAD_ARG;   // the td block is not wired into this entry point yet
+  if ((pb.n_pose && !in->pos_pose) || (pb.n_speed_bias && !in->pos_speed_bias) || (pb.n_ex_pose && !in->pos_ex_pose) ||
+      (pb.n_feature && !in->pos_feature))
+    return ISV_ERR_BAD_ARG;
+  const int n = in->pos - in->m_dense - in->m_diag;
+  if (in->pos < 1 || n < 1 || in->m_dense < 0 || in->m_diag < 0 || in->m_dense > kMgMaxDense) return ISV_ERR_BAD_ARG;
+  if (!out->A_red || !out->b_red || (!in->schur_only && (!out->linearized_jacobians || !out->linearized_residuals)))
+    return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const size_t D = sizeof(double), P = (size_t)pf.n, NI = (size_t)mf.n;
+  bool ex_live = false;
+  for (int e = 0; e < pb.n_ex_pose; ++e) ex_live = ex_live || in->pos_ex_pose[e] >= 0;
+  // ---- `values`: every Evaluate output, contiguous (offsets in doubles) ----------------------------------
+  size_t voff = 0;
+  auto vcarve = [&](size_t cnt) { size_t o = voff; voff += cnt; return o; };
+  const size_t v_pr = vcarve(2 * P), v_pi = vcarve(14 * P), v_pj = vcarve(14 * P), v_pe = vcarve(ex_live ? 14 * P : 0),
+               v_pfe = vcarve(2 * P), v_ir = vcarve(15 * NI), v_ij = vcarve(ISV_IMU_JAC_REC * NI),
+               v_rr = vcarve(6 * (size_t)sf.n_rel), v_rj = vcarve(84 * (size_t)sf.n_rel), v_sr = vcarve(6 * (size_t)sf.n_se3),
+               v_sj = vcarve(42 * (size_t)sf.n_se3), v_vr = vcarve(9 * (size_t)sf.n_vb), v_vj = vcarve(81 * (size_t)sf.n_vb),
+               v_qr = vcarve(2 * (size_t)sf.n_rp), v_qj = vcarve(14 * (size_t)sf.n_rp), v_yr = vcarve((size_t)sf.n_yaw),
+               v_yj = vcarve(7 * (size_t)sf.n_yaw);
+  // ---- block tables, built on the host from the factor index lists and the position tables ---------------
+  std::vector<isv_ne_factor> facs;
+  std::vector<isv_ne_block> blks;
+  bool bad_index = false;
+  auto add_block = [&](size_t jac, int stride, int ls, int position) {
+    if (position < 0) return;
+    blks.push_back(isv_ne_block{(int64_t)jac, stride, ls, position, 0});
+  };
+  auto chk = [&](int idx, int cnt) { if (idx < 0 || idx >= cnt) bad_index = true; return !(idx < 0 || idx >= cnt); };
+  for (size_t k = 0; k < P; ++k) {
+    const int i = pf.idx[k], j = pf.idx[pf.stride + k], e = pf.idx[2 * pf.stride + k], f = pf.idx[3 * pf.stride + k];
+    if (!chk(i, pb.n_pose) || !chk(j, pb.n_pose) || !chk(e, pb.n_ex_pose) || !chk(f, pb.n_feature)) continue;
+    const int first = (int)blks.size();
+    add_block(v_pi + 14 * k, 7, 6, in->pos_pose[i]);
+    add_block(v_pj + 14 * k, 7, 6, in->pos_pose[j]);
+    if (ex_live) add_block(v_pe + 14 * k, 7, 6, in->pos_ex_pose[e]);
+    add_block(v_pfe + 2 * k, 1, 1, in->pos_feature[f]);
+    if ((int)blks.size() > first) facs.push_back(isv_ne_factor{(int64_t)(v_pr + 2 * k), 2, (int)blks.size() - first, first, 0});
+  }
+  for (size_t k = 0; k < NI; ++k) {
+    const int i = mf.idx[2 * k], j = mf.idx[2 * k + 1];
+    if (!chk(i, pb.n_pose) || !chk(j, pb.n_pose) || !chk(i, pb.n_speed_bias) || !chk(j, pb.n_speed_bias)) continue;
+    const int first = (int)blks.size();
+    const size_t base = v_ij + ISV_IMU_JAC_REC * k;
+    add_block(base, 7, 6, in->pos_pose[i]);
+    add_block(base + 105, 9, 9, in->pos_speed_bias[i]);
+    add_block(base + 240, 7, 6, in->pos_pose[j]);
+    add_block(base + 345, 9, 9, in->pos_speed_bias[j]);
+    if ((int)blks.size() > first) facs.push_back(isv_ne_factor{(int64_t)(v_ir + 15 * k), 15, (int)blks.size() - first, first, 0});
+  }
+  for (int k = 0; k < sf.n_rel; ++k) {
+    const int i = sf.rel_idx[2 * k], j = sf.rel_idx[2 * k + 1];
+    if (!chk(i, pb.n_pose) || !chk(j, pb.n_pose)) continue;
+    const int first = (int)blks.size();
+    add_block(v_rj + 84 * (size_t)k, 7, 6, in->pos_pose[i]);
+    add_block(v_rj + 84 * (size_t)k + 42, 7, 6, in->pos_pose[j]);
+    if ((int)blks.size() > first) facs.push_back(isv_ne_factor{(int64_t)(v_rr + 6 * (size_t)k), 6, (int)blks.size() - first, first, 0});
+  }
+  auto single = [&](int cnt, const int32_t* idx, const int32_t* postab, int n_blocks_family, size_t vres, size_t vjac, int nres,
+                    int width, int stride, int ls) {
+    for (int k = 0; k < cnt; ++k) {
+      if (!chk(idx[k], n_blocks_family)) continue;
+      const int first = (int)blks.size();
+      add_block(vjac + (size_t)width * k, stride, ls, postab[idx[k]]);
+      if ((int)blks.size() > first) facs.push_back(isv_ne_factor{(int64_t)(vres + (size_t)nres * k), nres, 1, first, 0});
+    }
+  };
+  single(sf.n_se3, sf.se3_idx, in->pos_pose, pb.n_pose, v_sr, v_sj, 6, 42, 7, 6);
+  single(sf.n_vb, sf.vb_idx, in->pos_speed_bias, pb.n_speed_bias, v_vr, v_vj, 9, 81, 9, 9);
+  single(sf.n_rp, sf.rp_idx, in->pos_pose, pb.n_pose, v_qr, v_qj, 2, 14, 7, 6);
+  single(sf.n_yaw, sf.yaw_idx, in->pos_pose, pb.n_pose, v_yr, v_yj, 1, 7, 7, 6);
+  if (bad_index) { out->status = ISV_W_BAD_INDEX; return ISV_ERR_BAD_ARG; }
+  // ---- device mirror ---------------------------------------------------------------------------------------
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  const size_t pos = (size_t)in->pos;
+  const size_t o_pose = carve(pb.n_pose * 7 * D), o_sb = carve(pb.n_speed_bias * 9 * D), o_ex = carve(pb.n_ex_pose * 7 * D),
+               o_ft = carve(pb.n_feature * D), o_pidx = carve(4 * P * 4), o_pobs = carve(5 * P * D), o_iidx = carve(2 * NI * 4),
+               o_ipre = carve(NI * ISV_PREINT_REC * D), o_ridx = carve(2 * (size_t)sf.n_rel * 4),
+               o_rrec = carve((size_t)sf.n_rel * ISV_REL_REC * D), o_sidx = carve((size_t)sf.n_se3 * 4),
+               o_srec = carve((size_t)sf.n_se3 * ISV_SE3_REC * D), o_vidx = carve((size_t)sf.n_vb * 4),
+               o_vrec = carve((size_t)sf.n_vb * ISV_VB_REC * D), o_qidx = carve((size_t)sf.n_rp * 4),
+               o_qrec = carve((size_t)sf.n_rp * ISV_RP_REC * D), o_yidx = carve((size_t)sf.n_yaw * 4),
+               o_yrec = carve((size_t)sf.n_yaw * ISV_YAW_REC * D), o_val = carve(voff * D),
+               o_fac = carve(facs.size() * sizeof(isv_ne_factor)), o_blk = carve(blks.size() * sizeof(isv_ne_block)),
+               o_A = carve(pos * pos * D), o_b = carve(pos * D), o_Ar = carve((size_t)n * n * D), o_br = carve(n * D),
+               o_J = carve((size_t)n * n * D), o_r = carve(n * D), o_rank = carve(8), o_st = carve(8);
+  isv_status st = ensure_dbuf(h, off);
+  if (st != ISV_OK) return st;
+  char* d = h->dbuf;
+  cudaStream_t s = h->stream;
+  auto up = [&](size_t o, const void* src, size_t bytes) {
+    return bytes == 0 ? cudaSuccess : cudaMemcpyAsync(d + o, src, bytes, cudaMemcpyHostToDevice, s);
+  };
+  ISV_CUDA(up(o_pose, pb.pose, pb.n_pose * 7 * D));
+  ISV_CUDA(up(o_sb, pb.speed_bias, pb.n_speed_bias * 9 * D));
+  ISV_CUDA(up(o_ex, pb.ex_pose, pb.n_ex_pose * 7 * D));
+  ISV_CUDA(up(o_ft, pb.feature, pb.n_feature * D));
+  for (int c = 0; c < 4 && P; ++c) ISV_CUDA(up(o_pidx + c * P * 4, pf.idx + c * pf.stride, P * 4));
+  for (int c = 0; c < 5 && P; ++c) ISV_CUDA(up(o_pobs + c * P * D, pf.obs + c * pf.stride, P * D));
+  ISV_CUDA(up(o_iidx, mf.idx, 2 * NI * 4));
+  ISV_CUDA(up(o_ipre, mf.preint, NI * ISV_PREINT_REC * D));
+  ISV_CUDA(up(o_ridx, sf.rel_idx, 2 * (size_t)sf.n_rel * 4));
+  ISV_CUDA(up(o_rrec, sf.rel_rec, (size_t)sf.n_rel * ISV_REL_REC * D));
+  ISV_CUDA(up(o_sidx, sf.se3_idx, (size_t)sf.n_se3 * 4));
+  ISV_CUDA(up(o_srec, sf.se3_rec, (size_t)sf.n_se3 * ISV_SE3_REC * D));
+  ISV_CUDA(up(o_vidx, sf.vb_idx, (size_t)sf.n_vb * 4));
+  ISV_CUDA(up(o_vrec, sf.vb_rec, (size_t)sf.n_vb * ISV_VB_REC * D));
+  ISV_CUDA(up(o_qidx, sf.rp_idx, (size_t)sf.n_rp * 4));
+  ISV_CUDA(up(o_qrec, sf.rp_rec, (size_t)sf.n_rp * ISV_RP_REC * D));
+  ISV_CUDA(up(o_yidx, sf.yaw_idx, (size_t)sf.n_yaw * 4));
+  ISV_CUDA(up(o_yrec, sf.yaw_rec, (size_t)sf.n_yaw * ISV_YAW_REC * D));
+  ISV_CUDA(up(o_fac, facs.data(), facs.size() * sizeof(isv_ne_factor)));
+  ISV_CUDA(up(o_blk, blks.data(), blks.size() * sizeof(isv_ne_block)));
+  ISV_CUDA(cudaMemsetAsync(d + o_st, 0, 8, s));
+  // ---- preMarginalize: Evaluate every residual block -------------------------------------------------------
+  double* V = (double*)(d + o_val);
+  isv_param_blocks dpb = {pb.n_pose, pb.n_speed_bias, pb.n_ex_pose, pb.n_feature, (const double*)(d + o_pose),
+                          (const double*)(d + o_sb), (const double*)(d + o_ex), (const double*)(d + o_ft)};
+  int32_t* dst = (int32_t*)(d + o_st);
+  if (P) {
+    isv_proj_factors dpf = pf;
+    dpf.stride = (int64_t)P;
+    dpf.idx = (const int32_t*)(d + o_pidx);
+    dpf.obs = (const double*)(d + o_pobs);
+    isv_proj_eval po = {V + v_pr, V + v_pi, V + v_pj, ex_live ? V + v_pe : nullptr, V + v_pfe, nullptr};
+    st = eval_projection_on(h, s, &dpb, &dpf, &po, dst);
+    if (st != ISV_OK) return st;
+  }
+  if (NI) {
+    isv_imu_factors dmf = {mf.n, (const int32_t*)(d + o_iidx), (const double*)(d + o_ipre)};
+    isv_imu_eval mo = {V + v_ir, V + v_ij};
+    st = eval_imu_on(h, s, &dpb, &dmf, &mo, dst);
+    if (st != ISV_OK) return st;
+  }
+  if (sf.n_rel + sf.n_se3 + sf.n_vb + sf.n_rp + sf.n_yaw > 0) {
+    isv_small_factors dsf = sf;
+    dsf.rel_idx = (const int32_t*)(d + o_ridx); dsf.rel_rec = (const double*)(d + o_rrec);
+    dsf.se3_idx = (const int32_t*)(d + o_sidx); dsf.se3_rec = (const double*)(d + o_srec);
+    dsf.vb_idx = (const int32_t*)(d + o_vidx); dsf.vb_rec = (const double*)(d + o_vrec);
+    dsf.rp_idx = (const int32_t*)(d + o_qidx); dsf.rp_rec = (const double*)(d + o_qrec);
+    dsf.yaw_idx = (const int32_t*)(d + o_yidx); dsf.yaw_rec = (const double*)(d + o_yrec);
+    isv_small_eval so = {V + v_rr, V + v_rj, V + v_sr, V + v_sj, V + v_vr, V + v_vj, V + v_qr, V + v_qj, V + v_yr, V + v_yj};
+    st = eval_small_on(h, s, &dpb, &dsf, &so, dst);
+    if (st != ISV_OK) return st;
+  }
+  // ---- marginalize ---------------------------------------------------------------------------------------------
+  isv_marg_generic_in gi = {1, in->pos, in->m_dense, in->m_diag, (int64_t)facs.size(), (const isv_ne_factor*)(d + o_fac),
+                            (const isv_ne_block*)(d + o_blk), V, in->eps};
+  isv_marg_generic_out go = {(double*)(d + o_A), (double*)(d + o_b), (double*)(d + o_Ar), (double*)(d + o_br),
+                             (double*)(d + o_J), (double*)(d + o_r), (int32_t*)(d + o_rank), dst + 1};
+  ISV_CUDA(cudaMemsetAsync(d + o_rank, 0, 8, s));
+  // (isv_build_normal_equations zeroes status[problem]: give it its own word, merged below)
+  st = marginalize_generic_impl(h, &gi, &go, in->schur_only ? 1 : 0);
+  if (st != ISV_OK) return st;
+  int32_t hst[2] = {0, 0}, hrank = 0;
+  ISV_CUDA(cudaMemcpyAsync(out->A_red, d + o_Ar, (size_t)n * n * D, cudaMemcpyDeviceToHost, s));
+  ISV_CUDA(cudaMemcpyAsync(out->b_red, d + o_br, n * D, cudaMemcpyDeviceToHost, s));
+  if (!in->schur_only) {
+    ISV_CUDA(cudaMemcpyAsync(out->linearized_jacobians, d + o_J, (size_t)n * n * D, cudaMemcpyDeviceToHost, s));
+    ISV_CUDA(cudaMemcpyAsync(out->linearized_residuals, d + o_r, n * D, cudaMemcpyDeviceToHost, s));
+  }
+  ISV_CUDA(cudaMemcpyAsync(hst, d + o_st, 8, cudaMemcpyDeviceToHost, s));
+  ISV_CUDA(cudaMemcpyAsync(&hrank, d + o_rank, 4, cudaMemcpyDeviceToHost, s));
+  ISV_CUDA(cudaStreamSynchronize(s));
+  out->status = hst[0] | hst[1];
+  out->rank = hrank;
   return ISV_OK;
 }

@@ -14,6 +14,7 @@
 // 36 doubles of `Eigen::MatrixXd sqrt_info` (6x6), `R` the 9 doubles of `Eigen::Matrix3d R`, ... so a
 // build against the real classes replaces `std::memcpy(dst, src, n)` by `m.data()`.
 #pragma once
+#include <algorithm>
 #include <cstring>
 #include <queue>
 #include <stdexcept>

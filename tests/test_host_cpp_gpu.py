@@ -14,8 +14,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp", "host_shim_test.cpp")
 
 
-def build_host_test(out_path):
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", out_path, SRC, "-L" + os.path.join(ROOT, "is_vins_b200"),
+SRC_MI = os.path.join(ROOT, "tests", "cpp", "marginalization_info_test.cpp")
+
+
+def build_host_test(out_path, src=SRC):
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", out_path, src, "-L" + os.path.join(ROOT, "is_vins_b200"),
            "-lisv_b200", "-Wl,-rpath," + os.path.join(ROOT, "is_vins_b200")]
     subprocess.run(cmd, check=True)
 
@@ -74,6 +77,67 @@ def test_cpp_host_estimator_against_oracle(tmp_path):
     assert "0 mismatches" in p.stdout
 
 
+def write_marginalization_fixture(path, p):
+    """The MARGIN_OLD marginalization problem of tests/test_marginalization_info_gpu.py and its 80-bit
+    reduced system, in the order the C++ test adds the residual blocks."""
+    from is_vins_b200.marginalization import LOCAL_SIZE
+    from oracle import isv_oracle as O
+    N, F = p.poses.shape[0], len(p.feat)
+    hosted = [k for k in range(p.proj_idx.shape[1]) if int(p.proj_idx[0, k]) == 0]
+    d = [float(N), float(F), float(len(hosted))] + list(p.poses.ravel()) + list(p.sbs.ravel()) + list(p.ex.ravel()) + list(p.feat)
+    d += list(p.imu_pre[0].pack())
+    # ordering by first appearance: pose0, sb0 | features (in factor order) | pose1, sb1, other poses
+    order = [("pose", 0), ("speed_bias", 0)]
+    feats, kept = [], [("pose", 1), ("speed_bias", 1)]
+    ofac = []
+    r, js = O.IMUFactor(p.imu_pre[0]).EvaluateCeres([p.poses[0], p.sbs[0], p.poses[1], p.sbs[1]])
+    ofac.append((r, js, [("pose", 0), ("speed_bias", 0), ("pose", 1), ("speed_bias", 1)]))
+    s = p.cfg.proj_sqrt_info
+    for k in hosted:
+        i, j, e, f = [int(x) for x in p.proj_idx[:, k]]
+        pts_i, pts_j = p.proj_obs[0:3, k], np.array([p.proj_obs[3, k], p.proj_obs[4, k], 1.0])
+        d += [float(j), float(f)] + list(pts_i) + list(pts_j)
+        if ("feature", f) not in feats:
+            feats.append(("feature", f))
+        if ("pose", j) not in kept:
+            kept.append(("pose", j))
+        r, js = O.ProjectionFactor(pts_i, pts_j, s).EvaluateCeres([p.poses[i], p.poses[j], p.ex[e], p.feat[f:f + 1]])
+        ofac.append(sim.cauchy_correct(r, js, 1.0) + ([("pose", i), ("pose", j), ("ex_pose", e), ("feature", f)],))
+    se3, rel = p.se3[0], p.rel[0]
+    d += _rec48(se3.t, se3.R, se3.sqrt_info) + _rec48(rel.delta_t, rel.delta_R, rel.sqrt_info)
+    ofac.append(sim.cauchy_correct(*se3.EvaluateCeres([p.poses[0]]), 1.0) + ([("pose", 0)],))
+    ofac.append(sim.cauchy_correct(*rel.EvaluateCeres([p.poses[0], p.poses[1]]), 1.0) + ([("pose", 0), ("pose", 1)],))
+    idx, pos = {}, 0
+    for key in order + feats + kept:
+        idx[key] = pos
+        pos += LOCAL_SIZE[key[0]]
+    m = 15 + len(feats)
+    facs = [(r, [(idx[k], np.asarray(j)[:, :LOCAL_SIZE[k[0]]]) for k, j in zip(keys, js) if k[0] != "ex_pose"])
+            for r, js, keys in ofac]
+    ref = O.vins_mono_marginalize(facs, pos, m, eps=1e-8)
+    S_hp, s_hp = O.schur_complement_longdouble(ref["A"], ref["b"], m)
+    e_ref = np.linalg.norm(ref["A_red"] - S_hp) / np.linalg.norm(S_hp)
+    tol = max(1e-9, 2.0 * e_ref)
+    d += [float(m), float(pos - m), tol] + list(S_hp.T.ravel()) + list(s_hp)
+    np.asarray(d, dtype="<f8").tofile(path)
+
+
+@pytest.mark.gpu
+def test_cpp_marginalization_info_against_oracle(tmp_path):
+    """The C++ MarginalizationInfo (north_star API) vs the 80-bit reduced system of the same problem."""
+    exe = str(tmp_path / "marginalization_info_test")
+    build_host_test(exe, SRC_MI)
+    p = sim.make_problem(sim.seed_for(9, 1), n_features=120, max_track=9, host0=0.6)
+    fx = str(tmp_path / "mi_fixture.bin")
+    write_marginalization_fixture(fx, p)
+    r = subprocess.run([exe, fx], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "0 mismatches" in r.stdout
+
+
 def test_cpp_host_layer_compiles(tmp_path):
-    """CPU: the host layer and its test driver compile and link against the C ABI (no compute)."""
+    """CPU: the host layer, the C++ MarginalizationInfo and their test drivers compile and link against the
+    C ABI (no compute)."""
     build_host_test(str(tmp_path / "host_shim_test"))
+    build_host_test(str(tmp_path / "marginalization_info_test"), SRC_MI)
