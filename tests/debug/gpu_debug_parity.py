@@ -1,6 +1,6 @@
 """Prints per-factor relative errors of the CUDA path vs the oracle (debug aid; run under gpurun)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from is_vins_b200 import DeviceBatch, MargBackend, capi, pack_events
 from oracle import sim
