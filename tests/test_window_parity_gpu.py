@@ -63,7 +63,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
 @pytest.mark.parametrize("name", ["cfg1_L150_ragged.npz", "cfg2_L1000_literal.npz", "bench_windows_L1000.npz",
-                                  "bench_windows_L150.npz"])
+                                  "bench_windows_L150.npz", "bench_windows_L2000.npz"])
 def test_committed_golden_fixtures(backend, name):
     """cfg1 incl. ragged/empty windows (L = 0, 1, 31, 32, 33, 80); cfg2 = the literal dense oracle at L = 1000."""
     batch, ref, _ = load_batch(os.path.join(GOLD, name))
