@@ -442,7 +442,7 @@ typedef struct isv_ne_block {
 typedef struct isv_ne_factor {
   int64_t res_offset;            /* first residual in `values`                                        */
   int32_t n_res;                 /* <= 15                                                             */
-  int32_t n_blocks;              /* <= 4 (constant parameter blocks are simply not listed)            */
+  int32_t n_blocks;              /* <= 5 (constant parameter blocks are simply not listed)            */
   int32_t first_block;           /* index into the block table                                        */
   int32_t problem;               /* which problem of the batch                                        */
 } isv_ne_factor;

@@ -40,10 +40,10 @@ ne_build_kernel(isv_marg_generic_in in, double* __restrict__ A, double* __restri
   if (f >= in.n_factors) return;
   double* J = smem + warp * kNeSmemPerWarp;   // n_res x total columns, row-major, ld = kNeMaxCols
   double* r = J + kNeMaxRes * kNeMaxCols;
-  int* meta = reinterpret_cast<int*>(r + 16);  // per block: column offset in J, pos, local size (4 blocks)
+  int* meta = reinterpret_cast<int*>(r + 16);  // per block: column offset in J, pos, local size (<= 5 blocks)
   const isv_ne_factor fa = in.factors[f];
   const int nres = fa.n_res, nb = fa.n_blocks;
-  bool ok = nres >= 1 && nres <= kNeMaxRes && nb >= 1 && nb <= 4 && fa.problem >= 0 && fa.problem < in.n_problems;
+  bool ok = nres >= 1 && nres <= kNeMaxRes && nb >= 1 && nb <= 5 && fa.problem >= 0 && fa.problem < in.n_problems;
   int tot = 0;
   if (ok) {
     for (int k = 0; k < nb; ++k) {

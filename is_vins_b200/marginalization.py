@@ -21,12 +21,15 @@ from . import capi
 from .evaluate import DeviceProblem, FactorProblem, eval_problem, rel_record, rp_record, vb_record, yaw_record
 
 Key = Tuple[str, int]
-GLOBAL_SIZE = {"pose": 7, "speed_bias": 9, "ex_pose": 7, "feature": 1}
-LOCAL_SIZE = {"pose": 6, "speed_bias": 9, "ex_pose": 6, "feature": 1}     # MarginalizationInfo::localSize
+GLOBAL_SIZE = {"pose": 7, "speed_bias": 9, "ex_pose": 7, "feature": 1, "td": 1}
+LOCAL_SIZE = {"pose": 6, "speed_bias": 9, "ex_pose": 6, "feature": 1, "td": 1}     # MarginalizationInfo::localSize
 # per factor kind: parameter families in ceres argument order, residual size, (offset, row stride) of each
 # Jacobian block inside the kind's Evaluate output record
 KINDS = {
     "projection": (("pose", "pose", "ex_pose", "feature"), 2, None),
+    # VINS-Mono ProjectionTdFactor (5th block: the camera-IMU time offset para_Td); members pts_i, pts_j,
+    # velocity_i, velocity_j, td_i, td_j, row_i, row_j (rows already minus ROW / 2)
+    "projection_td": (("pose", "pose", "ex_pose", "feature", "td"), 2, None),
     "imu": (("pose", "speed_bias", "pose", "speed_bias"), 15, ((0, 7), (105, 9), (240, 7), (345, 9))),
     "rel": (("pose", "pose"), 6, ((0, 7), (42, 7))),
     "se3": (("pose",), 6, ((0, 7),)),
@@ -57,11 +60,13 @@ class isv_ne_factor(C.Structure):
 
 
 class MarginalizationInfo:
-    def __init__(self, backend, eps: float = 1e-8, cauchy_a: float = 1.0, constant: Sequence[Key] = ()):
+    def __init__(self, backend, eps: float = 1e-8, cauchy_a: float = 1.0, constant: Sequence[Key] = (),
+                 tr_over_row: float = 0.0):
         """cauchy_a: CauchyLoss scale of every non-IMU residual block (VINS passes `loss_function` to the
         projection and prior blocks and NULL to the IMU block); 0 disables.  constant: parameter blocks
         ceres holds constant (SetParameterBlockConstant) -- they get no column."""
         self.be, self.eps, self.cauchy_a, self.constant = backend, float(eps), float(cauchy_a), set(constant)
+        self.tr_over_row = float(tr_over_row)      # TR / ROW of ProjectionTdFactor (rolling shutter), 0 = global
         self.factors: List[ResidualBlockInfo] = []
         self.parameter_block_size: Dict[Key, int] = {}
         self.parameter_block_idx: Dict[Key, int] = {}
@@ -76,6 +81,9 @@ class MarginalizationInfo:
             self.parameter_block_size[k] = GLOBAL_SIZE[k[0]]
         for i in info.drop_set:
             k = info.parameter_blocks[i]
+            if k[0] == "td":
+                raise ValueError("the time offset couples with every ProjectionTdFactor: it cannot be a diagonal "
+                                 "marginalized scalar (VINS-Mono never marginalizes para_Td either)")
             if k not in self._drop:
                 self._drop.append(k)
 
@@ -112,6 +120,37 @@ class MarginalizationInfo:
             assert f.parameter_blocks[0][1] == f.parameter_blocks[1][1] and f.parameter_blocks[2][1] == f.parameter_blocks[3][1]
         self._dp = DeviceProblem(fp, f"cuda:{self.be.device}")
         eval_problem(self.be, self._dp, self.cauchy_a)
+        # ProjectionTdFactors: the same kernel with td_obs set (eval_projection_kernel<true>)
+        tdf = by["projection_td"]
+        self._td = None
+        if tdf:
+            import torch
+            dev = self._dp.device
+            T = len(tdf)
+            tidx = np.zeros((4, T), np.int32)
+            tobs = np.zeros((5, T))
+            tdo = np.zeros((8, T))
+            tdi = np.zeros((T,), np.int32)
+            for c, f in enumerate(tdf):
+                tidx[:, c] = [k[1] for k in f.parameter_blocks[:4]]
+                tdi[c] = f.parameter_blocks[4][1]
+                m_ = f.members
+                tobs[0:3, c], tobs[3:5, c] = m_["pts_i"], np.asarray(m_["pts_j"])[0:2]
+                tdo[0:2, c], tdo[2:4, c] = np.asarray(m_["velocity_i"])[0:2], np.asarray(m_["velocity_j"])[0:2]
+                tdo[4, c], tdo[5, c], tdo[6, c], tdo[7, c] = m_["td_i"], m_["td_j"], m_["row_i"], m_["row_j"]
+            t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt)
+            d = {"idx": t(tidx, torch.int32), "obs": t(tobs, torch.float64), "tdo": t(tdo, torch.float64),
+                 "tdi": t(tdi, torch.int32), "td": t(np.asarray(para["td"], float).reshape(-1), torch.float64)}
+            o = {k: torch.zeros((T, w), dtype=torch.float64, device=dev)
+                 for k, w in (("res", 2), ("ji", 14), ("jj", 14), ("je", 14), ("jf", 2), ("jt", 2))}
+            pb = self._dp.param_blocks()
+            pf = capi.isv_proj_factors(T, T, d["idx"].data_ptr(), d["obs"].data_ptr(), self.cauchy_a, d["tdo"].data_ptr(),
+                                       d["td"].data_ptr(), d["tdi"].data_ptr(), int(d["td"].numel()), 0, self.tr_over_row)
+            po = capi.isv_proj_eval(*[o[k].data_ptr() for k in ("res", "ji", "jj", "je", "jf", "jt")])
+            capi.check(self.be.lib.isv_eval_projection_batch(self.be.h, C.byref(pb), C.byref(pf), C.byref(po),
+                                                             C.c_void_p(self._dp.status.data_ptr())),
+                       "isv_eval_projection_batch")
+            self._td = (d, o)
 
     def marginalize(self, keep_tables: bool = False, schur_only: bool = False) -> None:
         """schur_only: stop after the Schur complement (A_red, b_red) -- with every feature dropped and no dense
@@ -143,8 +182,23 @@ class MarginalizationInfo:
         for nm in names:
             base[nm] = off
             off += dp.out[nm].numel()
-        values = torch.cat([dp.out[nm].reshape(-1) for nm in names])
+        parts = [dp.out[nm].reshape(-1) for nm in names]
+        if self._td is not None:
+            for nm in ("res", "ji", "jj", "je", "jf", "jt"):
+                base["td_" + nm] = off
+                off += self._td[1][nm].numel()
+                parts.append(self._td[1][nm].reshape(-1))
+        values = torch.cat(parts)
         facs, blks = [], []
+        for c, f in enumerate(by["projection_td"]):
+            first = len(blks)
+            for nm, k, w in (("td_ji", f.parameter_blocks[0], 14), ("td_jj", f.parameter_blocks[1], 14),
+                             ("td_je", f.parameter_blocks[2], 14), ("td_jf", f.parameter_blocks[3], 2),
+                             ("td_jt", f.parameter_blocks[4], 2)):
+                if k in self.constant:
+                    continue
+                blks.append((base[nm] + w * c, GLOBAL_SIZE[k[0]], LOCAL_SIZE[k[0]], self.parameter_block_idx[k]))
+            facs.append((base["td_res"] + 2 * c, 2, len(blks) - first, first))
         for c, f in enumerate(by["projection"]):
             first = len(blks)
             for nm, k, w in (("proj_ji", f.parameter_blocks[0], 14), ("proj_jj", f.parameter_blocks[1], 14),

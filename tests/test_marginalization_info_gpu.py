@@ -151,3 +151,52 @@ def test_reduced_camera_system_of_a_whole_window(backend):
     assert e_gpu <= max(1e-9, 2.0 * e_ref)
     assert rel_err(mi.b_red, s_hp) <= max(1e-9, 2.0 * rel_err(ref["b_red"], s_hp))
     assert np.array_equal(mi.A_red != 0, mi.A_red.T != 0)      # symmetric fill pattern
+
+
+def test_marginalization_with_projection_td_factors(backend):
+    """BASELINE configs[3] (online td estimation): VINS-Mono style marginalization of the oldest frame where
+    every visual factor is a ProjectionTdFactor and the time offset para_Td is a kept 1-d block.  Neither the
+    class nor the factor exists in the reference: oracle = the restated VINS-Mono formulas."""
+    p = sim.make_problem(sim.seed_for(9, 3), n_features=100, max_track=9, host0=0.6)
+    rng = np.random.default_rng(93)
+    tr = 0.033 / 480
+    td = np.array([0.007])
+    const = {("ex_pose", 0)}
+    mi = MarginalizationInfo(backend, eps=1e-8, cauchy_a=1.0, constant=list(const), tr_over_row=tr)
+    ofac = []
+    keys = [("pose", 0), ("speed_bias", 0), ("pose", 1), ("speed_bias", 1)]
+    mi.addResidualBlockInfo(ResidualBlockInfo("imu", keys, drop_set=[0, 1], preint=p.imu_pre[0].pack()))
+    ofac.append(O.IMUFactor(p.imu_pre[0]).EvaluateCeres([p.poses[0], p.sbs[0], p.poses[1], p.sbs[1]]) + (keys,))
+    s = p.cfg.proj_sqrt_info
+    for k in range(p.proj_idx.shape[1]):
+        i, j, e, f = [int(x) for x in p.proj_idx[:, k]]
+        if i != 0:
+            continue
+        keys = [("pose", i), ("pose", j), ("ex_pose", e), ("feature", f), ("td", 0)]
+        pts_i, pts_j = p.proj_obs[0:3, k], np.array([p.proj_obs[3, k], p.proj_obs[4, k], 1.0])
+        m = dict(velocity_i=rng.normal(0, 0.3, 2), velocity_j=rng.normal(0, 0.3, 2), td_i=rng.normal(0, 0.004),
+                 td_j=rng.normal(0, 0.004), row_i=rng.uniform(-240, 240), row_j=rng.uniform(-240, 240))
+        mi.addResidualBlockInfo(ResidualBlockInfo("projection_td", keys, drop_set=[0, 3], pts_i=pts_i, pts_j=pts_j, **m))
+        fac = O.ProjectionTdFactor(pts_i, pts_j, m["velocity_i"], m["velocity_j"], m["td_i"], m["td_j"], m["row_i"],
+                                   m["row_j"], s, tr)
+        r, js = fac.EvaluateCeres([p.poses[i], p.poses[j], p.ex[e], p.feat[f:f + 1], td])
+        ofac.append(sim.cauchy_correct(r, js, 1.0) + (keys,))
+    se3 = p.se3[0]
+    mi.addResidualBlockInfo(ResidualBlockInfo("se3", [("pose", 0)], drop_set=[0], t=se3.t, R=se3.R, sqrt_info=se3.sqrt_info))
+    ofac.append(sim.cauchy_correct(*se3.EvaluateCeres([p.poses[0]]), 1.0) + ([("pose", 0)],))
+    mi.preMarginalize({"pose": p.poses, "speed_bias": p.sbs, "ex_pose": p.ex, "feature": p.feat, "td": td})
+    mi.marginalize()
+    assert mi.status == 0, hex(mi.status)
+    idx = mi.parameter_block_idx
+    assert idx[("td", 0)] >= mi.m                      # the time offset is kept, with its own column
+    facs = [(r, [(idx[k], np.asarray(j)[:, :LOCAL_SIZE[k[0]]]) for k, j in zip(keys, js) if k not in const])
+            for r, js, keys in ofac]
+    ref = O.vins_mono_marginalize(facs, mi.pos, mi.m, eps=1e-8)
+    S_hp, s_hp = O.schur_complement_longdouble(ref["A"], ref["b"], mi.m)
+    e_ref, e_gpu = rel_err(ref["A_red"], S_hp), rel_err(mi.A_red, S_hp)
+    print(f"td marginalization vs 80-bit truth: literal FP64 {e_ref:.2e}, CUDA {e_gpu:.2e}")
+    assert e_gpu <= max(1e-9, 2.0 * e_ref)
+    assert rel_err(mi.b_red, s_hp) <= max(1e-9, 2.0 * rel_err(ref["b_red"], s_hp))
+    t0 = idx[("td", 0)] - mi.m
+    assert mi.A_red[t0, t0] > 0 and np.count_nonzero(mi.A_red[t0]) > 6      # td couples with the kept poses
+    assert rel_err(mi.linearized_jacobians.T @ mi.linearized_jacobians, mi.A_red) <= 1e-9
