@@ -583,7 +583,9 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
   double* Jrp = T + 72;      // 2 x 6
   double* JU = T + 88;       // 17 x 15 (fast path: Y) / up to 9 x 15 (eigen path)
   double* cov = T + 344;     // up to 9 x 9
-  for (int i = lane; i < 84; i += 32) T[i] = F[kFJ_REL + i];
+  // [Ji | Jj | Jrp] of the recovered factors: loaded now, parked in shared memory after the Cholesky (the
+  // global-load latency hides behind it)
+  const double jr0 = F[kFJ_REL + lane], jr1 = F[kFJ_REL + 32 + lane], jr2 = (lane < 20) ? F[kFJ_REL + 64 + lane] : 0.0;
 
   // ---- covariance = L L^T, one column per lane in registers (right-looking) ------------------------
   {
@@ -619,6 +621,9 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
 #pragma unroll
   for (int i = 0; i < 9; ++i) pr[i] = (lane >= 21 && lane < 30) ? pvb[9 + i + 9 * (lane - 21)] : 0.0;
 
+  T[lane] = jr0;
+  T[32 + lane] = jr1;
+  if (lane < 20) T[64 + lane] = jr2;
   // ---- sqrt_info^T sqrt_info = covariance^-1 (imu_factor.h:181): col <- L^-1 col ------------------
 #pragma unroll
   for (int i = 0; i < 15; ++i) {
@@ -716,15 +721,12 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
         dot = fma(v[c], row[c], dot);
       }
       const double sdot = tau * dot;
-      if (lane == j) {
-        row[j] = beta;
+      // uniform update (no divergence): the pivot lane's own tail becomes rounding-level garbage instead of
+      // exact zeros -- it is never read again (later reflectors read lane j' > j, the solve reads only the
+      // lower triangle of L)
+      row[j] = (lane == j) ? beta : row[j] - sdot;
 #pragma unroll
-        for (int c = j + 1; c < 21; ++c) row[c] = 0.0;
-      } else {
-        row[j] -= sdot;
-#pragma unroll
-        for (int c = j + 1; c < 21; ++c) row[c] = fma(-sdot, v[c], row[c]);
-      }
+      for (int c = j + 1; c < 21; ++c) row[c] = fma(-sdot, v[c], row[c]);
     }
   }
   // L (rows of lanes 0-14, lower triangular) -> shared; solve L^T y = rhs for all 32 lanes at once:
