@@ -75,6 +75,39 @@ __device__ ISV_HEAVY void w_gemm(int m, int n, int k, const double* A, int lda, 
   __syncwarp();
 }
 
+// Compile-time-shaped variant: index arithmetic folds to shifts / multiplies, the k loop is fully unrolled
+// with two accumulators and all its shared-memory loads issued up front (the window kernels are bound by
+// dependent-issue latency, so exposed LDS round trips matter more than instruction count).
+template <bool TA, bool TB, int M, int N, int K>
+__device__ __forceinline__ void w_gemm_t(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                                         double* __restrict__ C, int ldc, int mode, int lane) {
+#pragma unroll
+  for (int idx0 = 0; idx0 < M * N; idx0 += 32) {
+    const int idx = idx0 + lane;
+    if (idx < M * N) {
+      const int i = idx % M, j = idx / M;
+      double av[K], bv[K];
+#pragma unroll
+      for (int l = 0; l < K; ++l) {
+        av[l] = TA ? A[l + i * lda] : A[i + l * lda];
+        bv[l] = TB ? B[j + l * ldb] : B[l + j * ldb];
+      }
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int l = 0; l < K; ++l) {
+        if (l & 1) a1 = fma(av[l], bv[l], a1);
+        else a0 = fma(av[l], bv[l], a0);
+      }
+      const double acc = a0 + a1;
+      double* c = &C[i + j * ldc];
+      if (mode == 0) *c = acc;
+      else if (mode > 0) *c += acc;
+      else *c -= acc;
+    }
+  }
+  __syncwarp();
+}
+
 // Mirror the lower triangle onto the upper one (n x n).
 __device__ __forceinline__ void w_symmetrize_from_lower(double* A, int ld, int n, int lane) {
   for (int idx = lane; idx < n * n; idx += 32) {

@@ -381,6 +381,14 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
 
   const double* pose0 = in.pose_fwd + (size_t)win * 14;
   const double* pose1 = pose0 + 7;
+  // every global load of this kernel is issued here, up front: the factor-Jacobian record (252 doubles, 8
+  // per lane, parked in registers until the work area is free) and the Gram triangles
+  double fjr[8];
+  {
+    const double* F = fj + (size_t)win * kFJ;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) fjr[t] = (32 * t + lane < 252) ? F[32 * t + lane] : 0.0;
+  }
   // work map (doubles): S12[0] H12[144] Ye[288] Ys[324] tmp[360..432) ; then
   // Wst[288] G[432] Jr6[504] tA[612] tB[684] wk[756]
   double* S12 = X;
@@ -421,10 +429,10 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
   __syncwarp();
   {
     const double* Psi = K;
-    w_gemm<false, false>(12, 6, 6, Psi, 12, Ys, 6, Tm, 12, 0, lane);
-    w_gemm<false, true>(12, 12, 6, Tm, 12, Psi, 12, S12, 12, 0, lane);   // Schur over the landmarks
-    w_gemm<false, false>(12, 6, 6, Psi, 12, Ye, 6, Tm, 12, 0, lane);
-    w_gemm<false, true>(12, 12, 6, Tm, 12, Psi, 12, H12, 12, 0, lane);   // sum e e^T
+    w_gemm_t<false, false, 12, 6, 6>(Psi, 12, Ys, 6, Tm, 12, 0, lane);
+    w_gemm_t<false, true, 12, 12, 6>(Tm, 12, Psi, 12, S12, 12, 0, lane);   // Schur over the landmarks
+    w_gemm_t<false, false, 12, 6, 6>(Psi, 12, Ye, 6, Tm, 12, 0, lane);
+    w_gemm_t<false, true, 12, 12, 6>(Tm, 12, Psi, 12, H12, 12, 0, lane);   // sum e e^T
   }
   double* Wst = X + 288;
   double* G = X + 432;
@@ -436,22 +444,21 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
   double* o_pg = out.pg_out + (size_t)win * ISV_PG_REC;
   // Wst (12x12: rows 0-5 = sp [0 | Jp], rows 6-11 = sr [Jj | Ji]), G (6x12) and Jr6 (6x6) come from
   // marg_factor_jac_kernel; they are contiguous in the scratch in the order of the work map
-  {
-    const double* F = fj + (size_t)win * kFJ;
-    for (int i = lane; i < 252; i += 32) Wst[i] = F[i];
-  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+    if (32 * t + lane < 252) Wst[32 * t + lane] = fjr[t];
   __syncwarp();
   // S12 += Wst^T Wst ; H12 = E12 + S12  (= Lamda[0:12,0:12], :1243)
-  w_gemm<true, false>(12, 12, 12, Wst, 12, Wst, 12, S12, 12, 1, lane);
+  w_gemm_t<true, false, 12, 12, 12>(Wst, 12, Wst, 12, S12, 12, 1, lane);
   for (int idx = lane; idx < 144; idx += 32) H12[idx] += S12[idx];
   __syncwarp();
   // ---- pose-graph relative-pose factor (:1243-1259) -------------------------------------------
   // J = G (6x12, [Ji|Jj]) ; Jpinv = J^T (J J^T)^-1 (full row rank) ; rpOmega = Jpinv^T H12 Jpinv
-  w_gemm<false, true>(6, 6, 12, G, 6, G, 6, tA, 6, 0, lane);          // tA = J J^T
+  w_gemm_t<false, true, 6, 6, 12>(G, 6, G, 6, tA, 6, 0, lane);          // tA = J J^T
   if (w_spd_inverse_regs<6>(tA, 6, lane)) status |= ISV_W_SINGULAR;
-  w_gemm<true, false>(12, 6, 6, G, 6, tA, 6, tB, 12, 0, lane);        // tB = Jpinv (12x6)
-  w_gemm<false, false>(12, 6, 12, H12, 12, tB, 12, wk, 12, 0, lane);  // wk = H12 Jpinv
-  w_gemm<true, false>(6, 6, 12, tB, 12, wk, 12, tA, 6, 0, lane);      // tA = rpOmega
+  w_gemm_t<true, false, 12, 6, 6>(G, 6, tA, 6, tB, 12, 0, lane);        // tB = Jpinv (12x6)
+  w_gemm_t<false, false, 12, 6, 12>(H12, 12, tB, 12, wk, 12, 0, lane);  // wk = H12 Jpinv
+  w_gemm_t<true, false, 6, 6, 12>(tB, 12, wk, 12, tA, 6, 0, lane);      // tA = rpOmega
   w_copy(Wst, tA, 36, lane);
   if (chol_store_upper(Wst, 6, 6, o_pg + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
   w_copy(Wst, tA, 36, lane);
@@ -470,9 +477,9 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
     w_copy2d(tA, 6, S12 + 6 + 12 * 6, 12, 6, 6, lane);
     if (w_inverse(tA, 6, 6, wk, lane)) status |= ISV_W_SINGULAR;
   }
-  w_gemm<false, false>(6, 6, 6, S12 + 12 * 6, 12, tA, 6, tB, 6, 0, lane);        // tB = S[0:6,6:12] Smm^-1
+  w_gemm_t<false, false, 6, 6, 6>(S12 + 12 * 6, 12, tA, 6, tB, 6, 0, lane);        // tB = S[0:6,6:12] Smm^-1
   w_copy2d(Wst, 6, S12, 12, 6, 6, lane);                                          // Wst = S[0:6,0:6]
-  w_gemm<false, true>(6, 6, 6, tB, 6, S12 + 12 * 6, 12, Wst, 6, -1, lane);       // Lamda_prior (6x6)
+  w_gemm_t<false, true, 6, 6, 6>(tB, 6, S12 + 12 * 6, 12, Wst, 6, -1, lane);       // Lamda_prior (6x6)
   // ---- rank decision + recovery of the SE3 prior on T1 (:1304-1349) ---------------------------
   // Fast path: Lamda_prior^-1 by the SPD route; when ||A||_F ||A^-1||_F < 1e10 every pivot of
   // Eigen's FullPivHouseholderQR is > 5e-13 of the largest, far above both its early-exit test
@@ -499,8 +506,8 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
   }
   int out_rank = rank;
   if (rank == 6) {
-    w_gemm<false, false>(6, 6, 6, Jr6, 6, tA, 6, tB, 6, 0, lane);     // Jr cov
-    w_gemm<false, true>(6, 6, 6, tB, 6, Jr6, 6, tA, 6, 0, lane);      // covi = Jr cov Jr^T
+    w_gemm_t<false, false, 6, 6, 6>(Jr6, 6, tA, 6, tB, 6, 0, lane);     // Jr cov
+    w_gemm_t<false, true, 6, 6, 6>(tB, 6, Jr6, 6, tA, 6, 0, lane);      // covi = Jr cov Jr^T
   } else {
     status |= ISV_W_RANK_DEFICIENT;
     // truncated eigen path (:1311-1331), factored form: Lamda_prior = sum_k g_k g_k^T (rows of tB)
