@@ -31,7 +31,7 @@ namespace isv {
 constexpr int kWarpsPerCta = ISV_WARPS_PER_CTA;
 constexpr int kThreads = 32 * kWarpsPerCta;
 #ifndef ISV_FWD_MINB
-#define ISV_FWD_MINB 3
+#define ISV_FWD_MINB 2
 #endif
 #ifndef ISV_FWD_TAIL_MINB
 #define ISV_FWD_TAIL_MINB 4
@@ -289,58 +289,88 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
 #pragma unroll
   for (int i = 0; i < 21; ++i) { ae[i] = 0.0; aw[i] = 0.0; }
 
-  // software pipeline: the loads of the landmarks two iterations ahead are in flight
-  double nx[2] = {0, 0}, ny[2] = {0, 0}, nz[2] = {0, 0}, nl[2] = {1, 1};
+  // one landmark -> its two 6-vectors (see the derivation above); returns 1 for a degenerate observation
+  auto chain = [&](double px, double py, double pz, double lam, double* __restrict__ ye, double* __restrict__ yw) -> int {
+    double w[3], ph[3], qt[3];
 #pragma unroll
-  for (int d = 0; d < 2; ++d) {
-    const int k = d * 32 + lane;
-    if (k < L) { nx[d] = ob[k]; ny[d] = ob[st + k]; nz[d] = ob[2 * st + k]; nl[d] = ob[5 * st + k]; }
+    for (int r = 0; r < 3; ++r) {
+      w[r] = K[3 * r] * px + K[3 * r + 1] * py + K[3 * r + 2] * pz;
+      ph[r] = fma(lam, K[9 + r], w[r]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) qt[c] = ric[c] * w[0] + ric[3 + c] * w[1] + ric[6 + c] * w[2];
+    const double c0 = fma(lam, K[12], qt[0]), c1 = fma(lam, K[13], qt[1]), c2 = fma(lam, K[14], qt[2]);
+    // direction of s * jacobian_feature:  Pb q~ = [q0 - xb q2, q1 - yb q2] = lam / c2 * [q0 tp2 - q2 tp0,
+    // q1 tp2 - q2 tp1]  (c~ = q~ + lam tp).  Only the direction matters (u enters as u u^T, v as v v^T), so it
+    // is taken from the cancellation-free right-hand side -- and the rsqrt does not wait for the division.
+    const double nt0 = fma(qt[0], K[14], -qt[2] * K[12]), nt1 = fma(qt[1], K[14], -qt[2] * K[13]);
+    const double g0 = s00 * nt0 + s01 * nt1, g1 = s10 * nt0 + s11 * nt1;
+    const double n2 = g0 * g0 + g1 * g1;
+    const double rn = rsqrt(n2);
+    const double rho = 1.0 / c2;
+    const double xb = c0 * rho, yb = c1 * rho;
+    const bool ok = n2 > 0.0;
+    const double in_ = rn * rho;
+    const double u0 = ok ? g0 * in_ : rho, u1 = ok ? g1 * in_ : 0.0;        // (u, v) pre-scaled by rho
+    const double a0 = u0 * s00 + u1 * s10, a1 = u0 * s01 + u1 * s11;        // rho s^T u
+    const double b0 = -u1 * s00 + u0 * s10, b1 = -u1 * s01 + u0 * s11;      // rho s^T v
+    double al[3], be[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double n0 = fma(-xb, ric[3 * r + 2], ric[3 * r]), n1 = fma(-yb, ric[3 * r + 2], ric[3 * r + 1]);
+      al[r] = a0 * n0 + a1 * n1;
+      be[r] = b0 * n0 + b1 * n1;
+    }
+    ye[0] = ph[1] * al[2] - ph[2] * al[1];  ye[1] = ph[2] * al[0] - ph[0] * al[2];  ye[2] = ph[0] * al[1] - ph[1] * al[0];
+    yw[0] = ph[1] * be[2] - ph[2] * be[1];  yw[1] = ph[2] * be[0] - ph[0] * be[2];  yw[2] = ph[0] * be[1] - ph[1] * be[0];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { ye[3 + r] = lam * al[r]; yw[3 + r] = lam * be[r]; }
+    return ok ? 0 : 1;
+  };
+  auto syrk = [&](const double* __restrict__ ye, const double* __restrict__ yw) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        ae[t] = fma(ye[i], ye[j], ae[t]);
+        aw[t] = fma(yw[i], yw[j], aw[t]);
+        ++t;
+      }
+  };
+  // Two landmarks per lane and iteration (k and k + 32): their projection chains are independent, which
+  // doubles the instruction-level parallelism of the latency-bound part; loads run two iterations ahead.
+  constexpr int kPf = 4;
+  const double* __restrict__ obx = ob + lane;
+  const double* __restrict__ oby = ob + st + lane;
+  const double* __restrict__ obz = ob + 2 * st + lane;
+  const double* __restrict__ obl = ob + 5 * st + lane;
+  double nx[kPf], ny[kPf], nz[kPf], nl[kPf];
+#pragma unroll
+  for (int d = 0; d < kPf; ++d) {
+    nx[d] = 0.0; ny[d] = 0.0; nz[d] = 0.0; nl[d] = 1.0;
+    if (d * 32 + lane < L) { nx[d] = obx[d * 32]; ny[d] = oby[d * 32]; nz[d] = obz[d * 32]; nl[d] = obl[d * 32]; }
   }
-  for (int base = 0; base < L; base += 32) {
-    const int k = base + lane;
-    const double px = nx[0], py = ny[0], pz = nz[0], lam = nl[0];
-    nx[0] = nx[1]; ny[0] = ny[1]; nz[0] = nz[1]; nl[0] = nl[1];
-    const int kn = k + 64;
-    if (kn < L) { nx[1] = ob[kn]; ny[1] = ob[st + kn]; nz[1] = ob[2 * st + kn]; nl[1] = ob[5 * st + kn]; }
-    if (k < L) {
-      double w[3], ph[3], qt[3];
+  for (int base = 0; base < L; base += 64) {
+    const double pxa = nx[0], pya = ny[0], pza = nz[0], la = nl[0];
+    const double pxb = nx[1], pyb = ny[1], pzb = nz[1], lb = nl[1];
+    nx[0] = nx[2]; ny[0] = ny[2]; nz[0] = nz[2]; nl[0] = nl[2];
+    nx[1] = nx[3]; ny[1] = ny[3]; nz[1] = nz[3]; nl[1] = nl[3];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        w[r] = K[3 * r] * px + K[3 * r + 1] * py + K[3 * r + 2] * pz;
-        ph[r] = fma(lam, K[9 + r], w[r]);
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) qt[c] = ric[c] * w[0] + ric[3 + c] * w[1] + ric[6 + c] * w[2];
-      const double c0 = fma(lam, K[12], qt[0]), c1 = fma(lam, K[13], qt[1]), c2 = fma(lam, K[14], qt[2]);
-      const double rho = 1.0 / c2;
-      const double xb = c0 * rho, yb = c1 * rho;
-      const double pq0 = fma(-xb, qt[2], qt[0]), pq1 = fma(-yb, qt[2], qt[1]);
-      const double g0 = s00 * pq0 + s01 * pq1, g1 = s10 * pq0 + s11 * pq1;
-      const double n2 = g0 * g0 + g1 * g1;
-      double u0 = rho, u1 = 0.0;                       // (u, v) pre-scaled by rho
-      if (n2 > 0.0) { const double in_ = rsqrt(n2) * rho; u0 = g0 * in_; u1 = g1 * in_; } else { status |= ISV_W_SINGULAR; }
-      const double a0 = u0 * s00 + u1 * s10, a1 = u0 * s01 + u1 * s11;        // rho s^T u
-      const double b0 = -u1 * s00 + u0 * s10, b1 = -u1 * s01 + u0 * s11;      // rho s^T v
-      double ye[6], yw[6], al[3], be[3];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const double n0 = fma(-xb, ric[3 * r + 2], ric[3 * r]), n1 = fma(-yb, ric[3 * r + 2], ric[3 * r + 1]);
-        al[r] = a0 * n0 + a1 * n1;
-        be[r] = b0 * n0 + b1 * n1;
-      }
-      ye[0] = ph[1] * al[2] - ph[2] * al[1];  ye[1] = ph[2] * al[0] - ph[0] * al[2];  ye[2] = ph[0] * al[1] - ph[1] * al[0];
-      yw[0] = ph[1] * be[2] - ph[2] * be[1];  yw[1] = ph[2] * be[0] - ph[0] * be[2];  yw[2] = ph[0] * be[1] - ph[1] * be[0];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) { ye[3 + r] = lam * al[r]; yw[3 + r] = lam * be[r]; }
-      int t = 0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; ++j) {
-          ae[t] = fma(ye[i], ye[j], ae[t]);
-          aw[t] = fma(yw[i], yw[j], aw[t]);
-          ++t;
-        }
+    for (int d = 2; d < 4; ++d) {
+      const int kn = base + 32 * (d + 2);
+      if (kn + lane < L) { nx[d] = obx[kn]; ny[d] = oby[kn]; nz[d] = obz[kn]; nl[d] = obl[kn]; }
+    }
+    double yea[6], ywa[6], yeb[6], ywb[6];
+    if (base + 32 + lane < L) {
+      int bad = chain(pxa, pya, pza, la, yea, ywa);
+      bad |= chain(pxb, pyb, pzb, lb, yeb, ywb);
+      syrk(yea, ywa);
+      syrk(yeb, ywb);
+      if (bad) status |= ISV_W_SINGULAR;
+    } else if (base + lane < L) {
+      if (chain(pxa, pya, pza, la, yea, ywa)) status |= ISV_W_SINGULAR;
+      syrk(yea, ywa);
     }
   }
   // cross-lane reduction through shared memory: lane l parks its 21 partial sums in column l of a
