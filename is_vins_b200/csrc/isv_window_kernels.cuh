@@ -670,35 +670,39 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
     col[i] = sacc * Lc[225 + i];
   }
   // ---- Schur complement over VB_{V-1} (:1413-1419) as a QR elimination of columns 21..29 -----------
+  // Reflectors in unnormalised form  H = I - gamma w w^T ,  w = [x0 - beta ; tail] ,
+  // gamma = 1 / (|beta| (|beta| + |x0|)) ,  |beta| = sqrt(x0^2 + |tail|^2) = nrm * rsqrt(nrm):
+  // one rsqrt and one reciprocal per reflector instead of a sqrt and two divisions, and the tail is used
+  // as it is (no scaling pass).
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
     if (lane == 21 + k) {
-      double t2 = 0.0;
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll
-      for (int i = 0; i < 15; ++i) t2 = fma(col[i], col[i], t2);
+      for (int i = 0; i < 15; i += 3) { t0 = fma(col[i], col[i], t0); t1 = fma(col[i + 1], col[i + 1], t1); t2 = fma(col[i + 2], col[i + 2], t2); }
+      const double tt = (t0 + t1) + t2;
       const double x0 = pr[k];
-      double tau = 0.0;
-      if (t2 > 0.0) {
-        double beta = sqrt(fma(x0, x0, t2));
-        if (x0 >= 0.0) beta = -beta;
-        const double inv = 1.0 / (x0 - beta);
-        tau = (beta - x0) / beta;
-#pragma unroll
-        for (int i = 0; i < 15; ++i) hv[i] = col[i] * inv;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 15; ++i) hv[i] = 0.0;
+      double gamma = 0.0, w0 = 0.0;
+      if (tt > 0.0) {
+        const double nrm = fma(x0, x0, tt);
+        const double ab = nrm * rsqrt(nrm);            // |beta|
+        const double ax = fabs(x0);
+        gamma = 1.0 / (ab * (ab + ax));
+        w0 = (x0 >= 0.0) ? (ax + ab) : -(ax + ab);     // x0 - beta , beta = -sign(x0) |beta|
       }
-      hv[15] = tau;
+#pragma unroll
+      for (int i = 0; i < 15; ++i) hv[i] = col[i];
+      hv[15] = gamma;
+      hv[16] = w0;
     }
     __syncwarp();
     {
-      // apply (I - tau v v^T), v = [1 (row k) ; hv (IMU rows)], to every live column other than 21+k
-      const double tau = hv[15];
-      double dot = (lane > 21 + k && lane < 30) ? pr[k] : 0.0;   // row k is zero outside the VB columns
+      // apply H to every live column other than 21+k; row k is zero outside the VB columns
+      const double gamma = hv[15], w0 = hv[16];
+      double d0 = (lane > 21 + k && lane < 30) ? pr[k] * w0 : 0.0, d1 = 0.0, d2 = 0.0;
 #pragma unroll
-      for (int i = 0; i < 15; ++i) dot = fma(hv[i], col[i], dot);
-      const double sd = tau * dot;
+      for (int i = 0; i < 15; i += 3) { d0 = fma(hv[i], col[i], d0); d1 = fma(hv[i + 1], col[i + 1], d1); d2 = fma(hv[i + 2], col[i + 2], d2); }
+      const double sd = gamma * ((d0 + d1) + d2);
       if (lane < 21 || lane > 21 + k) {
 #pragma unroll
         for (int i = 0; i < 15; ++i) col[i] = fma(-sd, hv[i], col[i]);
@@ -738,30 +742,39 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
       for (int cc = 0; cc < 6; ++cc) row[15 + cc] = Jrp[(r - 15) + 2 * cc];
     }
   }
+  // (reflectors in the unnormalised form of the elimination above: H = I - gamma w w^T, w = [x0 - beta ; x_tail])
 #pragma unroll
   for (int j = 0; j < 15; ++j) {
-    double t2 = 0.0;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll
-    for (int c = j + 1; c < 21; ++c) t2 = fma(row[c], row[c], t2);
-    t2 = __shfl_sync(kFullMask, t2, j);
+    for (int c = j + 1; c < 21; ++c) {
+      if ((c - j) % 3 == 1) t0 = fma(row[c], row[c], t0);
+      else if ((c - j) % 3 == 2) t1 = fma(row[c], row[c], t1);
+      else t2 = fma(row[c], row[c], t2);
+    }
+    const double tt = __shfl_sync(kFullMask, (t0 + t1) + t2, j);
     const double x0 = __shfl_sync(kFullMask, row[j], j);
-    if (t2 > 0.0) {
-      double beta = sqrt(fma(x0, x0, t2));
-      if (x0 >= 0.0) beta = -beta;
-      const double inv = 1.0 / (x0 - beta);
-      const double tau = (beta - x0) / beta;
+    if (tt > 0.0) {
+      const double nrm = fma(x0, x0, tt);
+      const double ab = nrm * rsqrt(nrm);              // |beta|
+      const double ax = fabs(x0);
+      const double gamma = 1.0 / (ab * (ab + ax));
+      const double w0 = (x0 >= 0.0) ? (ax + ab) : -(ax + ab);   // x0 - beta
+      const double beta = (x0 >= 0.0) ? -ab : ab;
       double v[21];
-      double dot = row[j];
+      double d0 = row[j] * w0, d1 = 0.0, d2 = 0.0;
 #pragma unroll
       for (int c = j + 1; c < 21; ++c) {
-        v[c] = __shfl_sync(kFullMask, row[c], j) * inv;
-        dot = fma(v[c], row[c], dot);
+        v[c] = __shfl_sync(kFullMask, row[c], j);
+        if ((c - j) % 3 == 1) d0 = fma(v[c], row[c], d0);
+        else if ((c - j) % 3 == 2) d1 = fma(v[c], row[c], d1);
+        else d2 = fma(v[c], row[c], d2);
       }
-      const double sdot = tau * dot;
+      const double sdot = gamma * ((d0 + d1) + d2);
       // uniform update (no divergence): the pivot lane's own tail becomes rounding-level garbage instead of
       // exact zeros -- it is never read again (later reflectors read lane j' > j, the solve reads only the
       // lower triangle of L)
-      row[j] = (lane == j) ? beta : row[j] - sdot;
+      row[j] = (lane == j) ? beta : fma(-sdot, w0, row[j]);
 #pragma unroll
       for (int c = j + 1; c < 21; ++c) row[c] = fma(-sdot, v[c], row[c]);
     }
