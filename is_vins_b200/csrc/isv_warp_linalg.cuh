@@ -653,6 +653,49 @@ __device__ __forceinline__ int w_sqrt_info_from_cov_regs(const double* A, int ld
   return bad;
 }
 
+// Eigen `LLT(M).matrixL().transpose()` of a small SPD matrix entirely in registers: every lane loads the
+// lower triangle (broadcast LDS) and runs the same serial Cholesky (SIMT makes the redundancy free; one
+// rsqrt per column, no barriers), lane j < N stores column j of the upper-triangular factor (zeros below
+// the diagonal).  M (smem, ld) is only read.  out: N x N column-major.  Returns 1 when M is not SPD.
+template <int N>
+__device__ __forceinline__ int w_llt_upper_regs(const double* M, int ld, double* out, int lane, int& nonfinite) {
+  double l[N][N];
+  int bad = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) l[i][j] = M[i + j * ld];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double d = l[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d = fma(-l[j][k], l[j][k], d);
+    if (!(d > 0.0)) bad = 1;
+    const double ri = rsqrt(d);
+    l[j][j] = d * ri;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      double v = l[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v = fma(-l[i][k], l[j][k], v);
+      l[i][j] = v * ri;
+    }
+  }
+  if (lane < N) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double v = 0.0;   // U[i][lane] = L[lane][i] for i <= lane
+#pragma unroll
+      for (int c = 0; c < N; ++c)
+        if (c == lane && i <= c) v = l[c][i];
+      if (!isfinite(v)) nonfinite = 1;
+      out[i + N * lane] = v;
+    }
+  }
+  __syncwarp();
+  return bad;
+}
+
 // Several small SPD matrices turned into their sqrt-information factors AT ONCE, one column per lane:
 // lane (group g, column c) owns column c of its group's covariance A_g (N_g x N_g, column-major, ld N_g)
 // in registers; the reverse-order Cholesky A = U1 U1^T runs right-looking with the finished column

@@ -490,7 +490,7 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
   w_gemm_t<false, false, 12, 6, 12>(H12, 12, tB, 12, wk, 12, 0, lane);  // wk = H12 Jpinv
   w_gemm_t<true, false, 6, 6, 12>(tB, 12, wk, 12, tA, 6, 0, lane);      // tA = rpOmega
   w_copy(Wst, tA, 36, lane);
-  if (chol_store_upper(Wst, 6, 6, o_pg + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
+  if (w_llt_upper_regs<6>(Wst, 6, o_pg + 12, lane, nonfinite)) status |= ISV_W_NOT_SPD;
   w_copy(Wst, tA, 36, lane);
   if (w_spd_inverse_regs<6>(tA, 6, lane)) {                            // covRel = rpOmega^-1
     w_copy(tA, Wst, 36, lane);
