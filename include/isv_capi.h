@@ -473,6 +473,43 @@ isv_status isv_marginalize_generic(isv_handle* h, const isv_marg_generic_in* in,
  * DENSE_SCHUR forms inside problemSolve() (src/estimator.cpp:1124) -- SURVEY.md 8f rank 1.           */
 isv_status isv_reduced_system(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out);
 
+/* ---- MarginalizationFactor: the previous round's prior as a residual block ------------------------------
+ * VINS-Mono marginalization_factor.cpp `MarginalizationFactor::Evaluate` (IS-VINS deleted the class together
+ * with MarginalizationInfo; it is what lets the facade run frame after frame):
+ *     dx_b = x_b - x0_b                                   Euclidean blocks
+ *     dx_b = [ p - p0 ; +-2 vec(q0^-1 * q) ]              pose blocks (sign: minus when the w of q0^-1 q is < 0)
+ *     residual = linearized_residuals + linearized_jacobians * dx
+ *     jacobians[b] (n x global_size, row-major) = [ linearized_jacobians[:, idx_b : idx_b + local] | 0 ]
+ * All pointers are DEVICE pointers.                                                                       */
+typedef struct isv_prior_block {
+  int32_t global_size;           /* 7 = pose block (6 tangent columns); anything else is Euclidean           */
+  int32_t idx;                   /* first column of the block in the prior (keep_block_idx - m)              */
+  int32_t x_offset;              /* first double of the block in `x` and in `x0`                             */
+  int32_t pos;                   /* tangent position in the NEW problem (isv_add_marg_prior), -1 = constant  */
+} isv_prior_block;
+typedef struct isv_marg_prior {
+  int32_t n;                     /* rows = columns of linearized_jacobians                                   */
+  int32_t n_blocks;
+  const isv_prior_block* blocks;
+  const double* linearized_jacobians;   /* [n][n] column-major (as isv_marg_generic_out writes it)          */
+  const double* linearized_residuals;   /* [n]                                                               */
+  const double* x0;              /* keep_block_data: the kept blocks at the linearization point              */
+  const double* x;               /* the same blocks now                                                      */
+} isv_marg_prior;
+/* residuals [n]; jacobians (may be NULL): the blocks concatenated in table order, block b = n x global_size
+ * row-major.  ISV_W_BAD_INDEX in *status (may be NULL) when a block reaches outside the prior.             */
+isv_status isv_eval_marg_prior(isv_handle* h, const isv_marg_prior* prior, double* residuals, double* jacobians,
+                               int32_t* status);
+/* A += J^T J, b += J^T residuals of the prior, scattered by blocks[].pos into the normal equations of problem
+ * `problem` (out->A, out->b as isv_build_normal_equations left them); residuals from isv_eval_marg_prior.  */
+isv_status isv_add_marg_prior(isv_handle* h, const isv_marg_prior* prior, const double* residuals,
+                              const isv_marg_generic_in* in, const isv_marg_generic_out* out, int32_t problem);
+/* stage 2 alone on normal equations that are already built (isv_build_normal_equations [+ isv_add_marg_prior]):
+ * Schur complement (+ eigen-decomposition unless schur_only).  build -> add prior -> this == what
+ * isv_marginalize_generic does in one call when there is no prior.                                          */
+isv_status isv_schur_eig(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out,
+                         int32_t schur_only);
+
 /* The whole MarginalizationInfo::preMarginalize + marginalize step from HOST memory, blocking: H2D of the
  * parameter blocks and factor lists, `Evaluate` of every residual block on the GPU (isv_eval_*), the block
  * tables built from the per-family tangent positions, isv_marginalize_generic (or isv_reduced_system when

@@ -138,6 +138,15 @@ class isv_seq_host(C.Structure):
                                           "last_pg", "last_rel", "last_vb", "last_rp", "last_rank", "last_status")]
 
 
+class isv_prior_block(C.Structure):
+    _fields_ = [("global_size", C.c_int32), ("idx", C.c_int32), ("x_offset", C.c_int32), ("pos", C.c_int32)]
+
+
+class isv_marg_prior(C.Structure):
+    _fields_ = [("n", C.c_int32), ("n_blocks", C.c_int32), ("blocks", C.c_void_p), ("linearized_jacobians", C.c_void_p),
+                ("linearized_residuals", C.c_void_p), ("x0", C.c_void_p), ("x", C.c_void_p)]
+
+
 # every symbol include/isv_capi.h declares: (name, restype, argtypes)
 _H = C.c_void_p
 SYMBOLS = [
@@ -182,6 +191,9 @@ SYMBOLS = [
     ("isv_marginalize_generic", C.c_int, [_H, C.c_void_p, C.c_void_p]),
     ("isv_reduced_system", C.c_int, [_H, C.c_void_p, C.c_void_p]),
     ("isv_marginalize_host", C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    ("isv_eval_marg_prior", C.c_int, [_H, C.POINTER(isv_marg_prior), C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("isv_add_marg_prior", C.c_int, [_H, C.POINTER(isv_marg_prior), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    ("isv_schur_eig", C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32]),
     ("isv_test_psd_eig", C.c_int, [_H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int32_p]),
 ]
 

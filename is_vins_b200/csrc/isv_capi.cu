@@ -1056,12 +1056,72 @@ extern "C" isv_status isv_reduced_system(isv_handle* h, const isv_marg_generic_i
   return marginalize_generic_impl(h, in, &o, 1);
 }
 
+static isv_status schur_eig_impl(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out,
+                                 int schur_only);
+
 static isv_status marginalize_generic_impl(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out,
                                            int schur_only) {
   isv_status st = marg_generic_check(h, in, out, true);
   if (st != ISV_OK) return st;
   st = isv_build_normal_equations(h, in, out);
   if (st != ISV_OK) return st;
+  return schur_eig_impl(h, in, out, schur_only);
+}
+
+extern "C" isv_status isv_schur_eig(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out,
+                                    int32_t schur_only) {
+  if (schur_only) {
+    if (!out || !out->A_red || !out->b_red || !out->rank) return ISV_ERR_BAD_ARG;
+    isv_marg_generic_out o = *out;
+    if (!o.linearized_jacobians) o.linearized_jacobians = o.A_red;
+    if (!o.linearized_residuals) o.linearized_residuals = o.b_red;
+    isv_status st = marg_generic_check(h, in, &o, true);
+    return st != ISV_OK ? st : schur_eig_impl(h, in, &o, 1);
+  }
+  isv_status st = marg_generic_check(h, in, out, true);
+  return st != ISV_OK ? st : schur_eig_impl(h, in, out, 0);
+}
+
+// ---- MarginalizationFactor (the previous prior as a residual block) ----------------------------------------
+static bool prior_ok(const isv_marg_prior* p) {
+  return p && p->n >= 1 && p->n_blocks >= 1 && p->blocks && p->linearized_jacobians && p->linearized_residuals && p->x0 &&
+         p->x;
+}
+
+extern "C" isv_status isv_eval_marg_prior(isv_handle* h, const isv_marg_prior* prior, double* residuals, double* jacobians,
+                                          int32_t* status) {
+  if (!h || !prior_ok(prior) || !residuals) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const size_t sm = (size_t)prior->n * sizeof(double) + ((size_t)prior->n_blocks + 2) * sizeof(int);
+  if (sm > 200 * 1024) return ISV_ERR_BAD_ARG;
+  if (sm > 48 * 1024)
+    ISV_CUDA(cudaFuncSetAttribute(marg_prior_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  // rows of the residual split over the CTAs; with Jacobians requested, enough CTAs to stream the re-layout
+  int grid = (prior->n + kPriorThreads - 1) / kPriorThreads;
+  if (jacobians) grid = std::max(grid, std::min(2 * 148, (prior->n * prior->n) / (4 * kPriorThreads) + 1));
+  marg_prior_eval_kernel<<<grid, kPriorThreads, sm, h->stream>>>(*prior, residuals, jacobians, status);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+extern "C" isv_status isv_add_marg_prior(isv_handle* h, const isv_marg_prior* prior, const double* residuals,
+                                         const isv_marg_generic_in* in, const isv_marg_generic_out* out, int32_t problem) {
+  if (!h || !prior_ok(prior) || !residuals || !in || !out || !out->A || !out->b) return ISV_ERR_BAD_ARG;
+  if (problem < 0 || problem >= in->n_problems || in->pos < 1) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const int nt = (prior->n + kPaTile - 1) / kPaTile;
+  marg_prior_add_kernel<<<dim3(nt, nt), kPriorThreads, 0, h->stream>>>(
+      *prior, residuals, out->A + (size_t)problem * in->pos * in->pos, out->b + (size_t)problem * in->pos, in->pos,
+      out->status ? out->status + problem : nullptr);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+static isv_status schur_eig_impl(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out,
+                                 int schur_only) {
+  ISV_CUDA(cudaSetDevice(h->device));
   const size_t n = (size_t)(in->pos - in->m_dense - in->m_diag);
   // factor rows of the reduced system (n x n per problem): handle-owned scratch
   const size_t need = (size_t)in->n_problems * n * n * sizeof(double);

@@ -476,4 +476,135 @@ marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* 
   if (tid == 0 && out.status && s_status) atomicOr(out.status + prob, s_status);
 }
 
+// -------------------------------------------------------------------------------------------------
+// MarginalizationFactor (VINS-Mono marginalization_factor.cpp, `MarginalizationFactor::Evaluate`): the
+// previous prior |r0 + J dx|^2 as a residual block of the next round.
+// marg_prior_eval_kernel : dx (every CTA recomputes the few hundred entries in shared memory), then
+//                          residuals = r0 + J dx (thread per row: coalesced down the column-major J) and
+//                          the per-block ceres Jacobians (a re-layout of J, last pose column zero).
+// marg_prior_add_kernel  : A[pos, pos] += J^T J, b[pos] += J^T r -- 32 x 32 tiles of column pairs (upper
+//                          triangle, mirrored), rows staged through shared memory in slabs of 32.
+// -------------------------------------------------------------------------------------------------
+constexpr int kPriorThreads = 256;
+
+__device__ __forceinline__ int prior_local(int global_size) { return global_size == 7 ? 6 : global_size; }
+
+__global__ void __launch_bounds__(kPriorThreads)
+marg_prior_eval_kernel(isv_marg_prior pr, double* __restrict__ residuals, double* __restrict__ jacobians,
+                       int32_t* status) {
+  extern __shared__ double dx[];   // n doubles, then n_blocks + 1 ints (Jacobian record offsets)
+  const int n = pr.n, tid = threadIdx.x;
+  int* joff = reinterpret_cast<int*>(dx + n);
+  for (int i = tid; i < n; i += blockDim.x) dx[i] = 0.0;
+  if (tid == 0) {
+    int o = 0;
+    for (int b = 0; b < pr.n_blocks; ++b) { joff[b] = o; o += n * pr.blocks[b].global_size; }
+    joff[pr.n_blocks] = o;
+  }
+  __syncthreads();
+  for (int b = tid; b < pr.n_blocks; b += blockDim.x) {
+    const isv_prior_block bl = pr.blocks[b];
+    const int ls = prior_local(bl.global_size);
+    if (bl.global_size < 1 || bl.idx < 0 || bl.idx + ls > n || bl.x_offset < 0) {
+      if (status) atomicOr(status, ISV_W_BAD_INDEX);
+      continue;
+    }
+    const double* x = pr.x + bl.x_offset;
+    const double* x0 = pr.x0 + bl.x_offset;
+    if (bl.global_size == 7) {
+      for (int c = 0; c < 3; ++c) dx[bl.idx + c] = x[c] - x0[c];
+      // Eigen: q0.inverse() = conj / |q0|^2 (no normalisation)
+      const Quat d = qmul(qinv(quat_from_pose(x0)), quat_from_pose(x));
+      const double sgn = (d.w >= 0.0) ? 2.0 : -2.0;
+      dx[bl.idx + 3] = sgn * d.x; dx[bl.idx + 4] = sgn * d.y; dx[bl.idx + 5] = sgn * d.z;
+    } else {
+      for (int c = 0; c < ls; ++c) dx[bl.idx + c] = x[c] - x0[c];
+    }
+  }
+  __syncthreads();
+  const double* J = pr.linearized_jacobians;
+  for (int i = blockIdx.x * blockDim.x + tid; i < n; i += gridDim.x * blockDim.x) {
+    double a0 = 0.0, a1 = 0.0;
+    int j = 0;
+    for (; j + 1 < n; j += 2) {
+      a0 = fma(J[i + (size_t)n * j], dx[j], a0);
+      a1 = fma(J[i + (size_t)n * (j + 1)], dx[j + 1], a1);
+    }
+    if (j < n) a0 = fma(J[i + (size_t)n * j], dx[j], a0);
+    residuals[i] = pr.linearized_residuals[i] + (a0 + a1);
+  }
+  if (jacobians) {
+    const int total = joff[pr.n_blocks];
+    for (int e = blockIdx.x * blockDim.x + tid; e < total; e += gridDim.x * blockDim.x) {
+      int b = 0;
+      while (e >= joff[b + 1]) ++b;
+      const isv_prior_block bl = pr.blocks[b];
+      const int gs = bl.global_size, ls = prior_local(gs);
+      const int rem = e - joff[b], row = rem / gs, col = rem - row * gs;
+      const bool ok = col < ls && bl.idx >= 0 && bl.idx + ls <= n;
+      jacobians[e] = ok ? J[row + (size_t)n * (bl.idx + col)] : 0.0;
+    }
+  }
+}
+
+constexpr int kPaTile = 32;
+
+__global__ void __launch_bounds__(kPriorThreads)
+marg_prior_add_kernel(isv_marg_prior pr, const double* __restrict__ res, double* __restrict__ A, double* __restrict__ b,
+                      int pos, int32_t* status) {
+  __shared__ double Ja[kPaTile][kPaTile + 1], Jb[kPaTile][kPaTile + 1], rs[kPaTile];
+  __shared__ int cpa[kPaTile], cpb[kPaTile];
+  const int ci0 = blockIdx.x * kPaTile, cj0 = blockIdx.y * kPaTile;
+  if (ci0 > cj0) return;
+  const int n = pr.n, tid = threadIdx.x;
+  if (tid < 2 * kPaTile) {
+    const int col = (tid < kPaTile) ? ci0 + tid : cj0 + tid - kPaTile;
+    int p = -1;
+    for (int k = 0; k < pr.n_blocks; ++k) {
+      const isv_prior_block bl = pr.blocks[k];
+      const int ls = prior_local(bl.global_size);
+      if (col >= bl.idx && col < bl.idx + ls && bl.pos >= 0) {
+        if (bl.pos + ls > pos) {
+          if (status) atomicOr(status, ISV_W_BAD_INDEX);
+        } else {
+          p = bl.pos + col - bl.idx;
+        }
+      }
+    }
+    if (tid < kPaTile) cpa[tid] = p; else cpb[tid - kPaTile] = p;
+  }
+  const int a = tid & 31, cq = tid >> 5;   // this thread: column a of tile i, columns cq + 8 q of tile j
+  double acc[4] = {0.0, 0.0, 0.0, 0.0}, accb = 0.0;
+  const double* J = pr.linearized_jacobians;
+  for (int k0 = 0; k0 < n; k0 += kPaTile) {
+    __syncthreads();
+    const int kk = tid & 31, row = k0 + kk;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = cq + 8 * q;
+      Ja[kk][c] = (row < n && ci0 + c < n) ? J[row + (size_t)n * (ci0 + c)] : 0.0;
+      Jb[kk][c] = (row < n && cj0 + c < n) ? J[row + (size_t)n * (cj0 + c)] : 0.0;
+    }
+    if (tid < kPaTile) rs[tid] = (k0 + tid < n) ? res[k0 + tid] : 0.0;
+    __syncthreads();
+#pragma unroll 8
+    for (int l = 0; l < kPaTile; ++l) {
+      const double va = Ja[l][a];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fma(va, Jb[l][cq + 8 * q], acc[q]);
+      if (cq == 0) accb = fma(va, rs[l], accb);
+    }
+  }
+  const int pa = cpa[a];
+  if (pa < 0) return;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int pc = cpb[cq + 8 * q];
+    if (pc < 0) continue;
+    A[pa + (size_t)pos * pc] += acc[q];
+    if (ci0 != cj0) A[pc + (size_t)pos * pa] += acc[q];
+  }
+  if (ci0 == cj0 && cq == 0) b[pa] += accb;
+}
+
 }  // namespace isv

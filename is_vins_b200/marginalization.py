@@ -36,6 +36,10 @@ KINDS = {
     "vb": (("speed_bias",), 9, ((0, 9),)),
     "rp": (("pose",), 2, ((0, 7),)),
     "yaw": (("pose",), 1, ((0, 7),)),
+    # VINS-Mono MarginalizationFactor: the previous round's prior (member `prior` = the marginalized
+    # MarginalizationInfo); parameter blocks = its kept blocks, in getParameterBlocks() order, under the keys
+    # they have NOW (after the window slid: VINS-Mono's addr_shift)
+    "marginalization": (None, None, None),
 }
 
 
@@ -44,8 +48,13 @@ class ResidualBlockInfo:
 
     def __init__(self, kind: str, parameter_blocks: Sequence[Key], drop_set: Sequence[int] = (), **members):
         fam = KINDS[kind][0]
-        assert len(parameter_blocks) == len(fam) and all(k[0] == f for k, f in zip(parameter_blocks, fam)), \
-            f"{kind} takes parameter blocks {fam}"
+        if kind == "marginalization":
+            keep = members["prior"].getParameterBlocks()
+            assert [GLOBAL_SIZE[k[0]] for k in parameter_blocks] == [size for _, size, _ in keep], \
+                "parameter blocks must be the prior's kept blocks, in getParameterBlocks() order"
+        else:
+            assert len(parameter_blocks) == len(fam) and all(k[0] == f for k, f in zip(parameter_blocks, fam)), \
+                f"{kind} takes parameter blocks {fam}"
         self.kind, self.parameter_blocks, self.drop_set, self.members = kind, list(parameter_blocks), list(drop_set), members
 
 
@@ -120,6 +129,30 @@ class MarginalizationInfo:
             assert f.parameter_blocks[0][1] == f.parameter_blocks[1][1] and f.parameter_blocks[2][1] == f.parameter_blocks[3][1]
         self._dp = DeviceProblem(fp, f"cuda:{self.be.device}")
         eval_problem(self.be, self._dp, self.cauchy_a)
+        self._para = {k: np.array(v, float, copy=True).reshape((-1, GLOBAL_SIZE[k]) if GLOBAL_SIZE[k] > 1 else (-1,))
+                      for k, v in para.items()}
+        # MarginalizationFactor (at most one, like VINS-Mono): residual = r0 + J dx on the GPU (isv_eval_marg_prior)
+        self._prior = None
+        assert len(by["marginalization"]) <= 1, "one MarginalizationFactor per problem"
+        for f in by["marginalization"]:
+            import torch
+            dev = self._dp.device
+            prior = f.members["prior"]
+            keep = prior.getParameterBlocks()
+            n = prior.n
+            x0 = np.concatenate([np.asarray(prior.keep_block_data[k], float).reshape(-1) for k, _, _ in keep])
+            x = np.concatenate([self._block_value(k) for k in f.parameter_blocks])
+            offs = np.concatenate([[0], np.cumsum([size for _, size, _ in keep])])
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a, float)).to(dev)
+            d = {"J": t(prior.linearized_jacobians.T.reshape(-1)),        # column-major
+                 "r0": t(prior.linearized_residuals), "x0": t(x0), "x": t(x),
+                 "res": torch.zeros((n,), dtype=torch.float64, device=dev),
+                 "jac": torch.zeros((n * int(offs[-1]),), dtype=torch.float64, device=dev)}
+            self._prior = {"f": f, "keep": keep, "offs": offs, "d": d}
+            st = self._prior_struct(pos_of=lambda k: -1)
+            capi.check(self.be.lib.isv_eval_marg_prior(self.be.h, C.byref(st), C.c_void_p(d["res"].data_ptr()),
+                                                       C.c_void_p(d["jac"].data_ptr()),
+                                                       C.c_void_p(self._dp.status.data_ptr())), "isv_eval_marg_prior")
         # ProjectionTdFactors: the same kernel with td_obs set (eval_projection_kernel<true>)
         tdf = by["projection_td"]
         self._td = None
@@ -151,6 +184,32 @@ class MarginalizationInfo:
                                                              C.c_void_p(self._dp.status.data_ptr())),
                        "isv_eval_projection_batch")
             self._td = (d, o)
+
+    def _block_value(self, k: Key) -> np.ndarray:
+        return np.asarray(self._para[k[0]][k[1]], float).reshape(-1)
+
+    def _prior_struct(self, pos_of) -> "capi.isv_marg_prior":
+        import torch
+        pr = self._prior
+        blocks = (capi.isv_prior_block * len(pr["keep"]))(*[
+            capi.isv_prior_block(size, idx, int(pr["offs"][c]), int(pos_of(key)))
+            for c, ((_, size, idx), key) in enumerate(zip(pr["keep"], pr["f"].parameter_blocks))])
+        pr["d"]["blocks"] = torch.frombuffer(bytearray(bytes(blocks)), dtype=torch.uint8).to(self._dp.device)
+        d = pr["d"]
+        return capi.isv_marg_prior(pr["f"].members["prior"].n, len(pr["keep"]), d["blocks"].data_ptr(), d["J"].data_ptr(),
+                                   d["r0"].data_ptr(), d["x0"].data_ptr(), d["x"].data_ptr())
+
+    @property
+    def prior_residuals(self) -> np.ndarray:
+        return self._prior["d"]["res"].cpu().numpy()
+
+    @property
+    def prior_jacobians(self) -> List[np.ndarray]:
+        """ceres layout: per kept block an (n x global size) row-major Jacobian"""
+        pr = self._prior
+        flat, n = pr["d"]["jac"].cpu().numpy(), pr["f"].members["prior"].n
+        return [flat[n * int(pr["offs"][c]):n * int(pr["offs"][c + 1])].reshape(n, size)
+                for c, (_, size, _) in enumerate(pr["keep"])]
 
     def marginalize(self, keep_tables: bool = False, schur_only: bool = False) -> None:
         """schur_only: stop after the Schur complement (A_red, b_red) -- with every feature dropped and no dense
@@ -240,8 +299,15 @@ class MarginalizationInfo:
         go = _Out(o["A"].data_ptr(), o["b"].data_ptr(), o["A_red"].data_ptr(), o["b_red"].data_ptr(), o["J"].data_ptr(),
                   o["r"].data_ptr(), o["rank"].data_ptr(), o["status"].data_ptr())
         lib = self.be.lib
-        fn = lib.isv_reduced_system if schur_only else lib.isv_marginalize_generic
-        capi.check(fn(self.be.h, C.byref(gi), C.byref(go)), "isv_marginalize_generic")
+        if self._prior is None:
+            fn = lib.isv_reduced_system if schur_only else lib.isv_marginalize_generic
+            capi.check(fn(self.be.h, C.byref(gi), C.byref(go)), "isv_marginalize_generic")
+        else:   # normal equations of the ordinary blocks, + J^T J / J^T r of the prior, then Schur + eigen
+            st = self._prior_struct(pos_of=lambda k: -1 if k in self.constant else self.parameter_block_idx[k])
+            capi.check(lib.isv_build_normal_equations(self.be.h, C.byref(gi), C.byref(go)), "isv_build_normal_equations")
+            capi.check(lib.isv_add_marg_prior(self.be.h, C.byref(st), C.c_void_p(self._prior["d"]["res"].data_ptr()),
+                                              C.byref(gi), C.byref(go), 0), "isv_add_marg_prior")
+            capi.check(lib.isv_schur_eig(self.be.h, C.byref(gi), C.byref(go), 1 if schur_only else 0), "isv_schur_eig")
         self.be.synchronize()
         if keep_tables:   # for tools/bench_marg_generic.py: the device tables of this problem
             self._gi, self._go = gi, go
@@ -254,8 +320,15 @@ class MarginalizationInfo:
         self.rank = int(o["rank"].item())
         self.status = int(o["status"].item()) | int(dp.status.item())
         self.pos = pos
+        # keep_block_data: the kept blocks at this linearization point (what MarginalizationFactor needs later)
+        self.keep_block_data = {k: self._block_value(k).copy() for k, i in self.parameter_block_idx.items() if i >= self.m}
 
-    def getParameterBlocks(self) -> List[Tuple[Key, int, int]]:
-        """kept blocks in order: (key, global size, position in the reduced tangent vector = idx - m)"""
+    def getParameterBlocks(self, addr_shift: Optional[Dict[Key, Key]] = None):
+        """kept blocks in order: (key, global size, position in the reduced tangent vector = idx - m).  With
+        addr_shift (VINS-Mono: where each kept block lives after the window slides) returns just the shifted keys:
+        the parameter blocks of the MarginalizationFactor of the next problem."""
         keep = [(k, self.parameter_block_size[k], i - self.m) for k, i in self.parameter_block_idx.items() if i >= self.m]
-        return sorted(keep, key=lambda t: t[2])
+        keep = sorted(keep, key=lambda t: t[2])
+        if addr_shift is not None:
+            return [addr_shift[k] for k, _, _ in keep]
+        return keep

@@ -1544,6 +1544,39 @@ def vins_mono_marginalize(factors, pos: int, m: int, eps: float = 1e-8):
             "linearized_residuals": lin_r, "rank": int(np.sum(w2 > eps)), "min_eig_Amm": float(w.min())}
 
 
+class MarginalizationFactor:
+    """VINS-Mono marginalization_factor.cpp `MarginalizationFactor::Evaluate` (published algorithm; IS-VINS
+    deleted the class): the prior of the previous marginalization as a residual block.
+    keep: list of (global size, idx = keep_block_idx - m); x0: list of the kept blocks at the linearization
+    point (keep_block_data); lin_J (n x n), lin_r (n)."""
+
+    def __init__(self, lin_J, lin_r, keep, x0):
+        self.J, self.r0, self.keep = np.asarray(lin_J, float), np.asarray(lin_r, float), list(keep)
+        self.x0 = [np.asarray(v, float).copy() for v in x0]
+
+    def EvaluateCeres(self, params):
+        n = self.J.shape[0]
+        dx = np.zeros(n)
+        for (size, idx), x, x0 in zip(self.keep, params, self.x0):
+            x = np.asarray(x, float)
+            if size != 7:
+                dx[idx:idx + size] = x - x0
+            else:
+                dx[idx:idx + 3] = x[0:3] - x0[0:3]
+                q0 = np.array([x0[6], x0[3], x0[4], x0[5]])          # (w, x, y, z)
+                q = np.array([x[6], x[3], x[4], x[5]])
+                d = q_mul(q_inv(q0), q)
+                dx[idx + 3:idx + 6] = 2.0 * d[1:4] if d[0] >= 0 else 2.0 * -d[1:4]
+        r = self.r0 + self.J @ dx
+        js = []
+        for size, idx in self.keep:
+            local = 6 if size == 7 else size
+            j = np.zeros((n, size))
+            j[:, :local] = self.J[:, idx:idx + local]
+            js.append(j)
+        return r, js
+
+
 def schur_complement_longdouble(A, b, m: int):
     """Adjudicator for the generic marginalization: A_rr - A_rm A_mm^-1 A_mr and b_r - A_rm A_mm^-1 b_m in
     80-bit extended precision (np.longdouble, eps ~ 1e-19) by a Cholesky solve; valid when A_mm is positive

@@ -97,3 +97,40 @@ def test_projection_td_twin_matches_finite_differences():
     fd = _fd_blocks(lambda q: pf.EvaluateCeres(q, want=(False,) * 5)[0], params, (6, 6, 6, 1, 1))
     for a, b in zip(js, fd):
         assert np.allclose(np.asarray(a)[:, :b.shape[1]], b, rtol=2e-5, atol=2e-4 * np.abs(b).max())
+
+
+def test_oracle_marginalization_factor_fd_and_linearization_point():
+    """VINS-Mono MarginalizationFactor restated (oracle/isv_oracle.py): residual = r0 at the linearization
+    point, central-difference Jacobians in the PoseLocalParameterization tangent, q and -q are the same point."""
+    from oracle import isv_oracle as O
+    rng = np.random.default_rng(3)
+    keep = [(7, 0), (9, 6), (7, 15), (1, 21)]
+    n = 22
+    J, r0 = rng.normal(size=(n, n)), rng.normal(size=n)
+    q = lambda: (lambda v: v / np.linalg.norm(v))(rng.normal(size=4))
+    x0 = [np.concatenate([rng.normal(size=3), q()]), rng.normal(size=9), np.concatenate([rng.normal(size=3), q()]),
+          rng.normal(size=1)]
+    f = O.MarginalizationFactor(J, r0, keep, x0)
+    r, js = f.EvaluateCeres(x0)
+    assert np.allclose(r, r0, atol=1e-14)
+    x = [v.copy() for v in x0]
+    x[1] += 0.01 * rng.normal(size=9)
+    x[2][0:3] += 0.01
+    r1, js = f.EvaluateCeres(x)
+    xm = [v.copy() for v in x]
+    xm[2][3:7] *= -1.0
+    assert np.allclose(f.EvaluateCeres(xm)[0], r1, atol=1e-13)
+    h = 1e-6
+    for b, (size, idx) in enumerate(keep):
+        local = 6 if size == 7 else size
+        assert js[b].shape == (n, size) and (size != 7 or np.all(js[b][:, 6] == 0))
+        for c in range(local):
+            d = np.zeros(local)
+            d[c] = h
+            xp, xn = [v.copy() for v in x], [v.copy() for v in x]
+            if size == 7:
+                xp[b], xn[b] = O.pose_plus(x[b], d), O.pose_plus(x[b], -d)
+            else:
+                xp[b], xn[b] = x[b] + d, x[b] - d
+            fd = (f.EvaluateCeres(xp)[0] - f.EvaluateCeres(xn)[0]) / (2 * h)
+            assert np.allclose(fd, js[b][:, c], atol=1e-6), (b, c)
