@@ -501,7 +501,8 @@ typedef struct isv_marg_prior {
 isv_status isv_eval_marg_prior(isv_handle* h, const isv_marg_prior* prior, double* residuals, double* jacobians,
                                int32_t* status);
 /* A += J^T J, b += J^T residuals of the prior, scattered by blocks[].pos into the normal equations of problem
- * `problem` (out->A, out->b as isv_build_normal_equations left them); residuals from isv_eval_marg_prior.  */
+ * `problem` (out->A, out->b as isv_build_normal_equations left them; problem = -1: the same prior into every
+ * problem of the batch); residuals from isv_eval_marg_prior.                                                */
 isv_status isv_add_marg_prior(isv_handle* h, const isv_marg_prior* prior, const double* residuals,
                               const isv_marg_generic_in* in, const isv_marg_generic_out* out, int32_t problem);
 /* stage 2 alone on normal equations that are already built (isv_build_normal_equations [+ isv_add_marg_prior]):
@@ -528,6 +529,14 @@ typedef struct isv_marg_host_in {
   const int32_t* pos_feature;
   int32_t pos, m_dense, m_diag, schur_only;
   double eps;
+  /* ProjectionTdFactor problems (proj.td_obs != NULL; proj.td / proj.td_idx are HOST arrays here): tangent
+   * position of every para_Td block, -1 = held constant.  The time offset is never a diagonal marginalized
+   * scalar (it couples with every visual factor).                                                          */
+  const int32_t* pos_td;         /* [proj.n_td]                                                          */
+  /* MarginalizationFactor: the previous round's prior as one more residual block (at most one, as in
+   * VINS-Mono's Estimator::optimization), or NULL.  HOST pointers inside; blocks[].pos = tangent position of
+   * each kept block in THIS problem (-1 = constant), x = the blocks' current values.                      */
+  const isv_marg_prior* prior;
 } isv_marg_host_in;
 typedef struct isv_marg_host_out {
   double* A_red;                 /* [n][n] column-major, n = pos - m_dense - m_diag                    */

@@ -8,7 +8,8 @@ from .batch import WindowBatch, WindowOutputs, pack_events  # noqa: F401
 from .backend import DeviceBatch, MargBackend  # noqa: F401
 from .evaluate import DeviceProblem, FactorProblem, eval_problem  # noqa: F401
 from .sequence import SequenceState  # noqa: F401
-from .marginalization import MarginalizationInfo, ResidualBlockInfo  # noqa: F401
+from .marginalization import MarginalizationInfo, PriorState, ResidualBlockInfo, add_margin_old_blocks  # noqa: F401
 
 __all__ = ["capi", "WindowBatch", "WindowOutputs", "pack_events", "DeviceBatch", "MargBackend",
-           "FactorProblem", "DeviceProblem", "eval_problem", "SequenceState", "MarginalizationInfo", "ResidualBlockInfo"]
+           "FactorProblem", "DeviceProblem", "eval_problem", "SequenceState", "MarginalizationInfo", "PriorState", "ResidualBlockInfo",
+           "add_margin_old_blocks"]

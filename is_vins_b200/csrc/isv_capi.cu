@@ -1108,12 +1108,13 @@ extern "C" isv_status isv_eval_marg_prior(isv_handle* h, const isv_marg_prior* p
 extern "C" isv_status isv_add_marg_prior(isv_handle* h, const isv_marg_prior* prior, const double* residuals,
                                          const isv_marg_generic_in* in, const isv_marg_generic_out* out, int32_t problem) {
   if (!h || !prior_ok(prior) || !residuals || !in || !out || !out->A || !out->b) return ISV_ERR_BAD_ARG;
-  if (problem < 0 || problem >= in->n_problems || in->pos < 1) return ISV_ERR_BAD_ARG;
+  if (problem < -1 || problem >= in->n_problems || in->pos < 1 || in->n_problems > 65535) return ISV_ERR_BAD_ARG;
   ISV_CUDA(cudaSetDevice(h->device));
   const int nt = (prior->n + kPaTile - 1) / kPaTile;
-  marg_prior_add_kernel<<<dim3(nt, nt), kPriorThreads, 0, h->stream>>>(
-      *prior, residuals, out->A + (size_t)problem * in->pos * in->pos, out->b + (size_t)problem * in->pos, in->pos,
-      out->status ? out->status + problem : nullptr);
+  const int first = problem < 0 ? 0 : problem, count = problem < 0 ? in->n_problems : 1;   // -1: every problem of the batch
+  marg_prior_add_kernel<<<dim3(nt, nt, count), kPriorThreads, 0, h->stream>>>(
+      *prior, residuals, out->A + (size_t)first * in->pos * in->pos, out->b + (size_t)first * in->pos, in->pos,
+      out->status ? out->status + first : nullptr);
   ++h->launches;
   ISV_CUDA(cudaGetLastError());
   return ISV_OK;
@@ -1159,7 +1160,10 @@ extern "C" isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in
   const isv_imu_factors& mf = in->imu;
   const isv_small_factors& sf = in->small_factors;
   if (pf.n < 0 || mf.n < 0 || sf.n_rel < 0 || sf.n_se3 < 0 || sf.n_vb < 0 || sf.n_rp < 0 || sf.n_yaw < 0) return ISV_ERR_BAD_ARG;
-  if (pf.td_obs) return ISV_ERR_BAD_ARG;   // the td block is not wired into this entry point yet
+  const bool with_td = pf.td_obs != nullptr;
+  if (with_td && (!pf.td || pf.n_td < 1 || !in->pos_td)) return ISV_ERR_BAD_ARG;
+  const isv_marg_prior* prior = in->prior;
+  if (prior && !prior_ok(prior)) return ISV_ERR_BAD_ARG;
   if ((pb.n_pose && !in->pos_pose) || (pb.n_speed_bias && !in->pos_speed_bias) || (pb.n_ex_pose && !in->pos_ex_pose) ||
       (pb.n_feature && !in->pos_feature))
     return ISV_ERR_BAD_ARG;
@@ -1175,7 +1179,7 @@ extern "C" isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in
   size_t voff = 0;
   auto vcarve = [&](size_t cnt) { size_t o = voff; voff += cnt; return o; };
   const size_t v_pr = vcarve(2 * P), v_pi = vcarve(14 * P), v_pj = vcarve(14 * P), v_pe = vcarve(ex_live ? 14 * P : 0),
-               v_pfe = vcarve(2 * P), v_ir = vcarve(15 * NI), v_ij = vcarve(ISV_IMU_JAC_REC * NI),
+               v_pfe = vcarve(2 * P), v_pt = vcarve(with_td ? 2 * P : 0), v_ir = vcarve(15 * NI), v_ij = vcarve(ISV_IMU_JAC_REC * NI),
                v_rr = vcarve(6 * (size_t)sf.n_rel), v_rj = vcarve(84 * (size_t)sf.n_rel), v_sr = vcarve(6 * (size_t)sf.n_se3),
                v_sj = vcarve(42 * (size_t)sf.n_se3), v_vr = vcarve(9 * (size_t)sf.n_vb), v_vj = vcarve(81 * (size_t)sf.n_vb),
                v_qr = vcarve(2 * (size_t)sf.n_rp), v_qj = vcarve(14 * (size_t)sf.n_rp), v_yr = vcarve((size_t)sf.n_yaw),
@@ -1197,6 +1201,11 @@ extern "C" isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in
     add_block(v_pj + 14 * k, 7, 6, in->pos_pose[j]);
     if (ex_live) add_block(v_pe + 14 * k, 7, 6, in->pos_ex_pose[e]);
     add_block(v_pfe + 2 * k, 1, 1, in->pos_feature[f]);
+    if (with_td) {
+      const int t = pf.td_idx ? pf.td_idx[k] : 0;
+      if (!chk(t, pf.n_td)) { blks.resize(first); continue; }
+      add_block(v_pt + 2 * k, 1, 1, in->pos_td[t]);
+    }
     if ((int)blks.size() > first) facs.push_back(isv_ne_factor{(int64_t)(v_pr + 2 * k), 2, (int)blks.size() - first, first, 0});
   }
   for (size_t k = 0; k < NI; ++k) {
@@ -1231,6 +1240,15 @@ extern "C" isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in
   single(sf.n_vb, sf.vb_idx, in->pos_speed_bias, pb.n_speed_bias, v_vr, v_vj, 9, 81, 9, 9);
   single(sf.n_rp, sf.rp_idx, in->pos_pose, pb.n_pose, v_qr, v_qj, 2, 14, 7, 6);
   single(sf.n_yaw, sf.yaw_idx, in->pos_pose, pb.n_pose, v_yr, v_yj, 1, 7, 7, 6);
+  size_t prior_x = 0;   // doubles in the prior's x / x0
+  if (prior) {
+    for (int k = 0; k < prior->n_blocks; ++k) {
+      const isv_prior_block& bl = prior->blocks[k];
+      const int ls = bl.global_size == 7 ? 6 : bl.global_size;
+      if (bl.global_size < 1 || bl.idx < 0 || bl.idx + ls > prior->n || bl.x_offset < 0 || bl.pos + ls > in->pos) bad_index = true;
+      prior_x = std::max(prior_x, (size_t)bl.x_offset + (size_t)std::max(bl.global_size, 0));
+    }
+  }
   if (bad_index) { out->status = ISV_W_BAD_INDEX; return ISV_ERR_BAD_ARG; }
   // ---- device mirror ---------------------------------------------------------------------------------------
   size_t off = 0;
@@ -1246,7 +1264,12 @@ extern "C" isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in
                o_yrec = carve((size_t)sf.n_yaw * ISV_YAW_REC * D), o_val = carve(voff * D),
                o_fac = carve(facs.size() * sizeof(isv_ne_factor)), o_blk = carve(blks.size() * sizeof(isv_ne_block)),
                o_A = carve(pos * pos * D), o_b = carve(pos * D), o_Ar = carve((size_t)n * n * D), o_br = carve(n * D),
-               o_J = carve((size_t)n * n * D), o_r = carve(n * D), o_rank = carve(8), o_st = carve(8);
+               o_J = carve((size_t)n * n * D), o_r = carve(n * D), o_rank = carve(8), o_st = carve(8),
+               o_tdo = carve(with_td ? 8 * P * D : 0), o_td = carve(with_td ? (size_t)pf.n_td * D : 0),
+               o_tdi = carve(with_td && pf.td_idx ? P * 4 : 0);
+  const size_t pn = prior ? (size_t)prior->n : 0, pnb = prior ? (size_t)prior->n_blocks : 0;
+  const size_t o_pblk = carve(pnb * sizeof(isv_prior_block)), o_pJ = carve(pn * pn * D), o_pr0 = carve(pn * D),
+               o_px0 = carve(prior_x * D), o_px = carve(prior_x * D), o_pres = carve(pn * D);
   isv_status st = ensure_dbuf(h, off);
   if (st != ISV_OK) return st;
   char* d = h->dbuf;
@@ -1272,6 +1295,18 @@ extern "C" isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in
   ISV_CUDA(up(o_qrec, sf.rp_rec, (size_t)sf.n_rp * ISV_RP_REC * D));
   ISV_CUDA(up(o_yidx, sf.yaw_idx, (size_t)sf.n_yaw * 4));
   ISV_CUDA(up(o_yrec, sf.yaw_rec, (size_t)sf.n_yaw * ISV_YAW_REC * D));
+  if (with_td) {
+    for (int c = 0; c < 8 && P; ++c) ISV_CUDA(up(o_tdo + c * P * D, pf.td_obs + c * pf.stride, P * D));
+    ISV_CUDA(up(o_td, pf.td, (size_t)pf.n_td * D));
+    if (pf.td_idx) ISV_CUDA(up(o_tdi, pf.td_idx, P * 4));
+  }
+  if (prior) {
+    ISV_CUDA(up(o_pblk, prior->blocks, pnb * sizeof(isv_prior_block)));
+    ISV_CUDA(up(o_pJ, prior->linearized_jacobians, pn * pn * D));
+    ISV_CUDA(up(o_pr0, prior->linearized_residuals, pn * D));
+    ISV_CUDA(up(o_px0, prior->x0, prior_x * D));
+    ISV_CUDA(up(o_px, prior->x, prior_x * D));
+  }
   ISV_CUDA(up(o_fac, facs.data(), facs.size() * sizeof(isv_ne_factor)));
   ISV_CUDA(up(o_blk, blks.data(), blks.size() * sizeof(isv_ne_block)));
   ISV_CUDA(cudaMemsetAsync(d + o_st, 0, 8, s));
@@ -1285,7 +1320,12 @@ extern "C" isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in
     dpf.stride = (int64_t)P;
     dpf.idx = (const int32_t*)(d + o_pidx);
     dpf.obs = (const double*)(d + o_pobs);
-    isv_proj_eval po = {V + v_pr, V + v_pi, V + v_pj, ex_live ? V + v_pe : nullptr, V + v_pfe, nullptr};
+    if (with_td) {
+      dpf.td_obs = (const double*)(d + o_tdo);
+      dpf.td = (const double*)(d + o_td);
+      dpf.td_idx = pf.td_idx ? (const int32_t*)(d + o_tdi) : nullptr;
+    }
+    isv_proj_eval po = {V + v_pr, V + v_pi, V + v_pj, ex_live ? V + v_pe : nullptr, V + v_pfe, with_td ? V + v_pt : nullptr};
     st = eval_projection_on(h, s, &dpb, &dpf, &po, dst);
     if (st != ISV_OK) return st;
   }
@@ -1313,7 +1353,21 @@ extern "C" isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in
                              (double*)(d + o_J), (double*)(d + o_r), (int32_t*)(d + o_rank), dst + 1};
   ISV_CUDA(cudaMemsetAsync(d + o_rank, 0, 8, s));
   // (isv_build_normal_equations zeroes status[problem]: give it its own word, merged below)
-  st = marginalize_generic_impl(h, &gi, &go, in->schur_only ? 1 : 0);
+  if (!prior) {
+    st = marginalize_generic_impl(h, &gi, &go, in->schur_only ? 1 : 0);
+  } else {   // MarginalizationFactor::Evaluate, then its J^T J / J^T r on top of the ordinary blocks' normal equations
+    isv_marg_prior dp = *prior;
+    dp.blocks = (const isv_prior_block*)(d + o_pblk);
+    dp.linearized_jacobians = (const double*)(d + o_pJ);
+    dp.linearized_residuals = (const double*)(d + o_pr0);
+    dp.x0 = (const double*)(d + o_px0);
+    dp.x = (const double*)(d + o_px);
+    st = marg_generic_check(h, &gi, &go, true);
+    if (st == ISV_OK) st = isv_eval_marg_prior(h, &dp, (double*)(d + o_pres), nullptr, dst);
+    if (st == ISV_OK) st = isv_build_normal_equations(h, &gi, &go);
+    if (st == ISV_OK) st = isv_add_marg_prior(h, &dp, (const double*)(d + o_pres), &gi, &go, 0);
+    if (st == ISV_OK) st = schur_eig_impl(h, &gi, &go, in->schur_only ? 1 : 0);
+  }
   if (st != ISV_OK) return st;
   int32_t hst[2] = {0, 0}, hrank = 0;
   ISV_CUDA(cudaMemcpyAsync(out->A_red, d + o_Ar, (size_t)n * n * D, cudaMemcpyDeviceToHost, s));

@@ -552,6 +552,10 @@ constexpr int kPaTile = 32;
 __global__ void __launch_bounds__(kPriorThreads)
 marg_prior_add_kernel(isv_marg_prior pr, const double* __restrict__ res, double* __restrict__ A, double* __restrict__ b,
                       int pos, int32_t* status) {
+  // blockIdx.z: the problem of the batch this CTA adds the (shared) prior to
+  A += (size_t)blockIdx.z * pos * pos;
+  b += (size_t)blockIdx.z * pos;
+  if (status) status += blockIdx.z;
   __shared__ double Ja[kPaTile][kPaTile + 1], Jb[kPaTile][kPaTile + 1], rs[kPaTile];
   __shared__ int cpa[kPaTile], cpb[kPaTile];
   const int ci0 = blockIdx.x * kPaTile, cj0 = blockIdx.y * kPaTile;

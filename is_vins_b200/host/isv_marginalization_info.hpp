@@ -23,7 +23,23 @@ struct YawFactor {                 // include/factor/yaw_factor.h:11-72
   int index = -1;
 };
 
-enum class FactorKind { Projection, IMU, RelativePose, SE3Prior, Linear9, RollPitch, Yaw };
+// VINS-Mono projection_td_factor.h (absent from the reference): the 5th parameter block is
+// para_Td; rows are already minus ROW / 2.  All visual factors of one problem are either plain or td factors
+// (VINS-Mono's ESTIMATE_TD switch).
+struct ProjectionTdFactor {
+  double pts_i[3], pts_j[3];
+  double velocity_i[2], velocity_j[2];
+  double td_i = 0, td_j = 0, row_i = 0, row_j = 0;
+};
+class MarginalizationInfo;
+// VINS-Mono marginalization_factor.h `MarginalizationFactor`: the previous round's prior as a residual block; its
+// parameter blocks are what prior->getParameterBlocks(addr_shift) returned.
+struct MarginalizationFactor {
+  explicit MarginalizationFactor(MarginalizationInfo* info) : marginalization_info(info) {}
+  MarginalizationInfo* marginalization_info;
+};
+
+enum class FactorKind { Projection, IMU, RelativePose, SE3Prior, Linear9, RollPitch, Yaw, ProjectionTd, Marginalization };
 
 struct ResidualBlockInfo {
   ResidualBlockInfo(FactorKind k, const void* cost, std::vector<double*> blocks, std::vector<int> drop)
@@ -37,9 +53,12 @@ struct ResidualBlockInfo {
 class MarginalizationInfo {
  public:
   // families of the estimator's parameter arrays: para_Pose / para_SpeedBias / para_Ex_Pose / para_Feature
-  enum Family { POSE = 0, SPEED_BIAS = 1, EX_POSE = 2, FEATURE = 3 };
+  enum Family { POSE = 0, SPEED_BIAS = 1, EX_POSE = 2, FEATURE = 3, TD = 4 };
+  static constexpr int kFamilies = 5;
 
-  explicit MarginalizationInfo(isv_handle* h, double cauchy_a = 1.0, double eps_ = 1e-8) : eps(eps_), h_(h), cauchy_a_(cauchy_a) {}
+  // tr_over_row: TR / ROW of ProjectionTdFactor (rolling-shutter read-out per image row), 0 = global shutter
+  explicit MarginalizationInfo(isv_handle* h, double cauchy_a = 1.0, double eps_ = 1e-8, double tr_over_row = 0.0)
+      : eps(eps_), h_(h), cauchy_a_(cauchy_a), tr_over_row_(tr_over_row) {}
   ~MarginalizationInfo() {
     for (auto& kv : parameter_block_data) delete[] kv.second;
     for (auto* f : factors) delete f;
@@ -47,7 +66,7 @@ class MarginalizationInfo {
   MarginalizationInfo(const MarginalizationInfo&) = delete;
   MarginalizationInfo& operator=(const MarginalizationInfo&) = delete;
 
-  static int globalSize(Family f) { return f == POSE || f == EX_POSE ? 7 : (f == SPEED_BIAS ? 9 : 1); }
+  static int globalSize(Family f) { return f == POSE || f == EX_POSE ? 7 : (f == SPEED_BIAS ? 9 : 1); }   // FEATURE, TD: 1
   static int localSize(int size) { return size == 7 ? 6 : size; }      // MarginalizationInfo::localSize
 
   // ceres' SetParameterBlockConstant: the block gets no column
@@ -55,8 +74,20 @@ class MarginalizationInfo {
 
   void addResidualBlockInfo(ResidualBlockInfo* info) {
     factors.push_back(info);
-    const std::vector<Family> fam = families(info->kind);
+    std::vector<Family> fam = families(info->kind);
+    if (info->kind == FactorKind::Marginalization) {   // the prior's kept blocks, family by global size of the kept block
+      const auto* mf = static_cast<const MarginalizationFactor*>(info->cost_function);
+      const MarginalizationInfo* pr = mf->marginalization_info;
+      if (prior_factor_) throw std::runtime_error("one MarginalizationFactor per problem");
+      if (pr->keep_block_size.size() != info->parameter_blocks.size())
+        throw std::runtime_error("MarginalizationFactor: parameter blocks must be prior->getParameterBlocks(addr_shift)");
+      fam = pr->keep_block_family_;
+      prior_factor_ = info;
+    }
     if (fam.size() != info->parameter_blocks.size()) throw std::runtime_error("wrong number of parameter blocks for this factor kind");
+    if (info->kind == FactorKind::ProjectionTd) has_td_ = true;
+    if (info->kind == FactorKind::Projection) has_plain_ = true;
+    if (has_td_ && has_plain_) throw std::runtime_error("ProjectionFactor and ProjectionTdFactor cannot share a problem");
     for (size_t i = 0; i < fam.size(); ++i) {
       const long addr = reinterpret_cast<long>(info->parameter_blocks[i]);
       parameter_block_size[addr] = globalSize(fam[i]);
@@ -64,6 +95,7 @@ class MarginalizationInfo {
     }
     for (int i : info->drop_set) {
       const long addr = reinterpret_cast<long>(info->parameter_blocks[i]);
+      if (family_[addr] == TD) throw std::runtime_error("para_Td couples with every visual factor: it cannot be marginalized");
       if (!dropped_.count(addr)) { dropped_[addr] = true; drop_order_.push_back(addr); }
     }
   }
@@ -82,9 +114,9 @@ class MarginalizationInfo {
 
   void marginalize() {
     // ---- family arrays and indices ----------------------------------------------------------------------
-    std::vector<double> arr[4];
+    std::vector<double> arr[kFamilies];
     std::unordered_map<long, int> index;
-    std::vector<long> members[4];
+    std::vector<long> members[kFamilies];
     for (long addr : order_) {
       const Family f = family_[addr];
       index[addr] = (int)members[f].size();
@@ -105,8 +137,8 @@ class MarginalizationInfo {
     for (long addr : order_)
       if (!constant_.count(addr) && !dropped_.count(addr)) place(addr);
     n = pos - m;
-    std::vector<int32_t> postab[4];
-    for (int f = 0; f < 4; ++f) {
+    std::vector<int32_t> postab[kFamilies];
+    for (int f = 0; f < kFamilies; ++f) {
       postab[f].assign(members[f].size(), -1);
       for (size_t k = 0; k < members[f].size(); ++k) {
         auto it = parameter_block_idx.find(members[f][k]);
@@ -114,11 +146,12 @@ class MarginalizationInfo {
       }
     }
     // ---- factor lists in the C ABI's layout -----------------------------------------------------------------
-    std::vector<int32_t> pidx, iidx, ridx, sidx, vidx, qidx, yidx;
-    std::vector<double> pobs, ipre, rrec, srec, vrec, qrec, yrec;
+    std::vector<int32_t> pidx, iidx, ridx, sidx, vidx, qidx, yidx, tdidx;
+    std::vector<double> pobs, ipre, rrec, srec, vrec, qrec, yrec, tdobs;
     size_t P = 0;
-    for (auto* f : factors) P += f->kind == FactorKind::Projection;
+    for (auto* f : factors) P += f->kind == FactorKind::Projection || f->kind == FactorKind::ProjectionTd;
     pidx.resize(4 * P); pobs.resize(5 * P);
+    if (has_td_) { tdobs.resize(8 * P); tdidx.resize(P); }
     size_t p = 0;
     auto idx_of = [&](double* b) { return index.at(reinterpret_cast<long>(b)); };
     for (auto* f : factors) {
@@ -132,6 +165,19 @@ class MarginalizationInfo {
           ++p;
           break;
         }
+        case FactorKind::ProjectionTd: {
+          const auto* c = static_cast<const ProjectionTdFactor*>(f->cost_function);
+          for (int s = 0; s < 4; ++s) pidx[s * P + p] = idx_of(pbk[s]);
+          tdidx[p] = idx_of(pbk[4]);
+          for (int s = 0; s < 3; ++s) pobs[s * P + p] = c->pts_i[s];
+          pobs[3 * P + p] = c->pts_j[0]; pobs[4 * P + p] = c->pts_j[1];
+          tdobs[0 * P + p] = c->velocity_i[0]; tdobs[1 * P + p] = c->velocity_i[1];
+          tdobs[2 * P + p] = c->velocity_j[0]; tdobs[3 * P + p] = c->velocity_j[1];
+          tdobs[4 * P + p] = c->td_i; tdobs[5 * P + p] = c->td_j; tdobs[6 * P + p] = c->row_i; tdobs[7 * P + p] = c->row_j;
+          ++p;
+          break;
+        }
+        case FactorKind::Marginalization: break;   // handled below
         case FactorKind::IMU: {
           const auto* c = static_cast<const IMUFactor*>(f->cost_function);
           if (c->pre_integration->dirty) throw std::runtime_error("pre-integration record not up to date (Estimator::preintegrated)");
@@ -180,6 +226,31 @@ class MarginalizationInfo {
                              arr[FEATURE].data()};
     in.proj.n = (int64_t)P; in.proj.stride = (int64_t)P; in.proj.idx = pidx.data(); in.proj.obs = pobs.data();
     in.proj.cauchy_a = cauchy_a_;
+    if (has_td_) {
+      in.proj.td_obs = tdobs.data(); in.proj.td = arr[TD].data(); in.proj.td_idx = tdidx.data();
+      in.proj.n_td = (int32_t)members[TD].size(); in.proj.tr_over_row = tr_over_row_;
+      in.pos_td = postab[TD].data();
+    }
+    // MarginalizationFactor: blocks in the prior's keep order, located in THIS problem's tangent vector
+    std::vector<isv_prior_block> pblk;
+    std::vector<double> px0, px;
+    isv_marg_prior prior_in;
+    if (prior_factor_) {
+      const MarginalizationInfo* pr = static_cast<const MarginalizationFactor*>(prior_factor_->cost_function)->marginalization_info;
+      for (size_t k = 0; k < pr->keep_block_size.size(); ++k) {
+        const long addr = reinterpret_cast<long>(prior_factor_->parameter_blocks[k]);
+        const int sz = pr->keep_block_size[k];
+        auto it = parameter_block_idx.find(addr);
+        pblk.push_back(isv_prior_block{sz, pr->keep_block_idx[k] - pr->m, (int32_t)px0.size(),
+                                       it == parameter_block_idx.end() ? -1 : it->second});
+        px0.insert(px0.end(), pr->keep_block_data[k], pr->keep_block_data[k] + sz);
+        const double* cur = parameter_block_data.at(addr);
+        px.insert(px.end(), cur, cur + sz);
+      }
+      prior_in = isv_marg_prior{pr->n, (int32_t)pblk.size(), pblk.data(), pr->linearized_jacobians.data(),
+                                pr->linearized_residuals.data(), px0.data(), px.data()};
+      in.prior = &prior_in;
+    }
     in.imu = isv_imu_factors{(int32_t)(iidx.size() / 2), iidx.data(), ipre.data()};
     in.small_factors.n_rel = (int32_t)(ridx.size() / 2); in.small_factors.rel_idx = ridx.data(); in.small_factors.rel_rec = rrec.data();
     in.small_factors.n_se3 = (int32_t)sidx.size(); in.small_factors.se3_idx = sidx.data(); in.small_factors.se3_rec = srec.data();
@@ -201,7 +272,7 @@ class MarginalizationInfo {
   // kept blocks in position order; addr_shift maps old block addresses to the ones of the next window
   std::vector<double*> getParameterBlocks(std::unordered_map<long, double*>& addr_shift) {
     std::vector<double*> keep_block_addr;
-    keep_block_size.clear(); keep_block_idx.clear(); keep_block_data.clear();
+    keep_block_size.clear(); keep_block_idx.clear(); keep_block_data.clear(); keep_block_family_.clear();
     std::vector<std::pair<int, long>> kept;
     for (const auto& kv : parameter_block_idx)
       if (kv.second >= m) kept.emplace_back(kv.second, kv.first);
@@ -210,6 +281,7 @@ class MarginalizationInfo {
       keep_block_size.push_back(parameter_block_size[pr.second]);
       keep_block_idx.push_back(pr.first);
       keep_block_data.push_back(parameter_block_data[pr.second]);
+      keep_block_family_.push_back(family_[pr.second]);
       keep_block_addr.push_back(addr_shift[pr.second]);
     }
     return keep_block_addr;
@@ -230,6 +302,8 @@ class MarginalizationInfo {
   static std::vector<Family> families(FactorKind k) {
     switch (k) {
       case FactorKind::Projection: return {POSE, POSE, EX_POSE, FEATURE};
+      case FactorKind::ProjectionTd: return {POSE, POSE, EX_POSE, FEATURE, TD};
+      case FactorKind::Marginalization: return {};
       case FactorKind::IMU: return {POSE, SPEED_BIAS, POSE, SPEED_BIAS};
       case FactorKind::RelativePose: return {POSE, POSE};
       case FactorKind::Linear9: return {SPEED_BIAS};
@@ -240,7 +314,10 @@ class MarginalizationInfo {
     v.insert(v.end(), t, t + 3); v.insert(v.end(), R, R + 9); v.insert(v.end(), s, s + 36);
   }
   isv_handle* h_;
-  double cauchy_a_;
+  double cauchy_a_, tr_over_row_;
+  bool has_td_ = false, has_plain_ = false;
+  ResidualBlockInfo* prior_factor_ = nullptr;
+  std::vector<Family> keep_block_family_;   // of the kept blocks, filled by getParameterBlocks
   std::unordered_map<long, Family> family_;
   std::unordered_map<long, bool> dropped_, constant_;
   std::vector<long> order_, drop_order_;

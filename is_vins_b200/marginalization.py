@@ -58,6 +58,35 @@ class ResidualBlockInfo:
         self.kind, self.parameter_blocks, self.drop_set, self.members = kind, list(parameter_blocks), list(drop_set), members
 
 
+class PriorState:
+    """A marginalization prior outside the `MarginalizationInfo` that produced it -- what a checkpoint of
+    VINS-Mono's `last_marginalization_info` holds (linearized_jacobians / linearized_residuals / keep_block_size /
+    keep_block_idx / keep_block_data).  Usable as the `prior` member of a "marginalization" residual block.
+    keys: the kept blocks in position order; x0: their values at the linearization point."""
+
+    def __init__(self, keys: Sequence[Key], linearized_jacobians, linearized_residuals, x0: Sequence[np.ndarray]):
+        self.linearized_jacobians = np.ascontiguousarray(linearized_jacobians, float)
+        self.linearized_residuals = np.ascontiguousarray(linearized_residuals, float)
+        self.n, self.m = int(self.linearized_residuals.shape[0]), 0
+        self._keep, pos = [], 0
+        for k in keys:
+            self._keep.append((k, GLOBAL_SIZE[k[0]], pos))
+            pos += LOCAL_SIZE[k[0]]
+        assert pos == self.n and self.linearized_jacobians.shape == (self.n, self.n)
+        self.keep_block_data = {k: np.asarray(v, float).reshape(-1).copy() for k, v in zip(keys, x0)}
+
+    @classmethod
+    def from_info(cls, mi: "MarginalizationInfo") -> "PriorState":
+        keep = mi.getParameterBlocks()
+        return cls([k for k, _, _ in keep], mi.linearized_jacobians, mi.linearized_residuals,
+                   [mi.keep_block_data[k] for k, _, _ in keep])
+
+    def getParameterBlocks(self, addr_shift: Optional[Dict[Key, Key]] = None):
+        if addr_shift is not None:
+            return [addr_shift[k] for k, _, _ in self._keep]
+        return list(self._keep)
+
+
 class isv_ne_block(C.Structure):
     _fields_ = [("jac_offset", C.c_int64), ("row_stride", C.c_int32), ("local_size", C.c_int32), ("pos", C.c_int32),
                 ("reserved", C.c_int32)]
@@ -332,3 +361,34 @@ class MarginalizationInfo:
         if addr_shift is not None:
             return [addr_shift[k] for k, _, _ in keep]
         return keep
+
+
+def add_margin_old_blocks(mi: MarginalizationInfo, fp: FactorProblem, td_obs: Optional[np.ndarray] = None,
+                          prior=None, prior_keys: Optional[Sequence[Key]] = None) -> List[ResidualBlockInfo]:
+    """The residual blocks VINS-Mono's Estimator::optimization() hands to its MarginalizationInfo for MARGIN_OLD
+    (published estimator.cpp; not in the reference): the previous prior with the oldest frame's blocks in its drop
+    set, the IMU factor 0 -> 1 dropping pose 0 / speed-bias 0, and every visual factor hosted in frame 0 dropping
+    the host pose and the feature -- ProjectionTdFactor (5th block para_Td) when `td_obs` [8,P] is given."""
+    added = []
+
+    def add(info):
+        mi.addResidualBlockInfo(info)
+        added.append(info)
+    if prior is not None:
+        keys = list(prior_keys if prior_keys is not None else [k for k, _, _ in prior.getParameterBlocks()])
+        drop = [c for c, k in enumerate(keys) if k in (("pose", 0), ("speed_bias", 0))]
+        add(ResidualBlockInfo("marginalization", keys, drop_set=drop, prior=prior))
+    add(ResidualBlockInfo("imu", [("pose", 0), ("speed_bias", 0), ("pose", 1), ("speed_bias", 1)], drop_set=[0, 1],
+                          preint=fp.imu_preint[0]))
+    for k in np.nonzero(fp.proj_idx[0] == 0)[0]:
+        i, j, e, f = [int(x) for x in fp.proj_idx[:, k]]
+        keys = [("pose", i), ("pose", j), ("ex_pose", e), ("feature", f)]
+        pts_i, pts_j = fp.proj_obs[0:3, k].copy(), np.array([fp.proj_obs[3, k], fp.proj_obs[4, k], 1.0])
+        if td_obs is None:
+            add(ResidualBlockInfo("projection", keys, drop_set=[0, 3], pts_i=pts_i, pts_j=pts_j))
+        else:
+            t = td_obs[:, k]
+            add(ResidualBlockInfo("projection_td", keys + [("td", 0)], drop_set=[0, 3], pts_i=pts_i, pts_j=pts_j,
+                                  velocity_i=t[0:2].copy(), velocity_j=t[2:4].copy(), td_i=float(t[4]), td_j=float(t[5]),
+                                  row_i=float(t[6]), row_j=float(t[7])))
+    return added

@@ -441,3 +441,61 @@ def eval_problem_oracle(p: WindowProblem, cauchy_a: float = 0.0):
     for yf in p.yaw:
         out["yaw"].append(cauchy_correct(*yf.EvaluateCeres([p.poses[yf.index]]), cauchy_a))
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE configs[3] variant (b): WINDOW_SIZE = 20 with online td estimation, VINS-Mono style (neither
+# ProjectionTdFactor nor MarginalizationInfo exists in the reference, SURVEY.md section 0: parity unpinned).
+# ----------------------------------------------------------------------------------------------
+W20_SEED = seed_for(4, 100)
+W20_KW = dict(n_features=2000, max_track=15, host0=0.08)
+
+
+def w20_problem() -> WindowProblem:
+    """WINDOW_SIZE = 20 (21 frames), ~2000 live features with mean track length ~8, ~250 of them hosted in the oldest
+    frame (~1750 visual factors to marginalize): the problem behind tests/golden/problem_W20_F2000_td.npz."""
+    return make_problem(W20_SEED, cfg=O.Config(all_buf_size=21), **W20_KW)
+
+
+def make_td_observations(p: WindowProblem, seed: int):
+    """Per ProjectionTdFactor members the feature tracker would supply (image velocities, per-observation td,
+    rows minus ROW / 2) for every projection factor of `p`: td_obs [8,P] in the C ABI's component order, the
+    current para_Td and TR / ROW."""
+    rng = np.random.default_rng(seed)
+    P = p.proj_idx.shape[1]
+    td_obs = np.empty((8, P))
+    td_obs[0:4] = rng.normal(0, 0.3, (4, P))          # velocity_i.xy, velocity_j.xy (normalized plane / s)
+    td_obs[4:6] = rng.normal(0, 0.004, (2, P))        # td_i, td_j: para_Td when each observation was taken
+    td_obs[6:8] = rng.uniform(-240, 240, (2, P))      # row_i, row_j minus ROW / 2
+    return {"td_obs": td_obs, "td": np.array([0.007]), "tr_over_row": 0.033 / 480}
+
+
+def make_window_prior(p: WindowProblem, seed: int, with_td: bool = True):
+    """A `last_marginalization_info` in steady state: a prior |r0 + J dx|^2 over EVERY pose / speed-bias of the
+    window, the extrinsics and (with_td) the time offset -- what makes n_keep = 15 (N - 1) + 6 + 1 after the
+    oldest frame goes.  Synthetic (upper-triangular square-root information with per-family scales), linearized
+    a little away from the current estimates.  Returns (keys, J, r0, x0 list)."""
+    rng = np.random.default_rng(seed)
+    N = p.poses.shape[0]
+    keys, scale, x0 = [], [], []
+    for i in range(N):
+        keys += [("pose", i), ("speed_bias", i)]
+        scale += [300.0] * 3 + [600.0] * 3 + [50.0] * 3 + [100.0] * 3 + [2000.0] * 3
+        ps = p.poses[i].copy()
+        ps[0:3] += rng.normal(0, 0.005, 3)
+        q = O.q_normalized(O.q_mul(O.quat_from_pose(ps), O.SO3.exp(rng.normal(0, 0.002, 3)).q))
+        ps[3:6], ps[6] = q[1:4], q[0]
+        x0 += [ps, p.sbs[i] + rng.normal(0, 0.002, 9)]
+    keys.append(("ex_pose", 0))
+    scale += [1000.0] * 6
+    ex = p.ex[0].copy()
+    ex[0:3] += rng.normal(0, 0.001, 3)
+    x0.append(ex)
+    if with_td:
+        keys.append(("td", 0))
+        scale.append(1000.0)
+        x0.append(np.array([0.0065]))
+    n = len(scale)
+    J = np.triu(rng.normal(0, 1.0, (n, n)), 1) * 3.0 + np.diag(np.asarray(scale) * rng.uniform(0.7, 1.3, n))
+    r0 = rng.normal(0, 0.3, n)
+    return keys, J, r0, x0

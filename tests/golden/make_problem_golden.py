@@ -19,10 +19,15 @@ from oracle import sim  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def save(name, seed, **kw):
-    p = sim.make_problem(seed, **kw)
+def save(name, seed, td=False, **kw):
+    p = sim.w20_problem() if td else sim.make_problem(seed, **kw)
     fp = FactorProblem.from_factors(p)
     d = {k: getattr(fp, k) for k in DeviceProblem.IN}
+    if td:    # ProjectionTdFactor members + a steady-state previous prior over the whole window
+        t = sim.make_td_observations(p, seed + 1)
+        keys, J, r0, x0 = sim.make_window_prior(p, seed + 2)
+        d.update(td_obs=t["td_obs"], td=t["td"], tr_over_row=np.array([t["tr_over_row"]]),
+                 prior_J=J, prior_r0=r0, prior_x0=np.concatenate([np.ravel(v) for v in x0]))
     ref = sim.eval_problem_oracle(p, 1.0)
     n = min(64, len(ref["proj"]))
     d["ref_proj_res"] = np.array([r for r, _ in ref["proj"][:n]])
@@ -41,6 +46,7 @@ def main():
     save("problem_F1000.npz", sim.seed_for(6, 100), n_features=1000)                       # bench_eval workload
     save("problem_F300_host0.npz", sim.seed_for(9, 100), n_features=300, max_track=9, host0=0.8)  # marginalization
     save("problem_F60.npz", sim.seed_for(6, 101), n_features=60)                           # small regression anchor
+    save("problem_W20_F2000_td.npz", sim.W20_SEED, td=True)                                    # configs[3]: 21 frames, td
 
 
 if __name__ == "__main__":

@@ -15,6 +15,8 @@ SRC = os.path.join(ROOT, "tests", "cpp", "host_shim_test.cpp")
 
 
 SRC_MI = os.path.join(ROOT, "tests", "cpp", "marginalization_info_test.cpp")
+SRC_CHAIN = os.path.join(ROOT, "tests", "cpp", "marginalization_chain_test.cpp")
+O_SIZE = {"pose": 7, "speed_bias": 9, "ex_pose": 7, "feature": 1, "td": 1}
 
 
 def build_host_test(out_path, src=SRC):
@@ -136,8 +138,151 @@ def test_cpp_marginalization_info_against_oracle(tmp_path):
     assert "0 mismatches" in r.stdout
 
 
+def _chain_problem(p, use_td, seed):
+    """Both rounds of the chain as (fixture doubles, oracle factor builders).  Round 2 = the window slid by one
+    frame with every estimate moved a little (the next solve), frame 1 of `p` being the new oldest frame."""
+    from oracle import isv_oracle as O
+    rng = np.random.default_rng(seed)
+    N, F = p.poses.shape[0], len(p.feat)
+    tr = 0.033 / 480 if use_td else 0.0
+    td1, td2 = (0.007, 0.0062) if use_td else (0.0, 0.0)
+    s = p.cfg.proj_sqrt_info
+    d = [float(N), float(F), 1.0 if use_td else 0.0, tr]
+    d += list(p.poses.ravel()) + list(p.sbs.ravel()) + list(p.ex.ravel()) + list(p.feat) + [td1]
+    poses2 = p.poses[1:].copy()
+    poses2[:, 0:3] += rng.normal(0, 0.01, poses2[:, 0:3].shape)
+    for q in poses2:
+        dq = O.q_mul(O.quat_from_pose(q), np.concatenate([[1.0], rng.normal(0, 0.002, 3)]))
+        dq /= np.linalg.norm(dq)
+        q[3:6], q[6] = dq[1:4], dq[0]
+    poses2[2, 3:7] *= -1.0                     # q and -q: the `w < 0` branch of MarginalizationFactor::Evaluate
+    sbs2 = p.sbs[1:] + rng.normal(0, 0.003, p.sbs[1:].shape)
+    feat2 = p.feat * (1.0 + rng.normal(0, 0.01, p.feat.shape))
+    rounds = []
+    for host, poses, sbs, feat, td, shift in ((0, p.poses, p.sbs, p.feat, td1, 0), (1, poses2, sbs2, feat2, td2, 1)):
+        ofac = []
+        keys = [("pose", 0), ("speed_bias", 0), ("pose", 1), ("speed_bias", 1)]
+        r, js = O.IMUFactor(p.imu_pre[host]).EvaluateCeres([poses[0], sbs[0], poses[1], sbs[1]])
+        ofac.append((r, js, keys))
+        d += list(p.imu_pre[host].pack())
+        hosted = [k for k in range(p.proj_idx.shape[1]) if int(p.proj_idx[0, k]) == host]
+        d += [float(len(hosted))]
+        for k in hosted:
+            _, j, e, f = [int(x) for x in p.proj_idx[:, k]]
+            j -= shift
+            pts_i, pts_j = p.proj_obs[0:3, k], np.array([p.proj_obs[3, k], p.proj_obs[4, k], 1.0])
+            d += [float(j), float(f)] + list(pts_i) + list(pts_j)
+            keys = [("pose", 0), ("pose", j), ("ex_pose", e), ("feature", f)]
+            if use_td:
+                m = [rng.normal(0, 0.3, 2), rng.normal(0, 0.3, 2), rng.normal(0, 0.004), rng.normal(0, 0.004),
+                     rng.uniform(-240, 240), rng.uniform(-240, 240)]
+                d += list(m[0]) + list(m[1]) + m[2:]
+                fac = O.ProjectionTdFactor(pts_i, pts_j, m[0], m[1], m[2], m[3], m[4], m[5], s, tr)
+                r, js = fac.EvaluateCeres([poses[0], poses[j], p.ex[e], feat[f:f + 1], np.array([td])])
+                keys = keys + [("td", 0)]
+            else:
+                r, js = O.ProjectionFactor(pts_i, pts_j, s).EvaluateCeres([poses[0], poses[j], p.ex[e], feat[f:f + 1]])
+            ofac.append(sim.cauchy_correct(r, js, 1.0) + (keys,))
+        if host == 0:
+            se3, rel = p.se3[0], p.rel[0]
+            d += _rec48(se3.t, se3.R, se3.sqrt_info) + _rec48(rel.delta_t, rel.delta_R, rel.sqrt_info)
+            ofac.append(sim.cauchy_correct(*se3.EvaluateCeres([poses[0]]), 1.0) + ([("pose", 0)],))
+            ofac.append(sim.cauchy_correct(*rel.EvaluateCeres([poses[0], poses[1]]), 1.0) + ([("pose", 0), ("pose", 1)],))
+            d += list(poses2.ravel()) + list(sbs2.ravel()) + list(feat2) + [td2]
+        rounds.append({"ofac": ofac, "pose": poses, "speed_bias": sbs, "feature": feat, "td": np.array([td]), "ex_pose": p.ex})
+    return d, rounds
+
+
+def _read_round(a, o, N, F):
+    m, n, status, rank = [int(v) for v in a[o:o + 4]]
+    o += 4
+    out = {"m": m, "n": n, "status": status, "rank": rank}
+    out["A_red"] = a[o:o + n * n].reshape(n, n).T; o += n * n
+    out["b_red"] = a[o:o + n]; o += n
+    out["J"] = a[o:o + n * n].reshape(n, n).T; o += n * n
+    out["r"] = a[o:o + n]; o += n
+    nk = int(a[o]); o += 1
+    out["keep"] = [(int(a[o + 2 * k]), int(a[o + 2 * k + 1])) for k in range(nk)]; o += 2 * nk
+    idx = {}
+    for fam, cnt in (("pose", N), ("speed_bias", N), ("feature", F), ("td", 1)):
+        for i in range(cnt):
+            if a[o + i] >= 0:
+                idx[(fam, i)] = int(a[o + i])
+        o += cnt
+    out["idx"] = idx
+    return out, o
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_td", [False, True])
+def test_cpp_marginalization_chain_two_rounds(tmp_path, use_td):
+    """C++ MarginalizationInfo, two chained MARGIN_OLD rounds (MarginalizationFactor kind; with use_td every
+    visual factor is a ProjectionTdFactor and para_Td a kept block -- BASELINE configs[3]).  Each round's reduced
+    system vs the 80-bit truth of the oracle's factors in the block order the C++ class chose; the round-2 prior
+    block is the oracle's MarginalizationFactor built from the round-1 outputs."""
+    from is_vins_b200.marginalization import LOCAL_SIZE
+    from oracle import isv_oracle as O
+    from tests.helpers import rel_err
+    exe = str(tmp_path / "marginalization_chain_test")
+    build_host_test(exe, SRC_CHAIN)
+    p = sim.make_problem(sim.seed_for(9, 21 + int(use_td)), n_features=320, max_track=9, host0=0.4)
+    d, rounds = _chain_problem(p, use_td, 77)
+    fx, dump = str(tmp_path / "chain_fixture.bin"), str(tmp_path / "chain_dump.bin")
+    np.asarray(d, dtype="<f8").tofile(fx)
+    r = subprocess.run([exe, fx, dump], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stderr[-2000:]
+    a = np.fromfile(dump, dtype="<f8")
+    N, F = p.poses.shape[0], len(p.feat)
+    r1, o = _read_round(a, 0, N, F)
+    r2, o = _read_round(a, o, N, F)
+    assert o == len(a)
+    prev = None
+    for rnd, got in zip(rounds, (r1, r2)):
+        idx, m, n = got["idx"], got["m"], got["n"]
+        assert got["status"] == 0 and idx[("pose", 0)] == 0 and idx[("speed_bias", 0)] == 6
+        n_diag = sum(1 for k in idx if k[0] == "feature")
+        assert n_diag >= 4 and m == 15 + n_diag
+        assert sorted(v for k, v in idx.items() if k[0] == "feature") == list(range(15, m))
+        if use_td:
+            assert idx[("td", 0)] >= m                      # the time offset is kept
+        ofac = list(rnd["ofac"])
+        if prev is not None:     # the round-1 prior as a residual block of round 2 (VINS-Mono MarginalizationFactor)
+            g1, rnd1 = prev
+            inv = {v: k for k, v in g1["idx"].items()}
+            keys1 = [inv[i] for _, i in g1["keep"]]
+            assert [O_SIZE[k[0]] for k in keys1] == [sz for sz, _ in g1["keep"]]
+            x0 = [np.atleast_1d(rnd1[k[0]][k[1]]) for k in keys1]
+            keys2 = [((k[0], k[1] - 1) if k[0] in ("pose", "speed_bias") else k) for k in keys1]
+            mf = O.MarginalizationFactor(g1["J"], g1["r"], [(sz, i - g1["m"]) for sz, i in g1["keep"]], x0)
+            r_pr, j_pr = mf.EvaluateCeres([np.atleast_1d(rnd[k[0]][k[1]]) for k in keys2])
+            ofac.append((r_pr, j_pr, keys2))
+        pos = m + n
+        facs = [(r_, [(idx[k], np.asarray(j)[:, :LOCAL_SIZE[k[0]]]) for k, j in zip(keys, js) if k[0] != "ex_pose"])
+                for r_, js, keys in ofac]
+        ref = O.vins_mono_marginalize(facs, pos, m, eps=1e-8)
+        assert ref["min_eig_Amm"] > 1e-8
+        S_hp, s_hp = O.schur_complement_longdouble(ref["A"], ref["b"], m)
+        e_ref, e_gpu = rel_err(ref["A_red"], S_hp), rel_err(got["A_red"], S_hp)
+        print(f"round {1 if prev is None else 2} A_red vs 80-bit truth: literal FP64 oracle {e_ref:.2e}, C++/CUDA {e_gpu:.2e}")
+        assert e_gpu <= max(1e-9, 2.0 * e_ref)
+        assert rel_err(got["b_red"], s_hp) <= max(1e-9, 2.0 * rel_err(ref["b_red"], s_hp))
+        assert rel_err(got["J"].T @ got["J"], got["A_red"]) <= 1e-7
+        cols = 0
+        for sz, i in got["keep"]:
+            assert i == m + cols
+            cols += 6 if sz == 7 else sz
+        assert cols == n
+        prev = (got, rnd)
+    # the kept set of round 2 carries every block the round-1 prior touched, minus the dropped frame
+    kept1 = {((k[0], k[1] - 1) if k[0] in ("pose", "speed_bias") else k) for k, v in r1["idx"].items() if v >= r1["m"]}
+    kept2 = {k for k, v in r2["idx"].items() if v >= r2["m"]}
+    assert kept2 >= kept1 - {("pose", 0), ("speed_bias", 0)}
+
+
 def test_cpp_host_layer_compiles(tmp_path):
     """CPU: the host layer, the C++ MarginalizationInfo and their test drivers compile and link against the
     C ABI (no compute)."""
     build_host_test(str(tmp_path / "host_shim_test"))
     build_host_test(str(tmp_path / "marginalization_info_test"), SRC_MI)
+    build_host_test(str(tmp_path / "marginalization_chain_test"), SRC_CHAIN)

@@ -285,3 +285,64 @@ def test_marginalization_factor_chains_two_rounds(backend):
     # the kept set of round 2 still carries every block the round-1 prior touched, except the dropped frame
     kept2 = {k for k, _, _ in mi2.getParameterBlocks()}
     assert kept2 >= (set(keys2) - {("pose", 0), ("speed_bias", 0)} - const)
+
+
+def test_config4_window20_td_marginalization(backend):
+    """BASELINE configs[3] variant (b): WINDOW_SIZE = 20, ~2000 live features, online td estimation,
+    VINS-Mono style MARGIN_OLD through the facade: the steady-state previous prior over the whole window
+    (MarginalizationFactor), the IMU factor 0 -> 1 and ~1750 ProjectionTdFactors hosted in the oldest frame;
+    extrinsics estimated, para_Td kept => n_keep = 20 * 15 + 6 + 1 = 307.  Inputs = the committed fixture
+    tests/golden/problem_W20_F2000_td.npz (checked here against its generator).  Parity unpinned by the reference."""
+    import os
+    from is_vins_b200 import FactorProblem, PriorState, add_margin_old_blocks
+    path = os.path.join(os.path.dirname(__file__), "golden", "problem_W20_F2000_td.npz")
+    fp, z = FactorProblem.load(path), np.load(path)
+    p = sim.w20_problem()
+    assert np.array_equal(fp.pose, p.poses) and np.array_equal(fp.proj_obs, p.proj_obs) and np.array_equal(fp.feature, p.feat)
+    tdx = sim.make_td_observations(p, sim.W20_SEED + 1)
+    keys, Jp, r0, x0 = sim.make_window_prior(p, sim.W20_SEED + 2)
+    assert np.array_equal(z["td_obs"], tdx["td_obs"]) and np.array_equal(z["prior_J"], Jp) and np.array_equal(z["prior_r0"], r0)
+    td, tr = z["td"], float(z["tr_over_row"][0])
+    prior = PriorState(keys, z["prior_J"], z["prior_r0"], x0)
+    mi = MarginalizationInfo(backend, eps=1e-8, cauchy_a=1.0, tr_over_row=tr)       # ESTIMATE_EXTRINSIC: no constant block
+    blocks = add_margin_old_blocks(mi, fp, z["td_obs"], prior)
+    para = {"pose": p.poses, "speed_bias": p.sbs, "ex_pose": p.ex, "feature": p.feat, "td": td}
+    mi.preMarginalize(para)
+    mi.marginalize()
+    assert mi.status == 0, hex(mi.status)
+    idx = mi.parameter_block_idx
+    L0 = sum(1 for k in idx if k[0] == "feature")
+    n_fac = sum(1 for b in blocks if b.kind == "projection_td")
+    assert mi.n == 20 * 15 + 6 + 1 and mi.m == 15 + L0 and 200 <= L0 <= 300 and 1400 <= n_fac <= 2200
+    assert idx[("pose", 0)] == 0 and idx[("speed_bias", 0)] == 6 and idx[("td", 0)] >= mi.m and idx[("ex_pose", 0)] >= mi.m
+    # the oracle's restatement of the same residual blocks, in the block order the facade chose
+    s = p.cfg.proj_sqrt_info
+    ofac = []
+    for b in blocks:
+        val = [np.atleast_1d(np.asarray(para[k[0]][k[1]], float)) for k in b.parameter_blocks]
+        M = b.members
+        if b.kind == "marginalization":
+            mf = O.MarginalizationFactor(Jp, r0, [(size, i) for _, size, i in prior.getParameterBlocks()], x0)
+            r, js = mf.EvaluateCeres(val)
+            assert rel_err(mi.prior_residuals, r) <= 1e-12
+        elif b.kind == "imu":
+            r, js = O.IMUFactor(p.imu_pre[0]).EvaluateCeres(val)
+        else:
+            fac = O.ProjectionTdFactor(M["pts_i"], M["pts_j"], M["velocity_i"], M["velocity_j"], M["td_i"], M["td_j"],
+                                       M["row_i"], M["row_j"], s, tr)
+            r, js = sim.cauchy_correct(*fac.EvaluateCeres(val), 1.0)
+        ofac.append((r, js, b.parameter_blocks))
+    facs = [(r, [(idx[k], np.asarray(j)[:, :LOCAL_SIZE[k[0]]]) for k, j in zip(keys_, js)]) for r, js, keys_ in ofac]
+    ref = O.vins_mono_marginalize(facs, mi.pos, mi.m, eps=1e-8)
+    assert ref["min_eig_Amm"] > 1e-8
+    S_hp, s_hp = O.schur_complement_longdouble(ref["A"], ref["b"], mi.m)
+    e_ref, e_gpu = rel_err(ref["A_red"], S_hp), rel_err(mi.A_red, S_hp)
+    print(f"configs[3] (b) n_keep={mi.n} m={mi.m} factors={n_fac}: A_red vs 80-bit truth: literal FP64 {e_ref:.2e}, CUDA {e_gpu:.2e}")
+    assert e_gpu <= max(1e-9, 2.0 * e_ref)
+    assert rel_err(mi.b_red, s_hp) <= max(1e-9, 2.0 * rel_err(ref["b_red"], s_hp))
+    J, r = mi.linearized_jacobians, mi.linearized_residuals
+    assert mi.rank == mi.n                                   # the previous prior constrains every kept direction
+    assert rel_err(J.T @ J, mi.A_red) <= 1e-9 and rel_err(J.T @ r, mi.b_red) <= 1e-9
+    lam = np.linalg.norm(J, axis=1) ** 2
+    assert np.all(np.diff(lam) >= 0)
+    assert np.allclose(lam, np.linalg.eigvalsh(0.5 * (S_hp + S_hp.T)), rtol=1e-7)

@@ -95,19 +95,24 @@ def main():
     ap.add_argument("--reduced", action="store_true",
                     help="reduced camera system of a whole 18-frame window (problem_F1000.npz: every factor, all 1000 "
                          "features eliminated, isv_reduced_system) instead of the oldest-frame marginalization")
+    ap.add_argument("--w20", action="store_true",
+                    help="BASELINE configs[3] variant (b): WINDOW_SIZE = 20, ~2000 live features, ProjectionTdFactor, "
+                         "previous prior over the whole window (tests/golden/problem_W20_F2000_td.npz): n_keep = 307")
     args = ap.parse_args()
     if args.reduced:
         return reduced(args)
     import torch
-    from is_vins_b200 import FactorProblem, MargBackend, MarginalizationInfo, ResidualBlockInfo
+    from is_vins_b200 import FactorProblem, MargBackend, MarginalizationInfo, PriorState, ResidualBlockInfo, add_margin_old_blocks
     from is_vins_b200 import capi
-    from is_vins_b200.marginalization import isv_ne_factor
 
-    fp = FactorProblem.load(os.path.join(ROOT, "tests", "golden", "problem_F300_host0.npz"))
+    name = "problem_W20_F2000_td.npz" if args.w20 else "problem_F300_host0.npz"
+    fp = FactorProblem.load(os.path.join(ROOT, "tests", "golden", name))
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     be = MargBackend(0)
     be.use_torch_stream()
+    if args.w20:
+        return w20(args, be, fp, np.load(os.path.join(ROOT, "tests", "golden", name)))
     mi = MarginalizationInfo(be, eps=1e-8, cauchy_a=1.0, constant=[("ex_pose", 0)])
     mi.addResidualBlockInfo(ResidualBlockInfo("imu", [("pose", 0), ("speed_bias", 0), ("pose", 1), ("speed_bias", 1)],
                                               drop_set=[0, 1], preint=fp.imu_preint[0]))
@@ -126,6 +131,30 @@ def main():
     mi.preMarginalize({"pose": fp.pose, "speed_bias": fp.speed_bias, "ex_pose": fp.ex_pose, "feature": fp.feature})
     mi.marginalize(keep_tables=True)
     assert mi.status == 0
+    batch_bench(args, be, mi, "VINS-Mono style marginalization of the oldest frame", 6)
+
+
+def w20(args, be, fp, z):
+    from is_vins_b200 import MarginalizationInfo, PriorState, add_margin_old_blocks
+    N = fp.pose.shape[0]
+    keys = [k for i in range(N) for k in (("pose", i), ("speed_bias", i))] + [("ex_pose", 0), ("td", 0)]
+    sizes = [7, 9] * N + [7, 1]
+    x0 = np.split(z["prior_x0"], np.cumsum(sizes)[:-1])
+    prior = PriorState(keys, z["prior_J"], z["prior_r0"], x0)
+    mi = MarginalizationInfo(be, eps=1e-8, cauchy_a=1.0, tr_over_row=float(z["tr_over_row"][0]))
+    add_margin_old_blocks(mi, fp, z["td_obs"], prior)
+    mi.preMarginalize({"pose": fp.pose, "speed_bias": fp.speed_bias, "ex_pose": fp.ex_pose, "feature": fp.feature, "td": z["td"]})
+    mi.marginalize(keep_tables=True)
+    assert mi.status == 0 and mi.n == 307, (mi.status, mi.n)
+    batch_bench(args, be, mi, "BASELINE configs[3] (b): WINDOW_SIZE=20, ProjectionTdFactor, previous prior over the whole "
+                              "window, MARGIN_OLD", 0)
+
+
+def batch_bench(args, be, mi, what, rank_slack):
+    """Replicates the one problem `mi` just solved NP times (factor table with problem ids 0..NP-1; values / block
+    table shared, read-only) and times isv_build_normal_equations [+ isv_add_marg_prior] + isv_schur_eig."""
+    import torch
+    from is_vins_b200 import capi
     gi, tabs = mi._gi, mi._tables
     NP, nf = args.problems, gi.n_factors
     # replicate the factor table with problem ids 0..NP-1; values / block table are shared (read-only)
@@ -143,13 +172,27 @@ def main():
     go = type(mi._go)(o["A"].data_ptr(), o["b"].data_ptr(), o["A_red"].data_ptr(), o["b_red"].data_ptr(), o["J"].data_ptr(),
                       o["r"].data_ptr(), o["rank"].data_ptr(), o["status"].data_ptr())
     lib = be.lib
+    prior = None
+    if mi._prior is not None:
+        prior = mi._prior_struct(pos_of=lambda k: -1 if k in mi.constant else mi.parameter_block_idx[k])
+        pres = mi._prior["d"]["res"]
+
+    def build():
+        capi.check(lib.isv_build_normal_equations(be.h, C.byref(gi), C.byref(go)), "isv_build_normal_equations")
+        if prior is not None:
+            capi.check(lib.isv_add_marg_prior(be.h, C.byref(prior), C.c_void_p(pres.data_ptr()), C.byref(gi), C.byref(go), -1),
+                       "isv_add_marg_prior")
+
+    def run():
+        build()
+        capi.check(lib.isv_schur_eig(be.h, C.byref(gi), C.byref(go), 0), "isv_schur_eig")
     for _ in range(2):
-        capi.check(lib.isv_marginalize_generic(be.h, C.byref(gi), C.byref(go)), "isv_marginalize_generic")
+        run()
     torch.cuda.synchronize()
     assert int(torch.count_nonzero(o["status"]).item()) == 0
     # eigenvalues of unconstrained directions sit at the rounding-noise floor, on either side of eps, and the
     # atomic summation order differs per problem: the rank may differ by those few directions
-    assert int((o["rank"] - mi.rank).abs().max().item()) <= 6, o["rank"]
+    assert int((o["rank"] - mi.rank).abs().max().item()) <= rank_slack, o["rank"]
     # problems differ only by the order of the FP64 atomics in A, amplified by the Schur cancellation
     last = o["A_red"][NP - 1].T.cpu().numpy()
     spread = float(np.linalg.norm(last - mi.A_red) / np.linalg.norm(mi.A_red))
@@ -158,9 +201,9 @@ def main():
     t_ne = t_all = 0.0
     for _ in range(args.steps):
         e0.record()
-        capi.check(lib.isv_build_normal_equations(be.h, C.byref(gi), C.byref(go)), "isv_build_normal_equations")
+        build()
         e1.record()
-        capi.check(lib.isv_marginalize_generic(be.h, C.byref(gi), C.byref(go)), "isv_marginalize_generic")
+        run()
         e2.record()
         torch.cuda.synchronize()
         t_ne += e0.elapsed_time(e1)
@@ -168,11 +211,11 @@ def main():
     t_ne /= args.steps
     t_all /= args.steps
     print(json.dumps({"metric": "problems_marginalized_per_s", "value": NP / (t_all * 1e-3), "unit": "problems/s",
-                      "config": {"workload": "VINS-Mono style marginalization of the oldest frame, "
-                                             f"{NP} independent problems", "pos": pos, "m_dense": gi.m_dense,
-                                 "m_diag": gi.m_diag, "n_keep": n, "residual_blocks_per_problem": nf},
-                      "ms_per_step": t_all, "kernels_ms": {"ne_build_kernel(+memset)": t_ne,
-                                                           "marg_schur_eig_kernel": t_all - t_ne},
+                      "config": {"workload": f"{what}, {NP} independent problems", "pos": pos, "m_dense": gi.m_dense,
+                                 "m_diag": gi.m_diag, "n_keep": n, "residual_blocks_per_problem": nf,
+                                 "previous_prior": prior is not None},
+                      "ms_per_step": t_all, "kernels_ms": {"normal equations (memset + ne_build_kernel [+ prior])": t_ne,
+                                                           "schur_diag_dmma_kernel + marg_schur_eig_kernel": t_all - t_ne},
                       "rank": mi.rank}))
     be.close()
 
