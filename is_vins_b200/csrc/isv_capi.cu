@@ -13,6 +13,7 @@
 #include "isv_eval_kernels.cuh"
 #include "isv_init_kernel.cuh"
 #include "isv_marg_generic.cuh"
+#include "isv_sym_eig.cuh"
 #include "isv_preint_kernel.cuh"
 #include "isv_seq_kernels.cuh"
 #include "isv_window_kernels.cuh"
@@ -1149,6 +1150,44 @@ static isv_status schur_eig_impl(isv_handle* h, const isv_marg_generic_in* in, c
   marg_schur_eig_kernel<<<in->n_problems, kMgThreads, sm, h->stream>>>(*in, *out, h->gram, schur_only, 1);
   ++h->launches;
   ISV_CUDA(cudaGetLastError());
+  if (!schur_only) {   // SelfAdjointEigenSolver of the reduced system -> linearized_jacobians / residuals
+    if (n > (size_t)kSeMaxN) return ISV_ERR_BAD_ARG;
+    const int threads = sym_eig_threads((int)n);
+    const size_t se = sym_eig_smem_doubles((int)n, threads / 32) * sizeof(double);
+    ISV_CUDA(cudaFuncSetAttribute(sym_eig_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)se));
+    // W scratch = the (consumed) normal equations of each problem, Z scratch = the handle's factor buffer
+    sym_eig_prior_kernel<<<in->n_problems, threads, se, h->stream>>>(
+        (int)n, out->A_red, out->b_red, out->A, h->gram, out->linearized_jacobians, out->linearized_residuals, out->rank,
+        out->status, in->eps, (size_t)in->pos * in->pos);
+    ++h->launches;
+    ISV_CUDA(cudaGetLastError());
+  }
+  return ISV_OK;
+}
+
+extern "C" isv_status isv_test_sym_eig(isv_handle* h, int nb, int n, const double* A, double* lam, double* V, int32_t* info) {
+  if (!h || nb <= 0 || n < 1 || n > kSeMaxN || !A || !lam || !V || !info) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  double *dA, *dZ, *dV, *dl;
+  int* di;
+  const size_t mb = sizeof(double) * (size_t)nb * n * n;
+  ISV_CUDA(cudaMalloc(&dA, mb));
+  ISV_CUDA(cudaMalloc(&dZ, mb));
+  ISV_CUDA(cudaMalloc(&dV, mb));
+  ISV_CUDA(cudaMalloc(&dl, sizeof(double) * (size_t)nb * n));
+  ISV_CUDA(cudaMalloc(&di, sizeof(int) * (size_t)nb));
+  ISV_CUDA(cudaMemcpyAsync(dA, A, mb, cudaMemcpyHostToDevice, h->stream));
+  const int threads = sym_eig_threads(n);
+  const size_t se = sym_eig_smem_doubles(n, threads / 32) * sizeof(double);
+  ISV_CUDA(cudaFuncSetAttribute(sym_eig_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)se));
+  sym_eig_test_kernel<<<nb, threads, se, h->stream>>>(n, dA, dZ, dl, dV, di);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  ISV_CUDA(cudaMemcpyAsync(V, dV, mb, cudaMemcpyDeviceToHost, h->stream));
+  ISV_CUDA(cudaMemcpyAsync(lam, dl, sizeof(double) * (size_t)nb * n, cudaMemcpyDeviceToHost, h->stream));
+  ISV_CUDA(cudaMemcpyAsync(info, di, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+  ISV_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(dA); cudaFree(dZ); cudaFree(dV); cudaFree(dl); cudaFree(di);
   return ISV_OK;
 }
 

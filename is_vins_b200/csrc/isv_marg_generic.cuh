@@ -7,9 +7,10 @@
 //   ne_build_kernel        ThreadsConstructA: A += J_i^T J_j , b += J_i^T r over all residual blocks,
 //                          scattered by parameter-block position -- one warp per residual block, its
 //                          Jacobians staged in shared memory, one FP64 atomic per (entry, factor)
-//   marg_schur_eig_kernel  A_rr - A_rm A_mm^+ A_mr ,  b_rr - A_rm A_mm^+ b_mm ,  eigen-decomposition of
-//                          the reduced system, linearized_jacobians = S^1/2 V^T , residuals = S^-1/2 V^T b
-//                          -- one CTA per problem.
+//   marg_schur_eig_kernel  A_rr - A_rm A_mm^+ A_mr ,  b_rr - A_rm A_mm^+ b_mm  (eigen-thresholded pseudo-inverse of
+//                          the dense marginalized block) -- one CTA per problem
+//   sym_eig_prior_kernel   (isv_sym_eig.cuh) eigen-decomposition of the reduced system,
+//                          linearized_jacobians = S^1/2 V^T , residuals = S^-1/2 V^T b
 // Layout of the tangent vector: [ m_dense | m_diag | n_keep ].  `m_diag` marginalized blocks are
 // scalars that no residual block couples with each other (inverse depths: every ProjectionFactor
 // touches exactly one), so that part of A_mm is diagonal and its elimination is the dense product
@@ -229,12 +230,11 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // smem (doubles): P[32*32] V[32*32] cs[6*16] red[32] + ints
 __global__ void __launch_bounds__(kMgThreads)
 marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* __restrict__ Gbuf, int schur_only,
-                      int phase_a_done) {
+                      int phase_a_done) {   // Gbuf: n x md scratch per problem (stride n * n)
   extern __shared__ double smem[];
   double* P = smem;                       // m_dense x m_dense
   double* V = P + kMgMaxDense * kMgMaxDense;
   double* cs = V + kMgMaxDense * kMgMaxDense;
-  double* red = cs + 6 * 16;              // 32
   __shared__ int s_status;
   if (threadIdx.x == 0) s_status = 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kMgThreads / 32;
@@ -342,138 +342,13 @@ marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* 
     br[i] = acc;
   }
   __syncthreads();
-  if (schur_only) {   // reduced system only (DENSE_SCHUR's reduced camera system): no eigen-decomposition
-    if (tid == 0) out.rank[prob] = -1;
-    if (status) atomicOr(&s_status, status);
-    __syncthreads();
-    if (tid == 0 && out.status && s_status) atomicOr(out.status + prob, s_status);
-    return;
-  }
-  // ---- phase C: A_red ~= G^T G by outer-product Cholesky with diagonal pivoting (A_red is PSD up to
-  //      rounding; what is dropped is below n * eps_mach * max diagonal).  Works on a copy in A's kept block.
-  double* W = A;   // reuse the first n*n doubles of this problem's A as the work copy (A is consumed)
-  for (int idx = tid; idx < n * n; idx += kMgThreads) {
-    const int i = idx % n, j = idx / n;
-    W[idx] = 0.5 * (Ar[i + (size_t)n * j] + Ar[j + (size_t)n * i]);
-  }
-  __syncthreads();
-  double dmax0 = 0.0;
-  for (int i = tid; i < n; i += kMgThreads) dmax0 = fmax(dmax0, W[i + (size_t)n * i]);
-  dmax0 = warp_max(dmax0);
-  if (lane == 0) red[warp] = dmax0;
-  __syncthreads();
-  dmax0 = 0.0;
-  for (int w = 0; w < nw; ++w) dmax0 = fmax(dmax0, red[w]);
-  const double stop = (double)n * 2.220446049250313e-16 * dmax0;
-  int rank = 0;
-  for (int k = 0; k < n; ++k) {
-    // pivot = arg max of the remaining diagonal
-    double best = -1.0;
-    int bi = -1;
-    for (int i = tid; i < n; i += kMgThreads) {
-      const double d = W[i + (size_t)n * i];
-      if (d > best) { best = d; bi = i; }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(kFullMask, best, o);
-      const int oi = __shfl_xor_sync(kFullMask, bi, o);
-      if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
-    }
-    __syncthreads();
-    if (lane == 0) { red[warp] = best; reinterpret_cast<int*>(red + 16)[warp] = bi; }
-    __syncthreads();
-    best = -1.0; bi = -1;
-    for (int w = 0; w < nw; ++w) {
-      const double ob = red[w];
-      const int oi = reinterpret_cast<int*>(red + 16)[w];
-      if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
-    }
-    if (!(best > stop) || bi < 0) break;
-    const double ri = rsqrt(best);
-    double* g = G + (size_t)rank * n;
-    for (int j = tid; j < n; j += kMgThreads) g[j] = W[bi + (size_t)n * j] * ri;
-    __syncthreads();
-    for (int idx = tid; idx < n * n; idx += kMgThreads) {
-      const int i = idx % n, j = idx / n;
-      W[idx] = fma(-g[i], g[j], W[idx]);
-    }
-    __syncthreads();
-    if (tid == 0) W[bi + (size_t)n * bi] = 0.0;   // exactly eliminated
-    ++rank;
-    __syncthreads();
-  }
-  // ---- phase D: one-sided Jacobi on the rows of G (rank x n): afterwards A_red = sum_k g_k g_k^T with
-  //      mutually orthogonal g_k, eigenvalues |g_k|^2 ----------------------------------------------------
-  {
-    const int mm = (rank + 1) & ~1, half = mm / 2;
-    const double tol = 2.220446049250313e-16 * sqrt((double)n);
-    for (int sweep = 0; sweep < 40 && rank >= 2; ++sweep) {
-      int rotated = 0;
-      for (int rr = 0; rr < mm - 1; ++rr) {
-        for (int kp = warp; kp < half; kp += nw) {
-          int p, q;
-          jacobi_pair(kp, rr, mm, p, q);
-          if (q >= rank) continue;
-          double* gp = G + (size_t)p * n;
-          double* gq = G + (size_t)q * n;
-          double a = 0.0, bq = 0.0, gm = 0.0;
-          for (int j = lane; j < n; j += 32) {
-            const double x = gp[j], y = gq[j];
-            a = fma(x, x, a); bq = fma(y, y, bq); gm = fma(x, y, gm);
-          }
-          a = warp_sum(a); bq = warp_sum(bq); gm = warp_sum(gm);
-          if (fabs(gm) > tol * sqrt(a * bq) && gm != 0.0) {
-            double c, s;
-            jacobi_cs(a, bq, gm, c, s);
-            for (int j = lane; j < n; j += 32) {
-              const double x = gp[j], y = gq[j];
-              gp[j] = c * x - s * y;
-              gq[j] = s * x + c * y;
-            }
-            rotated = 1;
-          }
-        }
-        __syncthreads();
-      }
-      if (!__syncthreads_or(rotated)) break;
-      if (sweep == 39) status |= ISV_W_EIG_NOCONV;
-    }
-  }
-  // ---- phase E: outputs, rows in ascending eigenvalue order (Eigen's convention): n - kept zero rows
-  //      first, then sqrt(lam_k) v_k^T = g_k^T ; residual_k = g_k . b_red / lam_k -------------------------
-  double* LJ = out.linearized_jacobians + (size_t)prob * n * n;   // column-major n x n
-  double* LR = out.linearized_residuals + (size_t)prob * n;
-  for (int idx = tid; idx < n * n; idx += kMgThreads) LJ[idx] = 0.0;
-  for (int i = tid; i < n; i += kMgThreads) LR[i] = 0.0;
-  __syncthreads();
-  // lam_k and g_k.b per row (warp per row), staged in W[0..2n)
-  for (int k = warp; k < rank; k += nw) {
-    const double* g = G + (size_t)k * n;
-    double l2 = 0.0, gb = 0.0;
-    for (int j = lane; j < n; j += 32) { l2 = fma(g[j], g[j], l2); gb = fma(g[j], br[j], gb); }
-    l2 = warp_sum(l2); gb = warp_sum(gb);
-    if (lane == 0) { W[k] = l2; W[n + k] = gb; }
-  }
-  __syncthreads();
-  int kept = 0;
-  for (int k = 0; k < rank; ++k) kept += (W[k] > eps) ? 1 : 0;
-  for (int k = warp; k < rank; k += nw) {
-    const double lam = W[k];
-    if (!(lam > eps)) continue;
-    int below = 0;   // kept eigenvalues smaller than this one (ties by index)
-    for (int t = 0; t < rank; ++t) {
-      const double lt = W[t];
-      if (lt > eps && (lt < lam || (lt == lam && t < k))) ++below;
-    }
-    const int row = (n - kept) + below;
-    const double* g = G + (size_t)k * n;
-    for (int j = lane; j < n; j += 32) LJ[row + (size_t)n * j] = g[j];
-    if (lane == 0) LR[row] = W[n + k] / lam;
-  }
-  if (tid == 0) out.rank[prob] = kept;
+  // the eigen-decomposition of the reduced system is its own kernel (isv_sym_eig.cuh); schur_only callers (the
+  // reduced camera system of DENSE_SCHUR) get rank = -1
+  if (schur_only && tid == 0) out.rank[prob] = -1;
   if (status) atomicOr(&s_status, status);
   __syncthreads();
   if (tid == 0 && out.status && s_status) atomicOr(out.status + prob, s_status);
+  (void)br; (void)nw;
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -53,3 +53,36 @@ def test_psd_eig_matches_eigh(backend, n, rank):
         k = ww > 0.1
         Sig_ref = (V[:, k] / ww[k]) @ V[:, k].T
         assert np.linalg.norm(Sig - Sig_ref) <= 1e-8 * np.linalg.norm(Sig_ref)
+
+
+@pytest.mark.parametrize("n,nb", [(1, 4), (2, 8), (6, 16), (57, 32), (58, 8), (129, 8), (307, 4)])
+def test_sym_eig_matches_eigh(backend, n, nb):
+    """The CTA-level symmetric eigensolver of the generic engine's reduced system (Householder tridiagonalization +
+    implicit QL = the algorithm class of Eigen's SelfAdjointEigenSolver) against LAPACK: graded spectra like a
+    marginal information matrix, incl. rank-deficient ones and a block-diagonal one (interior deflation)."""
+    rng = np.random.default_rng(1000 + n)
+    A = np.zeros((nb, n, n))
+    for b in range(nb):
+        Q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+        w = 10.0 ** rng.uniform(-2, 9, n)
+        if b % 3 == 1:
+            w[: n // 3] = 0.0                              # rank-deficient (unobservable directions)
+        A[b] = (Q * w) @ Q.T
+        if b % 4 == 2 and n >= 4:                          # decoupled blocks: zero sub-diagonals inside the tridiagonal
+            A[b][: n // 2, n // 2:] = 0.0
+            A[b][n // 2:, : n // 2] = 0.0
+        A[b] = 0.5 * (A[b] + A[b].T)
+    Af = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))
+    lam, V = np.zeros((nb, n)), np.zeros((nb, n, n))
+    info = np.zeros((nb,), np.int32)
+    p = lambda a: a.ctypes.data_as(capi.c_double_p)
+    capi.check(backend.lib.isv_test_sym_eig(backend.h, nb, n, p(Af), p(lam), p(V), info.ctypes.data_as(capi.c_int32_p)))
+    assert not info.any()
+    for b in range(nb):
+        w_ref = np.linalg.eigvalsh(A[b])
+        nrm = np.abs(w_ref).max()
+        Vb = V[b].T                                        # columns = eigenvectors
+        assert np.all(np.diff(lam[b]) >= 0)
+        assert np.abs(lam[b] - w_ref).max() <= 1e-13 * n * nrm
+        assert np.abs(Vb.T @ Vb - np.eye(n)).max() <= 1e-13 * n
+        assert np.linalg.norm((Vb * lam[b]) @ Vb.T - A[b]) <= 1e-13 * n * np.linalg.norm(A[b])
