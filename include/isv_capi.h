@@ -556,9 +556,10 @@ isv_status isv_test_psd_eig(isv_handle* h, int nb, int n, const double* A, doubl
                             int32_t* info);
 
 /* ---- unit-test hook: the symmetric eigensolver of the generic engine's reduced system (VINS-Mono
- * `SelfAdjointEigenSolver<MatrixXd> saes2(A)`; Householder tridiagonalization + implicit QL, one CTA per matrix).
- * nb symmetric n x n matrices A (column-major, host) -> lam [nb][n] ascending, V [nb][n][n] column-major with
- * column r the eigenvector of lam[r]; info [nb] != 0: QL did not converge.  n <= 1024.              */
+ * `SelfAdjointEigenSolver<MatrixXd> saes2(A)`; Householder tridiagonalization + implicit QL with a rotation log,
+ * is_vins_b200/csrc/isv_sym_eig.cuh).  nb symmetric n x n matrices A (column-major, host) -> lam [nb][n] ascending,
+ * V [nb][n][n] column-major with column r the eigenvector of lam[r]; info [nb][2] = {QL failure flags, rotations
+ * logged}.  n <= 1024.                                                                              */
 isv_status isv_test_sym_eig(isv_handle* h, int nb, int n, const double* A, double* lam, double* V, int32_t* info);
 
 #ifdef __cplusplus

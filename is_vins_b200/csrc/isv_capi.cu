@@ -35,6 +35,8 @@ struct isv_handle {
   size_t dbuf_bytes;
   char* pinned;
   size_t pinned_bytes;
+  char* eig;             // eigensolver scratch of the generic engine (tridiagonal + rotation log per problem), grow-only
+  size_t eig_bytes;
   double* gram;          // [n][42 + kFJ] scratch handed between the kernels of one batch, grow-only:
   size_t gram_bytes;     //   landmark Gram triangles (forward stage 1 -> 2) and the factor-Jacobian records
   cudaEvent_t jac_ev[6]; // fork / join events of launch_batch, three per launching stream
@@ -130,6 +132,7 @@ void isv_destroy(isv_handle* h) {
   cudaStreamSynchronize(h->stream);
   if (h->dbuf) cudaFree(h->dbuf);
   if (h->gram) cudaFree(h->gram);
+  if (h->eig) cudaFree(h->eig);
   if (h->pinned) cudaFreeHost(h->pinned);
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -1121,6 +1124,47 @@ extern "C" isv_status isv_add_marg_prior(isv_handle* h, const isv_marg_prior* pr
   return ISV_OK;
 }
 
+// tridiagonalization + QL (rotation log) + log applied to Z for `np` symmetric n x n matrices A (stride a_stride
+// doubles, read-only); W: n x n scratch per problem (stride w_stride), Z: [np][n][n] receives the eigenvectors
+// (columns, unsorted); eigenvalues + flags stay in the handle's eigensolver scratch (h->eig).
+static isv_status sym_eig_launch(isv_handle* h, int n, int np, const double* A, size_t a_stride, double* W, size_t w_stride,
+                                 double* Z) {
+  if (n < 1 || n > kSeMaxN || np < 1 || np > 65535) return ISV_ERR_BAD_ARG;
+  const size_t need = (size_t)np * sym_eig_scratch_bytes(n);
+  if (h->eig_bytes < need) {
+    if (h->eig) {
+      ISV_CUDA(cudaStreamSynchronize(h->stream));
+      ISV_CUDA(cudaFree(h->eig));
+      h->eig = nullptr;
+      h->eig_bytes = 0;
+    }
+    if (cudaMalloc(&h->eig, need) != cudaSuccess) {
+      cudaGetLastError();
+      return ISV_ERR_ALLOC;
+    }
+    h->eig_bytes = need;
+  }
+  const size_t sm1 = sym_tridiag_smem_doubles(n) * sizeof(double);
+  ISV_CUDA(cudaFuncSetAttribute(sym_tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+  sym_tridiag_kernel<<<np, kSeThreads, sm1, h->stream>>>(n, A, a_stride, W, w_stride, h->eig);
+  const int rows = ql_apply_rows(n);
+  const size_t sm3 = ql_apply_smem_bytes(n, rows);
+  const dim3 slabs((n + rows - 1) / rows, np);
+  ISV_CUDA(cudaFuncSetAttribute(q_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+  ISV_CUDA(cudaFuncSetAttribute(ql_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+  // fork: the rows of Q need only the reflectors, the serial QL only (d, e) -- they overlap on two streams
+  ISV_CUDA(cudaEventRecord(h->aux_ev[0], h->stream));
+  ISV_CUDA(cudaStreamWaitEvent(h->aux[0], h->aux_ev[0], 0));
+  q_rows_kernel<<<slabs, kQaThreads, sm3, h->aux[0]>>>(n, rows, W, w_stride, Z, h->eig);
+  ISV_CUDA(cudaEventRecord(h->aux_ev[1], h->aux[0]));
+  tridiag_ql_kernel<<<np, 32, 2 * (size_t)n * sizeof(double), h->stream>>>(n, h->eig);
+  ISV_CUDA(cudaStreamWaitEvent(h->stream, h->aux_ev[1], 0));
+  ql_apply_kernel<<<slabs, kQaThreads, sm3, h->stream>>>(n, rows, Z, h->eig);
+  h->launches += 4;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
 static isv_status schur_eig_impl(isv_handle* h, const isv_marg_generic_in* in, const isv_marg_generic_out* out,
                                  int schur_only) {
   ISV_CUDA(cudaSetDevice(h->device));
@@ -1151,14 +1195,12 @@ static isv_status schur_eig_impl(isv_handle* h, const isv_marg_generic_in* in, c
   ++h->launches;
   ISV_CUDA(cudaGetLastError());
   if (!schur_only) {   // SelfAdjointEigenSolver of the reduced system -> linearized_jacobians / residuals
-    if (n > (size_t)kSeMaxN) return ISV_ERR_BAD_ARG;
-    const int threads = sym_eig_threads((int)n);
-    const size_t se = sym_eig_smem_doubles((int)n, threads / 32) * sizeof(double);
-    ISV_CUDA(cudaFuncSetAttribute(sym_eig_prior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)se));
     // W scratch = the (consumed) normal equations of each problem, Z scratch = the handle's factor buffer
-    sym_eig_prior_kernel<<<in->n_problems, threads, se, h->stream>>>(
-        (int)n, out->A_red, out->b_red, out->A, h->gram, out->linearized_jacobians, out->linearized_residuals, out->rank,
-        out->status, in->eps, (size_t)in->pos * in->pos);
+    isv_status st = sym_eig_launch(h, (int)n, in->n_problems, out->A_red, n * n, out->A, (size_t)in->pos * in->pos, h->gram);
+    if (st != ISV_OK) return st;
+    eig_prior_kernel<<<in->n_problems, 256, n * (sizeof(double) + sizeof(int)), h->stream>>>(
+        (int)n, out->b_red, h->gram, h->eig, out->linearized_jacobians, out->linearized_residuals, out->rank, out->status,
+        in->eps);
     ++h->launches;
     ISV_CUDA(cudaGetLastError());
   }
@@ -1168,27 +1210,28 @@ static isv_status schur_eig_impl(isv_handle* h, const isv_marg_generic_in* in, c
 extern "C" isv_status isv_test_sym_eig(isv_handle* h, int nb, int n, const double* A, double* lam, double* V, int32_t* info) {
   if (!h || nb <= 0 || n < 1 || n > kSeMaxN || !A || !lam || !V || !info) return ISV_ERR_BAD_ARG;
   ISV_CUDA(cudaSetDevice(h->device));
-  double *dA, *dZ, *dV, *dl;
+  double *dA, *dW, *dZ, *dV, *dl;
   int* di;
   const size_t mb = sizeof(double) * (size_t)nb * n * n;
   ISV_CUDA(cudaMalloc(&dA, mb));
+  ISV_CUDA(cudaMalloc(&dW, mb));
   ISV_CUDA(cudaMalloc(&dZ, mb));
   ISV_CUDA(cudaMalloc(&dV, mb));
   ISV_CUDA(cudaMalloc(&dl, sizeof(double) * (size_t)nb * n));
-  ISV_CUDA(cudaMalloc(&di, sizeof(int) * (size_t)nb));
+  ISV_CUDA(cudaMalloc(&di, sizeof(int) * 2 * (size_t)nb));
   ISV_CUDA(cudaMemcpyAsync(dA, A, mb, cudaMemcpyHostToDevice, h->stream));
-  const int threads = sym_eig_threads(n);
-  const size_t se = sym_eig_smem_doubles(n, threads / 32) * sizeof(double);
-  ISV_CUDA(cudaFuncSetAttribute(sym_eig_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)se));
-  sym_eig_test_kernel<<<nb, threads, se, h->stream>>>(n, dA, dZ, dl, dV, di);
-  ++h->launches;
-  ISV_CUDA(cudaGetLastError());
-  ISV_CUDA(cudaMemcpyAsync(V, dV, mb, cudaMemcpyDeviceToHost, h->stream));
-  ISV_CUDA(cudaMemcpyAsync(lam, dl, sizeof(double) * (size_t)nb * n, cudaMemcpyDeviceToHost, h->stream));
-  ISV_CUDA(cudaMemcpyAsync(info, di, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
-  ISV_CUDA(cudaStreamSynchronize(h->stream));
-  cudaFree(dA); cudaFree(dZ); cudaFree(dV); cudaFree(dl); cudaFree(di);
-  return ISV_OK;
+  isv_status st = sym_eig_launch(h, n, nb, dA, (size_t)n * n, dW, (size_t)n * n, dZ);
+  if (st == ISV_OK) {
+    eig_test_out_kernel<<<nb, 256, n * sizeof(int), h->stream>>>(n, dZ, h->eig, dl, dV, di);
+    ++h->launches;
+    ISV_CUDA(cudaGetLastError());
+    ISV_CUDA(cudaMemcpyAsync(V, dV, mb, cudaMemcpyDeviceToHost, h->stream));
+    ISV_CUDA(cudaMemcpyAsync(lam, dl, sizeof(double) * (size_t)nb * n, cudaMemcpyDeviceToHost, h->stream));
+    ISV_CUDA(cudaMemcpyAsync(info, di, sizeof(int) * 2 * (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+    ISV_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  cudaFree(dA); cudaFree(dW); cudaFree(dZ); cudaFree(dV); cudaFree(dl); cudaFree(di);
+  return st;
 }
 
 // ---- MarginalizationInfo::preMarginalize + marginalize from host memory ---------------------------------------
