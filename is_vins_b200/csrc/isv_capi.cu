@@ -1146,7 +1146,9 @@ static isv_status sym_eig_launch(isv_handle* h, int n, int np, const double* A, 
   }
   const size_t sm1 = sym_tridiag_smem_doubles(n) * sizeof(double);
   ISV_CUDA(cudaFuncSetAttribute(sym_tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
-  sym_tridiag_kernel<<<np, kSeThreads, sm1, h->stream>>>(n, A, a_stride, W, w_stride, h->eig);
+  // small matrices: fewer threads per CTA so that several problems share an SM
+  const int t1 = n <= 64 ? 128 : (n <= 128 ? 256 : kSeThreads);
+  sym_tridiag_kernel<<<np, t1, sm1, h->stream>>>(n, A, a_stride, W, w_stride, h->eig);
   const int rows = ql_apply_rows(n);
   const size_t sm3 = ql_apply_smem_bytes(n, rows);
   const dim3 slabs((n + rows - 1) / rows, np);

@@ -6,7 +6,8 @@
 //
 //   ne_build_kernel        ThreadsConstructA: A += J_i^T J_j , b += J_i^T r over all residual blocks,
 //                          scattered by parameter-block position -- one warp per residual block, its
-//                          Jacobians staged in shared memory, one FP64 atomic per (entry, factor)
+//                          Jacobians staged in shared memory, every upper-triangle product formed once and
+//                          reduced into A (and its mirror) with FP64 atomics
 //   marg_schur_eig_kernel  A_rr - A_rm A_mm^+ A_mr ,  b_rr - A_rm A_mm^+ b_mm  (eigen-thresholded pseudo-inverse of
 //                          the dense marginalized block) -- one CTA per problem
 //   sym_eig_prior_kernel   (isv_sym_eig.cuh) eigen-decomposition of the reduced system,
@@ -30,66 +31,80 @@
 
 namespace isv {
 
-constexpr int kNeMaxRes = 15, kNeMaxCols = 36, kNeWarps = 4;
-constexpr int kNeSmemPerWarp = kNeMaxRes * kNeMaxCols + 16 + 8;
+constexpr int kNeMaxRes = 15, kNeMaxCols = 36, kNeWarps = 4, kNeLd = kNeMaxCols + 1;
+constexpr int kNeSmemPerWarp = kNeMaxRes * kNeLd + 16 + kNeMaxCols / 2 + 2;   // J | r | colpos (ints) in doubles
 
+// One warp per residual block.  Its row-major Jacobian blocks are staged into shared memory as one
+// n_res x tot matrix (ld 37: conflict-free down a column), together with the tangent position of every staged
+// column; then every lane takes column PAIRS (a <= c) of the upper triangle -- decoded from a flat pair index, so all
+// 32 lanes are busy whatever tot is -- forms J[:,a] . J[:,c] once and adds it to A at (pos(a), pos(c)) and at the
+// mirrored entry with FP64 reductions (RED.ADD.F64).  The block -> position map is the caller's table: bit-exact.
 __global__ void __launch_bounds__(32 * kNeWarps)
 ne_build_kernel(isv_marg_generic_in in, double* __restrict__ A, double* __restrict__ b, int32_t* status) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long f = (long long)blockIdx.x * kNeWarps + warp;
   if (f >= in.n_factors) return;
-  double* J = smem + warp * kNeSmemPerWarp;   // n_res x total columns, row-major, ld = kNeMaxCols
-  double* r = J + kNeMaxRes * kNeMaxCols;
-  int* meta = reinterpret_cast<int*>(r + 16);  // per block: column offset in J, pos, local size (<= 5 blocks)
+  double* J = smem + warp * kNeSmemPerWarp;   // n_res x tot, row-major, ld = kNeLd
+  double* r = J + kNeMaxRes * kNeLd;
+  int* colpos = reinterpret_cast<int*>(r + 16);   // tangent position of every staged column
   const isv_ne_factor fa = in.factors[f];
   const int nres = fa.n_res, nb = fa.n_blocks;
   bool ok = nres >= 1 && nres <= kNeMaxRes && nb >= 1 && nb <= 5 && fa.problem >= 0 && fa.problem < in.n_problems;
-  int tot = 0;
-  if (ok) {
-    for (int k = 0; k < nb; ++k) {
-      const isv_ne_block bl = in.blocks[fa.first_block + k];
-      if (bl.local_size < 1 || bl.local_size > 9 || bl.pos < 0 || bl.pos + bl.local_size > in.pos) ok = false;
-      if (lane == 0) { meta[3 * k] = tot; meta[3 * k + 1] = bl.pos; meta[3 * k + 2] = bl.local_size; }
-      tot += bl.local_size;
-    }
+  // lane k < nb owns block k: its record, and by a shuffle scan its first staged column
+  isv_ne_block bl = {0, 0, 0, 0, 0};
+  if (ok && lane < nb) {
+    bl = in.blocks[fa.first_block + lane];
+    if (bl.local_size < 1 || bl.local_size > 9 || bl.pos < 0 || bl.pos + bl.local_size > in.pos) ok = false;
   }
+  ok = __all_sync(kFullMask, ok);
+  int c0 = lane < nb ? bl.local_size : 0;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const int up = __shfl_up_sync(kFullMask, c0, o);
+    if (lane >= o) c0 += up;
+  }
+  const int tot = __shfl_sync(kFullMask, c0, 7);    // inclusive scan: lanes >= nb repeat the total
+  c0 -= lane < nb ? bl.local_size : 0;
   if (!ok || tot > kNeMaxCols) {
     if (lane == 0 && status) atomicOr(status, ISV_W_BAD_INDEX);
     return;
   }
-  for (int i = lane; i < nres; i += 32) r[i] = in.values[fa.res_offset + i];
+  if (lane < nres) r[lane] = in.values[fa.res_offset + lane];
   for (int k = 0; k < nb; ++k) {
-    const isv_ne_block bl = in.blocks[fa.first_block + k];
-    int c0 = 0;
-    for (int kk = 0; kk < k; ++kk) c0 += in.blocks[fa.first_block + kk].local_size;
-    for (int idx = lane; idx < nres * bl.local_size; idx += 32) {
-      const int row = idx / bl.local_size, col = idx - row * bl.local_size;
-      J[row * kNeMaxCols + c0 + col] = in.values[bl.jac_offset + (long long)row * bl.row_stride + col];
-    }
+    const long long jo = __shfl_sync(kFullMask, bl.jac_offset, k);
+    const int rs = __shfl_sync(kFullMask, bl.row_stride, k), ls = __shfl_sync(kFullMask, bl.local_size, k);
+    const int ck = __shfl_sync(kFullMask, c0, k), pk = __shfl_sync(kFullMask, bl.pos, k);
+    if (lane < ls) colpos[ck + lane] = pk + lane;
+    // rows x local columns of the block; lanes along the columns first (ls <= 9: rows per pass = 32 / ls)
+    const int rpp = 32 / ls, row_l = lane / ls, col_l = lane - row_l * ls;
+    if (row_l < rpp)
+      for (int row = row_l; row < nres; row += rpp)
+        J[row * kNeLd + ck + col_l] = in.values[jo + (long long)row * rs + col_l];
   }
   __syncwarp();
   double* Ap = A + (size_t)fa.problem * in.pos * in.pos;
   double* bp = b + (size_t)fa.problem * in.pos;
-  // every (a, c) column pair of the staged Jacobian: A[pos(a), pos(c)] += J[:,a] . J[:,c]
-  for (int idx = lane; idx < tot * tot; idx += 32) {
-    const int a = idx / tot, c = idx - a * tot;
+  const size_t ldA = (size_t)in.pos;
+  const int npair = tot * (tot + 1) / 2;
+  for (int p = lane; p < npair; p += 32) {
+    // p = c (c + 1) / 2 + a with a <= c
+    int c = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+    if ((c + 1) * (c + 2) / 2 <= p) ++c;
+    if (c * (c + 1) / 2 > p) --c;
+    const int a = p - c * (c + 1) / 2;
     double acc = 0.0;
-    for (int l = 0; l < nres; ++l) acc = fma(J[l * kNeMaxCols + a], J[l * kNeMaxCols + c], acc);
-    int pa = 0, pc = 0;
-    for (int k = 0; k < nb; ++k) {
-      if (a >= meta[3 * k] && a < meta[3 * k] + meta[3 * k + 2]) pa = meta[3 * k + 1] + a - meta[3 * k];
-      if (c >= meta[3 * k] && c < meta[3 * k] + meta[3 * k + 2]) pc = meta[3 * k + 1] + c - meta[3 * k];
+    for (int l = 0; l < nres; ++l) acc = fma(J[l * kNeLd + a], J[l * kNeLd + c], acc);
+    if (acc != 0.0) {
+      const int pa = colpos[a], pc = colpos[c];
+      atomicAdd(Ap + pa + ldA * pc, acc);
+      if (a != c) atomicAdd(Ap + pc + ldA * pa, acc);
     }
-    if (acc != 0.0) atomicAdd(Ap + pa + (size_t)in.pos * pc, acc);
   }
   for (int a = lane; a < tot; a += 32) {
     double acc = 0.0;
-    for (int l = 0; l < nres; ++l) acc = fma(J[l * kNeMaxCols + a], r[l], acc);
-    int pa = 0;
-    for (int k = 0; k < nb; ++k)
-      if (a >= meta[3 * k] && a < meta[3 * k] + meta[3 * k + 2]) pa = meta[3 * k + 1] + a - meta[3 * k];
-    if (acc != 0.0) atomicAdd(bp + pa, acc);
+    for (int l = 0; l < nres; ++l) acc = fma(J[l * kNeLd + a], r[l], acc);
+    if (acc != 0.0) atomicAdd(bp + colpos[a], acc);
   }
 }
 
