@@ -246,23 +246,7 @@ class MarginalizationInfo:
         import torch
         assert self._dp is not None, "call preMarginalize first"
         dp, by = self._dp, self._by
-        # ---- ordering (see module docstring) -> parameter_block_idx, m, n --------------------------------
-        order: List[Key] = [k for k in self._drop if LOCAL_SIZE[k[0]] > 1 and k not in self.constant]
-        m_dense = sum(LOCAL_SIZE[k[0]] for k in order)
-        diag = [k for k in self._drop if LOCAL_SIZE[k[0]] == 1 and k not in self.constant]
-        order += diag
-        seen = set(order)
-        for f in self.factors:
-            for k in f.parameter_blocks:
-                if k not in seen and k not in self.constant:
-                    seen.add(k)
-                    order.append(k)
-        pos = 0
-        self.parameter_block_idx = {}
-        for k in order:
-            self.parameter_block_idx[k] = pos
-            pos += LOCAL_SIZE[k[0]]
-        self.m, self.n = m_dense + len(diag), pos - m_dense - len(diag)
+        pos, m_dense, diag = self.order_blocks()
         # ---- one `values` array: the Evaluate outputs, concatenated ---------------------------------------
         names = ["proj_res", "proj_ji", "proj_jj", "proj_je", "proj_jf", "imu_res", "imu_jac", "rel_res", "rel_jac",
                  "se3_res", "se3_jac", "vb_res", "vb_jac", "rp_res", "rp_jac", "yaw_res", "yaw_jac"]
@@ -351,6 +335,28 @@ class MarginalizationInfo:
         self.pos = pos
         # keep_block_data: the kept blocks at this linearization point (what MarginalizationFactor needs later)
         self.keep_block_data = {k: self._block_value(k).copy() for k, i in self.parameter_block_idx.items() if i >= self.m}
+
+    def order_blocks(self):
+        """The block order of the tangent vector (see module docstring): marginalized blocks of local size > 1 in
+        drop order, marginalized scalars (the diagonal block), kept blocks by first appearance; blocks held constant
+        get no column.  Sets parameter_block_idx, m, n; returns (pos, m_dense, [diagonal keys]).  Pure host logic."""
+        order: List[Key] = [k for k in self._drop if LOCAL_SIZE[k[0]] > 1 and k not in self.constant]
+        m_dense = sum(LOCAL_SIZE[k[0]] for k in order)
+        diag = [k for k in self._drop if LOCAL_SIZE[k[0]] == 1 and k not in self.constant]
+        order += diag
+        seen = set(order)
+        for f in self.factors:
+            for k in f.parameter_blocks:
+                if k not in seen and k not in self.constant:
+                    seen.add(k)
+                    order.append(k)
+        pos = 0
+        self.parameter_block_idx = {}
+        for k in order:
+            self.parameter_block_idx[k] = pos
+            pos += LOCAL_SIZE[k[0]]
+        self.m, self.n = m_dense + len(diag), pos - m_dense - len(diag)
+        return pos, m_dense, diag
 
     def getParameterBlocks(self, addr_shift: Optional[Dict[Key, Key]] = None):
         """kept blocks in order: (key, global size, position in the reduced tangent vector = idx - m).  With
