@@ -201,6 +201,12 @@ typedef struct isv_bwd_out {
 
 isv_status isv_marg_forward(isv_handle* h, const isv_fwd_in* in, isv_fwd_out* out);
 isv_status isv_marg_backward(isv_handle* h, const isv_bwd_in* in, isv_bwd_out* out);
+/* One whole MARGIN_OLD event -- `MargForward(); MargBackward();` as Estimator::backendOptimization() calls them back to
+ * back (src/estimator.cpp:1555-1558; the two read disjoint members and neither reads the other's outputs) -- in ONE
+ * blocking call: one pinned block in, the forward and backward kernel chains forked on two streams, one block out.
+ * Results are bit-identical to the two separate calls; both `status` fields carry the OR of the event's warnings.  */
+isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fwd_in, const isv_bwd_in* bwd_in, isv_fwd_out* fwd_out,
+                          isv_bwd_out* bwd_out);
 
 /* ---- initFactorGraph sparsification tail (src/estimator.cpp:745-1001) ---------------------------
  * One-time: the V-1 IMU factors of the initial window -> V-1 RelativePoseFactors

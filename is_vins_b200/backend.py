@@ -139,6 +139,20 @@ class MargBackend:
         capi.check(self.lib.isv_marg_backward(self.h, C.byref(bi), C.byref(bo)), "isv_marg_backward")
         return np.array(bo.rel), np.array(bo.vb), np.array(bo.rp), int(bo.rank), int(bo.status)
 
+    def marg_event(self, fwd_args, bwd_args):
+        """`MargForward(); MargBackward();` of one MARGIN_OLD event in one blocking call (isv_marg_event): fwd_args /
+        bwd_args are the argument tuples of marg_forward / marg_backward; returns their two result tuples."""
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in fwd_args[:8]]
+        rp = None if len(fwd_args) < 9 or fwd_args[8] is None else np.ascontiguousarray(fwd_args[8], dtype=np.float64)
+        fi = capi.isv_fwd_in(int(a[3].shape[0]), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), _dp(a[4]), _dp(a[5]),
+                             _dp(a[6]), _dp(a[7]), None if rp is None else _dp(rp))
+        b = [np.ascontiguousarray(x, dtype=np.float64) for x in bwd_args]
+        bi = capi.isv_bwd_in(*[_dp(x) for x in b])
+        fo, bo = capi.isv_fwd_out(), capi.isv_bwd_out()
+        capi.check(self.lib.isv_marg_event(self.h, C.byref(fi), C.byref(bi), C.byref(fo), C.byref(bo)), "isv_marg_event")
+        return ((np.array(fo.se3), np.array(fo.pg), int(fo.rank), int(fo.status)),
+                (np.array(bo.rel), np.array(bo.vb), np.array(bo.rp), int(bo.rank), int(bo.status)))
+
     # ---- initFactorGraph sparsification tail (one-time, src/estimator.cpp:745-1001) ---------------
     def init_sparsify(self, poses, sbs, preint):
         """poses [n,V,7], sbs [n,V,9], preint [n,V-1,467] (host) -> dict of recovered-factor records."""

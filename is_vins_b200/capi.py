@@ -166,6 +166,7 @@ SYMBOLS = [
     ("isv_marg_window_batch_host", C.c_int, [_H, C.POINTER(isv_batch_in), C.POINTER(isv_batch_out), C.c_int]),
     ("isv_marg_forward", C.c_int, [_H, C.POINTER(isv_fwd_in), C.POINTER(isv_fwd_out)]),
     ("isv_marg_backward", C.c_int, [_H, C.POINTER(isv_bwd_in), C.POINTER(isv_bwd_out)]),
+    ("isv_marg_event", C.c_int, [_H, C.POINTER(isv_fwd_in), C.POINTER(isv_bwd_in), C.POINTER(isv_fwd_out), C.POINTER(isv_bwd_out)]),
     ("isv_init_sparsify_batch", C.c_int, [_H, C.POINTER(isv_init_in), C.POINTER(isv_init_out)]),
     ("isv_init_sparsify_host", C.c_int, [_H, C.POINTER(isv_init_in), C.POINTER(isv_init_out)]),
     ("isv_preintegrate_batch", C.c_int, [_H, C.POINTER(isv_preint_in), C.c_void_p]),

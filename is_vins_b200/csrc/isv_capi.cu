@@ -585,6 +585,94 @@ isv_status isv_marg_backward(isv_handle* h, const isv_bwd_in* in, isv_bwd_out* o
   return ISV_OK;
 }
 
+isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in* bin, isv_fwd_out* fout, isv_bwd_out* bout) {
+  if (!h || !fin || !bin || !fout || !bout || fin->n_landmarks < 0) return ISV_ERR_BAD_ARG;
+  if (!fin->pose0 || !fin->pose1 || !fin->ex_pose || !fin->prior_se3 || !fin->prior_rel) return ISV_ERR_BAD_ARG;
+  if (!bin->pose_i || !bin->sb_i || !bin->pose_j || !bin->sb_j || !bin->prior_vb || !bin->preint) return ISV_ERR_BAD_ARG;
+  const size_t L = (size_t)fin->n_landmarks;
+  if (L > 0 && (!fin->inv_dep || !fin->pts_i || !fin->pts_j)) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  // in  = [lm_offset 2 (as int64)] [obs 6L] [pose_fwd 14] [ex 7] [se3 48] [rel 48] [rp 5] | [pose_bwd 14] [sb_bwd 18] [vb 90] [preint 467]
+  // out = [se3 48] [pg 89] [rel 48] [vb 90] [rp 13] [rank 2 x i32 = 1] [status i32 = 1]
+  const size_t n_f = 2 + 6 * L + 14 + 7 + ISV_SE3_REC + ISV_REL_REC + ISV_RP_IN_REC;
+  const size_t n_b = 14 + 18 + ISV_VB_REC + ISV_PREINT_REC;
+  const size_t n_in = n_f + n_b;
+  const size_t n_out = ISV_SE3_REC + ISV_PG_REC + ISV_REL_REC + ISV_VB_REC + ISV_RP_REC + 2;
+  isv_status st = ensure_pinned(h, (n_in + n_out) * sizeof(double));
+  if (st != ISV_OK) return st;
+  st = ensure_dbuf(h, (n_in + n_out + kScratchPerWindow + 64) * sizeof(double));
+  if (st != ISV_OK) return st;
+  double* hp = (double*)h->pinned;
+  int64_t* off = (int64_t*)hp;
+  off[0] = 0; off[1] = (int64_t)L;
+  double* obs = hp + 2;
+  for (size_t k = 0; k < L; ++k) {
+    obs[k] = fin->pts_i[3 * k];
+    obs[L + k] = fin->pts_i[3 * k + 1];
+    obs[2 * L + k] = fin->pts_i[3 * k + 2];
+    obs[3 * L + k] = fin->pts_j[3 * k];
+    obs[4 * L + k] = fin->pts_j[3 * k + 1];
+    obs[5 * L + k] = fin->inv_dep[k];
+  }
+  double* q = obs + 6 * L;
+  memcpy(q, fin->pose0, 56); memcpy(q + 7, fin->pose1, 56); memcpy(q + 14, fin->ex_pose, 56);
+  memcpy(q + 21, fin->prior_se3, ISV_SE3_REC * 8); memcpy(q + 21 + ISV_SE3_REC, fin->prior_rel, ISV_REL_REC * 8);
+  double* rp = q + 21 + ISV_SE3_REC + ISV_REL_REC;
+  if (fin->prior_rp) memcpy(rp, fin->prior_rp, ISV_RP_IN_REC * 8); else memset(rp, 0, ISV_RP_IN_REC * 8);
+  double* hb = hp + n_f;
+  memcpy(hb, bin->pose_i, 56); memcpy(hb + 7, bin->pose_j, 56);
+  memcpy(hb + 14, bin->sb_i, 72); memcpy(hb + 23, bin->sb_j, 72);
+  memcpy(hb + 32, bin->prior_vb, ISV_VB_REC * 8);
+  memcpy(hb + 32 + ISV_VB_REC, bin->preint, ISV_PREINT_REC * 8);
+  double* d = (double*)h->dbuf;
+  cudaStream_t s = h->stream;
+  ISV_CUDA(cudaMemcpyAsync(d, hp, n_in * sizeof(double), cudaMemcpyHostToDevice, s));
+  double* dq = d + 2 + 6 * L;
+  double* db = d + n_f;
+  double* dout = d + n_in;
+  isv_batch_in bi;
+  memset(&bi, 0, sizeof(bi));
+  bi.n_windows = 1;
+  bi.ex_pose_shared = 1;
+  bi.lm_offset = (const int64_t*)d;
+  bi.lm_obs = d + 2;
+  bi.lm_stride = (int64_t)L;
+  bi.pose_fwd = dq;
+  bi.ex_pose = dq + 14;
+  bi.prior_se3 = dq + 21;
+  bi.prior_rel = dq + 21 + ISV_SE3_REC;
+  bi.prior_rp = dq + 21 + ISV_SE3_REC + ISV_REL_REC;
+  bi.pose_bwd = db;
+  bi.sb_bwd = db + 14;
+  bi.prior_vb = db + 32;
+  bi.preint = db + 32 + ISV_VB_REC;
+  isv_batch_out bo;
+  memset(&bo, 0, sizeof(bo));
+  bo.se3_out = dout;
+  bo.pg_out = bo.se3_out + ISV_SE3_REC;
+  bo.rel_out = bo.pg_out + ISV_PG_REC;
+  bo.vb_out = bo.rel_out + ISV_REL_REC;
+  bo.rp_out = bo.vb_out + ISV_VB_REC;
+  bo.rank = (int32_t*)(bo.rp_out + ISV_RP_REC);
+  bo.status = (int32_t*)(bo.rp_out + ISV_RP_REC + 1);
+  ISV_CUDA(cudaMemsetAsync(bo.rank, 0, 8, s));
+  st = launch_batch(h, &bi, &bo, ISV_RUN_BOTH, s, dout + n_out);
+  if (st != ISV_OK) return st;
+  double* ho = hp + n_in;
+  ISV_CUDA(cudaMemcpyAsync(ho, dout, n_out * sizeof(double), cudaMemcpyDeviceToHost, s));
+  ISV_CUDA(cudaStreamSynchronize(s));
+  const double* o = ho;
+  memcpy(fout->se3, o, ISV_SE3_REC * 8); o += ISV_SE3_REC;
+  memcpy(fout->pg, o, ISV_PG_REC * 8); o += ISV_PG_REC;
+  memcpy(bout->rel, o, ISV_REL_REC * 8); o += ISV_REL_REC;
+  memcpy(bout->vb, o, ISV_VB_REC * 8); o += ISV_VB_REC;
+  memcpy(bout->rp, o, ISV_RP_REC * 8); o += ISV_RP_REC;
+  fout->rank = ((const int32_t*)o)[0];
+  bout->rank = ((const int32_t*)o)[1];
+  fout->status = bout->status = ((const int32_t*)(o + 1))[0];
+  return ISV_OK;
+}
+
 }  // extern "C"
 
 // ---- unit-test hook for the warp linear algebra (tests/test_linalg_gpu.py) ---------------------

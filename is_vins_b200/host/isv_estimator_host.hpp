@@ -193,60 +193,36 @@ class Estimator {
   }
 
   void MargForward() {                                                // :1149-1352
-    const int L = (int)MargPointIdx.size();
-    std::vector<double> inv_dep(L), pts_i(3 * (size_t)L), pts_j(3 * (size_t)L);
-    for (int k = 0; k < L; ++k) {      // order == MargPointIdx == OrderMap (:1159-1162)
-      inv_dep[k] = para_Feature[MargPointIdx[k]][0];
-      std::memcpy(&pts_i[3 * (size_t)k], forwardProjectiontoSparsify[k]->pts_i, 24);
-      std::memcpy(&pts_j[3 * (size_t)k], forwardProjectiontoSparsify[k]->pts_j, 24);
-    }
-    double pse3[ISV_SE3_REC], prel[ISV_REL_REC], prp[ISV_RP_IN_REC] = {0};
-    pack48(vioPosePriorEdge->t, vioPosePriorEdge->R, vioPosePriorEdge->sqrt_info, pse3);
-    const RelativePoseFactor* r1 = vioRelativePoseEdges[1];
-    pack48(r1->delta_t, r1->delta_R, r1->sqrt_info, prel);
-    const bool rp_valid = !vioRollPitchEdges.empty() && vioRollPitchEdges[0]->index == 0;   // :1265-1271
-    if (rp_valid) { prp[0] = 1.0; std::memcpy(prp + 1, vioRollPitchEdges[0]->sqrt_info, 32); }
-    isv_fwd_in in{L, para_Pose[0], para_Pose[1], para_Ex_Pose[0], inv_dep.data(), pts_i.data(), pts_j.data(), pse3, prel, prp};
+    FwdPack p;
+    packForward(p);
     isv_fwd_out out;
-    check(isv_marg_forward(h_, &in, &out), "isv_marg_forward");
-    last_fwd_rank = out.rank;
-    last_status = out.status;
-    auto* se3 = new SE3PriorFactor();                                  // forwardPosePriorEdgeToAdd (:1291-1351)
-    unpack48(out.se3, se3->t, se3->R, se3->sqrt_info);
-    forwardPosePriorEdgeToAdd = se3;
-    auto* pg = new RelativePoseFactor();                               // CombinedFactors (:1243-1283)
-    unpack48(out.pg, pg->delta_t, pg->delta_R, pg->sqrt_info);
-    auto* cmb = new CombinedFactors();
-    cmb->relativePoseFactor = pg;
-    cmb->rollPitchFactor = rp_valid ? vioRollPitchEdges[0] : nullptr;
-    if (rp_valid) std::memcpy(cmb->covAbs, out.pg + 85, 32);
-    std::memcpy(cmb->covRel, out.pg + 48, 288);
-    cmb->distance = out.pg[84];
-    cmb->vio_index = PoseGraphFactorCount++;
-    cmb->ts = Headers[0];
-    std::memcpy(cmb->Ri, Rs[0], 72); std::memcpy(cmb->ti, Ps[0], 24);
-    pose_graph_factors_buf.push(cmb);
+    check(isv_marg_forward(h_, &p.in, &out), "isv_marg_forward");
+    last_status = 0;
+    unpackForward(out, p.rp_valid);
   }
 
   void MargBackward() {                                               // :1354-1539
-    double pvb[ISV_VB_REC];
-    std::memcpy(pvb, vioVBPrior->VB, 72); std::memcpy(pvb + 9, vioVBPrior->sqrt_info, 648);
-    const double* pre = preintegrated(backwardIMUtoSparsify->pre_integration);
-    isv_bwd_in in{para_Pose[Vo_SIZE - 1], para_SpeedBias[Vo_SIZE - 1], para_Pose[Vo_SIZE], para_SpeedBias[Vo_SIZE], pvb, pre};
+    BwdPack p;
+    packBackward(p);
     isv_bwd_out out;
-    check(isv_marg_backward(h_, &in, &out), "isv_marg_backward");
-    last_bwd_rank = out.rank;
-    last_status |= out.status;
-    auto* rel = new RelativePoseFactor();
-    unpack48(out.rel, rel->delta_t, rel->delta_R, rel->sqrt_info);
-    auto* vbp = new Linear9Factor();
-    std::memcpy(vbp->VB, out.vb, 72); std::memcpy(vbp->sqrt_info, out.vb + 9, 648);
-    auto* rp = new RollPitchFactor();
-    std::memcpy(rp->R, out.rp, 72); std::memcpy(rp->sqrt_info, out.rp + 9, 32);
-    rp->setIndex(Vo_SIZE - 1);                                         // :1516
-    vioRollPitchEdges.push_back(rp);                                   // :1536-1538
-    backwardVBEdgeToAdd = vbp;
-    backwardRelativePoseEdgeToAdd = rel;
+    check(isv_marg_backward(h_, &p.in, &out), "isv_marg_backward");
+    unpackBackward(out);
+  }
+
+  // `MargForward(); MargBackward();` of one MARGIN_OLD event (:1555-1558) in ONE blocking C-ABI call: the two read
+  // disjoint members and neither reads the other's outputs, so their kernel chains run forked on two streams behind a
+  // single host-to-device / device-to-host round trip.  Same members written, bit-identical values.
+  void MargForwardBackward() {
+    FwdPack pf;
+    BwdPack pb;
+    packForward(pf);
+    packBackward(pb);
+    isv_fwd_out fo;
+    isv_bwd_out bo;
+    check(isv_marg_event(h_, &pf.in, &pb.in, &fo, &bo), "isv_marg_event");
+    last_status = 0;
+    unpackForward(fo, pf.rp_valid);
+    unpackBackward(bo);
   }
 
   // the factor rotation inside slideWindow() (:1605-1638); ownership exactly as the reference
@@ -274,6 +250,71 @@ class Estimator {
   isv_handle* handle() { return h_; }
 
  private:
+  struct FwdPack {
+    std::vector<double> inv_dep, pts_i, pts_j;
+    double pse3[ISV_SE3_REC], prel[ISV_REL_REC], prp[ISV_RP_IN_REC];
+    bool rp_valid;
+    isv_fwd_in in;
+  };
+  struct BwdPack {
+    double pvb[ISV_VB_REC];
+    isv_bwd_in in;
+  };
+  void packForward(FwdPack& p) {
+    const int L = (int)MargPointIdx.size();
+    p.inv_dep.resize(L); p.pts_i.resize(3 * (size_t)L); p.pts_j.resize(3 * (size_t)L);
+    for (int k = 0; k < L; ++k) {      // order == MargPointIdx == OrderMap (:1159-1162)
+      p.inv_dep[k] = para_Feature[MargPointIdx[k]][0];
+      std::memcpy(&p.pts_i[3 * (size_t)k], forwardProjectiontoSparsify[k]->pts_i, 24);
+      std::memcpy(&p.pts_j[3 * (size_t)k], forwardProjectiontoSparsify[k]->pts_j, 24);
+    }
+    std::memset(p.prp, 0, sizeof(p.prp));
+    pack48(vioPosePriorEdge->t, vioPosePriorEdge->R, vioPosePriorEdge->sqrt_info, p.pse3);
+    const RelativePoseFactor* r1 = vioRelativePoseEdges[1];
+    pack48(r1->delta_t, r1->delta_R, r1->sqrt_info, p.prel);
+    p.rp_valid = !vioRollPitchEdges.empty() && vioRollPitchEdges[0]->index == 0;   // :1265-1271
+    if (p.rp_valid) { p.prp[0] = 1.0; std::memcpy(p.prp + 1, vioRollPitchEdges[0]->sqrt_info, 32); }
+    p.in = isv_fwd_in{L, para_Pose[0], para_Pose[1], para_Ex_Pose[0], p.inv_dep.data(), p.pts_i.data(), p.pts_j.data(),
+                      p.pse3, p.prel, p.prp};
+  }
+  void unpackForward(const isv_fwd_out& out, bool rp_valid) {
+    last_fwd_rank = out.rank;
+    last_status |= out.status;
+    auto* se3 = new SE3PriorFactor();                                  // forwardPosePriorEdgeToAdd (:1291-1351)
+    unpack48(out.se3, se3->t, se3->R, se3->sqrt_info);
+    forwardPosePriorEdgeToAdd = se3;
+    auto* pg = new RelativePoseFactor();                               // CombinedFactors (:1243-1283)
+    unpack48(out.pg, pg->delta_t, pg->delta_R, pg->sqrt_info);
+    auto* cmb = new CombinedFactors();
+    cmb->relativePoseFactor = pg;
+    cmb->rollPitchFactor = rp_valid ? vioRollPitchEdges[0] : nullptr;
+    if (rp_valid) std::memcpy(cmb->covAbs, out.pg + 85, 32);
+    std::memcpy(cmb->covRel, out.pg + 48, 288);
+    cmb->distance = out.pg[84];
+    cmb->vio_index = PoseGraphFactorCount++;
+    cmb->ts = Headers[0];
+    std::memcpy(cmb->Ri, Rs[0], 72); std::memcpy(cmb->ti, Ps[0], 24);
+    pose_graph_factors_buf.push(cmb);
+  }
+  void packBackward(BwdPack& p) {
+    std::memcpy(p.pvb, vioVBPrior->VB, 72); std::memcpy(p.pvb + 9, vioVBPrior->sqrt_info, 648);
+    const double* pre = preintegrated(backwardIMUtoSparsify->pre_integration);
+    p.in = isv_bwd_in{para_Pose[Vo_SIZE - 1], para_SpeedBias[Vo_SIZE - 1], para_Pose[Vo_SIZE], para_SpeedBias[Vo_SIZE], p.pvb, pre};
+  }
+  void unpackBackward(const isv_bwd_out& out) {
+    last_bwd_rank = out.rank;
+    last_status |= out.status;
+    auto* rel = new RelativePoseFactor();
+    unpack48(out.rel, rel->delta_t, rel->delta_R, rel->sqrt_info);
+    auto* vbp = new Linear9Factor();
+    std::memcpy(vbp->VB, out.vb, 72); std::memcpy(vbp->sqrt_info, out.vb + 9, 648);
+    auto* rp = new RollPitchFactor();
+    std::memcpy(rp->R, out.rp, 72); std::memcpy(rp->sqrt_info, out.rp + 9, 32);
+    rp->setIndex(Vo_SIZE - 1);                                         // :1516
+    vioRollPitchEdges.push_back(rp);                                   // :1536-1538
+    backwardVBEdgeToAdd = vbp;
+    backwardRelativePoseEdgeToAdd = rel;
+  }
   static void pack48(const double* t, const double* R, const double* s, double* rec) {
     std::memcpy(rec, t, 24); std::memcpy(rec + 3, R, 72); std::memcpy(rec + 12, s, 288);
   }

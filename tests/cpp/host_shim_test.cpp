@@ -112,8 +112,12 @@ int main(int argc, char** argv) {
     imu.setIndex(V - 1, V);
     est.backwardIMUtoSparsify = &imu;
 
-    est.MargForward();
-    est.MargBackward();
+    if (r & 1) {
+      est.MargForwardBackward();   // the fused single-event entry point (isv_marg_event): bit-identical results
+    } else {
+      est.MargForward();
+      est.MargBackward();
+    }
 
     expect_int("fwd rank", r, est.last_fwd_rank);
     expect_int("bwd rank", r, est.last_bwd_rank);

@@ -53,6 +53,13 @@ def test_host_batch_and_single_window(backend):
                                                       batch.preint[1])
     assert status == 0 and rank == ev.bwd_out.rank
     assert np.array_equal(rel, out.rel[1]) and np.array_equal(vb, out.vb[1]) and np.array_equal(rp, out.rp[1])
+    # the whole MARGIN_OLD event in one call: bit-identical to the two separate calls
+    (se3e, pge, rke, ste), (rele, vbe, rpe, rkb, stb) = backend.marg_event(
+        (f.pose0, f.pose1, f.ex_pose, f.inv_dep, f.pts_i, f.pts_j, batch.prior_se3[1], batch.prior_rel[1], batch.prior_rp[1]),
+        (b.pose_i, b.sb_i, b.pose_j, b.sb_j, batch.prior_vb[1], batch.preint[1]))
+    assert ste == 0 and stb == 0 and rke == 6 and rkb == ev.bwd_out.rank
+    assert np.array_equal(se3e, se3) and np.array_equal(pge, pg)
+    assert np.array_equal(rele, rel) and np.array_equal(vbe, vb) and np.array_equal(rpe, rp)
 
 
 import os
