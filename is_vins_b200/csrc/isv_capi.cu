@@ -1426,6 +1426,8 @@ extern "C" isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
   const size_t pos = (size_t)in->pos;
+  // layout: [ every host input, one contiguous upload ] [ device-only ] [ every result, one contiguous download ]
+  const size_t pn = prior ? (size_t)prior->n : 0, pnb = prior ? (size_t)prior->n_blocks : 0;
   const size_t o_pose = carve(pb.n_pose * 7 * D), o_sb = carve(pb.n_speed_bias * 9 * D), o_ex = carve(pb.n_ex_pose * 7 * D),
                o_ft = carve(pb.n_feature * D), o_pidx = carve(4 * P * 4), o_pobs = carve(5 * P * D), o_iidx = carve(2 * NI * 4),
                o_ipre = carve(NI * ISV_PREINT_REC * D), o_ridx = carve(2 * (size_t)sf.n_rel * 4),
@@ -1433,21 +1435,30 @@ extern "C" isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in
                o_srec = carve((size_t)sf.n_se3 * ISV_SE3_REC * D), o_vidx = carve((size_t)sf.n_vb * 4),
                o_vrec = carve((size_t)sf.n_vb * ISV_VB_REC * D), o_qidx = carve((size_t)sf.n_rp * 4),
                o_qrec = carve((size_t)sf.n_rp * ISV_RP_REC * D), o_yidx = carve((size_t)sf.n_yaw * 4),
-               o_yrec = carve((size_t)sf.n_yaw * ISV_YAW_REC * D), o_val = carve(voff * D),
+               o_yrec = carve((size_t)sf.n_yaw * ISV_YAW_REC * D),
                o_fac = carve(facs.size() * sizeof(isv_ne_factor)), o_blk = carve(blks.size() * sizeof(isv_ne_block)),
-               o_A = carve(pos * pos * D), o_b = carve(pos * D), o_Ar = carve((size_t)n * n * D), o_br = carve(n * D),
-               o_J = carve((size_t)n * n * D), o_r = carve(n * D), o_rank = carve(8), o_st = carve(8),
                o_tdo = carve(with_td ? 8 * P * D : 0), o_td = carve(with_td ? (size_t)pf.n_td * D : 0),
-               o_tdi = carve(with_td && pf.td_idx ? P * 4 : 0);
-  const size_t pn = prior ? (size_t)prior->n : 0, pnb = prior ? (size_t)prior->n_blocks : 0;
-  const size_t o_pblk = carve(pnb * sizeof(isv_prior_block)), o_pJ = carve(pn * pn * D), o_pr0 = carve(pn * D),
-               o_px0 = carve(prior_x * D), o_px = carve(prior_x * D), o_pres = carve(pn * D);
+               o_tdi = carve(with_td && pf.td_idx ? P * 4 : 0),
+               o_pblk = carve(pnb * sizeof(isv_prior_block)), o_pJ = carve(pn * pn * D), o_pr0 = carve(pn * D),
+               o_px0 = carve(prior_x * D), o_px = carve(prior_x * D);
+  const size_t in_bytes = off;
+  const size_t o_val = carve(voff * D), o_A = carve(pos * pos * D), o_b = carve(pos * D), o_pres = carve(pn * D);
+  const size_t out_begin = off;
+  const size_t o_Ar = carve((size_t)n * n * D), o_br = carve(n * D), o_J = carve((size_t)n * n * D), o_r = carve(n * D),
+               o_rank = carve(8), o_st = carve(8);
+  const size_t out_bytes = off - out_begin;
   isv_status st = ensure_dbuf(h, off);
   if (st != ISV_OK) return st;
+  st = ensure_pinned(h, in_bytes + out_bytes);
+  if (st != ISV_OK) return st;
   char* d = h->dbuf;
+  char* hp = h->pinned;
   cudaStream_t s = h->stream;
+  // the ~25 small arrays are packed into the pinned block and go up in ONE copy (each pageable cudaMemcpyAsync costs
+  // ~10 us of staging: a quarter of the call at VINS problem sizes)
   auto up = [&](size_t o, const void* src, size_t bytes) {
-    return bytes == 0 ? cudaSuccess : cudaMemcpyAsync(d + o, src, bytes, cudaMemcpyHostToDevice, s);
+    if (bytes) memcpy(hp + o, src, bytes);
+    return cudaSuccess;
   };
   ISV_CUDA(up(o_pose, pb.pose, pb.n_pose * 7 * D));
   ISV_CUDA(up(o_sb, pb.speed_bias, pb.n_speed_bias * 9 * D));
@@ -1481,6 +1492,7 @@ extern "C" isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in
   }
   ISV_CUDA(up(o_fac, facs.data(), facs.size() * sizeof(isv_ne_factor)));
   ISV_CUDA(up(o_blk, blks.data(), blks.size() * sizeof(isv_ne_block)));
+  ISV_CUDA(cudaMemcpyAsync(d, hp, in_bytes, cudaMemcpyHostToDevice, s));
   ISV_CUDA(cudaMemsetAsync(d + o_st, 0, 8, s));
   // ---- preMarginalize: Evaluate every residual block -------------------------------------------------------
   double* V = (double*)(d + o_val);
@@ -1541,16 +1553,18 @@ extern "C" isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in
     if (st == ISV_OK) st = schur_eig_impl(h, &gi, &go, in->schur_only ? 1 : 0);
   }
   if (st != ISV_OK) return st;
-  int32_t hst[2] = {0, 0}, hrank = 0;
-  ISV_CUDA(cudaMemcpyAsync(out->A_red, d + o_Ar, (size_t)n * n * D, cudaMemcpyDeviceToHost, s));
-  ISV_CUDA(cudaMemcpyAsync(out->b_red, d + o_br, n * D, cudaMemcpyDeviceToHost, s));
-  if (!in->schur_only) {
-    ISV_CUDA(cudaMemcpyAsync(out->linearized_jacobians, d + o_J, (size_t)n * n * D, cudaMemcpyDeviceToHost, s));
-    ISV_CUDA(cudaMemcpyAsync(out->linearized_residuals, d + o_r, n * D, cudaMemcpyDeviceToHost, s));
-  }
-  ISV_CUDA(cudaMemcpyAsync(hst, d + o_st, 8, cudaMemcpyDeviceToHost, s));
-  ISV_CUDA(cudaMemcpyAsync(&hrank, d + o_rank, 4, cudaMemcpyDeviceToHost, s));
+  char* ho = hp + in_bytes;   // results come down in one copy into the pinned block
+  ISV_CUDA(cudaMemcpyAsync(ho, d + out_begin, out_bytes, cudaMemcpyDeviceToHost, s));
   ISV_CUDA(cudaStreamSynchronize(s));
+  memcpy(out->A_red, ho + (o_Ar - out_begin), (size_t)n * n * D);
+  memcpy(out->b_red, ho + (o_br - out_begin), n * D);
+  if (!in->schur_only) {
+    memcpy(out->linearized_jacobians, ho + (o_J - out_begin), (size_t)n * n * D);
+    memcpy(out->linearized_residuals, ho + (o_r - out_begin), n * D);
+  }
+  int32_t hst[2], hrank;
+  memcpy(hst, ho + (o_st - out_begin), 8);
+  memcpy(&hrank, ho + (o_rank - out_begin), 4);
   out->status = hst[0] | hst[1];
   out->rank = hrank;
   return ISV_OK;

@@ -5,6 +5,7 @@
 // kept 1-d block (BASELINE configs[3]).  The driver only drives the API and dumps what it got; the numbers are
 // checked by tests/test_host_cpp_gpu.py against the oracle's restatement evaluated in the SAME block order.
 //   usage: marginalization_chain_test <fixture.bin> <dump.bin>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -154,6 +155,17 @@ int main(int argc, char** argv) {
   addr_shift2[reinterpret_cast<long>(para_Td[0])] = para_Td[0];
   std::vector<double*> keep2 = marginalization_info->getParameterBlocks(addr_shift2);
   dump_round(marginalization_info, est, N, F, keep2);
+
+  // host latency of one warm marginalize() (pack + H2D + Evaluate + normal equations + Schur + eigen + D2H, blocking)
+  double best_us = 1e30;
+  for (int it = 0; it < 6; ++it) {
+    const auto t0 = std::chrono::steady_clock::now();
+    marginalization_info->marginalize();
+    const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    if (it > 0 && us < best_us) best_us = us;
+  }
+  printf("marginalization_chain_test: warm marginalize() of round 2 (m=%d n=%d): %.0f us\n", marginalization_info->m,
+         marginalization_info->n, best_us);
 
   FILE* o = fopen(argv[2], "wb");
   if (!o || fwrite(g_dump.data(), 8, g_dump.size(), o) != g_dump.size()) { perror("dump"); return 2; }

@@ -88,3 +88,24 @@ def test_sym_eig_matches_eigh(backend, n, nb):
         assert np.abs(lam[b] - w_ref).max() <= 1e-13 * n * nrm
         assert np.abs(Vb.T @ Vb - np.eye(n)).max() <= 1e-13 * n
         assert np.linalg.norm((Vb * lam[b]) @ Vb.T - A[b]) <= 1e-13 * n * np.linalg.norm(A[b])
+
+
+def test_sym_eig_flags_non_finite_input_and_terminates(backend):
+    """A NaN in the reduced system must not hang the serial QL (bounded sweeps, bounded rotation log) and must be
+    reported: info[.,0] != 0 -> ISV_W_EIG_NOCONV in the marginalization status."""
+    n, nb = 24, 3
+    rng = np.random.default_rng(5)
+    A = np.zeros((nb, n, n))
+    for b in range(nb):
+        M = rng.normal(size=(n, n))
+        A[b] = M @ M.T
+    A[1][3, 7] = A[1][7, 3] = np.nan
+    Af = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))
+    lam, V = np.zeros((nb, n)), np.zeros((nb, n, n))
+    info = np.zeros((nb, 2), np.int32)
+    p = lambda a: a.ctypes.data_as(capi.c_double_p)
+    capi.check(backend.lib.isv_test_sym_eig(backend.h, nb, n, p(Af), p(lam), p(V), info.ctypes.data_as(capi.c_int32_p)))
+    assert info[1, 0] != 0 and info[0, 0] == 0 and info[2, 0] == 0
+    assert info[1, 1] <= 3 * n * n + 64
+    for b in (0, 2):                                       # the neighbours of the bad problem are untouched
+        assert np.abs(lam[b] - np.linalg.eigvalsh(A[b])).max() <= 1e-12 * np.abs(lam[b]).max()
