@@ -385,43 +385,61 @@ ql_apply_kernel(int n, int rows, double* __restrict__ Zbuf, const char* __restri
   const bool live = tid < nr;
   double* mine = slab + (size_t)tid * ld;
   const int nsweep = sc.meta[2];
-  auto stage = [&](int sw, int buf) {     // asynchronous copy of sweep sw's rotations into ccs[buf]
-    if (sw < nsweep) {
-      const int4 h = sc.sweep[sw];
-      for (int t = tid; t < h.z; t += nt) cp_async16(&ccs[buf][t], sc.cs + h.x + t);
-    }
+  // sweep headers travel two iterations ahead in registers: neither the staging nor the compute waits on a global load
+  const int4 none = make_int4(0, 0, 0, 0);
+  int4 h_cur = nsweep > 0 ? sc.sweep[0] : none, h_nxt = nsweep > 1 ? sc.sweep[1] : none;
+  auto stage = [&](const int4& h, int buf) {     // asynchronous copy of one sweep's rotations into ccs[buf]
+    for (int t = tid; t < h.z; t += nt) cp_async16(&ccs[buf][t], sc.cs + h.x + t);
     asm volatile("cp.async.commit_group;\n" ::);
   };
-  stage(0, 0);
-  for (int idx = tid; idx < nr * n; idx += nt) {           // slab in (rows of Q from q_rows_kernel)
-    const int r = idx % nr, c = idx / nr;
-    slab[(size_t)r * ld + c] = Z[(size_t)(row0 + r) + (size_t)n * c];
+  stage(h_cur, 0);
+  if (tid < nr) {                                          // slab in (rows of Q from q_rows_kernel), thread = row
+    const double* src = Z + (size_t)(row0 + tid);
+    double* dst = slab + (size_t)tid * ld;
+#pragma unroll 8
+    for (int c = 0; c < n; ++c) dst[c] = src[(size_t)n * c];
   }
   // rotation t of a sweep acts on the column pair (m-1-t, m-t)
   for (int sw = 0; sw < nsweep; ++sw) {
-    const int4 hdr = sc.sweep[sw];
-    const int m = hdr.y, cnt = hdr.z;
+    const int m = h_cur.y, cnt = h_cur.z;
     const double2* rc = ccs[sw & 1];
     asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();                      // sweep sw staged and visible; everyone is done with buffer (sw + 1) & 1
-    stage(sw + 1, (sw + 1) & 1);
+    const int4 h_nn = sw + 2 < nsweep ? sc.sweep[sw + 2] : none;
+    stage(h_nxt, (sw + 1) & 1);
     if (live && cnt > 0) {
       // running column in a register (one DFMA on the dependent chain per rotation); the row entries of the next four
       // rotations are loaded before the current four are computed, so the shared-memory latency stays off the chain
       double carry = mine[m];
       int i = m - 1, t = 0;
-      double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
-      if (cnt >= 4) { z0 = mine[i]; z1 = mine[i - 1]; z2 = mine[i - 2]; z3 = mine[i - 3]; }
-      for (; t + 4 <= cnt; t += 4, i -= 4) {
-        const double2 r0 = rc[t], r1 = rc[t + 1], r2 = rc[t + 2], r3 = rc[t + 3];
-        double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
-        if (t + 8 <= cnt) { y0 = mine[i - 4]; y1 = mine[i - 5]; y2 = mine[i - 6]; y3 = mine[i - 7]; }
-        const double o0 = fma(r0.x, carry, r0.y * z0); carry = fma(-r0.y, carry, r0.x * z0);
-        const double o1 = fma(r1.x, carry, r1.y * z1); carry = fma(-r1.y, carry, r1.x * z1);
-        const double o2 = fma(r2.x, carry, r2.y * z2); carry = fma(-r2.y, carry, r2.x * z2);
-        const double o3 = fma(r3.x, carry, r3.y * z3); carry = fma(-r3.y, carry, r3.x * z3);
-        mine[i + 1] = o0; mine[i] = o1; mine[i - 1] = o2; mine[i - 2] = o3;
-        z0 = y0; z1 = y1; z2 = y2; z3 = y3;
+      constexpr int U = 8;                 // rotations per software-pipelined group
+      // group g + 1's operands -- row entries AND (c, s) pairs -- are loaded while group g is computed, so no
+      // shared-memory latency sits between two groups; out-of-range prefetches are clamped to valid addresses
+      double z[U], y[U];
+      double2 r[U], rn[U];
+      const int ngroups = cnt / U;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        z[u] = mine[max(i - u, 0)];
+        r[u] = rc[min(u, kSeMaxN - 1)];
+      }
+      for (int g = 0; g < ngroups; ++g, t += U, i -= U) {
+        const int tn = (g + 1 < ngroups) ? t + U : t;          // last group: harmless re-load of its own operands
+        const int in = (g + 1 < ngroups) ? i - U : i;
+#pragma unroll
+        for (int u = 0; u < U; ++u) { y[u] = mine[in - u]; rn[u] = rc[tn + u]; }
+        double a[U], b[U], o[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { a[u] = r[u].x * z[u]; b[u] = r[u].y * z[u]; }   // off the chain
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          o[u] = fma(r[u].x, carry, b[u]);
+          carry = fma(-r[u].y, carry, a[u]);      // the dependent chain: one DFMA per rotation
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) mine[i + 1 - u] = o[u];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { z[u] = y[u]; r[u] = rn[u]; }
       }
       for (; t < cnt; ++t, --i) {
         const double2 r = rc[t];
@@ -431,6 +449,8 @@ ql_apply_kernel(int n, int rows, double* __restrict__ Zbuf, const char* __restri
       }
       mine[i + 1] = carry;
     }
+    h_cur = h_nxt;
+    h_nxt = h_nn;
   }
   asm volatile("cp.async.wait_group 0;\n" ::);
   __syncthreads();
