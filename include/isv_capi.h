@@ -554,6 +554,14 @@ typedef struct isv_marg_host_out {
 } isv_marg_host_out;
 isv_status isv_marginalize_host(isv_handle* h, const isv_marg_host_in* in, isv_marg_host_out* out);
 
+/* ---- PoseLocalParameterization  src/factor/pose_local_parameterization.cpp:3-27 ------------------------------
+ * Plus: x_plus_delta = [p + dp ; normalize(q * deltaQ(dtheta))] for n pose blocks (x [n][7], delta [n][6],
+ * x_plus_delta [n][7]; DEVICE pointers; in place allowed) -- what ceres applies to para_Pose / para_Ex_Pose after a
+ * step, batched over every pose block of every window.  ComputeJacobian is the constant [I6 ; 0] (7 x 6 row-major):
+ * written to `jacobian` [42] (HOST pointer).                                                                    */
+isv_status isv_pose_plus_batch(isv_handle* h, int64_t n, const double* x, const double* delta, double* x_plus_delta);
+void isv_pose_plus_jacobian(double* jacobian);
+
 /* ---- unit-test hook: the PSD eigensolver that replaces SelfAdjointEigenSolver on this path -----
  * (src/estimator.cpp:920,1311,1479).  nb symmetric n x n matrices A (column-major, host) ->
  * G [nb][n][n] row-major factor rows with  A ~= sum_k g_k g_k^T, g_k mutually orthogonal;

@@ -195,6 +195,8 @@ SYMBOLS = [
     ("isv_eval_marg_prior", C.c_int, [_H, C.POINTER(isv_marg_prior), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("isv_add_marg_prior", C.c_int, [_H, C.POINTER(isv_marg_prior), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     ("isv_schur_eig", C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32]),
+    ("isv_pose_plus_batch", C.c_int, [_H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("isv_pose_plus_jacobian", None, [c_double_p]),
     ("isv_test_psd_eig", C.c_int, [_H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int32_p]),
     ("isv_test_sym_eig", C.c_int, [_H, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, c_int32_p]),
 ]

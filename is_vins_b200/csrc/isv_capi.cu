@@ -673,6 +673,24 @@ isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in
   return ISV_OK;
 }
 
+isv_status isv_pose_plus_batch(isv_handle* h, int64_t n, const double* x, const double* delta, double* x_plus_delta) {
+  if (!h || n < 0 || (n > 0 && (!x || !delta || !x_plus_delta))) return ISV_ERR_BAD_ARG;
+  if (n == 0) return ISV_OK;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const long long grid = (n + 127) / 128;
+  if (grid > 0x7fffffffLL) return ISV_ERR_BAD_ARG;
+  pose_plus_kernel<<<(unsigned)grid, 128, 0, h->stream>>>((long long)n, x, delta, x_plus_delta);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+void isv_pose_plus_jacobian(double* jacobian) {
+  if (!jacobian) return;
+  for (int i = 0; i < 42; ++i) jacobian[i] = 0.0;
+  for (int i = 0; i < 6; ++i) jacobian[6 * i + i] = 1.0;   // 7 x 6 row-major: top 6 rows identity, last row zero
+}
+
 }  // extern "C"
 
 // ---- unit-test hook for the warp linear algebra (tests/test_linalg_gpu.py) ---------------------

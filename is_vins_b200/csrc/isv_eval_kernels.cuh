@@ -401,4 +401,21 @@ eval_small_kernel(isv_param_blocks pb, isv_small_factors fs, isv_small_eval out,
   }
 }
 
+// PoseLocalParameterization::Plus  src/factor/pose_local_parameterization.cpp:3-19 -- the manifold update ceres applies
+// to every pose block after a step (and the convention every Jacobian above assumes: right-multiplicative
+// q * deltaQ(dtheta), deltaQ = (1, dtheta / 2) NOT normalised, utility.h:11-24, then normalised).  Thread per block.
+__global__ void __launch_bounds__(128)
+pose_plus_kernel(long long n, const double* __restrict__ x, const double* __restrict__ delta, double* __restrict__ out) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double* xs = x + 7 * k;
+  const double* dl = delta + 6 * k;
+  double* o = out + 7 * k;
+  const Quat q = quat_from_pose(xs);
+  const Quat dq = Quat{1.0, dl[3] / 2.0, dl[4] / 2.0, dl[5] / 2.0};
+  const Quat r = qnormalized(qmul(q, dq));
+  o[0] = xs[0] + dl[0]; o[1] = xs[1] + dl[1]; o[2] = xs[2] + dl[2];
+  o[3] = r.x; o[4] = r.y; o[5] = r.z; o[6] = r.w;
+}
+
 }  // namespace isv

@@ -94,3 +94,12 @@ def test_product_does_not_import_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in src.replace("oracle/ (test", "").replace("`oracle/`", ""), fn
+
+
+def test_pose_local_parameterization_jacobian_is_identity_over_zero():
+    """PoseLocalParameterization::ComputeJacobian (src/factor/pose_local_parameterization.cpp:20-27): [I6 ; 0], 7 x 6
+    row-major -- host-side constant, the same bytes as the oracle's."""
+    lib = capi.load()
+    j = np.full(42, np.nan)
+    lib.isv_pose_plus_jacobian(j.ctypes.data_as(capi.c_double_p))
+    assert np.array_equal(j.reshape(7, 6), O.pose_compute_jacobian())

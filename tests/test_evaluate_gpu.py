@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from is_vins_b200 import DeviceProblem, FactorProblem, capi, eval_problem
+from oracle import isv_oracle as O
 from oracle import sim
 from tests.helpers import rel_err
 
@@ -145,3 +146,34 @@ def test_committed_problem_fixtures(backend, name):
     # the IMU factor carries no loss function (problemSolve passes NULL): cauchy_a must not touch it
     assert rel_err(h["imu_res"], z["ref_imu_res"]) <= TOL
     assert rel_err(h["imu_jac"], z["ref_imu_jac"]) <= TOL
+
+
+def test_pose_local_parameterization_plus_matches_oracle(backend):
+    """PoseLocalParameterization::Plus (src/factor/pose_local_parameterization.cpp:3-19), batched: p + dp,
+    normalize(q * deltaQ(dtheta)) with the unnormalised small-angle deltaQ of utility.h:11-24 -- including large steps
+    (where deltaQ is far from a rotation) and in-place operation.  Tolerance 1e-15 (one normalisation)."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(11)
+    n = 1000
+    x = np.zeros((n, 7))
+    x[:, 0:3] = rng.normal(0, 3.0, (n, 3))
+    q = rng.normal(size=(n, 4))
+    x[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    delta = rng.normal(0, 0.01, (n, 6))
+    delta[::7] *= 100.0                                     # large steps
+    delta[1] = 0.0                                          # zero step: x unchanged (up to the normalisation)
+    ref = np.array([O.pose_plus(x[k], delta[k]) for k in range(n)])
+    dx, dd = torch.from_numpy(x).cuda(), torch.from_numpy(delta).cuda()
+    out = torch.empty_like(dx)
+    capi.check(backend.lib.isv_pose_plus_batch(backend.h, n, C.c_void_p(dx.data_ptr()), C.c_void_p(dd.data_ptr()),
+                                               C.c_void_p(out.data_ptr())), "isv_pose_plus_batch")
+    backend.synchronize()
+    got = out.cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-15 * max(1.0, np.abs(ref).max())
+    assert np.abs(np.linalg.norm(got[:, 3:7], axis=1) - 1.0).max() <= 4e-16
+    assert np.abs(got[1] - x[1]).max() <= 2e-16
+    capi.check(backend.lib.isv_pose_plus_batch(backend.h, n, C.c_void_p(dx.data_ptr()), C.c_void_p(dd.data_ptr()),
+                                               C.c_void_p(dx.data_ptr())), "isv_pose_plus_batch")   # in place
+    backend.synchronize()
+    assert np.array_equal(dx.cpu().numpy(), got)
