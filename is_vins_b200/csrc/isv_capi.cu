@@ -1338,7 +1338,7 @@ static isv_status schur_eig_impl(isv_handle* h, const isv_marg_generic_in* in, c
     }
     h->gram_bytes = need + 256;
   }
-  const size_t sm = (2 * kMgMaxDense * kMgMaxDense + 6 * 16 + 32) * sizeof(double);
+  const size_t sm = (4 * kMgMaxDense * kMgMaxDense + 6 * 16 + 32) * sizeof(double);
   ISV_CUDA(cudaFuncSetAttribute(marg_schur_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   if (in->m_diag > 0) {
     const int nt = (in->pos - in->m_diag + kSdTile - 1) / kSdTile;

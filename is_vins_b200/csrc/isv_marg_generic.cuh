@@ -242,7 +242,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;
 }
 
-// smem (doubles): P[32*32] V[32*32] cs[6*16] red[32] + ints
+// smem (doubles): P[32*32] V[32*32] cs[6*16] (32 spare) wk[2*32*32]
 __global__ void __launch_bounds__(kMgThreads)
 marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* __restrict__ Gbuf, int schur_only,
                       int phase_a_done) {   // Gbuf: n x md scratch per problem (stride n * n)
@@ -250,6 +250,7 @@ marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* 
   double* P = smem;                       // m_dense x m_dense
   double* V = P + kMgMaxDense * kMgMaxDense;
   double* cs = V + kMgMaxDense * kMgMaxDense;
+  double* wk = cs + 6 * 16 + 32;          // 2 x m_dense x m_dense: Gauss-Jordan work space
   __shared__ int s_status;
   if (threadIdx.x == 0) s_status = 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kMgThreads / 32;
@@ -321,6 +322,26 @@ marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* 
   }
   __syncthreads();
   if (warp == 0 && md > 0) {
+    // fast path: A_mm^-1 by Gauss-Jordan, accepted when the smallest eigenvalue is provably > eps (see below), so
+    // VINS-Mono's eigen-thresholded pseudo-inverse keeps every eigenvalue and IS the inverse.
+    // Otherwise (rank-deficient, indefinite or badly scaled block) the literal eigen-decomposition below decides.
+    for (int idx = lane; idx < md * md; idx += 32) V[idx] = P[idx];
+    __syncwarp();
+    const int sing = w_inverse(V, md, md, wk, lane);
+    double fn = 0.0, an = 0.0;
+    for (int idx = lane; idx < md * md; idx += 32) { fn = fma(V[idx], V[idx], fn); an = fma(P[idx], P[idx], an); }
+    fn = warp_sum(fn);
+    an = warp_sum(an);
+    // |lam|_min >= 1 / ||A^-1||_F must exceed eps, and cond_F < 1e12 so that rounding (<= n eps_mach ||A||) cannot have
+    // flipped the sign of an eigenvalue of this sum of J^T J: then every eigenvalue is positive and > eps
+    const bool fast = !sing && isfinite(fn) && fn > 0.0 && fn * eps * eps < 1.0 && fn * an < 1e24;
+    if (fast) {
+      __syncwarp();
+      for (int idx = lane; idx < md * md; idx += 32) {
+        const int i = idx % md, j = idx / md;
+        P[idx] = 0.5 * (V[i + md * j] + V[j + md * i]);
+      }
+    } else {
     if (w_jacobi_eig(P, md, V, md, md, cs, lane) >= 30) status |= ISV_W_EIG_NOCONV;
     // pinv = V diag(lam > eps ? 1/lam : 0) V^T  -> back into P (cs reused for the inverted spectrum)
     for (int k = lane; k < md; k += 32) {
@@ -334,6 +355,7 @@ marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* 
       double acc = 0.0;
       for (int k = 0; k < md; ++k) acc = fma(V[i + md * k] * cs[k], V[j + md * k], acc);
       P[idx] = acc;
+    }
     }
   }
   __syncthreads();
