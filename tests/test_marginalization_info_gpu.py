@@ -346,3 +346,47 @@ def test_config4_window20_td_marginalization(backend):
     lam = np.linalg.norm(J, axis=1) ** 2
     assert np.all(np.diff(lam) >= 0)
     assert np.allclose(lam, np.linalg.eigvalsh(0.5 * (S_hp + S_hp.T)), rtol=1e-7)
+
+
+def test_rank_deficient_dense_block_takes_the_eigen_path_and_is_flagged(backend):
+    """The dense marginalized block normally gets its inverse on a fast path (Gauss-Jordan + a provable eigenvalue
+    bound).  When the block is rank deficient -- here pose 0 is dropped with only two visual factors (4 residual rows
+    for 6 tangent dimensions) constraining it -- the literal VINS-Mono step must run instead: eigen-decomposition,
+    eigenvalues <= eps zeroed (pseudo-inverse), ISV_W_RANK_DEFICIENT raised.  eps = 1 keeps the threshold above the
+    rounding noise of the null directions so that the oracle's `eigh` and the CUDA Jacobi agree on what is dropped."""
+    p = sim.make_problem(sim.seed_for(9, 31), n_features=40, max_track=6, host0=0.5)
+    hosted, seen = [], set()
+    for k in range(p.proj_idx.shape[1]):                    # the first observation of two different features of frame 0
+        if int(p.proj_idx[0, k]) == 0 and int(p.proj_idx[3, k]) not in seen and len(hosted) < 2:
+            seen.add(int(p.proj_idx[3, k]))
+            hosted.append(k)
+    assert len(hosted) == 2
+    const = {("ex_pose", 0)}
+    mi = MarginalizationInfo(backend, eps=1.0, cauchy_a=0.0, constant=list(const))
+    ofac = []
+    s = p.cfg.proj_sqrt_info
+    for k in hosted:
+        i, j, e, f = [int(x) for x in p.proj_idx[:, k]]
+        keys = [("pose", i), ("pose", j), ("ex_pose", e), ("feature", f)]
+        pts_i, pts_j = p.proj_obs[0:3, k], np.array([p.proj_obs[3, k], p.proj_obs[4, k], 1.0])
+        mi.addResidualBlockInfo(ResidualBlockInfo("projection", keys, drop_set=[0], pts_i=pts_i, pts_j=pts_j))   # features kept
+        ofac.append(O.ProjectionFactor(pts_i, pts_j, s).EvaluateCeres([p.poses[i], p.poses[j], p.ex[e], p.feat[f:f + 1]]) + (keys,))
+    # a prior on the kept pose(s) so that the reduced system is not itself degenerate
+    rel = p.rel[1]
+    keys = [("pose", rel.imu_i), ("pose", rel.imu_j)]
+    mi.addResidualBlockInfo(ResidualBlockInfo("rel", keys, delta_t=rel.delta_t, delta_R=rel.delta_R, sqrt_info=rel.sqrt_info))
+    ofac.append(rel.EvaluateCeres([p.poses[rel.imu_i], p.poses[rel.imu_j]]) + (keys,))
+    mi.preMarginalize({"pose": p.poses, "speed_bias": p.sbs, "ex_pose": p.ex, "feature": p.feat})
+    mi.marginalize()
+    assert mi.status & 0x02, hex(mi.status)                 # ISV_W_RANK_DEFICIENT
+    assert mi.status & ~0x02 == 0, hex(mi.status)
+    idx = mi.parameter_block_idx
+    assert mi.m == 6 and idx[("pose", 0)] == 0
+    facs = [(r, [(idx[k], np.asarray(j)[:, :LOCAL_SIZE[k[0]]]) for k, j in zip(keys, js) if k not in const])
+            for r, js, keys in ofac]
+    ref = O.vins_mono_marginalize(facs, mi.pos, mi.m, eps=1.0)
+    lam_mm = np.linalg.eigvalsh(0.5 * (ref["A"][:6, :6] + ref["A"][:6, :6].T))
+    assert int(np.sum(lam_mm > 1.0)) == 4 and lam_mm[1] < 1e-3 * lam_mm[2]     # rank 4, clear gap
+    assert rel_err(mi.A_red, ref["A_red"]) <= 1e-9 and rel_err(mi.b_red, ref["b_red"]) <= 1e-9
+    assert np.all(np.isfinite(mi.linearized_jacobians))
+    assert rel_err(mi.linearized_jacobians.T @ mi.linearized_jacobians, ref["linearized_jacobians"].T @ ref["linearized_jacobians"]) <= 1e-9
