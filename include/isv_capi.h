@@ -266,6 +266,9 @@ typedef struct isv_param_blocks {
 } isv_param_blocks;
 
 #define ISV_W_BAD_INDEX      0x40  /* a factor referenced a parameter block out of range: skipped  */
+#define ISV_W_DIAG_COUPLED   0x80  /* two DIFFERENT scalars of the diagonal marginalized block [m_dense, m_dense + m_diag)
+                                      are coupled by a factor (or by the previous prior): the diagonal elimination would
+                                      silently drop that coupling -- put such blocks into the dense block instead      */
 
 /* ProjectionFactor::Evaluate  src/factor/projection_factor.cpp:24-122 ; sqrt_info = isv_config    */
 typedef struct isv_proj_factors {

@@ -88,6 +88,13 @@ class MargBackend:
     def use_torch_stream(self):
         import torch
         s = torch.cuda.current_stream(self.device).cuda_stream
+        if not s:
+            # isv_set_stream(h, NULL) means "back to the handle's own non-blocking stream": torch's legacy default stream
+            # (handle 0) can therefore not be shared, and silently staying unordered with torch would let
+            # DeviceBatch.outputs() read results before the kernels finish
+            raise capi.IsvError("use_torch_stream(): torch's current stream is the default stream (handle 0), which the "
+                                "library cannot share; run under `torch.cuda.stream(torch.cuda.Stream())` or call "
+                                "MargBackend.synchronize() before reading results")
         capi.check(self.lib.isv_set_stream(self.h, C.c_void_p(s)), "isv_set_stream")
 
     def synchronize(self):

@@ -83,6 +83,20 @@ class WindowBatch:
                            s(self.preint), s(self.imu_raw), s(self.imu_init))
 
 
+    def take(self, idx: Sequence[int]) -> "WindowBatch":
+        """The windows `idx` (any order, repeats allowed) as a new batch -- e.g. the sample a checker re-computes."""
+        idx = np.asarray(idx, dtype=np.int64)
+        counts = np.diff(self.lm_offset)[idx]
+        off = np.zeros(len(idx) + 1, np.int64)
+        np.cumsum(counts, out=off[1:])
+        cols = np.concatenate([np.arange(self.lm_offset[w], self.lm_offset[w + 1]) for w in idx]) if len(idx) else np.zeros(0, np.int64)
+        s = lambda x: None if x is None else np.ascontiguousarray(x[idx])
+        return WindowBatch(len(idx), off, np.ascontiguousarray(self.lm_obs[:, cols.astype(np.int64)]), s(self.pose_fwd),
+                           self.ex_pose if self.ex_pose.ndim == 1 else s(self.ex_pose), s(self.prior_se3),
+                           s(self.prior_rel), s(self.prior_rp), s(self.pose_bwd), s(self.sb_bwd), s(self.prior_vb),
+                           s(self.preint), s(self.imu_raw), s(self.imu_init))
+
+
 def pack_events(events: Sequence, with_rp: bool = True) -> WindowBatch:
     """Pack records exposing the reference's member names (``fwd_in``/``bwd_in`` with pose0, pose1,
     ex_pose, inv_dep, pts_i, pts_j, prior_t, prior_R, prior_sqrt_info, rel_dt, rel_dR, rel_sqrt_info,
@@ -185,3 +199,23 @@ class WindowOutputs:
 
     def rp_sqrt_info(self, w):
         return self.rp[w, 9:13].reshape(2, 2).T
+
+
+# sub-blocks of each output record, compared separately so that a large-magnitude block cannot mask a small one
+OUTPUT_BLOCKS = {"se3": [(0, 3), (3, 12), (12, 48)], "pg": [(0, 3), (3, 12), (12, 48), (48, 84), (84, 85), (85, 89)],
+                 "rel": [(0, 3), (3, 12), (12, 48)], "vb": [(0, 9), (9, 90)], "rp": [(0, 9), (9, 13)]}
+
+
+def outputs_rel_diff(a: WindowOutputs, b: WindowOutputs, which: int = 3) -> np.ndarray:
+    """Per window: the worst relative Frobenius difference over every block of every recovered-factor record
+    (`which` & 1: MargForward's se3 / pg, & 2: MargBackward's rel / vb / rp)."""
+    n = a.rank.shape[0]
+    worst = np.zeros(n)
+    fams = (["se3", "pg"] if which & 1 else []) + (["rel", "vb", "rp"] if which & 2 else [])
+    for f in fams:
+        x, y = getattr(a, f), getattr(b, f)
+        for lo, hi in OUTPUT_BLOCKS[f]:
+            d = np.linalg.norm(x[:, lo:hi] - y[:, lo:hi], axis=1)
+            r = np.linalg.norm(y[:, lo:hi], axis=1)
+            worst = np.maximum(worst, np.where(r > 0, d / np.where(r > 0, r, 1.0), d))
+    return worst

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("ISV_B200_LIB", os.path.join(_HERE, "libisv_b200.so"))
 ISV_OK, ISV_ERR_BAD_ARG, ISV_ERR_CUDA, ISV_ERR_ALLOC = 0, 1, 2, 3
 W_NOT_SPD, W_RANK_DEFICIENT, W_NONFINITE, W_NONUNIT_QUAT, W_EIG_NOCONV, W_SINGULAR = 1, 2, 4, 8, 16, 32
 W_BAD_INDEX = 64
+W_DIAG_COUPLED = 128
 IMU_JAC_REC, YAW_REC = 480, 4
 ACC_REC, ACC_COVREL, ACC_DISTANCE, ACC_LENGTH, ACC_VIO_INDEX, ACC_PG_INDEX, ACC_TS = 119, 48, 84, 85, 86, 87, 88
 ACC_RI, ACC_TI, ACC_RP_VALID, ACC_RP, ACC_COVABS = 89, 98, 101, 102, 115

@@ -862,6 +862,9 @@ extern "C" isv_status isv_preintegrate_host(isv_handle* h, const isv_preint_in* 
   if (in->k_max > 0 && !in->imu_raw) return ISV_ERR_BAD_ARG;
   const size_t n = (size_t)in->n, K = (size_t)in->k_max, D = sizeof(double);
   if (n == 0) return ISV_OK;
+  if (in->k_count)   // host pointers here: a count outside [0, k_max] is a caller bug, not something to clamp silently
+    for (size_t w = 0; w < n; ++w)
+      if (in->k_count[w] < 0 || in->k_count[w] > in->k_max) return ISV_ERR_BAD_ARG;
   ISV_CUDA(cudaSetDevice(h->device));
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
@@ -1270,7 +1273,7 @@ extern "C" isv_status isv_add_marg_prior(isv_handle* h, const isv_marg_prior* pr
   const int first = problem < 0 ? 0 : problem, count = problem < 0 ? in->n_problems : 1;   // -1: every problem of the batch
   marg_prior_add_kernel<<<dim3(nt, nt, count), kPriorThreads, 0, h->stream>>>(
       *prior, residuals, out->A + (size_t)first * in->pos * in->pos, out->b + (size_t)first * in->pos, in->pos,
-      out->status ? out->status + first : nullptr);
+      out->status ? out->status + first : nullptr, in->m_dense, in->m_dense + in->m_diag);
   ++h->launches;
   ISV_CUDA(cudaGetLastError());
   return ISV_OK;
@@ -1323,8 +1326,10 @@ static isv_status schur_eig_impl(isv_handle* h, const isv_marg_generic_in* in, c
                                  int schur_only) {
   ISV_CUDA(cudaSetDevice(h->device));
   const size_t n = (size_t)(in->pos - in->m_dense - in->m_diag);
-  // factor rows of the reduced system (n x n per problem): handle-owned scratch
-  const size_t need = (size_t)in->n_problems * n * n * sizeof(double);
+  // handle-owned scratch per problem: T = A_rm pinv (n x m_dense) of marg_schur_eig_kernel, later the eigenvector
+  // buffer Z (n x n) of the reduced system -- sized for the larger of the two (m_dense may exceed n)
+  const size_t gcols = n > (size_t)in->m_dense ? n : (size_t)in->m_dense;
+  const size_t need = (size_t)in->n_problems * n * gcols * sizeof(double);
   if (h->gram_bytes < need) {
     if (h->gram) {
       ISV_CUDA(cudaStreamSynchronize(h->stream));

@@ -87,6 +87,8 @@ ne_build_kernel(isv_marg_generic_in in, double* __restrict__ A, double* __restri
   double* bp = b + (size_t)fa.problem * in.pos;
   const size_t ldA = (size_t)in.pos;
   const int npair = tot * (tot + 1) / 2;
+  const int dlo = in.m_dense, dhi = in.m_dense + in.m_diag;   // the diagonal marginalized block
+  int coupled = 0;
   for (int p = lane; p < npair; p += 32) {
     // p = c (c + 1) / 2 + a with a <= c
     int c = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
@@ -99,8 +101,11 @@ ne_build_kernel(isv_marg_generic_in in, double* __restrict__ A, double* __restri
       const int pa = colpos[a], pc = colpos[c];
       atomicAdd(Ap + pa + ldA * pc, acc);
       if (a != c) atomicAdd(Ap + pc + ldA * pa, acc);
+      if (pa != pc && pa >= dlo && pa < dhi && pc >= dlo && pc < dhi) coupled = 1;
     }
   }
+  // an off-diagonal entry inside the "diagonal" block: schur_diag_dmma_kernel reads only A[d, d] and would drop it
+  if (__any_sync(kFullMask, coupled) && lane == 0 && status) atomicOr(status + fa.problem, ISV_W_DIAG_COUPLED);
   for (int a = lane; a < tot; a += 32) {
     double acc = 0.0;
     for (int l = 0; l < nres; ++l) acc = fma(J[l * kNeLd + a], r[l], acc);
@@ -245,7 +250,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // smem (doubles): P[32*32] V[32*32] cs[6*16] (32 spare) wk[2*32*32]
 __global__ void __launch_bounds__(kMgThreads)
 marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* __restrict__ Gbuf, int schur_only,
-                      int phase_a_done) {   // Gbuf: n x md scratch per problem (stride n * n)
+                      int phase_a_done) {   // Gbuf: n x md scratch per problem (stride n * max(n, md))
   extern __shared__ double smem[];
   double* P = smem;                       // m_dense x m_dense
   double* V = P + kMgMaxDense * kMgMaxDense;
@@ -260,7 +265,7 @@ marg_schur_eig_kernel(isv_marg_generic_in in, isv_marg_generic_out out, double* 
   double* b = out.b + (size_t)prob * pos;
   double* Ar = out.A_red + (size_t)prob * n * n;
   double* br = out.b_red + (size_t)prob * n;
-  double* G = Gbuf + (size_t)prob * n * n;   // rows of the factor, row-major
+  double* G = Gbuf + (size_t)prob * n * (n > md ? n : md);   // T = A_rm pinv (n x md); the stride covers md > n too
   const double eps = in.eps;
   int status = 0;
   auto R = [&](int i) { return i < md ? i : i + mg; };   // compact index -> position in A
@@ -463,7 +468,7 @@ constexpr int kPaTile = 32;
 
 __global__ void __launch_bounds__(kPriorThreads)
 marg_prior_add_kernel(isv_marg_prior pr, const double* __restrict__ res, double* __restrict__ A, double* __restrict__ b,
-                      int pos, int32_t* status) {
+                      int pos, int32_t* status, int dlo, int dhi) {   // [dlo, dhi): the diagonal marginalized block
   // blockIdx.z: the problem of the batch this CTA adds the (shared) prior to
   A += (size_t)blockIdx.z * pos * pos;
   b += (size_t)blockIdx.z * pos;
@@ -484,6 +489,9 @@ marg_prior_add_kernel(isv_marg_prior pr, const double* __restrict__ res, double*
           if (status) atomicOr(status, ISV_W_BAD_INDEX);
         } else {
           p = bl.pos + col - bl.idx;
+          // the prior is a dense J^T J over all of its blocks: a block of it inside the diagonal marginalized range is
+          // coupled with everything else the prior holds
+          if (p >= dlo && p < dhi && status) atomicOr(status, ISV_W_DIAG_COUPLED);
         }
       }
     }

@@ -27,7 +27,10 @@ preintegrate_kernel(int n, int k_max, const int32_t* __restrict__ k_count, const
   double* V = T + 225;
   double* sc = V + 270;
   const double* init = imu_init + (size_t)w * 12;
-  const int K = k_count ? k_count[w] : k_max;
+  // a count outside [0, k_max] would read the next window's samples (or past the buffer): clamp it; the host entry
+  // point rejects such counts up front, device callers get the clamped record
+  int K = k_count ? k_count[w] : k_max;
+  K = K < 0 ? 0 : (K > k_max ? k_max : K);
   for (int i = lane; i < 225; i += 32) { J[i] = (i % 16 == 0) ? 1.0 : 0.0; P[i] = 0.0; }
   // lane 0 carries the navigation state (:188-203)
   double dp[3] = {0, 0, 0}, dv[3] = {0, 0, 0}, a0[3], g0[3], ba[3], bg[3], sum_dt = 0.0;

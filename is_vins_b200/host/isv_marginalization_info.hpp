@@ -73,7 +73,8 @@ class MarginalizationInfo {
   void setParameterBlockConstant(double* block) { constant_[reinterpret_cast<long>(block)] = true; }
 
   void addResidualBlockInfo(ResidualBlockInfo* info) {
-    factors.push_back(info);
+    // every check runs BEFORE a member is touched: a rejected factor leaves no half-registered state
+    if (!info) throw std::runtime_error("addResidualBlockInfo: null ResidualBlockInfo");
     std::vector<Family> fam = families(info->kind);
     if (info->kind == FactorKind::Marginalization) {   // the prior's kept blocks, family by global size of the kept block
       const auto* mf = static_cast<const MarginalizationFactor*>(info->cost_function);
@@ -82,12 +83,28 @@ class MarginalizationInfo {
       if (pr->keep_block_size.size() != info->parameter_blocks.size())
         throw std::runtime_error("MarginalizationFactor: parameter blocks must be prior->getParameterBlocks(addr_shift)");
       fam = pr->keep_block_family_;
-      prior_factor_ = info;
     }
     if (fam.size() != info->parameter_blocks.size()) throw std::runtime_error("wrong number of parameter blocks for this factor kind");
+    if ((info->kind == FactorKind::ProjectionTd && has_plain_) || (info->kind == FactorKind::Projection && has_td_))
+      throw std::runtime_error("ProjectionFactor and ProjectionTdFactor cannot share a problem");
+    for (size_t i = 0; i < fam.size(); ++i) {   // a block seen before must come back with the same family (same global size)
+      const long addr = reinterpret_cast<long>(info->parameter_blocks[i]);
+      auto it = family_.find(addr);
+      if (it != family_.end() && it->second != fam[i])
+        throw std::runtime_error("a parameter block address is used with two different block families");
+    }
+    for (int i : info->drop_set) {
+      if (i < 0 || (size_t)i >= info->parameter_blocks.size()) throw std::runtime_error("drop_set index out of range");
+      if (fam[i] == TD) throw std::runtime_error("para_Td couples with every visual factor: it cannot be marginalized");
+      // a scalar block that the previous prior kept cannot be dropped: the prior couples it with the other kept
+      // blocks, and scalar blocks are eliminated as a DIAGONAL block (isv_marg_generic.cuh)
+      if (info->kind == FactorKind::Marginalization && globalSize(fam[i]) == 1)
+        throw std::runtime_error("a scalar block kept by the previous prior cannot be marginalized (diagonal elimination)");
+    }
+    if (info->kind == FactorKind::Marginalization) prior_factor_ = info;
+    factors.push_back(info);
     if (info->kind == FactorKind::ProjectionTd) has_td_ = true;
     if (info->kind == FactorKind::Projection) has_plain_ = true;
-    if (has_td_ && has_plain_) throw std::runtime_error("ProjectionFactor and ProjectionTdFactor cannot share a problem");
     for (size_t i = 0; i < fam.size(); ++i) {
       const long addr = reinterpret_cast<long>(info->parameter_blocks[i]);
       parameter_block_size[addr] = globalSize(fam[i]);
@@ -95,7 +112,6 @@ class MarginalizationInfo {
     }
     for (int i : info->drop_set) {
       const long addr = reinterpret_cast<long>(info->parameter_blocks[i]);
-      if (family_[addr] == TD) throw std::runtime_error("para_Td couples with every visual factor: it cannot be marginalized");
       if (!dropped_.count(addr)) { dropped_[addr] = true; drop_order_.push_back(addr); }
     }
   }

@@ -114,14 +114,18 @@ class MarginalizationInfo:
 
     # ---- VINS-Mono API ------------------------------------------------------------------------------
     def addResidualBlockInfo(self, info: ResidualBlockInfo) -> None:
+        # validate first: a rejected factor leaves no half-registered state
+        for i in info.drop_set:
+            if not 0 <= i < len(info.parameter_blocks):
+                raise ValueError(f"drop_set index {i} out of range for {len(info.parameter_blocks)} parameter blocks")
+            if info.parameter_blocks[i][0] == "td":
+                raise ValueError("the time offset couples with every ProjectionTdFactor: it cannot be a diagonal "
+                                 "marginalized scalar (VINS-Mono never marginalizes para_Td either)")
         self.factors.append(info)
         for k in info.parameter_blocks:
             self.parameter_block_size[k] = GLOBAL_SIZE[k[0]]
         for i in info.drop_set:
             k = info.parameter_blocks[i]
-            if k[0] == "td":
-                raise ValueError("the time offset couples with every ProjectionTdFactor: it cannot be a diagonal "
-                                 "marginalized scalar (VINS-Mono never marginalizes para_Td either)")
             if k not in self._drop:
                 self._drop.append(k)
 
@@ -343,6 +347,12 @@ class MarginalizationInfo:
         order: List[Key] = [k for k in self._drop if LOCAL_SIZE[k[0]] > 1 and k not in self.constant]
         m_dense = sum(LOCAL_SIZE[k[0]] for k in order)
         diag = [k for k in self._drop if LOCAL_SIZE[k[0]] == 1 and k not in self.constant]
+        # scalar blocks are eliminated as a DIAGONAL block (only A[d, d] is read): a scalar the previous prior kept is
+        # coupled with the prior's other blocks and cannot go there (the kernels raise ISV_W_DIAG_COUPLED for raw callers)
+        prior_keys = {k for f in self.factors if f.kind == "marginalization" for k in f.parameter_blocks}
+        coupled = [k for k in diag if k in prior_keys]
+        if coupled:
+            raise ValueError(f"scalar blocks kept by the previous prior cannot be marginalized as a diagonal block: {coupled}")
         order += diag
         seen = set(order)
         for f in self.factors:

@@ -1527,7 +1527,14 @@ def vins_mono_marginalize(factors, pos: int, m: int, eps: float = 1e-8):
                 if j != i:
                     A[pj:pj + Jj.shape[1], pi:pi + Ji.shape[1]] += blk.T
             b[pi:pi + Ji.shape[1]] += Ji.T @ r
-    n = pos - m
+    out = vins_mono_schur_eig(A, b, m, eps)
+    out.update({"A": A, "b": b})
+    return out
+
+
+def vins_mono_schur_eig(A, b, m: int, eps: float = 1e-8):
+    """The back half of VINS-Mono's MarginalizationInfo::marginalize on assembled normal equations: joint
+    eigen-thresholded pseudo-inverse of Amm, Schur complement, eigen-decomposition of the reduced system."""
     Amm = 0.5 * (A[:m, :m] + A[:m, :m].T)
     w, V = np.linalg.eigh(Amm)
     winv = np.where(w > eps, 1.0 / np.where(w > eps, w, 1.0), 0.0)
@@ -1540,7 +1547,7 @@ def vins_mono_marginalize(factors, pos: int, m: int, eps: float = 1e-8):
     S_inv = np.where(w2 > eps, 1.0 / np.where(w2 > eps, w2, 1.0), 0.0)
     lin_J = np.sqrt(S)[:, None] * V2.T
     lin_r = np.sqrt(S_inv) * (V2.T @ b_red)
-    return {"A": A, "b": b, "A_red": A_red, "b_red": b_red, "linearized_jacobians": lin_J,
+    return {"A_red": A_red, "b_red": b_red, "linearized_jacobians": lin_J,
             "linearized_residuals": lin_r, "rank": int(np.sum(w2 > eps)), "min_eig_Amm": float(w.min())}
 
 

@@ -84,3 +84,20 @@ def test_prior_state_hands_over_the_kept_blocks():
     assert kept[:4] == [("pose", 1), ("ex_pose", 0), ("td", 0), ("speed_bias", 1)]
     with pytest.raises(AssertionError):                                # blocks must match the prior's kept blocks
         ResidualBlockInfo("marginalization", keys[:-1], prior=prior)
+
+
+def test_bad_drop_sets_are_rejected_before_any_state_changes():
+    """drop_set indices are validated first; a scalar block the previous prior kept cannot be dropped into the
+    diagonal block (its coupling through the prior would be ignored by the diagonal elimination)."""
+    mi = MarginalizationInfo(None)
+    with pytest.raises(ValueError):
+        mi.addResidualBlockInfo(ResidualBlockInfo("se3", [("pose", 0)], drop_set=[1], t=np.zeros(3), R=np.eye(3),
+                                                  sqrt_info=np.eye(6)))
+    assert mi.factors == [] and mi.parameter_block_size == {}
+    # a prior that kept feature 3, and a new round that wants to drop it as a scalar
+    keys = [("pose", 0), ("feature", 3)]
+    prior = PriorState(keys, np.eye(7), np.zeros(7), [np.zeros(7), np.zeros(1)])
+    mi = MarginalizationInfo(None)
+    mi.addResidualBlockInfo(ResidualBlockInfo("marginalization", keys, drop_set=[1], prior=prior))
+    with pytest.raises(ValueError, match="diagonal"):
+        mi.order_blocks()

@@ -390,3 +390,60 @@ def test_rank_deficient_dense_block_takes_the_eigen_path_and_is_flagged(backend)
     assert rel_err(mi.A_red, ref["A_red"]) <= 1e-9 and rel_err(mi.b_red, ref["b_red"]) <= 1e-9
     assert np.all(np.isfinite(mi.linearized_jacobians))
     assert rel_err(mi.linearized_jacobians.T @ mi.linearized_jacobians, ref["linearized_jacobians"].T @ ref["linearized_jacobians"]) <= 1e-9
+
+
+def test_more_dense_marginalized_columns_than_kept_columns_in_a_batch(backend):
+    """m_dense = 15 (pose 0 + speed-bias 0) against a single kept pose (n = 6).  The Schur kernel's
+    per-problem scratch T = A_rm pinv is n x m_dense: with a stride of n * n the CTAs of a batch overwrote each other's
+    slice (and the last one wrote past the allocation).  Every problem of a 5-problem batch must reproduce the
+    single-problem result, which must match the VINS-Mono oracle."""
+    import ctypes as C
+
+    import torch
+
+    from is_vins_b200 import capi
+    p = sim.make_problem(sim.seed_for(9, 77), n_features=8, max_track=4)
+    mi = MarginalizationInfo(backend, eps=1e-8, cauchy_a=0.0)
+    se3, rel, vb = p.se3[0], p.rel[0], p.vb[0]
+    ofac = []
+    keys = [("pose", 0)]
+    mi.addResidualBlockInfo(ResidualBlockInfo("se3", keys, drop_set=[0], t=se3.t, R=se3.R, sqrt_info=se3.sqrt_info))
+    ofac.append(se3.EvaluateCeres([p.poses[0]]) + (keys,))
+    keys = [("pose", 0), ("pose", 1)]
+    mi.addResidualBlockInfo(ResidualBlockInfo("rel", keys, drop_set=[0], delta_t=rel.delta_t, delta_R=rel.delta_R,
+                                              sqrt_info=rel.sqrt_info))
+    ofac.append(rel.EvaluateCeres([p.poses[0], p.poses[1]]) + (keys,))
+    keys = [("speed_bias", 0)]
+    mi.addResidualBlockInfo(ResidualBlockInfo("vb", keys, drop_set=[0], VB=vb.VB, sqrt_info=vb.sqrt_info))
+    ofac.append(vb.EvaluateCeres([p.sbs[0]]) + (keys,))
+    mi.preMarginalize({"pose": p.poses, "speed_bias": p.sbs, "ex_pose": p.ex, "feature": p.feat})
+    mi.marginalize(keep_tables=True)
+    assert mi.status == 0 and mi.m == 15 and mi.n == 6
+    idx = mi.parameter_block_idx
+    facs = [(r, [(idx[k], np.asarray(j)[:, :LOCAL_SIZE[k[0]]]) for k, j in zip(keys, js)]) for r, js, keys in ofac]
+    ref = O.vins_mono_marginalize(facs, mi.pos, mi.m, eps=1e-8)
+    assert rel_err(mi.A_red, ref["A_red"]) <= 1e-9 and rel_err(mi.b_red, ref["b_red"]) <= 1e-9
+    # the same problem five times in one call
+    gi, tabs = mi._gi, mi._tables
+    NP, nf, pos, n = 5, gi.n_factors, gi.pos, mi.n
+    fa = np.frombuffer(tabs["factors_bytes"], dtype=np.dtype([("res", "<i8"), ("nres", "<i4"), ("nb", "<i4"),
+                                                               ("fb", "<i4"), ("prob", "<i4")])).copy()
+    big = np.tile(fa, NP)
+    big["prob"] = np.repeat(np.arange(NP, dtype=np.int32), nf)
+    dev = "cuda:0"
+    d_f = torch.from_numpy(big.view(np.uint8)).to(dev)
+    z = lambda *s: torch.zeros(s, dtype=torch.float64, device=dev)
+    o = {"A": z(NP, pos, pos), "b": z(NP, pos), "A_red": z(NP, n, n), "b_red": z(NP, n), "J": z(NP, n, n), "r": z(NP, n),
+         "rank": torch.zeros((NP,), dtype=torch.int32, device=dev), "status": torch.zeros((NP,), dtype=torch.int32, device=dev)}
+    gi.n_problems, gi.n_factors, gi.factors = NP, NP * nf, d_f.data_ptr()
+    go = type(mi._go)(o["A"].data_ptr(), o["b"].data_ptr(), o["A_red"].data_ptr(), o["b_red"].data_ptr(), o["J"].data_ptr(),
+                      o["r"].data_ptr(), o["rank"].data_ptr(), o["status"].data_ptr())
+    capi.check(backend.lib.isv_marginalize_generic(backend.h, C.byref(gi), C.byref(go)), "isv_marginalize_generic")
+    backend.synchronize()
+    assert int(torch.count_nonzero(o["status"]).item()) == 0
+    for q in range(NP):
+        A = o["A_red"][q].T.cpu().numpy()
+        assert rel_err(A, mi.A_red) <= 1e-12, q
+        assert rel_err(o["b_red"][q].cpu().numpy(), mi.b_red) <= 1e-12, q
+        J = o["J"][q].T.cpu().numpy()
+        assert rel_err(J.T @ J, ref["A_red"]) <= 1e-9, q

@@ -146,8 +146,18 @@ def w20(args, be, fp, z):
     mi.preMarginalize({"pose": fp.pose, "speed_bias": fp.speed_bias, "ex_pose": fp.ex_pose, "feature": fp.feature, "td": z["td"]})
     mi.marginalize(keep_tables=True)
     assert mi.status == 0 and mi.n == 307, (mi.status, mi.n)
-    batch_bench(args, be, mi, "BASELINE configs[3] (b): WINDOW_SIZE=20, ProjectionTdFactor, previous prior over the whole "
-                              "window, MARGIN_OLD", 0)
+    return batch_bench(args, be, mi, "BASELINE configs[3] (b): WINDOW_SIZE=20, ProjectionTdFactor, previous prior over the whole "
+                                     "window, MARGIN_OLD", 0)
+
+
+def w20_from_bench(be, problems, steps):
+    """bench.py's configs[3] (b) line: the same measurement on an existing backend; returns the result dict (with the
+    normal equations A, b of one problem for the CPU leg)."""
+    import types
+    from is_vins_b200 import FactorProblem
+    name = os.path.join(ROOT, "tests", "golden", "problem_W20_F2000_td.npz")
+    args = types.SimpleNamespace(problems=problems, steps=steps, emit=False, keep_A=True)
+    return w20(args, be, FactorProblem.load(name), np.load(name))
 
 
 def batch_bench(args, be, mi, what, rank_slack):
@@ -210,14 +220,24 @@ def batch_bench(args, be, mi, what, rank_slack):
         t_all += e1.elapsed_time(e2)
     t_ne /= args.steps
     t_all /= args.steps
-    print(json.dumps({"metric": "problems_marginalized_per_s", "value": NP / (t_all * 1e-3), "unit": "problems/s",
+    res = ({"metric": "problems_marginalized_per_s", "value": NP / (t_all * 1e-3), "unit": "problems/s",
                       "config": {"workload": f"{what}, {NP} independent problems", "pos": pos, "m_dense": gi.m_dense,
                                  "m_diag": gi.m_diag, "n_keep": n, "residual_blocks_per_problem": nf,
                                  "previous_prior": prior is not None},
                       "ms_per_step": t_all, "kernels_ms": {"normal equations (memset + ne_build_kernel [+ prior])": t_ne,
                                                            "schur_diag_dmma_kernel + marg_schur_eig_kernel": t_all - t_ne},
-                      "rank": mi.rank}))
-    be.close()
+                      "rank": mi.rank})
+    res["A_one"] = res["b_one"] = None
+    if getattr(args, "keep_A", False):   # bench.py's CPU leg: the normal equations of one problem before the Schur stage consumes them
+        build()
+        torch.cuda.synchronize()
+        res["A_one"], res["b_one"] = o["A"][0].T.cpu().numpy().copy(), o["b"][0].cpu().numpy().copy()
+    res["m"] = gi.m_dense + gi.m_diag
+    if getattr(args, "emit", True):
+        res.pop("A_one"); res.pop("b_one")
+        print(json.dumps(res))
+        be.close()
+    return res
 
 
 if __name__ == "__main__":
