@@ -421,7 +421,9 @@ def measure(cx, L, n, which, steps, warmup, seed, full, e2e=True):
     assert int(torch.count_nonzero(db.out["status"]).item()) == 0, "a window reported a status flag"
     r["out"] = db.outputs() if cx.rank == 0 else None     # results of the timed run (for the parity sample)
 
-    if full:
+    if full and cx.sustain_s <= 0:
+        r["sustained_ms"], r["sustained_steps"], r["sustained_2nd_half_ms_per_step"] = ms_total, steps, ms_total / steps
+    if full and cx.sustain_s > 0:
         # ---- sustained: the same loop for >= cx.sustain_s seconds, clocks and power sampled inside ------------------
         chunk = max(8, int(0.05 / max(ms_total / steps * 1e-3, 1e-6)))    # ~50 ms of work per chunk
         sclk = ClockSampler(cx.local).start() if cx.rank == 0 else None
@@ -450,6 +452,7 @@ def measure(cx, L, n, which, steps, warmup, seed, full, e2e=True):
         if sclk is not None:
             r["sustained_clocks"] = sclk.stop(ts0 + 0.1, ts1)
         cx.barrier()
+    if full:
         # ---- per-kernel timing for the roofline (same stream, CUDA events) ---------------------------------------
         per = {}
         be.marg_window_batch(db, capi.RUN_BOTH)
@@ -469,7 +472,7 @@ def measure(cx, L, n, which, steps, warmup, seed, full, e2e=True):
 
     # ---- end to end through the host-pointer C ABI (pinned host buffers) ----------------------------------------
     if e2e:
-        for f in batch.FIELDS[:11]:
+        for f in batch.FIELDS:
             a = getattr(batch, f)
             if a is not None:
                 t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -482,29 +485,41 @@ def measure(cx, L, n, which, steps, warmup, seed, full, e2e=True):
         hout_t["status"] = torch.zeros((n,), dtype=torch.int32).pin_memory()
         hout = WindowOutputs(*[hout_t[k].numpy() for k in ("se3", "pg", "rel", "vb", "rp", "rank", "status")])
         fwd_f = ("lm_offset", "pose_fwd", "ex_pose", "prior_se3", "prior_rel", "prior_rp")
-        bwd_f = ("pose_bwd", "sb_bwd", "prior_vb", "preint")
-        h2d = 0
-        if which & 1:   # pts_j (2 of the 6 landmark components) is never read by the information-only marginalization
-            h2d += sum(getattr(batch, f).nbytes for f in fwd_f) + 4 * batch.n_landmarks * 8
-        if which & 2:
-            h2d += sum(getattr(batch, f).nbytes for f in bwd_f)
         d2h = sum(hout_t[k].numpy().nbytes for k in ((["se3", "pg"] if which & 1 else []) + (["rel", "vb", "rp"] if which & 2 else [])
                                                     + ["rank", "status"]))
-        for _ in range(max(1, min(warmup, 3))):
-            be.marg_window_batch_host(batch, which, hout)
-        cx.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            be.marg_window_batch_host(batch, which, hout)   # synchronises internally after the D2H
-        e1.record()
-        cx.barrier()
-        r["e2e_ms"] = e0.elapsed_time(e1)
-        r["h2d"], r["d2h"] = h2d, d2h
-        assert int(np.count_nonzero(hout.status)) == 0
-        if cx.rank == 0:   # the e2e path's results must be the device path's results, bit for bit
-            r["e2e_equals_device_path"] = bool(all(np.array_equal(getattr(hout, f), getattr(r["out"], f))
-                                                   for f in ((["se3", "pg"] if which & 1 else []) + (["rel", "vb", "rp"] if which & 2 else []))))
+        fams = (["se3", "pg"] if which & 1 else []) + (["rel", "vb", "rp"] if which & 2 else [])
+        # (a) ABI 2 inputs: raw IMU samples instead of the 467-double pre-integration record (the library runs
+        #     preintegrate_kernel first) and pts_i.z == 1 promised (src/System.cpp:346): 3 of the 6 landmark components
+        #     cross PCIe (pts_j is never read by the information-only marginalization, pts_i.z is the constant 1);
+        # (b) ABI 1 inputs (the full records), for comparison
+        for tag, kw, lm_comp, bwd_f in (("", dict(raw_imu=True, z_one=True), 3, ("pose_bwd", "sb_bwd", "prior_vb", "imu_raw", "imu_init")),
+                                        ("_abi1", dict(), 4, ("pose_bwd", "sb_bwd", "prior_vb", "preint"))):
+            if tag and not full:
+                continue
+            h2d = 0
+            if which & 1:
+                h2d += sum(getattr(batch, f).nbytes for f in fwd_f) + lm_comp * batch.n_landmarks * 8
+            if which & 2:
+                h2d += sum(getattr(batch, f).nbytes for f in bwd_f)
+            for _ in range(max(1, min(warmup, 3))):
+                be.marg_window_batch_host(batch, which, hout, **kw)
+            cx.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                be.marg_window_batch_host(batch, which, hout, **kw)   # synchronises internally after the D2H
+            e1.record()
+            cx.barrier()
+            r["e2e_ms" + tag] = e0.elapsed_time(e1)
+            r["h2d" + tag], r["d2h"] = h2d, d2h
+            assert int(np.count_nonzero(hout.status)) == 0
+            if cx.rank == 0 and not tag:
+                # the e2e path's results against the device path's: equal to rounding (z == 1 is folded into the arithmetic,
+                # the pre-integration record was rebuilt on the GPU from the raw samples)
+                from is_vins_b200.batch import outputs_rel_diff
+                r["e2e_vs_device_path_max_rel"] = float(outputs_rel_diff(hout, r["out"], which).max())
+            if cx.rank == 0 and tag:
+                r["e2e_abi1_bits_equal"] = bool(all(np.array_equal(getattr(hout, f), getattr(r["out"], f)) for f in fams))
     del db
     return r
 
@@ -618,12 +633,20 @@ def run_cuda(args, L):
 
     # ---- headline: BASELINE configs[1] (or --features) -----------------------------------------------------------
     n = args.windows
+    if args.quick:   # kernel development: device-timed value and the per-kernel times only
+        cx.sustain_s = 0.0
+        h = measure(cx, L, n, capi.RUN_BOTH, args.steps, args.warmup, 1000 + rank, full=True, e2e=False)
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": world * n * args.steps / (h["ms_total"] * 1e-3), "ms_per_step": h["ms_total"] / args.steps,
+                              "kernels_ms": h["per"], "L": L, "windows": n, "lib": os.environ.get("ISV_B200_LIB", "default")}), flush=True)
+        be.close()
+        return
     h = measure(cx, L, n, capi.RUN_BOTH, args.steps, args.warmup, 1000 + rank, full=True)
     names = list(KERNELS)
-    tl = maxr([h["ms_total"], h["e2e_ms"], h["sustained_ms"] / h["sustained_steps"], h["sustained_2nd_half_ms_per_step"]]
-              + [h["per"][k] for k in names])
-    ms_total, e2e_ms, sus_ms, sus2_ms = tl[0:4]
-    per = dict(zip(names, tl[4:]))
+    tl = maxr([h["ms_total"], h["e2e_ms"], h["sustained_ms"] / h["sustained_steps"], h["sustained_2nd_half_ms_per_step"],
+               h["e2e_ms_abi1"]] + [h["per"][k] for k in names])
+    ms_total, e2e_ms, sus_ms, sus2_ms, e2e1_ms = tl[0:5]
+    per = dict(zip(names, tl[5:]))
     tot_lm = maxr([float(h["n_lm"])])[0]
     line = None
     if rank == 0:
@@ -665,7 +688,12 @@ def run_cuda(args, L):
             "clocks": h["clocks"],
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h["h2d"], "d2h_bytes_per_step": h["d2h"],
                     "ms_per_step": e2e_ms / args.steps, "gb_per_s": (h["h2d"] + h["d2h"]) / (e2e_ms / args.steps * 1e-3) / 1e9,
-                    "results_equal_device_path": h.get("e2e_equals_device_path")},
+                    "inputs": "ABI 2: raw IMU samples (12 + 7 K doubles; preintegrate_kernel runs inside the call) instead of the "
+                              "467-double pre-integration record; pts_i.z == 1 promised (ISV_IN_PTS_I_Z_ONE): 3 doubles per landmark",
+                    "max_rel_diff_vs_device_path": h.get("e2e_vs_device_path_max_rel"),
+                    "abi1": {"value": world * n * args.steps / (e2e1_ms * 1e-3), "h2d_bytes_per_step": h["h2d_abi1"],
+                             "ms_per_step": e2e1_ms / args.steps, "results_bit_equal_device_path": h.get("e2e_abi1_bits_equal"),
+                             "inputs": "ABI 1: the full records (467-double pre-integration, 4 doubles per landmark)"}},
             "gpu_launches": h["launches"],
             "kernels_ms": per,
             # The contract's object, always for the same kernel (the landmark kernel: the one that streams O(L) bytes per
@@ -801,6 +829,7 @@ def main():
     ap.add_argument("--parity-windows", type=int, default=64, help="windows of the timed batch re-computed by the C oracle")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-configs", action="store_true", help="headline workload only")
+    ap.add_argument("--quick", action="store_true", help="kernel development: `value` and the per-kernel times only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ISV_ABI_VERSION 1
+#define ISV_ABI_VERSION 2   /* 2: isv_batch_in grew imu_raw / imu_init / imu_count / imu_k_max / flags (zero = v1 behaviour) */
 
 /* ---- status codes (SURVEY.md 8b "error conventions": the reference has none -- void + assert) */
 typedef enum isv_status {
@@ -122,8 +122,23 @@ typedef struct isv_batch_in {
   const double* pose_bwd;        /* [n][2][7] para_Pose[V-1], para_Pose[V]                      */
   const double* sb_bwd;          /* [n][2][9] para_SpeedBias[V-1], para_SpeedBias[V]            */
   const double* prior_vb;        /* [n][90]  vioVBPrior                                         */
-  const double* preint;          /* [n][467] backwardIMUtoSparsify->pre_integration             */
+  const double* preint;          /* [n][467] backwardIMUtoSparsify->pre_integration; NULL: rebuilt
+                                    on the GPU from imu_raw / imu_init below                    */
+  /* ---- ABI 2 (all zero = ABI 1 behaviour) --------------------------------------------------
+   * The pre-integration record is a pure function of the interval's raw IMU samples
+   * (IntegrationBase::push_back, include/factor/integration_base.h:30-158): a caller on the far
+   * side of PCIe ships 12 + 7 K doubles instead of 467 and the batch call runs
+   * preintegrate_kernel first.                                                                 */
+  const double* imu_raw;         /* [n][imu_k_max][7] dt, acc[3], gyr[3] (dt_buf/acc_buf/gyr_buf) */
+  const double* imu_init;        /* [n][12] acc_0, gyr_0, linearized_ba, linearized_bg          */
+  const int32_t* imu_count;      /* [n] samples used per window, or NULL = imu_k_max everywhere */
+  int32_t imu_k_max;             /* samples stored per window                                   */
+  int32_t flags;                 /* ISV_IN_* bits                                               */
 } isv_batch_in;
+
+/* pts_i.z == 1 for every landmark (the feature tracker normalises: src/System.cpp:346): component 2 of
+ * lm_obs is neither read by the kernels nor copied by the host entry point (which spot-checks it). */
+#define ISV_IN_PTS_I_Z_ONE 1
 
 typedef struct isv_batch_out {
   double* se3_out;               /* [n][48]  forwardPosePriorEdgeToAdd                          */

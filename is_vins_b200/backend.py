@@ -27,8 +27,13 @@ def _dp(a: np.ndarray):
 class DeviceBatch:
     """A WindowBatch resident in HBM (torch CUDA tensors) plus preallocated outputs."""
 
-    def __init__(self, batch: WindowBatch, device, pinned_src: bool = False):
+    def __init__(self, batch: WindowBatch, device, pinned_src: bool = False, raw_imu: bool = False, z_one: bool = False):
+        """raw_imu: hand the library the raw IMU samples (imu_raw / imu_init) instead of the pre-integration record (ABI
+        2: it runs preintegrate_kernel first); z_one: promise pts_i.z == 1 (ISV_IN_PTS_I_Z_ONE)."""
         import torch
+        self.raw_imu, self.flags = bool(raw_imu), (capi.IN_PTS_I_Z_ONE if z_one else 0)
+        if raw_imu and (batch.imu_raw is None or batch.imu_init is None):
+            raise ValueError("raw_imu=True needs batch.imu_raw / batch.imu_init")
         self.torch = torch
         self.device = torch.device(device)
         self.n = batch.n
@@ -54,7 +59,10 @@ class DeviceBatch:
         g = lambda k: t[k].data_ptr() if k in t else None
         bi = capi.isv_batch_in(self.n, 1 if self.ex_shared else 0, g("lm_offset"), g("lm_obs"), self.n_lm,
                                g("pose_fwd"), g("ex_pose"), g("prior_se3"), g("prior_rel"), g("prior_rp"),
-                               g("pose_bwd"), g("sb_bwd"), g("prior_vb"), g("preint"))
+                               g("pose_bwd"), g("sb_bwd"), g("prior_vb"), None if self.raw_imu else g("preint"))
+        if self.raw_imu:
+            bi.imu_raw, bi.imu_init, bi.imu_k_max = g("imu_raw"), g("imu_init"), int(t["imu_raw"].shape[1])
+        bi.flags = self.flags
         o = self.out
         bo = capi.isv_batch_out(o["se3"].data_ptr(), o["pg"].data_ptr(), o["rel"].data_ptr(), o["vb"].data_ptr(),
                                 o["rp"].data_ptr(), o["rank"].data_ptr(), o["status"].data_ptr())
@@ -112,7 +120,10 @@ class MargBackend:
 
     # ---- batched, host pointers (H2D + kernels + D2H inside the call) ---------------------------
     def marg_window_batch_host(self, batch: WindowBatch, which: int = capi.RUN_BOTH,
-                               out: Optional[WindowOutputs] = None) -> WindowOutputs:
+                               out: Optional[WindowOutputs] = None, raw_imu: bool = False,
+                               z_one: bool = False) -> WindowOutputs:
+        """raw_imu / z_one: see DeviceBatch (fewer bytes cross PCIe: 12 + 7 K doubles instead of the 467-double
+        pre-integration record, 3 instead of 4 doubles per landmark)."""
         n = batch.n
         if out is None:
             out = WindowOutputs(np.zeros((n, capi.SE3_REC)), np.zeros((n, capi.PG_REC)), np.zeros((n, capi.REL_REC)),
@@ -121,7 +132,10 @@ class MargBackend:
         bi = capi.isv_batch_in(n, 1 if batch.ex_pose.ndim == 1 else 0, _p(batch.lm_offset), _p(batch.lm_obs),
                                batch.lm_obs.shape[1], _p(batch.pose_fwd), _p(batch.ex_pose), _p(batch.prior_se3),
                                _p(batch.prior_rel), _p(batch.prior_rp), _p(batch.pose_bwd), _p(batch.sb_bwd),
-                               _p(batch.prior_vb), _p(batch.preint))
+                               _p(batch.prior_vb), None if raw_imu else _p(batch.preint))
+        if raw_imu:
+            bi.imu_raw, bi.imu_init, bi.imu_k_max = _p(batch.imu_raw), _p(batch.imu_init), int(batch.imu_raw.shape[1])
+        bi.flags = capi.IN_PTS_I_Z_ONE if z_one else 0
         bo = capi.isv_batch_out(_p(out.se3), _p(out.pg), _p(out.rel), _p(out.vb), _p(out.rp), _p(out.rank),
                                 _p(out.status))
         capi.check(self.lib.isv_marg_window_batch_host(self.h, C.byref(bi), C.byref(bo), which),

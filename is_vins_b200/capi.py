@@ -16,6 +16,7 @@ ISV_OK, ISV_ERR_BAD_ARG, ISV_ERR_CUDA, ISV_ERR_ALLOC = 0, 1, 2, 3
 W_NOT_SPD, W_RANK_DEFICIENT, W_NONFINITE, W_NONUNIT_QUAT, W_EIG_NOCONV, W_SINGULAR = 1, 2, 4, 8, 16, 32
 W_BAD_INDEX = 64
 W_DIAG_COUPLED = 128
+IN_PTS_I_Z_ONE = 1
 IMU_JAC_REC, YAW_REC = 480, 4
 ACC_REC, ACC_COVREL, ACC_DISTANCE, ACC_LENGTH, ACC_VIO_INDEX, ACC_PG_INDEX, ACC_TS = 119, 48, 84, 85, 86, 87, 88
 ACC_RI, ACC_TI, ACC_RP_VALID, ACC_RP, ACC_COVABS = 89, 98, 101, 102, 115
@@ -41,7 +42,10 @@ class isv_batch_in(C.Structure):
                 ("lm_obs", C.c_void_p), ("lm_stride", C.c_int64), ("pose_fwd", C.c_void_p),
                 ("ex_pose", C.c_void_p), ("prior_se3", C.c_void_p), ("prior_rel", C.c_void_p),
                 ("prior_rp", C.c_void_p), ("pose_bwd", C.c_void_p), ("sb_bwd", C.c_void_p),
-                ("prior_vb", C.c_void_p), ("preint", C.c_void_p)]
+                ("prior_vb", C.c_void_p), ("preint", C.c_void_p),
+                # ABI 2: raw IMU samples instead of the pre-integration record, and the ISV_IN_* flags
+                ("imu_raw", C.c_void_p), ("imu_init", C.c_void_p), ("imu_count", C.c_void_p),
+                ("imu_k_max", C.c_int32), ("flags", C.c_int32)]
 
 
 class isv_batch_out(C.Structure):

@@ -121,12 +121,16 @@ isv_status isv_create(const isv_config* cfg, int device, isv_handle** out) {
   for (int i = 0; i < 3; ++i) cudaEventCreateWithFlags(&h->aux_ev[i], cudaEventDisableTiming);
   for (int i = 0; i < 6; ++i) cudaEventCreateWithFlags(&h->jac_ev[i], cudaEventDisableTiming);
   h->stream = h->own_stream;
-  cudaFuncSetAttribute(marg_forward_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(marg_forward_accum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(kWarpsPerCta * kAccSmemPerWarp * sizeof(double)));
+  cudaFuncSetAttribute(marg_forward_accum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kWarpsPerCta * kAccSmemPerWarp * sizeof(double)));
   cudaFuncSetAttribute(marg_forward_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kWarpsPerCta * kFwdSmemPerWarp * sizeof(double)));
   cudaFuncSetAttribute(marg_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kWarpsPerCta * kBwdSmemPerWarp * sizeof(double)));
+  cudaFuncSetAttribute(preintegrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(kWarpsPerCta * kPreSmemPerWarp * sizeof(double)));
   *out = h;
   return ISV_OK;
 }
@@ -207,24 +211,33 @@ static isv_status check_batch(const isv_batch_in* in, const isv_batch_out* out, 
       return ISV_ERR_BAD_ARG;
     if (!in->lm_obs && in->lm_stride != 0) return ISV_ERR_BAD_ARG;
   }
+  if (in->flags & ~ISV_IN_PTS_I_Z_ONE) return ISV_ERR_BAD_ARG;
   if (which & (ISV_RUN_BACKWARD | ISV_RUN_BACKWARD_STAGE2 | ISV_RUN_FACTOR_JAC)) {
-    if (!in->pose_bwd || !in->sb_bwd || !in->prior_vb || !in->preint || !out->rel_out || !out->vb_out || !out->rp_out)
+    if (!in->pose_bwd || !in->sb_bwd || !in->prior_vb || !out->rel_out || !out->vb_out || !out->rp_out)
       return ISV_ERR_BAD_ARG;
+    // the pre-integration record itself, or the raw samples it is rebuilt from (ABI 2)
+    if (!in->preint && !(in->imu_init && in->imu_k_max >= 0 && (in->imu_raw || in->imu_k_max == 0))) return ISV_ERR_BAD_ARG;
   }
   return ISV_OK;
 }
 
 // scratch: device memory [n_windows][kScratchPerWindow]: the landmark Gram triangles (42) handed from the
 // landmark kernel to the tail kernel, then the factor-Jacobian records (kFJ) of marg_factor_jac_kernel
-constexpr size_t kScratchPerWindow = 42 + kFJ;
+// and (when the caller hands raw IMU samples instead of the record) the pre-integration records
+constexpr size_t kScratchPerWindow = 42 + kFJ + ISV_PREINT_REC;
 
-static isv_status launch_batch(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, int which,
+static isv_status launch_batch(isv_handle* h, const isv_batch_in* in_arg, const isv_batch_out* out, int which,
                                cudaStream_t stream, double* scratch) {
-  const int n = in->n_windows;
+  const int n = in_arg->n_windows;
   if (n == 0) return ISV_OK;
   if (!scratch) return ISV_ERR_BAD_ARG;
   double* gram = scratch;
   double* fj = scratch + (size_t)n * 42;
+  // raw IMU in, no record: preintegrate_kernel fills the scratch record first, on the backward chain's stream
+  isv_batch_in in_local = *in_arg;
+  const bool need_preint = !in_arg->preint && (which & (ISV_RUN_BACKWARD | ISV_RUN_FACTOR_JAC | ISV_RUN_BACKWARD_STAGE2));
+  if (need_preint) in_local.preint = scratch + (size_t)n * (42 + kFJ);
+  const isv_batch_in* in = &in_local;
   const bool stage1 = which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE1);
   const bool stage2 = which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE2);
   const bool jac_fwd = which & (ISV_RUN_FORWARD | ISV_RUN_FACTOR_JAC);
@@ -251,6 +264,12 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in, const isv_
     ++h->launches;
     if (fork_f) ISV_CUDA(cudaEventRecord(ev[2], fs));
   }
+  if (need_preint && jac_bwd) {
+    NoiseCfg nz{h->cfg.acc_n, h->cfg.gyr_n, h->cfg.acc_w, h->cfg.gyr_w};
+    preintegrate_kernel<<<grid, kThreads, kWarpsPerCta * kPreSmemPerWarp * sizeof(double), bs>>>(
+        n, in->imu_k_max, in->imu_count, in->imu_raw, in->imu_init, const_cast<double*>(in->preint), nz);
+    ++h->launches;
+  }
   if (jac_bwd) {
     // the IMU Jacobian record is sparse: zero-fill it, the kernel writes the non-zero blocks
     ISV_CUDA(cudaMemset2DAsync(fj + kFJ_IMU, kFJ * sizeof(double), 0, 450 * sizeof(double), (size_t)n, bs));
@@ -258,8 +277,12 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in, const isv_
     ++h->launches;
   }
   if (stage1) {
-    marg_forward_accum_kernel<<<grid, kThreads, kWarpsPerCta * kAccSmemPerWarp * sizeof(double), stream>>>(
-        *in, gram, out->status, h->dcfg);
+    if (in->flags & ISV_IN_PTS_I_Z_ONE)
+      marg_forward_accum_kernel<true><<<grid, kThreads, kWarpsPerCta * kAccSmemPerWarp * sizeof(double), stream>>>(
+          *in, gram, out->status, h->dcfg);
+    else
+      marg_forward_accum_kernel<false><<<grid, kThreads, kWarpsPerCta * kAccSmemPerWarp * sizeof(double), stream>>>(
+          *in, gram, out->status, h->dcfg);
     ++h->launches;
   }
   if (bwd) {
@@ -389,7 +412,22 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   const size_t o_poseb = carve(bwd ? n * 14 * D : 0);
   const size_t o_sbb = carve(bwd ? n * 18 * D : 0);
   const size_t o_pvb = carve(bwd ? n * ISV_VB_REC * D : 0);
-  const size_t o_pre = carve(bwd ? n * ISV_PREINT_REC * D : 0);
+  const bool raw_imu = bwd && !in->preint;      // ABI 2: ship the raw samples, rebuild the record on the GPU
+  const size_t K = raw_imu ? (size_t)in->imu_k_max : 0;
+  const size_t o_pre = carve(bwd && !raw_imu ? n * ISV_PREINT_REC * D : 0);
+  const size_t o_iraw = carve(raw_imu ? n * K * 7 * D : 0);
+  const size_t o_iinit = carve(raw_imu ? n * 12 * D : 0);
+  const size_t o_icnt = carve(raw_imu && in->imu_count ? n * sizeof(int32_t) : 0);
+  const bool z_one = fwd && (in->flags & ISV_IN_PTS_I_Z_ONE);
+  if (z_one && n_lm > 0) {   // spot-check the caller's promise: first, last and every 4096th landmark
+    const double* z = in->lm_obs + 2 * (size_t)in->lm_stride;
+    for (int64_t k = 0; k < n_lm; k += 4096)
+      if (z[k] != 1.0) return ISV_ERR_BAD_ARG;
+    if (z[n_lm - 1] != 1.0) return ISV_ERR_BAD_ARG;
+  }
+  if (raw_imu && in->imu_count)
+    for (size_t w = 0; w < n; ++w)
+      if (in->imu_count[w] < 0 || in->imu_count[w] > in->imu_k_max) return ISV_ERR_BAD_ARG;
   const size_t o_se3 = carve(fwd ? n * ISV_SE3_REC * D : 0);
   const size_t o_pg = carve(fwd ? n * ISV_PG_REC * D : 0);
   const size_t o_rel = carve(bwd ? n * ISV_REL_REC * D : 0);
@@ -421,7 +459,9 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   ISV_CUDA(cudaStreamWaitEvent(ss[1], h->ev[1], 0));
   size_t n_chunks = n / 512;
   if (n_chunks < 1) n_chunks = 1;
-  if (n_chunks > 8) n_chunks = 8;
+  static const int max_chunks = getenv("ISV_HOST_CHUNKS") ? atoi(getenv("ISV_HOST_CHUNKS")) : 4;   // measured at 9472 windows: 2 / 4 / 8 / 16 chunks
+                                                                                                   // -> 1.68 / 1.76 / 1.73 / 1.56 M windows/s
+  if (n_chunks > (size_t)max_chunks) n_chunks = max_chunks > 0 ? max_chunks : 1;
   for (size_t c = 0; c < n_chunks; ++c) {
     const size_t w0 = n * c / n_chunks, w1 = n * (c + 1) / n_chunks, m = w1 - w0;
     if (m == 0) continue;
@@ -432,11 +472,12 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     memset(&dout, 0, sizeof(dout));
     din.n_windows = (int32_t)m;
     din.ex_pose_shared = in->ex_pose_shared;
+    din.flags = in->flags;
     if (fwd) {
       const int64_t a = in->lm_offset[w0], b = in->lm_offset[w1];
       // components 3,4 (pts_j) are never read by the information-only marginalization: not copied
-      static const int comps[4] = {0, 1, 2, 5};
-      for (int ci = 0; ci < 4 && b > a; ++ci)
+      static const int comps[4] = {0, 1, 5, 2};     // pts_i.z last: skipped under ISV_IN_PTS_I_Z_ONE
+      for (int ci = 0; ci < (z_one ? 3 : 4) && b > a; ++ci)
         ISV_CUDA(cudaMemcpyAsync(d + o_obs + ((size_t)comps[ci] * n_lm + a) * D,
                                  in->lm_obs + (size_t)comps[ci] * in->lm_stride + a, (size_t)(b - a) * D,
                                  cudaMemcpyHostToDevice, s));
@@ -464,12 +505,23 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
       ISV_CUDA(cudaMemcpyAsync(d + o_sbb + w0 * 18 * D, in->sb_bwd + w0 * 18, m * 18 * D, cudaMemcpyHostToDevice, s));
       ISV_CUDA(cudaMemcpyAsync(d + o_pvb + w0 * ISV_VB_REC * D, in->prior_vb + w0 * ISV_VB_REC, m * ISV_VB_REC * D,
                                cudaMemcpyHostToDevice, s));
-      ISV_CUDA(cudaMemcpyAsync(d + o_pre + w0 * ISV_PREINT_REC * D, in->preint + w0 * ISV_PREINT_REC,
-                               m * ISV_PREINT_REC * D, cudaMemcpyHostToDevice, s));
+      if (!raw_imu) {
+        ISV_CUDA(cudaMemcpyAsync(d + o_pre + w0 * ISV_PREINT_REC * D, in->preint + w0 * ISV_PREINT_REC,
+                                 m * ISV_PREINT_REC * D, cudaMemcpyHostToDevice, s));
+      } else {
+        if (K) ISV_CUDA(cudaMemcpyAsync(d + o_iraw + w0 * K * 7 * D, in->imu_raw + w0 * K * 7, m * K * 7 * D, cudaMemcpyHostToDevice, s));
+        ISV_CUDA(cudaMemcpyAsync(d + o_iinit + w0 * 12 * D, in->imu_init + w0 * 12, m * 12 * D, cudaMemcpyHostToDevice, s));
+        if (in->imu_count)
+          ISV_CUDA(cudaMemcpyAsync(d + o_icnt + w0 * sizeof(int32_t), in->imu_count + w0, m * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        din.imu_raw = (const double*)(d + o_iraw) + w0 * K * 7;
+        din.imu_init = (const double*)(d + o_iinit) + w0 * 12;
+        din.imu_count = in->imu_count ? (const int32_t*)(d + o_icnt) + w0 : nullptr;
+        din.imu_k_max = in->imu_k_max;
+      }
       din.pose_bwd = (const double*)(d + o_poseb) + w0 * 14;
       din.sb_bwd = (const double*)(d + o_sbb) + w0 * 18;
       din.prior_vb = (const double*)(d + o_pvb) + w0 * ISV_VB_REC;
-      din.preint = (const double*)(d + o_pre) + w0 * ISV_PREINT_REC;
+      din.preint = raw_imu ? nullptr : (const double*)(d + o_pre) + w0 * ISV_PREINT_REC;
       dout.rel_out = (double*)(d + o_rel) + w0 * ISV_REL_REC;
       dout.vb_out = (double*)(d + o_vb) + w0 * ISV_VB_REC;
       dout.rp_out = (double*)(d + o_rp) + w0 * ISV_RP_REC;

@@ -45,7 +45,7 @@ constexpr int kFwdConst = 72;                // Psi (12 x 6)
 constexpr int kFwdWork = 832;                // tail matrices
 constexpr int kFwdSmemPerWarp = kFwdConst + kFwdWork;
 // ---- backward ---------------------------------------------------------------------------------
-constexpr int kBwdSmemPerWarp = 240 + 24 + 315 + 472 + 48;   // Lc | hv | Gs | T | sc (isv_window_kernels.cuh)
+constexpr int kBwdSmemPerWarp = 272 + 24 + 48 + 316 + 472 + 48;   // Lc | hv | pivot rows | Gs | T | sc (all even: 16-byte aligned)
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -239,8 +239,10 @@ marg_factor_jac_kernel(isv_batch_in in, isv_batch_out out, double* __restrict__ 
 // ---- kernel 1: landmark phase.  One warp per window, one landmark per lane and iteration;
 // writes the 21 + 21 lower-triangle entries of the two Gram matrices to gram[win][42].
 constexpr int kAccLd = 33;                         // reduction staging: [21][33] doubles per warp
-constexpr int kAccSmemPerWarp = 24 + 21 * kAccLd;  // constants F f tp ric + staging
+constexpr int kAccSmemPerWarp = 24 + 21 * kAccLd + 1;  // constants F f tp ric + staging (even: 16-byte aligned per warp)
 
+// ZONE = ISV_IN_PTS_I_Z_ONE: the caller guarantees pts_i.z == 1 (src/System.cpp:346); component 2 is then not read
+template <bool ZONE>
 __global__ void __launch_bounds__(kThreads, ISV_FWD_MINB)
 marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* wstatus, DevCfg cfg) {
   extern __shared__ double smem[];
@@ -276,7 +278,6 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
 
   const long long lm0 = in.lm_offset[win];
   const int L = (int)(in.lm_offset[win + 1] - lm0);
-  const double* __restrict__ ob = in.lm_obs + lm0;
   const long long st = in.lm_stride;
   const double s00 = cfg.ps[0], s10 = cfg.ps[1], s01 = cfg.ps[2], s11 = cfg.ps[3];
   // ric is used three times per landmark: keep it in registers; F, f, tp are broadcast LDS
@@ -294,7 +295,7 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
     double w[3], ph[3], qt[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      w[r] = K[3 * r] * px + K[3 * r + 1] * py + K[3 * r + 2] * pz;
+      w[r] = ZONE ? fma(K[3 * r], px, fma(K[3 * r + 1], py, K[3 * r + 2])) : K[3 * r] * px + K[3 * r + 1] * py + K[3 * r + 2] * pz;
       ph[r] = fma(lam, K[9 + r], w[r]);
     }
 #pragma unroll
@@ -302,15 +303,18 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
     const double c0 = fma(lam, K[12], qt[0]), c1 = fma(lam, K[13], qt[1]), c2 = fma(lam, K[14], qt[2]);
     // direction of s * jacobian_feature:  Pb q~ = [q0 - xb q2, q1 - yb q2] = lam / c2 * [q0 tp2 - q2 tp0,
     // q1 tp2 - q2 tp1]  (c~ = q~ + lam tp).  Only the direction matters (u enters as u u^T, v as v v^T), so it
-    // is taken from the cancellation-free right-hand side -- and the rsqrt does not wait for the division.
+    // is taken from the cancellation-free right-hand side.
     const double nt0 = fma(qt[0], K[14], -qt[2] * K[12]), nt1 = fma(qt[1], K[14], -qt[2] * K[13]);
     const double g0 = s00 * nt0 + s01 * nt1, g1 = s10 * nt0 + s11 * nt1;
     const double n2 = g0 * g0 + g1 * g1;
-    const double rn = rsqrt(n2);
-    const double rho = 1.0 / c2;
-    const double xb = c0 * rho, yb = c1 * rho;
+    // ONE reciprocal square root gives both 1 / (|g| c2) and rho = 1 / c2 (the FP64 division and rsqrt are the two
+    // longest instruction sequences of the chain):  r = rsqrt(n2 c2^2) ;  1 / (|g| c2) = sign(c2) r ;  rho = r^2 n2 c2
+    const double r = rsqrt(n2 * (c2 * c2));
     const bool ok = n2 > 0.0;
-    const double in_ = rn * rho;
+    double rho = (r * r) * (n2 * c2);
+    double in_ = copysign(r, c2);
+    if (__builtin_expect(!ok, 0)) { rho = 1.0 / c2; in_ = 0.0; }      // degenerate observation (flagged below)
+    const double xb = c0 * rho, yb = c1 * rho;
     const double u0 = ok ? g0 * in_ : rho, u1 = ok ? g1 * in_ : 0.0;        // (u, v) pre-scaled by rho
     const double a0 = u0 * s00 + u1 * s10, a1 = u0 * s01 + u1 * s11;        // rho s^T u
     const double b0 = -u1 * s00 + u0 * s10, b1 = -u1 * s01 + u0 * s11;      // rho s^T v
@@ -338,40 +342,47 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
         ++t;
       }
   };
-  // Two landmarks per lane and iteration (k and k + 32): their projection chains are independent, which
-  // doubles the instruction-level parallelism of the latency-bound part; loads run two iterations ahead.
-  constexpr int kPf = 4;
-  const double* __restrict__ obx = ob + lane;
-  const double* __restrict__ oby = ob + st + lane;
-  const double* __restrict__ obz = ob + 2 * st + lane;
-  const double* __restrict__ obl = ob + 5 * st + lane;
-  double nx[kPf], ny[kPf], nz[kPf], nl[kPf];
+  // Two landmarks per lane and step (k and k + 32): their projection chains are independent, which doubles the
+  // instruction-level parallelism of the latency-bound part.  The observations travel through a ring of four register
+  // entries (entry e = landmarks base + 32 e + lane); an entry is refilled -- for the landmark 128 further on, i.e. two
+  // steps ahead -- as soon as its values have been copied out.  The loop is unrolled over the ring, so ring indices are
+  // compile-time (no register shuffling) and the loads use immediate offsets from four running pointers.
+  const double* __restrict__ qx = in.lm_obs + lm0 + lane;
+  const double* __restrict__ qy = qx + st;
+  const double* __restrict__ qz = qx + 2 * st;
+  const double* __restrict__ ql = qx + 5 * st;
+  double rx[4], ry[4], rz[4], rl[4];
 #pragma unroll
-  for (int d = 0; d < kPf; ++d) {
-    nx[d] = 0.0; ny[d] = 0.0; nz[d] = 0.0; nl[d] = 1.0;
-    if (d * 32 + lane < L) { nx[d] = obx[d * 32]; ny[d] = oby[d * 32]; nz[d] = obz[d * 32]; nl[d] = obl[d * 32]; }
+  for (int e = 0; e < 4; ++e) {
+    rx[e] = 0.0; ry[e] = 0.0; rz[e] = 1.0; rl[e] = 1.0;
+    if (32 * e + lane < L) { rx[e] = qx[32 * e]; ry[e] = qy[32 * e]; if (!ZONE) rz[e] = qz[32 * e]; rl[e] = ql[32 * e]; }
   }
-  for (int base = 0; base < L; base += 64) {
-    const double pxa = nx[0], pya = ny[0], pza = nz[0], la = nl[0];
-    const double pxb = nx[1], pyb = ny[1], pzb = nz[1], lb = nl[1];
-    nx[0] = nx[2]; ny[0] = ny[2]; nz[0] = nz[2]; nl[0] = nl[2];
-    nx[1] = nx[3]; ny[1] = ny[3]; nz[1] = nz[3]; nl[1] = nl[3];
+  for (int base = 0; base < L; base += 128) {
 #pragma unroll
-    for (int d = 2; d < 4; ++d) {
-      const int kn = base + 32 * (d + 2);
-      if (kn + lane < L) { nx[d] = obx[kn]; ny[d] = oby[kn]; nz[d] = obz[kn]; nl[d] = obl[kn]; }
+    for (int h = 0; h < 2; ++h) {
+      const int i0 = base + 64 * h;
+      if (i0 >= L) break;
+      const double pxa = rx[2 * h], pya = ry[2 * h], pza = rz[2 * h], la = rl[2 * h];
+      const double pxb = rx[2 * h + 1], pyb = ry[2 * h + 1], pzb = rz[2 * h + 1], lb = rl[2 * h + 1];
+#pragma unroll
+      for (int e = 2 * h; e < 2 * h + 2; ++e)
+        if (base + 128 + 32 * e + lane < L) {
+          rx[e] = qx[128 + 32 * e]; ry[e] = qy[128 + 32 * e]; if (!ZONE) rz[e] = qz[128 + 32 * e]; rl[e] = ql[128 + 32 * e];
+        }
+      double yea[6], ywa[6], yeb[6], ywb[6];
+      if (i0 + 32 + lane < L) {
+        int bad = chain(pxa, pya, pza, la, yea, ywa);
+        bad |= chain(pxb, pyb, pzb, lb, yeb, ywb);
+        syrk(yea, ywa);
+        syrk(yeb, ywb);
+        if (bad) status |= ISV_W_SINGULAR;
+      } else if (i0 + lane < L) {
+        if (chain(pxa, pya, pza, la, yea, ywa)) status |= ISV_W_SINGULAR;
+        syrk(yea, ywa);
+      }
     }
-    double yea[6], ywa[6], yeb[6], ywb[6];
-    if (base + 32 + lane < L) {
-      int bad = chain(pxa, pya, pza, la, yea, ywa);
-      bad |= chain(pxb, pyb, pzb, lb, yeb, ywb);
-      syrk(yea, ywa);
-      syrk(yeb, ywb);
-      if (bad) status |= ISV_W_SINGULAR;
-    } else if (base + lane < L) {
-      if (chain(pxa, pya, pza, la, yea, ywa)) status |= ISV_W_SINGULAR;
-      syrk(yea, ywa);
-    }
+    qx += 128; qy += 128; ql += 128;
+    if (!ZONE) qz += 128;
   }
   // cross-lane reduction through shared memory: lane l parks its 21 partial sums in column l of a
   // [21][33] tile, then lane t adds up row t (conflict-free both ways) -- 4x fewer instructions than
@@ -594,7 +605,8 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
 // STS and two DFMA.  The prior's sqrt_info is upper triangular (LLT(...).matrixL().transpose()), so
 // reflector k only touches row k and the 15 IMU rows.
 constexpr int kGld = 21;  // G rows in shared memory: element (k, c) at Gs[k * 21 + c]
-constexpr int kBwdLc = 0, kBwdHv = 240, kBwdGs = 264, kBwdT = 579;
+constexpr int kBwdLc = 0, kBwdHv = 272, kBwdPv = 296, kBwdGs = 344, kBwdT = 660;
+constexpr int kLcLd = 16;   // Cholesky factor of the covariance: column k at Lc[16 k + i] (16-byte aligned pairs), [256..271) = 1 / L_kk
 __global__ void __launch_bounds__(kThreads, ISV_BWD_MINB)
 marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restrict__ fj, DevCfg cfg, int vo_size) {
   extern __shared__ double smem[];
@@ -603,8 +615,9 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
   const int win = blockIdx.x * kWarpsPerCta + warp;
   if (win >= in.n_windows) return;
   double* S = smem + warp * kBwdSmemPerWarp;
-  double* Lc = S + kBwdLc;     // Cholesky factor of the covariance, column k at Lc[15 k + i]; [225..240) = 1 / L_kk
+  double* Lc = S + kBwdLc;     // Cholesky factor of the covariance, column k at Lc[16 k + i]; [256..271) = 1 / L_kk
   double* hv = S + kBwdHv;     // current Householder vector (15) + tau
+  double* pvt = S + kBwdPv;    // LQ: the pivot row of the current step (two buffers of 24, alternating)
   double* Gs = S + kBwdGs;     // 15 x 21
   double* T = S + kBwdT;       // Jrel (72) | Jrp (16) | JU / Ls (256) | cov 9x9, 6x6, 2x2 (128)
   double* sc = T + 472;        // scratch of the general path: dinv[0..21), lam[24..)
@@ -636,15 +649,27 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
         const double d = a[k];
         if (!(d > 0.0)) status |= ISV_W_NOT_SPD;
         const double ri = rsqrt(d);
-        Lc[225 + k] = ri;
+        Lc[256 + k] = ri;
+        // column k, rows k..14, stored as aligned pairs (row k - 1 of an odd k rides along: never read)
+        double2* c2 = reinterpret_cast<double2*>(Lc + kLcLd * k);
 #pragma unroll
-        for (int i = k; i < 15; ++i) Lc[15 * k + i] = (i == k) ? d * ri : a[i] * ri;
+        for (int i = k & ~1; i < 16; i += 2) {
+          const double lo = (i == k) ? d * ri : a[i < 15 ? i : 14] * ri;
+          const double hi = (i + 1 == k) ? d * ri : a[i + 1 < 15 ? i + 1 : 14] * ri;
+          c2[i >> 1] = make_double2(lo, hi);
+        }
       }
       __syncwarp();
       if (lane > k && lane < 15) {
-        const double ljk = Lc[15 * k + j];
+        const double ljk = Lc[kLcLd * k + j];
+        const double2* c2 = reinterpret_cast<const double2*>(Lc + kLcLd * k);
+        // rows < j are dead weight; row k itself (when the first pair starts at k) is dead after its pivot
 #pragma unroll
-        for (int i = k + 1; i < 15; ++i) a[i] = fma(-Lc[15 * k + i], ljk, a[i]);   // rows < j are dead weight
+        for (int i = (k + 1) & ~1; i < 15; i += 2) {
+          const double2 l2 = c2[i >> 1];
+          if (i > k) a[i] = fma(-l2.x, ljk, a[i]);
+          if (i + 1 < 15) a[i + 1] = fma(-l2.y, ljk, a[i + 1]);
+        }
       }
     }
     __syncwarp();
@@ -666,8 +691,8 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
   for (int i = 0; i < 15; ++i) {
     double sacc = col[i];
 #pragma unroll
-    for (int l = 0; l < i; ++l) sacc = fma(-Lc[15 * l + i], col[l], sacc);
-    col[i] = sacc * Lc[225 + i];
+    for (int l = 0; l < i; ++l) sacc = fma(-Lc[kLcLd * l + i], col[l], sacc);
+    col[i] = sacc * Lc[256 + i];
   }
   // ---- Schur complement over VB_{V-1} (:1413-1419) as a QR elimination of columns 21..29 -----------
   // Reflectors in unnormalised form  H = I - gamma w w^T ,  w = [x0 - beta ; tail] ,
@@ -690,22 +715,28 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
         gamma = 1.0 / (ab * (ab + ax));
         w0 = (x0 >= 0.0) ? (ax + ab) : -(ax + ab);     // x0 - beta , beta = -sign(x0) |beta|
       }
+      // the reflector travels as nine 16-byte words: [0..14] tail, [15] gamma, [16] w0 ([17] unused)
+      double2* h2 = reinterpret_cast<double2*>(hv);
 #pragma unroll
-      for (int i = 0; i < 15; ++i) hv[i] = col[i];
-      hv[15] = gamma;
-      hv[16] = w0;
+      for (int i = 0; i < 14; i += 2) h2[i >> 1] = make_double2(col[i], col[i + 1]);
+      h2[7] = make_double2(col[14], gamma);
+      h2[8] = make_double2(w0, 0.0);
     }
     __syncwarp();
     {
       // apply H to every live column other than 21+k; row k is zero outside the VB columns
-      const double gamma = hv[15], w0 = hv[16];
+      const double2* h2 = reinterpret_cast<const double2*>(hv);
+      double hr[16];
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) { const double2 t = h2[i >> 1]; hr[i] = t.x; hr[i + 1] = t.y; }
+      const double gamma = hr[15], w0 = h2[8].x;
       double d0 = (lane > 21 + k && lane < 30) ? pr[k] * w0 : 0.0, d1 = 0.0, d2 = 0.0;
 #pragma unroll
-      for (int i = 0; i < 15; i += 3) { d0 = fma(hv[i], col[i], d0); d1 = fma(hv[i + 1], col[i + 1], d1); d2 = fma(hv[i + 2], col[i + 2], d2); }
+      for (int i = 0; i < 15; i += 3) { d0 = fma(hr[i], col[i], d0); d1 = fma(hr[i + 1], col[i + 1], d1); d2 = fma(hr[i + 2], col[i + 2], d2); }
       const double sd = gamma * ((d0 + d1) + d2);
       if (lane < 21 || lane > 21 + k) {
 #pragma unroll
-        for (int i = 0; i < 15; ++i) col[i] = fma(-sd, hv[i], col[i]);
+        for (int i = 0; i < 15; ++i) col[i] = fma(-sd, hr[i], col[i]);
       }
     }
     __syncwarp();
@@ -743,6 +774,11 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
     }
   }
   // (reflectors in the unnormalised form of the elimination above: H = I - gamma w w^T, w = [x0 - beta ; x_tail])
+  // The pivot row of step j is broadcast through shared memory: its owner stores the tail (and |tail|^2, x0) as
+  // 16-byte words, everybody reads them back with 128-bit broadcast loads -- a quarter of the MIO instructions of the
+  // 64-bit shuffles this replaced (ncu: the shuffles were MIO-throttled half of the time).  Two buffers alternate so
+  // that one __syncwarp per step suffices.  A zero tail (tt == 0: the row is already reduced) gives gamma = 0, i.e. the
+  // identity, without a branch: the steps stay in one basic block and overlap.
 #pragma unroll
   for (int j = 0; j < 15; ++j) {
     double t0 = 0.0, t1 = 0.0, t2 = 0.0;
@@ -752,49 +788,66 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
       else if ((c - j) % 3 == 2) t1 = fma(row[c], row[c], t1);
       else t2 = fma(row[c], row[c], t2);
     }
-    const double tt = __shfl_sync(kFullMask, (t0 + t1) + t2, j);
-    const double x0 = __shfl_sync(kFullMask, row[j], j);
-    if (tt > 0.0) {
-      const double nrm = fma(x0, x0, tt);
-      const double ab = nrm * rsqrt(nrm);              // |beta|
-      const double ax = fabs(x0);
-      const double gamma = 1.0 / (ab * (ab + ax));
-      const double w0 = (x0 >= 0.0) ? (ax + ab) : -(ax + ab);   // x0 - beta
-      const double beta = (x0 >= 0.0) ? -ab : ab;
-      double v[21];
-      double d0 = row[j] * w0, d1 = 0.0, d2 = 0.0;
+    double2* pw = reinterpret_cast<double2*>(pvt + 24 * (j & 1));
+    constexpr int kFirstPair = 0;   // (placeholder so the pair index below reads naturally)
+    if (lane == j) {
 #pragma unroll
-      for (int c = j + 1; c < 21; ++c) {
-        v[c] = __shfl_sync(kFullMask, row[c], j);
-        if ((c - j) % 3 == 1) d0 = fma(v[c], row[c], d0);
-        else if ((c - j) % 3 == 2) d1 = fma(v[c], row[c], d1);
-        else d2 = fma(v[c], row[c], d2);
-      }
-      const double sdot = gamma * ((d0 + d1) + d2);
-      // uniform update (no divergence): the pivot lane's own tail becomes rounding-level garbage instead of
-      // exact zeros -- it is never read again (later reflectors read lane j' > j, the solve reads only the
-      // lower triangle of L)
-      row[j] = (lane == j) ? beta : fma(-sdot, w0, row[j]);
-#pragma unroll
-      for (int c = j + 1; c < 21; ++c) row[c] = fma(-sdot, v[c], row[c]);
+      for (int pp = (j + 1) >> 1; pp < 11; ++pp) pw[pp] = make_double2(row[2 * pp], (2 * pp + 1 < 21) ? row[2 * pp + 1] : 0.0);
+      pw[11] = make_double2((t0 + t1) + t2, row[j]);
     }
-  }
-  // L (rows of lanes 0-14, lower triangular) -> shared; solve L^T y = rhs for all 32 lanes at once:
-  // lanes 0-14: rhs = e_lane (columns of L^-T, for the eigenvalue bound), lanes 15-31: rhs = (Jr Q^T)_r
-  double* Ls = T + 88;  // 15 x 15 (ld 15) + 15 reciprocal diagonals; overlays JU, which is written later
-  if (lane < 15) {
+    __syncwarp();
+    const double2 hx = pw[11];
+    const double tt = hx.x, x0 = hx.y;
+    const bool nzt = tt > 0.0;
+    const double nrm = fma(x0, x0, tt);
+    const double ab = nrm * rsqrt(nrm);              // |beta|
+    const double ax = fabs(x0);
+    const double gamma = nzt ? 1.0 / (ab * (ab + ax)) : 0.0;
+    const double w0 = nzt ? ((x0 >= 0.0) ? (ax + ab) : -(ax + ab)) : 0.0;   // x0 - beta
+    const double beta = nzt ? ((x0 >= 0.0) ? -ab : ab) : x0;
+    double v[22];
 #pragma unroll
-    for (int c = 0; c < 15; ++c) Ls[lane + 15 * c] = row[c];
-    Ls[225 + lane] = 1.0 / row[lane];
+    for (int pp = (j + 1) >> 1; pp < 11; ++pp) { const double2 t = pw[pp]; v[2 * pp] = t.x; v[2 * pp + 1] = t.y; }
+    double d0 = row[j] * w0, d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int c = j + 1; c < 21; ++c) {
+      if ((c - j) % 3 == 1) d0 = fma(v[c], row[c], d0);
+      else if ((c - j) % 3 == 2) d1 = fma(v[c], row[c], d1);
+      else d2 = fma(v[c], row[c], d2);
+    }
+    const double sdot = gamma * ((d0 + d1) + d2);
+    // uniform update (no divergence): the pivot lane's own tail becomes rounding-level garbage instead of
+    // exact zeros -- it is never read again (later reflectors read lane j' > j, the solve reads only the
+    // lower triangle of L)
+    row[j] = (lane == j) ? beta : fma(-sdot, w0, row[j]);
+#pragma unroll
+    for (int c = j + 1; c < 21; ++c) row[c] = fma(-sdot, v[c], row[c]);
+    (void)kFirstPair;
   }
   __syncwarp();
-  double y[15];
+  // L (rows of lanes 0-14, lower triangular) -> shared; solve L^T y = rhs for all 32 lanes at once:
+  // lanes 0-14: rhs = e_lane (columns of L^-T, for the eigenvalue bound), lanes 15-31: rhs = (Jr Q^T)_r
+  double* Ls = T + 88;  // 15 x 15 (ld 16: column k at Ls[16 k + m], 16-byte aligned pairs) + 15 reciprocal diagonals at [240..);
+                        // overlays JU, which is written later
+  if (lane < 15) {
+#pragma unroll
+    for (int c = 0; c < 15; ++c) Ls[lane + 16 * c] = row[c];
+    Ls[240 + lane] = 1.0 / row[lane];
+  }
+  __syncwarp();
+  double y[16];
+  y[15] = 0.0;
 #pragma unroll
   for (int k = 14; k >= 0; --k) {
     double sacc = (lane < 15) ? ((lane == k) ? 1.0 : 0.0) : row[k];
+    const double2* l2 = reinterpret_cast<const double2*>(Ls + 16 * k);
 #pragma unroll
-    for (int m2 = k + 1; m2 < 15; ++m2) sacc = fma(-Ls[m2 + 15 * k], y[m2], sacc);
-    y[k] = sacc * Ls[225 + k];
+    for (int m2 = (k + 1) & ~1; m2 < 15; m2 += 2) {
+      const double2 t = l2[m2 >> 1];
+      if (m2 > k) sacc = fma(-t.x, y[m2], sacc);
+      if (m2 + 1 < 15) sacc = fma(-t.y, y[m2 + 1], sacc);
+    }
+    y[k] = sacc * Ls[240 + k];
   }
   double ninv2 = 0.0;
 #pragma unroll

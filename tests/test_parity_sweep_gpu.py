@@ -216,3 +216,31 @@ def test_full_size_ragged_batch_is_schedule_independent(backend):
     assert np.all(np.tril(S, -1) == 0) and np.all(np.diagonal(S, axis1=1, axis2=2) > 0)
     S9 = out.vb[:, 9:90].reshape(-1, 9, 9).transpose(0, 2, 1)
     assert np.all(np.tril(S9, -1) == 0) and np.all(np.diagonal(S9, axis1=1, axis2=2) > 0)
+
+
+def test_raw_imu_and_z_one_inputs(backend):
+    """ABI 2 inputs: raw IMU samples instead of the pre-integration record (preintegrate_kernel runs inside the batch
+    call) and ISV_IN_PTS_I_Z_ONE (pts_i.z not read / not copied).  Forward results agree with the ABI 1 path to rounding,
+    backward results match the oracle (whose record came from the NumPy IntegrationBase) at 1e-9; the host-pointer entry
+    point gives the device path's bits and rejects a broken z promise."""
+    b = bench.make_batch(150, 700, 801)
+    ref = ref_c.marg_window_batch(b, 3, 0, True)
+    out0 = _run_gpu(backend, b)
+    db = DeviceBatch(b, "cuda:0", raw_imu=True, z_one=True)
+    backend.marg_window_batch(db, capi.RUN_BOTH)
+    backend.synchronize()
+    out1 = db.outputs()
+    # z == 1 folded into the arithmetic (F p = F[:,0] x + F[:,1] y + F[:,2]): same value, different rounding
+    assert outputs_rel_diff(out1, out0, 1).max() <= 1e-12
+    assert not out1.status.any() and np.array_equal(out1.rank, ref.rank)
+    e_ref, e_01 = outputs_rel_diff(out1, ref, 3).max(), outputs_rel_diff(out1, out0, 2).max()
+    print(f"\nraw-IMU path: vs oracle {e_ref:.2e}, vs record path {e_01:.2e}")
+    assert e_ref <= TOL and e_01 <= 1e-10
+    out2 = backend.marg_window_batch_host(b, capi.RUN_BOTH, raw_imu=True, z_one=True)
+    for f in FIELDS:
+        assert np.array_equal(getattr(out1, f), getattr(out2, f)), f
+    out3 = backend.marg_window_batch_host(b, capi.RUN_BACKWARD, raw_imu=True)
+    assert np.array_equal(out3.vb, out1.vb) and np.array_equal(out3.rel, out1.rel)
+    b.lm_obs[2, 0] = 2.0                                   # the promise is spot-checked on the host path
+    with pytest.raises(capi.IsvError):
+        backend.marg_window_batch_host(b, capi.RUN_BOTH, z_one=True)
