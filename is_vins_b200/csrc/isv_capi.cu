@@ -122,9 +122,9 @@ isv_status isv_create(const isv_config* cfg, int device, isv_handle** out) {
   for (int i = 0; i < 6; ++i) cudaEventCreateWithFlags(&h->jac_ev[i], cudaEventDisableTiming);
   h->stream = h->own_stream;
   cudaFuncSetAttribute(marg_forward_accum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)(kWarpsPerCta * kAccSmemPerWarp * sizeof(double)));
+                       (int)(kAccWarps * kAccSmemPerWarp * sizeof(double)));
   cudaFuncSetAttribute(marg_forward_accum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)(kWarpsPerCta * kAccSmemPerWarp * sizeof(double)));
+                       (int)(kAccWarps * kAccSmemPerWarp * sizeof(double)));
   cudaFuncSetAttribute(marg_forward_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kWarpsPerCta * kFwdSmemPerWarp * sizeof(double)));
   cudaFuncSetAttribute(marg_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -277,11 +277,12 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in_arg, const 
     ++h->launches;
   }
   if (stage1) {
+    const int agrid = (n + kAccWarps - 1) / kAccWarps;
     if (in->flags & ISV_IN_PTS_I_Z_ONE)
-      marg_forward_accum_kernel<true><<<grid, kThreads, kWarpsPerCta * kAccSmemPerWarp * sizeof(double), stream>>>(
+      marg_forward_accum_kernel<true><<<agrid, 32 * kAccWarps, kAccWarps * kAccSmemPerWarp * sizeof(double), stream>>>(
           *in, gram, out->status, h->dcfg);
     else
-      marg_forward_accum_kernel<false><<<grid, kThreads, kWarpsPerCta * kAccSmemPerWarp * sizeof(double), stream>>>(
+      marg_forward_accum_kernel<false><<<agrid, 32 * kAccWarps, kAccWarps * kAccSmemPerWarp * sizeof(double), stream>>>(
           *in, gram, out->status, h->dcfg);
     ++h->launches;
   }

@@ -242,13 +242,29 @@ constexpr int kAccLd = 33;                         // reduction staging: [21][33
 constexpr int kAccSmemPerWarp = 24 + 21 * kAccLd + 1;  // constants F f tp ric + staging (even: 16-byte aligned per warp)
 
 // ZONE = ISV_IN_PTS_I_Z_ONE: the caller guarantees pts_i.z == 1 (src/System.cpp:346); component 2 is then not read
+// Warps per CTA of the landmark kernel.  A warp owns a whole window, so a CTA lives as long as its LONGEST window: with
+// ragged landmark counts (L ~ U{0.75 .. 1.25} mean) four windows per CTA idle ~15 % of their slots waiting for the
+// largest one.  One warp per CTA removes that, and 224 registers x 32 threads also packs 9 instead of 8 warps per SM.
+#ifndef ISV_ACC_WARPS
+#define ISV_ACC_WARPS 1
+#endif
+constexpr int kAccWarps = ISV_ACC_WARPS;
+#ifndef ISV_ACC_MINB
+#define ISV_ACC_MINB (ISV_FWD_MINB * kWarpsPerCta / kAccWarps)
+#endif
+
+#ifdef ISV_ACC_MAXNREG
+#define ISV_ACC_BOUNDS __maxnreg__(ISV_ACC_MAXNREG)
+#else
+#define ISV_ACC_BOUNDS __launch_bounds__(32 * kAccWarps, ISV_ACC_MINB)
+#endif
 template <bool ZONE>
-__global__ void __launch_bounds__(kThreads, ISV_FWD_MINB)
+__global__ void ISV_ACC_BOUNDS
 marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* wstatus, DevCfg cfg) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int win = blockIdx.x * kWarpsPerCta + warp;
+  const int win = blockIdx.x * kAccWarps + warp;
   if (win >= in.n_windows) return;
   double* K = smem + warp * kAccSmemPerWarp;  // [0]F [9]f [12]tp [15]ric
   double* R = K + 24;                         // reduction staging
@@ -357,11 +373,14 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
     rx[e] = 0.0; ry[e] = 0.0; rz[e] = 1.0; rl[e] = 1.0;
     if (32 * e + lane < L) { rx[e] = qx[32 * e]; ry[e] = qy[32 * e]; if (!ZONE) rz[e] = qz[32 * e]; rl[e] = ql[32 * e]; }
   }
-  for (int base = 0; base < L; base += 128) {
+  // Main loop: whole super-steps of 128 landmarks.  Every lane has work, so the body carries no predicate and no branch:
+  // one basic block of four chains and four SYRKs that the scheduler is free to interleave (the SYRK of one step hides
+  // the dependent chain of the next).  Only the refills are predicated (the prefetch runs past the window's end).
+  int base = 0;
+#pragma unroll 1
+  for (; base + 128 <= L; base += 128) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int i0 = base + 64 * h;
-      if (i0 >= L) break;
       const double pxa = rx[2 * h], pya = ry[2 * h], pza = rz[2 * h], la = rl[2 * h];
       const double pxb = rx[2 * h + 1], pyb = ry[2 * h + 1], pzb = rz[2 * h + 1], lb = rl[2 * h + 1];
 #pragma unroll
@@ -370,19 +389,33 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
           rx[e] = qx[128 + 32 * e]; ry[e] = qy[128 + 32 * e]; if (!ZONE) rz[e] = qz[128 + 32 * e]; rl[e] = ql[128 + 32 * e];
         }
       double yea[6], ywa[6], yeb[6], ywb[6];
+      int bad = chain(pxa, pya, pza, la, yea, ywa);
+      bad |= chain(pxb, pyb, pzb, lb, yeb, ywb);
+      syrk(yea, ywa);
+      syrk(yeb, ywb);
+      if (bad) status |= ISV_W_SINGULAR;
+    }
+    qx += 128; qy += 128; ql += 128;
+    if (!ZONE) qz += 128;
+  }
+  // Tail: fewer than 128 landmarks left (already in the ring), predicated per lane.
+  if (base < L) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i0 = base + 64 * h;
+      if (i0 >= L) break;
+      double yea[6], ywa[6], yeb[6], ywb[6];
       if (i0 + 32 + lane < L) {
-        int bad = chain(pxa, pya, pza, la, yea, ywa);
-        bad |= chain(pxb, pyb, pzb, lb, yeb, ywb);
+        int bad = chain(rx[2 * h], ry[2 * h], rz[2 * h], rl[2 * h], yea, ywa);
+        bad |= chain(rx[2 * h + 1], ry[2 * h + 1], rz[2 * h + 1], rl[2 * h + 1], yeb, ywb);
         syrk(yea, ywa);
         syrk(yeb, ywb);
         if (bad) status |= ISV_W_SINGULAR;
       } else if (i0 + lane < L) {
-        if (chain(pxa, pya, pza, la, yea, ywa)) status |= ISV_W_SINGULAR;
+        if (chain(rx[2 * h], ry[2 * h], rz[2 * h], rl[2 * h], yea, ywa)) status |= ISV_W_SINGULAR;
         syrk(yea, ywa);
       }
     }
-    qx += 128; qy += 128; ql += 128;
-    if (!ZONE) qz += 128;
   }
   // cross-lane reduction through shared memory: lane l parks its 21 partial sums in column l of a
   // [21][33] tile, then lane t adds up row t (conflict-free both ways) -- 4x fewer instructions than
