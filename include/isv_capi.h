@@ -175,6 +175,34 @@ isv_status isv_marg_window_batch(isv_handle* h, const isv_batch_in* in, const is
 isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in,
                                       const isv_batch_out* out, int which);
 
+/* ---- forensic mode (NOT the hot path; SURVEY.md 7.3 item 5: the dense route "must be available") --------------
+ * isv_marg_forensic_batch = isv_marg_window_batch(ISV_RUN_BOTH) plus:
+ *   - the structured route's intermediates: Lamda_prior of MargForward (src/estimator.cpp:1288) and the factor G with
+ *     G^T G = Lamda_prior of MargBackward (:1419), so that a parity break can be localised on the GPU;
+ *   - the reference's KLD diagnostics (computed and discarded there): forward :1333-1345, backward :1522-1534 together
+ *     with the absolute-position / yaw informations of :1518-1519 that only feed it.
+ * All pointers are DEVICE pointers; stream-ordered.                                                              */
+typedef struct isv_forensic_out {
+  double* lamda_prior_fwd;       /* [n][36]  6x6 column-major (required)                                */
+  double* g_bwd;                 /* [n][315] 15x21, row k at [21 k + c] (required)                       */
+  double* kld_fwd;               /* [n] NaN when FullPivHouseholderQR's rank < 6 (required)              */
+  double* kld_bwd;               /* [n] (required)                                                       */
+  double* lamda_prior_bwd;       /* [n][441] 21x21 = G^T G, column-major (may be NULL)                   */
+  double* eig_bwd;               /* [n][21] eigenvalues of it, ascending (may be NULL)                   */
+  double* info_abs;              /* [n][9]  (may be NULL)                                                */
+  double* info_yaw;              /* [n]     (may be NULL)                                                */
+} isv_forensic_out;
+isv_status isv_marg_forensic_batch(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out,
+                                   const isv_forensic_out* dbg);
+/* The reference's dense route on normal equations that are already assembled (isv_build_normal_equations):
+ * A [n_problems][n*n] column-major symmetric, kept block [0, m0), marginalized block [m0, n).  Inverts the WHOLE
+ * marginalized block with a full-pivot elimination (the algorithm class of `fullPivLu().solve(Identity)`,
+ * src/estimator.cpp:1286, :1417; dependent unknowns zero-filled) and returns A_rr - A_rm A_mm^-1 A_rm^T
+ * (A_prior [n_problems][m0*m0]), optionally the inverse (Amm_inv [n_problems][m*m], may be NULL) and the number of
+ * accepted pivots (rank, may be NULL).  n - m0 <= 1024.  Device pointers, stream-ordered, O(m^3) per problem.  */
+isv_status isv_literal_schur(isv_handle* h, int n_problems, int n, int m0, const double* A, double* A_prior,
+                             double* Amm_inv, int32_t* rank);
+
 /* ---- single-window convenience wrappers (host pointers, blocking) ----------------------------
  * These are what the shim's Estimator::MargForward()/MargBackward() call.                       */
 typedef struct isv_fwd_in {

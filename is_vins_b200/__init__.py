@@ -13,3 +13,4 @@ from .marginalization import MarginalizationInfo, PriorState, ResidualBlockInfo,
 __all__ = ["capi", "WindowBatch", "WindowOutputs", "pack_events", "DeviceBatch", "MargBackend",
            "FactorProblem", "DeviceProblem", "eval_problem", "SequenceState", "MarginalizationInfo", "PriorState", "ResidualBlockInfo",
            "add_margin_old_blocks"]
+from .forensic import forensic_batch, literal_forward  # noqa: F401

@@ -53,6 +53,11 @@ class isv_batch_out(C.Structure):
                 ("vb_out", C.c_void_p), ("rp_out", C.c_void_p), ("rank", C.c_void_p), ("status", C.c_void_p)]
 
 
+class isv_forensic_out(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("lamda_prior_fwd", "g_bwd", "kld_fwd", "kld_bwd", "lamda_prior_bwd", "eig_bwd",
+                                          "info_abs", "info_yaw")]
+
+
 class isv_init_in(C.Structure):
     _fields_ = [("n_windows", C.c_int32), ("poses", C.c_void_p), ("sbs", C.c_void_p), ("preint", C.c_void_p)]
 
@@ -169,6 +174,8 @@ SYMBOLS = [
     ("isv_order_map_backward", C.c_int, [C.c_int, c_int32_p]),
     ("isv_marg_window_batch", C.c_int, [_H, C.POINTER(isv_batch_in), C.POINTER(isv_batch_out), C.c_int]),
     ("isv_marg_window_batch_host", C.c_int, [_H, C.POINTER(isv_batch_in), C.POINTER(isv_batch_out), C.c_int]),
+    ("isv_marg_forensic_batch", C.c_int, [_H, C.POINTER(isv_batch_in), C.POINTER(isv_batch_out), C.POINTER(isv_forensic_out)]),
+    ("isv_literal_schur", C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("isv_marg_forward", C.c_int, [_H, C.POINTER(isv_fwd_in), C.POINTER(isv_fwd_out)]),
     ("isv_marg_backward", C.c_int, [_H, C.POINTER(isv_bwd_in), C.POINTER(isv_bwd_out)]),
     ("isv_marg_event", C.c_int, [_H, C.POINTER(isv_fwd_in), C.POINTER(isv_bwd_in), C.POINTER(isv_fwd_out), C.POINTER(isv_bwd_out)]),

@@ -17,6 +17,7 @@
 #include "isv_preint_kernel.cuh"
 #include "isv_seq_kernels.cuh"
 #include "isv_window_kernels.cuh"
+#include "isv_forensic.cuh"
 
 using namespace isv;
 
@@ -226,8 +227,10 @@ static isv_status check_batch(const isv_batch_in* in, const isv_batch_out* out, 
 // and (when the caller hands raw IMU samples instead of the record) the pre-integration records
 constexpr size_t kScratchPerWindow = 42 + kFJ + ISV_PREINT_REC;
 
+struct DbgStores { double* lamda_prior_fwd; double* g_bwd; };
+
 static isv_status launch_batch(isv_handle* h, const isv_batch_in* in_arg, const isv_batch_out* out, int which,
-                               cudaStream_t stream, double* scratch) {
+                               cudaStream_t stream, double* scratch, DbgStores dbg = DbgStores{nullptr, nullptr}) {
   const int n = in_arg->n_windows;
   if (n == 0) return ISV_OK;
   if (!scratch) return ISV_ERR_BAD_ARG;
@@ -288,14 +291,14 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in_arg, const 
   }
   if (bwd) {
     marg_backward_kernel<<<grid, kThreads, kWarpsPerCta * kBwdSmemPerWarp * sizeof(double), bs>>>(*in, *out, fj, h->dcfg,
-                                                                                                 h->cfg.vo_size);
+                                                                                                 h->cfg.vo_size, dbg.g_bwd);
     ++h->launches;
   }
   if (fork_b) ISV_CUDA(cudaEventRecord(ev[1], bs));
   if (fork_f) ISV_CUDA(cudaStreamWaitEvent(stream, ev[2], 0));
   if (stage2) {
-    marg_forward_tail_kernel<<<grid, kThreads, kWarpsPerCta * kFwdSmemPerWarp * sizeof(double), stream>>>(*in, *out, gram,
-                                                                                                        fj, h->dcfg);
+    marg_forward_tail_kernel<<<grid, kThreads, kWarpsPerCta * kFwdSmemPerWarp * sizeof(double), stream>>>(
+        *in, *out, gram, fj, h->dcfg, dbg.lamda_prior_fwd);
     ++h->launches;
   }
   if (fork_b) ISV_CUDA(cudaStreamWaitEvent(stream, ev[1], 0));
@@ -546,6 +549,56 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   }
   ISV_CUDA(cudaStreamSynchronize(ss[0]));
   ISV_CUDA(cudaStreamSynchronize(ss[1]));
+  return ISV_OK;
+}
+
+// ---- forensic mode: the structured path's intermediates, the KLD diagnostics, the reference's dense Schur route ------
+isv_status isv_marg_forensic_batch(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, const isv_forensic_out* dbg) {
+  if (!h || !dbg) return ISV_ERR_BAD_ARG;
+  isv_status st = check_batch(in, out, ISV_RUN_BOTH);
+  if (st != ISV_OK) return st;
+  if (!dbg->lamda_prior_fwd || !dbg->g_bwd || !dbg->kld_fwd || !dbg->kld_bwd) return ISV_ERR_BAD_ARG;
+  const int n = in->n_windows;
+  if (n == 0) return ISV_OK;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const size_t need = (size_t)n * kScratchPerWindow * sizeof(double);
+  if (h->gram_bytes < need) {
+    if (h->gram) { ISV_CUDA(cudaStreamSynchronize(h->stream)); ISV_CUDA(cudaFree(h->gram)); h->gram = nullptr; h->gram_bytes = 0; }
+    if (cudaMalloc(&h->gram, need + 256) != cudaSuccess) { cudaGetLastError(); return ISV_ERR_ALLOC; }
+    h->gram_bytes = need + 256;
+  }
+  st = launch_batch(h, in, out, ISV_RUN_BOTH, h->stream, h->gram, DbgStores{dbg->lamda_prior_fwd, dbg->g_bwd});
+  if (st != ISV_OK) return st;
+  st = ensure_dbuf(h, (size_t)n * kKldScratch * sizeof(double));   // the host-pointer staging buffer is idle on this path
+  if (st != ISV_OK) return st;
+  isv_kld_args a;
+  a.scratch = (double*)h->dbuf;
+  a.n = n;
+  a.pose_bwd = in->pose_bwd;
+  a.fj = h->gram + (size_t)n * 42;
+  a.lp_fwd = dbg->lamda_prior_fwd;
+  a.g_bwd = dbg->g_bwd;
+  a.se3_out = out->se3_out; a.rel_out = out->rel_out; a.vb_out = out->vb_out; a.rp_out = out->rp_out;
+  a.rank = out->rank;
+  a.alpha = h->dcfg.alpha;
+  a.kld_fwd = dbg->kld_fwd; a.kld_bwd = dbg->kld_bwd;
+  a.lp_bwd = dbg->lamda_prior_bwd; a.eig_bwd = dbg->eig_bwd; a.info_abs = dbg->info_abs; a.info_yaw = dbg->info_yaw;
+  marg_kld_kernel<<<(n + 63) / 64, 64, 0, h->stream>>>(a);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
+isv_status isv_literal_schur(isv_handle* h, int n_problems, int n, int m0, const double* A, double* A_prior, double* Amm_inv,
+                             int32_t* rank) {
+  if (!h || n_problems < 1 || m0 < 1 || n <= m0 || n - m0 > 1024 || !A || !A_prior) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  const size_t m = (size_t)(n - m0);
+  isv_status st = ensure_dbuf(h, (size_t)n_problems * m * 2 * m * sizeof(double));
+  if (st != ISV_OK) return st;
+  literal_schur_kernel<<<n_problems, kLitThreads, m * sizeof(int), h->stream>>>(n, m0, A, (double*)h->dbuf, A_prior, Amm_inv, rank);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
   return ISV_OK;
 }
 

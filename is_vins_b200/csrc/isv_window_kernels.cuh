@@ -442,7 +442,7 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
 // ---- kernel 2: everything after the landmark sums (12x12 / 6x6 algebra), one warp per window ----
 __global__ void __launch_bounds__(kThreads, ISV_FWD_TAIL_MINB)
 marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __restrict__ gram,
-                         const double* __restrict__ fj, DevCfg cfg) {
+                         const double* __restrict__ fj, DevCfg cfg, double* __restrict__ dbg_lamda_prior) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -560,6 +560,8 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
   // (6 eps) and the 1e-16 rank threshold, i.e. qr.rank() == 6 without running the QR.  Otherwise
   // the QR is restated literally on one lane.
   w_copy(tA, Wst, 36, lane);
+  if (dbg_lamda_prior)   // forensic store: Lamda_prior (:1288) of the structured route, column-major 6 x 6
+    for (int i = lane; i < 36; i += 32) dbg_lamda_prior[(size_t)win * 36 + i] = Wst[i];
   int rank = 0;
   {
     double fa = 0.0, fi = 0.0;
@@ -641,7 +643,8 @@ constexpr int kGld = 21;  // G rows in shared memory: element (k, c) at Gs[k * 2
 constexpr int kBwdLc = 0, kBwdHv = 272, kBwdPv = 296, kBwdGs = 344, kBwdT = 660;
 constexpr int kLcLd = 16;   // Cholesky factor of the covariance: column k at Lc[16 k + i] (16-byte aligned pairs), [256..271) = 1 / L_kk
 __global__ void __launch_bounds__(kThreads, ISV_BWD_MINB)
-marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restrict__ fj, DevCfg cfg, int vo_size) {
+marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restrict__ fj, DevCfg cfg, int vo_size,
+                     double* __restrict__ dbg_g) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -778,6 +781,9 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
   if (lane < 21) {
 #pragma unroll
     for (int i = 0; i < 15; ++i) Gs[i * kGld + lane] = col[i];
+    if (dbg_g)   // forensic store: G (15 x 21) with G^T G = Lamda_prior (:1419)
+#pragma unroll
+      for (int i = 0; i < 15; ++i) dbg_g[(size_t)win * 315 + i * 21 + lane] = col[i];
   }
   __syncwarp();
   // ---- fast path: no eigen-decomposition when every non-zero eigenvalue is provably > ALPHA ----

@@ -244,9 +244,10 @@ class MarginalizationInfo:
         return [flat[n * int(pr["offs"][c]):n * int(pr["offs"][c + 1])].reshape(n, size)
                 for c, (_, size, _) in enumerate(pr["keep"])]
 
-    def marginalize(self, keep_tables: bool = False, schur_only: bool = False) -> None:
+    def marginalize(self, keep_tables: bool = False, schur_only: bool = False, build_only: bool = False) -> None:
         """schur_only: stop after the Schur complement (A_red, b_red) -- with every feature dropped and no dense
-        block this is the reduced camera system of DENSE_SCHUR (`isv_reduced_system`)."""
+        block this is the reduced camera system of DENSE_SCHUR (`isv_reduced_system`).  build_only: stop after the
+        normal equations (isv_build_normal_equations [+ prior]): `A_dev` [pos, pos], `b_dev` [pos] stay on the device."""
         import torch
         assert self._dp is not None, "call preMarginalize first"
         dp, by = self._dp, self._by
@@ -316,6 +317,16 @@ class MarginalizationInfo:
         go = _Out(o["A"].data_ptr(), o["b"].data_ptr(), o["A_red"].data_ptr(), o["b_red"].data_ptr(), o["J"].data_ptr(),
                   o["r"].data_ptr(), o["rank"].data_ptr(), o["status"].data_ptr())
         lib = self.be.lib
+        if build_only:
+            capi.check(lib.isv_build_normal_equations(self.be.h, C.byref(gi), C.byref(go)), "isv_build_normal_equations")
+            if self._prior is not None:
+                st = self._prior_struct(pos_of=lambda k: -1 if k in self.constant else self.parameter_block_idx[k])
+                capi.check(lib.isv_add_marg_prior(self.be.h, C.byref(st), C.c_void_p(self._prior["d"]["res"].data_ptr()),
+                                                  C.byref(gi), C.byref(go), 0), "isv_add_marg_prior")
+            self.be.synchronize()
+            self.pos, self.A_dev, self.b_dev = pos, o["A"], o["b"]
+            self.status = int(o["status"].item()) | int(dp.status.item())
+            return
         if self._prior is None:
             fn = lib.isv_reduced_system if schur_only else lib.isv_marginalize_generic
             capi.check(fn(self.be.h, C.byref(gi), C.byref(go)), "isv_marginalize_generic")

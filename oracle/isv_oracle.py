@@ -1233,6 +1233,7 @@ class ForwardOutput:
     pg_covRel: np.ndarray
     pg_distance: float
     pg_covAbs: Optional[np.ndarray]
+    kld: float = float("nan")    # :1333-1345 (diagnostic)
 
 
 def marg_forward(inp: ForwardInput, cfg: Config, structured: bool = False) -> ForwardOutput:
@@ -1303,9 +1304,16 @@ def marg_forward(inp: ForwardInput, cfg: Config, structured: bool = False) -> Fo
         U, D, eig_rank, _ = _truncated_eig(Lamda_prior, cfg.alpha)
         Dinv = partial_piv_inverse(D) if eig_rank > 0 else np.zeros((0, 0))
         covi = Jr @ U @ Dinv @ (Jr @ U).T
-    se3.sqrt_info = llt_upper(partial_piv_inverse(covi))                    # :1349
+    X = partial_piv_inverse(covi)                                           # :1330-1332
+    kld = float("nan")
+    if rank == 6:                                                           # :1333-1345 (computed, never used: Q7)
+        phi = Jr.T @ X @ Jr
+        cov = solve(np.eye(6))
+        with np.errstate(all="ignore"):
+            kld = float(0.5 * (np.trace(phi @ cov) - np.log(np.linalg.det(phi)) - np.log(np.linalg.det(cov)) - 6))
+    se3.sqrt_info = llt_upper(X)                                            # :1349
     return ForwardOutput(Lamda, Lamda_prior, rank, used_eig, eig_rank, se3.t, se3.R, se3.sqrt_info,
-                         pg.delta_t, pg.delta_R, pg.sqrt_info, rpCov, float(np.linalg.norm(pg.delta_t)), covAbs)
+                         pg.delta_t, pg.delta_R, pg.sqrt_info, rpCov, float(np.linalg.norm(pg.delta_t)), covAbs, kld)
 
 
 # ----------------------------------------------------------------------------------------------
