@@ -66,7 +66,9 @@ KERNELS = {
         "flops": lambda L: 6.0e3,
         "limiter": "uncoalesced global access: one thread per (window, factor) walks a 384-3736 B strided record"},
     "marg_forward_accum_kernel": {
-        "which": 4, "bytes": lambda L: 32 * L + 8 * (14 + 7) + 8 * 42, "flops": lambda L: 282.0 * L,
+        # 265 flops per landmark with the isotropic ProjectionFactor::sqrt_info of the reference (the chain drops the 2x2
+        # weighting: 282 in the general case); 42 of the DFMA are the two 6x6 SYRKs
+        "which": 4, "bytes": lambda L: 32 * L + 8 * (14 + 7) + 8 * 42, "flops": lambda L: 265.0 * L,
         "limiter": "FP64 pipe (DFMA) / HBM stream of the landmark observations"},
     "marg_forward_tail_kernel": {
         "which": 8, "bytes": lambda L: 8 * (42 + 14 + 252) + 8 * (36 + 72) + 8, "flops": lambda L: 1.6e4,
@@ -520,6 +522,35 @@ def measure(cx, L, n, which, steps, warmup, seed, full, e2e=True):
                 r["e2e_vs_device_path_max_rel"] = float(outputs_rel_diff(hout, r["out"], which).max())
             if cx.rank == 0 and tag:
                 r["e2e_abi1_bits_equal"] = bool(all(np.array_equal(getattr(hout, f), getattr(r["out"], f)) for f in fams))
+    # ---- the copy ceiling the e2e number runs under: the same byte counts as plain pinned cudaMemcpyAsync, H2D and D2H
+    #      overlapped on two streams, every rank at once (what the host / PCIe can feed; tools/h2d_peak.py is the long form)
+    if e2e and full:
+        hs = torch.empty(r["h2d"], dtype=torch.uint8).pin_memory()
+        hd = torch.empty(r["d2h"], dtype=torch.uint8).pin_memory()
+        ds = torch.empty(r["h2d"], dtype=torch.uint8, device=dev)
+        dd = torch.ones(r["d2h"], dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream()
+
+        def copies():
+            s1.wait_stream(cur)
+            s2.wait_stream(cur)
+            with torch.cuda.stream(s1):
+                ds.copy_(hs, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hd.copy_(dd, non_blocking=True)
+            cur.wait_stream(s1)
+            cur.wait_stream(s2)
+        copies()
+        cx.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            copies()
+        c1.record()
+        cx.barrier()
+        r["copy_ceiling_ms"] = c0.elapsed_time(c1) / 5
+        del hs, hd, ds, dd
     del db
     return r
 
@@ -644,9 +675,9 @@ def run_cuda(args, L):
     h = measure(cx, L, n, capi.RUN_BOTH, args.steps, args.warmup, 1000 + rank, full=True)
     names = list(KERNELS)
     tl = maxr([h["ms_total"], h["e2e_ms"], h["sustained_ms"] / h["sustained_steps"], h["sustained_2nd_half_ms_per_step"],
-               h["e2e_ms_abi1"]] + [h["per"][k] for k in names])
-    ms_total, e2e_ms, sus_ms, sus2_ms, e2e1_ms = tl[0:5]
-    per = dict(zip(names, tl[5:]))
+               h["e2e_ms_abi1"], h["copy_ceiling_ms"]] + [h["per"][k] for k in names])
+    ms_total, e2e_ms, sus_ms, sus2_ms, e2e1_ms, ceil_ms = tl[0:6]
+    per = dict(zip(names, tl[6:]))
     tot_lm = maxr([float(h["n_lm"])])[0]
     line = None
     if rank == 0:
@@ -691,6 +722,12 @@ def run_cuda(args, L):
                     "inputs": "ABI 2: raw IMU samples (12 + 7 K doubles; preintegrate_kernel runs inside the call) instead of the "
                               "467-double pre-integration record; pts_i.z == 1 promised (ISV_IN_PTS_I_Z_ONE): 3 doubles per landmark",
                     "max_rel_diff_vs_device_path": h.get("e2e_vs_device_path_max_rel"),
+                    "copy_ceiling": {"ms_per_step": ceil_ms, "value": world * n / (ceil_ms * 1e-3), "unit": UNIT,
+                                     "frac": (e2e_ms / args.steps and ceil_ms / (e2e_ms / args.steps)),
+                                     "note": "the same H2D + D2H byte counts as plain pinned cudaMemcpyAsync on two streams, all "
+                                             "ranks at once, max over ranks: what host memory / PCIe can feed on this box (the "
+                                             "aggregate saturates near 115 GB/s at 2-4 GPUs and 186 GB/s at 8: "
+                                             "profiles/r02n_h2d_peak_*gpu.json)"},
                     "abi1": {"value": world * n * args.steps / (e2e1_ms * 1e-3), "h2d_bytes_per_step": h["h2d_abi1"],
                              "ms_per_step": e2e1_ms / args.steps, "results_bit_equal_device_path": h.get("e2e_abi1_bits_equal"),
                              "inputs": "ABI 1: the full records (467-double pre-integration, 4 doubles per landmark)"}},

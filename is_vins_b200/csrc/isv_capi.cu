@@ -122,10 +122,13 @@ isv_status isv_create(const isv_config* cfg, int device, isv_handle** out) {
   for (int i = 0; i < 3; ++i) cudaEventCreateWithFlags(&h->aux_ev[i], cudaEventDisableTiming);
   for (int i = 0; i < 6; ++i) cudaEventCreateWithFlags(&h->jac_ev[i], cudaEventDisableTiming);
   h->stream = h->own_stream;
-  cudaFuncSetAttribute(marg_forward_accum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)(kAccWarps * kAccSmemPerWarp * sizeof(double)));
-  cudaFuncSetAttribute(marg_forward_accum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)(kAccWarps * kAccSmemPerWarp * sizeof(double)));
+  {
+    const int sm = (int)(kAccWarps * kAccSmemPerWarp * sizeof(double));
+    cudaFuncSetAttribute(marg_forward_accum_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(marg_forward_accum_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(marg_forward_accum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaFuncSetAttribute(marg_forward_accum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  }
   cudaFuncSetAttribute(marg_forward_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kWarpsPerCta * kFwdSmemPerWarp * sizeof(double)));
   cudaFuncSetAttribute(marg_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -281,12 +284,15 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in_arg, const 
   }
   if (stage1) {
     const int agrid = (n + kAccWarps - 1) / kAccWarps;
-    if (in->flags & ISV_IN_PTS_I_Z_ONE)
-      marg_forward_accum_kernel<true><<<agrid, 32 * kAccWarps, kAccWarps * kAccSmemPerWarp * sizeof(double), stream>>>(
-          *in, gram, out->status, h->dcfg);
-    else
-      marg_forward_accum_kernel<false><<<agrid, 32 * kAccWarps, kAccWarps * kAccSmemPerWarp * sizeof(double), stream>>>(
-          *in, gram, out->status, h->dcfg);
+    const size_t asm_ = kAccWarps * kAccSmemPerWarp * sizeof(double);
+    const bool zone = (in->flags & ISV_IN_PTS_I_Z_ONE) != 0;
+    // ProjectionFactor::sqrt_info = c I (always, in the reference: src/estimator.cpp:35) takes the leaner chain
+    static const bool no_iso = getenv("ISV_NO_ISO") != nullptr;   // A/B switch for measurements
+    const bool iso = !no_iso && h->dcfg.ps[1] == 0.0 && h->dcfg.ps[2] == 0.0 && h->dcfg.ps[0] == h->dcfg.ps[3];
+    if (zone && iso) marg_forward_accum_kernel<true, true><<<agrid, 32 * kAccWarps, asm_, stream>>>(*in, gram, out->status, h->dcfg);
+    else if (zone) marg_forward_accum_kernel<true, false><<<agrid, 32 * kAccWarps, asm_, stream>>>(*in, gram, out->status, h->dcfg);
+    else if (iso) marg_forward_accum_kernel<false, true><<<agrid, 32 * kAccWarps, asm_, stream>>>(*in, gram, out->status, h->dcfg);
+    else marg_forward_accum_kernel<false, false><<<agrid, 32 * kAccWarps, asm_, stream>>>(*in, gram, out->status, h->dcfg);
     ++h->launches;
   }
   if (bwd) {

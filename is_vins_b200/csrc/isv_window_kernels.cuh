@@ -239,7 +239,7 @@ marg_factor_jac_kernel(isv_batch_in in, isv_batch_out out, double* __restrict__ 
 // ---- kernel 1: landmark phase.  One warp per window, one landmark per lane and iteration;
 // writes the 21 + 21 lower-triangle entries of the two Gram matrices to gram[win][42].
 constexpr int kAccLd = 33;                         // reduction staging: [21][33] doubles per warp
-constexpr int kAccSmemPerWarp = 24 + 21 * kAccLd + 1;  // constants F f tp ric + staging (even: 16-byte aligned per warp)
+constexpr int kAccSmemPerWarp = 34 + 21 * kAccLd + 1;  // constants F f tp ric M + staging (even: 16-byte aligned per warp)
 
 // ZONE = ISV_IN_PTS_I_Z_ONE: the caller guarantees pts_i.z == 1 (src/System.cpp:346); component 2 is then not read
 // Warps per CTA of the landmark kernel.  A warp owns a whole window, so a CTA lives as long as its LONGEST window: with
@@ -247,6 +247,9 @@ constexpr int kAccSmemPerWarp = 24 + 21 * kAccLd + 1;  // constants F f tp ric +
 // largest one.  One warp per CTA removes that, and 224 registers x 32 threads also packs 9 instead of 8 warps per SM.
 #ifndef ISV_ACC_WARPS
 #define ISV_ACC_WARPS 1
+#endif
+#ifndef ISV_ACC_MQ
+#define ISV_ACC_MQ 0   // q~ = (ric^T F) p straight from the observation: shorter chain, but measured slower (register pressure)
 #endif
 constexpr int kAccWarps = ISV_ACC_WARPS;
 #ifndef ISV_ACC_MINB
@@ -258,7 +261,9 @@ constexpr int kAccWarps = ISV_ACC_WARPS;
 #else
 #define ISV_ACC_BOUNDS __launch_bounds__(32 * kAccWarps, ISV_ACC_MINB)
 #endif
-template <bool ZONE>
+// ISO = ProjectionFactor::sqrt_info is a multiple of the identity (it always is in the reference: FOCAL_LENGTH / 1.5 * I,
+//       src/estimator.cpp:35): the weighting commutes with the direction and drops out of the per-landmark chain.
+template <bool ZONE, bool ISO>
 __global__ void ISV_ACC_BOUNDS
 marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* wstatus, DevCfg cfg) {
   extern __shared__ double smem[];
@@ -266,8 +271,8 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
   const int warp = threadIdx.x >> 5;
   const int win = blockIdx.x * kAccWarps + warp;
   if (win >= in.n_windows) return;
-  double* K = smem + warp * kAccSmemPerWarp;  // [0]F [9]f [12]tp [15]ric
-  double* R = K + 24;                         // reduction staging
+  double* K = smem + warp * kAccSmemPerWarp;  // [0]F [9]f [12]tp [15]ric [24]M = ric^T F
+  double* R = K + 34;                         // reduction staging
   int status = 0;
 
   const double* pose0 = in.pose_fwd + (size_t)win * 14;
@@ -289,6 +294,9 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
     mat3_tvec(ric, t3, tp);
     for (int i = 0; i < 9; ++i) { K[i] = F[i]; K[15 + i] = ric[i]; }
     for (int i = 0; i < 3; ++i) { K[9 + i] = fv[i]; K[12 + i] = tp[i]; }
+    double Mq[9];
+    mat3_tmul(ric, F, Mq);         // M = ric^T F: q~ = M p straight from the observation (not through w = F p)
+    for (int i = 0; i < 9; ++i) K[24 + i] = Mq[i];
   }
   __syncwarp();
 
@@ -313,15 +321,20 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
     for (int r = 0; r < 3; ++r) {
       w[r] = ZONE ? fma(K[3 * r], px, fma(K[3 * r + 1], py, K[3 * r + 2])) : K[3 * r] * px + K[3 * r + 1] * py + K[3 * r + 2] * pz;
       ph[r] = fma(lam, K[9 + r], w[r]);
+#if ISV_ACC_MQ
+      qt[r] = ZONE ? fma(K[24 + 3 * r], px, fma(K[25 + 3 * r], py, K[26 + 3 * r])) : K[24 + 3 * r] * px + K[25 + 3 * r] * py + K[26 + 3 * r] * pz;
+#endif
     }
+#if !ISV_ACC_MQ
 #pragma unroll
     for (int c = 0; c < 3; ++c) qt[c] = ric[c] * w[0] + ric[3 + c] * w[1] + ric[6 + c] * w[2];
+#endif
     const double c0 = fma(lam, K[12], qt[0]), c1 = fma(lam, K[13], qt[1]), c2 = fma(lam, K[14], qt[2]);
     // direction of s * jacobian_feature:  Pb q~ = [q0 - xb q2, q1 - yb q2] = lam / c2 * [q0 tp2 - q2 tp0,
     // q1 tp2 - q2 tp1]  (c~ = q~ + lam tp).  Only the direction matters (u enters as u u^T, v as v v^T), so it
     // is taken from the cancellation-free right-hand side.
     const double nt0 = fma(qt[0], K[14], -qt[2] * K[12]), nt1 = fma(qt[1], K[14], -qt[2] * K[13]);
-    const double g0 = s00 * nt0 + s01 * nt1, g1 = s10 * nt0 + s11 * nt1;
+    const double g0 = ISO ? nt0 : s00 * nt0 + s01 * nt1, g1 = ISO ? nt1 : s10 * nt0 + s11 * nt1;   // ISO: s = s00 I, direction unchanged
     const double n2 = g0 * g0 + g1 * g1;
     // ONE reciprocal square root gives both 1 / (|g| c2) and rho = 1 / c2 (the FP64 division and rsqrt are the two
     // longest instruction sequences of the chain):  r = rsqrt(n2 c2^2) ;  1 / (|g| c2) = sign(c2) r ;  rho = r^2 n2 c2
@@ -331,9 +344,11 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
     double in_ = copysign(r, c2);
     if (__builtin_expect(!ok, 0)) { rho = 1.0 / c2; in_ = 0.0; }      // degenerate observation (flagged below)
     const double xb = c0 * rho, yb = c1 * rho;
-    const double u0 = ok ? g0 * in_ : rho, u1 = ok ? g1 * in_ : 0.0;        // (u, v) pre-scaled by rho
-    const double a0 = u0 * s00 + u1 * s10, a1 = u0 * s01 + u1 * s11;        // rho s^T u
-    const double b0 = -u1 * s00 + u0 * s10, b1 = -u1 * s01 + u0 * s11;      // rho s^T v
+    if (ISO) in_ *= s00;
+    const double u0 = ok ? g0 * in_ : (ISO ? rho * s00 : rho), u1 = ok ? g1 * in_ : 0.0;        // (u, v) pre-scaled by rho [s00]
+    // ISO: (u, v) additionally pre-scaled by s00 below, so rho s^T u = u and rho s^T v = (-u1, u0)
+    const double a0 = ISO ? u0 : u0 * s00 + u1 * s10, a1 = ISO ? u1 : u0 * s01 + u1 * s11;        // rho s^T u
+    const double b0 = ISO ? -u1 : -u1 * s00 + u0 * s10, b1 = ISO ? u0 : -u1 * s01 + u0 * s11;     // rho s^T v
     double al[3], be[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
