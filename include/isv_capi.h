@@ -76,6 +76,14 @@ isv_status isv_set_stream(isv_handle* h, void* cuda_stream);
 isv_status isv_synchronize(isv_handle* h);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
 int64_t isv_launch_count(const isv_handle* h);
+/* Tuning knobs (A/B measurements, tests).  Environment variables of the same meaning seed them at isv_create:
+ *   ISV_TUNE_FUSED_MAX_WINDOWS (env ISV_FUSED_MAX, default 148): isv_marg_window_batch(ISV_RUN_BOTH) calls of at most this
+ *       many windows take the one-launch fused kernel (one CTA per window); 0 = always the warp-per-window batch kernels.
+ *   ISV_TUNE_EVENT_MODE (env ISV_EVENT_MODE, default 0): route of isv_marg_event -- 0 zero-copy fused kernel, 1 fused
+ *       kernel on a device-side mirror (H2D, launch, D2H, stream synchronise), 2 batch kernels on the mirror.          */
+#define ISV_TUNE_FUSED_MAX_WINDOWS 1
+#define ISV_TUNE_EVENT_MODE 2
+isv_status isv_set_tuning(isv_handle* h, int knob, int value);
 
 /* ---- index maps: the bit-exact contract -------------------------------
  * Each writes (offset, dim) per block into out[2*i], out[2*i+1] and returns the number of blocks.
@@ -246,8 +254,12 @@ isv_status isv_marg_forward(isv_handle* h, const isv_fwd_in* in, isv_fwd_out* ou
 isv_status isv_marg_backward(isv_handle* h, const isv_bwd_in* in, isv_bwd_out* out);
 /* One whole MARGIN_OLD event -- `MargForward(); MargBackward();` as Estimator::backendOptimization() calls them back to
  * back (src/estimator.cpp:1555-1558; the two read disjoint members and neither reads the other's outputs) -- in ONE
- * blocking call: one pinned block in, the forward and backward kernel chains forked on two streams, one block out.
- * Results are bit-identical to the two separate calls; both `status` fields carry the OR of the event's warnings.  */
+ * blocking call and ONE kernel launch (marg_event_fused_kernel: a CTA of eight warps owns the event; the factor-Jacobian
+ * chains, the landmark phase split over seven warps, the forward tail and the backward chain run side by side).  By default
+ * the event is packed into a mapped pinned block that the kernel reads and writes over PCIe (no copy engine, no stream
+ * synchronisation: the host spins on a completion word) -- ISV_TUNE_EVENT_MODE selects the staged routes instead.
+ * Results equal the two separate calls to rounding (<= 1e-12 relative: the landmark Gram is summed as seven partial sums);
+ * with ISV_TUNE_EVENT_MODE = 2 they are bit-identical.  Both `status` fields carry the OR of the event's warnings.  */
 isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fwd_in, const isv_bwd_in* bwd_in, isv_fwd_out* fwd_out,
                           isv_bwd_out* bwd_out);
 
@@ -614,6 +626,18 @@ void isv_pose_plus_jacobian(double* jacobian);
  * lam [nb][n] = |g_k|^2 (eigenvalues, zero-padded); info [nb][2] = {rows, sweeps}.  n <= 63.      */
 isv_status isv_test_psd_eig(isv_handle* h, int nb, int n, const double* A, double* G, double* lam,
                             int32_t* info);
+
+/* ---- measurement hook: `iters` back-to-back isv_marg_event calls of the same event, timed one by one on the host with
+ * CLOCK_MONOTONIC from inside the library (i.e. the latency a C/C++ estimator sees, without a binding's marshalling).
+ * us [iters] = microseconds of each call; the last call's results are left in fwd_out / bwd_out.                    */
+isv_status isv_test_event_latency(isv_handle* h, const isv_fwd_in* fwd_in, const isv_bwd_in* bwd_in, isv_fwd_out* fwd_out,
+                                  isv_bwd_out* bwd_out, int iters, double* us);
+
+/* ---- profiling hook: the fused single-event kernel on a DEVICE batch with the SM cycle counter sampled at the phase
+ * boundaries of the eight warps of window 0.  stamps_dev: device int64 [8 warps][8]: [0] entry, [1] after the start barrier,
+ * then per role -- warp 0: [2] end of MargBackward; warps 1-7: [2] factor-Jacobian task done, [3] landmark share done;
+ * warp 7: [4] forward barrier passed, [5] tail done; [7] = after the final barrier (all warps).                        */
+isv_status isv_test_fused_stamps(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, int64_t* stamps_dev);
 
 /* ---- unit-test hook: the symmetric eigensolver of the generic engine's reduced system (VINS-Mono
  * `SelfAdjointEigenSolver<MatrixXd> saes2(A)`; Householder tridiagonalization + implicit QL with a rotation log,

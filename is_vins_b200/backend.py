@@ -112,6 +112,10 @@ class MargBackend:
     def launch_count(self) -> int:
         return int(self.lib.isv_launch_count(self.h))
 
+    def set_tuning(self, knob: int, value: int) -> None:
+        """isv_set_tuning: capi.TUNE_FUSED_MAX_WINDOWS (0 = always the batch kernels) / capi.TUNE_EVENT_MODE (0, 1, 2)."""
+        capi.check(self.lib.isv_set_tuning(self.h, int(knob), int(value)), "isv_set_tuning")
+
     # ---- batched, device-resident ---------------------------------------------------------------
     def marg_window_batch(self, dbatch: DeviceBatch, which: int = capi.RUN_BOTH) -> None:
         """Stream-ordered MargForward+MargBackward over dbatch; results land in dbatch.out."""
@@ -173,6 +177,21 @@ class MargBackend:
         capi.check(self.lib.isv_marg_event(self.h, C.byref(fi), C.byref(bi), C.byref(fo), C.byref(bo)), "isv_marg_event")
         return ((np.array(fo.se3), np.array(fo.pg), int(fo.rank), int(fo.status)),
                 (np.array(bo.rel), np.array(bo.vb), np.array(bo.rp), int(bo.rank), int(bo.status)))
+
+    def event_latency_us(self, fwd_args, bwd_args, iters: int = 300) -> np.ndarray:
+        """isv_test_event_latency: `iters` isv_marg_event calls of one event timed inside the library (no ctypes / NumPy
+        marshalling in the timed region) -> microseconds per call."""
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in fwd_args[:8]]
+        rp = None if len(fwd_args) < 9 or fwd_args[8] is None else np.ascontiguousarray(fwd_args[8], dtype=np.float64)
+        fi = capi.isv_fwd_in(int(a[3].shape[0]), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), _dp(a[4]), _dp(a[5]),
+                             _dp(a[6]), _dp(a[7]), None if rp is None else _dp(rp))
+        b = [np.ascontiguousarray(x, dtype=np.float64) for x in bwd_args]
+        bi = capi.isv_bwd_in(*[_dp(x) for x in b])
+        fo, bo = capi.isv_fwd_out(), capi.isv_bwd_out()
+        us = np.zeros(iters)
+        capi.check(self.lib.isv_test_event_latency(self.h, C.byref(fi), C.byref(bi), C.byref(fo), C.byref(bo), iters, _dp(us)),
+                   "isv_test_event_latency")
+        return us
 
     # ---- initFactorGraph sparsification tail (one-time, src/estimator.cpp:745-1001) ---------------
     def init_sparsify(self, poses, sbs, preint):

@@ -22,6 +22,7 @@ ACC_REC, ACC_COVREL, ACC_DISTANCE, ACC_LENGTH, ACC_VIO_INDEX, ACC_PG_INDEX, ACC_
 ACC_RI, ACC_TI, ACC_RP_VALID, ACC_RP, ACC_COVABS = 89, 98, 101, 102, 115
 RUN_FORWARD, RUN_BACKWARD, RUN_BOTH = 1, 2, 3
 RUN_FORWARD_STAGE1, RUN_FORWARD_STAGE2, RUN_FACTOR_JAC, RUN_BACKWARD_STAGE2 = 4, 8, 16, 32
+TUNE_FUSED_MAX_WINDOWS, TUNE_EVENT_MODE = 1, 2   # isv_set_tuning knobs (include/isv_capi.h)
 POSE, SB, SE3_REC, REL_REC, VB_REC, RP_IN_REC, RP_REC, PG_REC, PREINT_REC = 7, 9, 48, 48, 90, 5, 13, 89, 467
 IMU_RAW_REC = 7
 
@@ -169,6 +170,7 @@ SYMBOLS = [
     ("isv_set_stream", C.c_int, [_H, C.c_void_p]),
     ("isv_synchronize", C.c_int, [_H]),
     ("isv_launch_count", C.c_int64, [_H]),
+    ("isv_set_tuning", C.c_int, [_H, C.c_int, C.c_int]),
     ("isv_order_map_init", C.c_int, [C.c_int, c_int32_p]),
     ("isv_order_map_forward", C.c_int, [C.c_int, c_int32_p]),
     ("isv_order_map_backward", C.c_int, [C.c_int, c_int32_p]),
@@ -179,6 +181,9 @@ SYMBOLS = [
     ("isv_marg_forward", C.c_int, [_H, C.POINTER(isv_fwd_in), C.POINTER(isv_fwd_out)]),
     ("isv_marg_backward", C.c_int, [_H, C.POINTER(isv_bwd_in), C.POINTER(isv_bwd_out)]),
     ("isv_marg_event", C.c_int, [_H, C.POINTER(isv_fwd_in), C.POINTER(isv_bwd_in), C.POINTER(isv_fwd_out), C.POINTER(isv_bwd_out)]),
+    ("isv_test_fused_stamps", C.c_int, [_H, C.POINTER(isv_batch_in), C.POINTER(isv_batch_out), C.c_void_p]),
+    ("isv_test_event_latency", C.c_int, [_H, C.POINTER(isv_fwd_in), C.POINTER(isv_bwd_in), C.POINTER(isv_fwd_out),
+                                         C.POINTER(isv_bwd_out), C.c_int, C.POINTER(C.c_double)]),
     ("isv_init_sparsify_batch", C.c_int, [_H, C.POINTER(isv_init_in), C.POINTER(isv_init_out)]),
     ("isv_init_sparsify_host", C.c_int, [_H, C.POINTER(isv_init_in), C.POINTER(isv_init_out)]),
     ("isv_preintegrate_batch", C.c_int, [_H, C.POINTER(isv_preint_in), C.c_void_p]),

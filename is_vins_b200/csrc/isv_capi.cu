@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <vector>
 
@@ -17,6 +18,7 @@
 #include "isv_preint_kernel.cuh"
 #include "isv_seq_kernels.cuh"
 #include "isv_window_kernels.cuh"
+#include "isv_event_kernel.cuh"
 #include "isv_forensic.cuh"
 
 using namespace isv;
@@ -36,6 +38,12 @@ struct isv_handle {
   size_t dbuf_bytes;
   char* pinned;
   size_t pinned_bytes;
+  char* mapped;          // isv_marg_event: mapped pinned block the fused kernel reads / writes over PCIe (zero-copy)
+  char* mapped_dev;      //   its device alias
+  size_t mapped_bytes;
+  int32_t event_seq;     //   completion-flag sequence number
+  int fused_max;         // ISV_TUNE_FUSED_MAX_WINDOWS
+  int event_mode;        // ISV_TUNE_EVENT_MODE
   char* eig;             // eigensolver scratch of the generic engine (tridiagonal + rotation log per problem), grow-only
   size_t eig_bytes;
   double* gram;          // [n][42 + kFJ] scratch handed between the kernels of one batch, grow-only:
@@ -48,6 +56,8 @@ struct isv_handle {
   int bgraph_next, bgraph_miss;   // after 8 consecutive misses (a caller that never repeats a batch) capturing stops
   cudaEvent_t ev[4];
 };
+
+constexpr int kFusedMaxWindows = 148;   // one CTA per SM: see launch_fused
 
 #define ISV_CUDA(call)                                                                       \
   do {                                                                                       \
@@ -123,6 +133,13 @@ isv_status isv_create(const isv_config* cfg, int device, isv_handle** out) {
   for (int i = 0; i < 6; ++i) cudaEventCreateWithFlags(&h->jac_ev[i], cudaEventDisableTiming);
   h->stream = h->own_stream;
   {
+    const char* e = getenv("ISV_FUSED_MAX");
+    h->fused_max = e ? atoi(e) : kFusedMaxWindows;
+    e = getenv("ISV_EVENT_MODE");
+    h->event_mode = e ? atoi(e) : 0;
+    if (h->event_mode < 0 || h->event_mode > 2) h->event_mode = 0;
+  }
+  {
     const int sm = (int)(kAccWarps * kAccSmemPerWarp * sizeof(double));
     cudaFuncSetAttribute(marg_forward_accum_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     cudaFuncSetAttribute(marg_forward_accum_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
@@ -135,6 +152,10 @@ isv_status isv_create(const isv_config* cfg, int device, isv_handle** out) {
                        (int)(kWarpsPerCta * kBwdSmemPerWarp * sizeof(double)));
   cudaFuncSetAttribute(preintegrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kWarpsPerCta * kPreSmemPerWarp * sizeof(double)));
+  cudaFuncSetAttribute(marg_event_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(kEvSmemDoubles * sizeof(double)));
+  cudaFuncSetAttribute(marg_event_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(kEvSmemDoubles * sizeof(double)));
   *out = h;
   return ISV_OK;
 }
@@ -147,6 +168,7 @@ void isv_destroy(isv_handle* h) {
   if (h->gram) cudaFree(h->gram);
   if (h->eig) cudaFree(h->eig);
   if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->mapped) cudaFreeHost(h->mapped);
   for (int i = 0; i < 4; ++i)
     if (h->bgraph[i].exec) cudaGraphExecDestroy(h->bgraph[i].exec);
   for (int i = 0; i < 4; ++i)
@@ -178,6 +200,13 @@ isv_status isv_synchronize(isv_handle* h) {
 }
 
 int64_t isv_launch_count(const isv_handle* h) { return h ? h->launches : 0; }
+
+isv_status isv_set_tuning(isv_handle* h, int knob, int value) {
+  if (!h) return ISV_ERR_BAD_ARG;
+  if (knob == ISV_TUNE_FUSED_MAX_WINDOWS && value >= 0) { h->fused_max = value; return ISV_OK; }
+  if (knob == ISV_TUNE_EVENT_MODE && value >= 0 && value <= 2) { h->event_mode = value; return ISV_OK; }
+  return ISV_ERR_BAD_ARG;
+}
 
 // ---- index maps -------------------------------------------------------------------------------
 int isv_order_map_init(int V, int32_t* out) {
@@ -312,11 +341,32 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in_arg, const 
   return ISV_OK;
 }
 
+// ---- the latency path: one fused launch, one CTA per window (isv_event_kernel.cuh) --------------------------------------
+// Eligible: both halves wanted, the pre-integration record given, ProjectionFactor::sqrt_info = c I (always, in the reference:
+// src/estimator.cpp:35).  Measured on B200 (profiles/r02q_*): wins up to kFusedMaxWindows windows, where the grid stops
+// fitting one CTA per SM; beyond that the warp-per-window batch kernels have the higher throughput.
+static bool fused_eligible(const isv_handle* h, const isv_batch_in* in, int which) {
+  const bool iso = h->dcfg.ps[1] == 0.0 && h->dcfg.ps[2] == 0.0 && h->dcfg.ps[0] == h->dcfg.ps[3];
+  return which == ISV_RUN_BOTH && in->preint && iso && in->n_windows >= 1 && in->n_windows <= h->fused_max;
+}
+static isv_status launch_fused(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, cudaStream_t stream,
+                               int32_t* done_flag, int32_t done_seq, long long* stamps = nullptr) {
+  const size_t sm = kEvSmemDoubles * sizeof(double);
+  if (in->flags & ISV_IN_PTS_I_Z_ONE)
+    marg_event_fused_kernel<true, true><<<in->n_windows, kEvThreads, sm, stream>>>(*in, *out, h->dcfg, done_flag, done_seq, stamps);
+  else
+    marg_event_fused_kernel<false, true><<<in->n_windows, kEvThreads, sm, stream>>>(*in, *out, h->dcfg, done_flag, done_seq, stamps);
+  ++h->launches;
+  ISV_CUDA(cudaGetLastError());
+  return ISV_OK;
+}
+
 isv_status isv_marg_window_batch(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, int which) {
   if (!h) return ISV_ERR_BAD_ARG;
   isv_status st = check_batch(in, out, which);
   if (st != ISV_OK) return st;
   ISV_CUDA(cudaSetDevice(h->device));
+  if (fused_eligible(h, in, which)) return launch_fused(h, in, out, h->stream, nullptr, 0);
   double* gram = nullptr;
   {
     const size_t need = (size_t)in->n_windows * kScratchPerWindow * sizeof(double);
@@ -743,6 +793,39 @@ isv_status isv_marg_backward(isv_handle* h, const isv_bwd_in* in, isv_bwd_out* o
   return ISV_OK;
 }
 
+// Mapped pinned block for the zero-copy event path (grow-only).
+static isv_status ensure_mapped(isv_handle* h, size_t bytes) {
+  if (h->mapped_bytes >= bytes) return ISV_OK;
+  if (h->mapped) {
+    cudaStreamSynchronize(h->stream);
+    cudaFreeHost(h->mapped);
+    h->mapped = nullptr;
+    h->mapped_dev = nullptr;
+    h->mapped_bytes = 0;
+  }
+  if (cudaHostAlloc((void**)&h->mapped, bytes + bytes / 2, cudaHostAllocMapped) != cudaSuccess) {
+    cudaGetLastError();
+    return ISV_ERR_ALLOC;
+  }
+  void* dp = nullptr;
+  if (cudaHostGetDevicePointer(&dp, h->mapped, 0) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFreeHost(h->mapped);
+    h->mapped = nullptr;
+    return ISV_ERR_CUDA;
+  }
+  h->mapped_dev = (char*)dp;
+  h->mapped_bytes = bytes + bytes / 2;
+  return ISV_OK;
+}
+
+// One MARGIN_OLD event, blocking.  Three routes (ISV_EVENT_MODE = 0 / 1 / 2 selects one for A/B measurements):
+//   0 (default)  zero-copy: the event is packed into a mapped pinned block, the fused kernel reads it over PCIe, writes the
+//                recovered factors back into the same block and publishes a completion word the host spins on: no copy
+//                engine, no stream synchronisation on the critical path;
+//   1            the fused kernel on a device-side mirror: one H2D, one launch, one D2H, cudaStreamSynchronize;
+//   2            the batch kernels (five launches over three streams) on the device-side mirror -- the only route when
+//                ProjectionFactor::sqrt_info is not a multiple of the identity.
 isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in* bin, isv_fwd_out* fout, isv_bwd_out* bout) {
   if (!h || !fin || !bin || !fout || !bout || fin->n_landmarks < 0) return ISV_ERR_BAD_ARG;
   if (!fin->pose0 || !fin->pose1 || !fin->ex_pose || !fin->prior_se3 || !fin->prior_rel) return ISV_ERR_BAD_ARG;
@@ -751,25 +834,44 @@ isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in
   if (L > 0 && (!fin->inv_dep || !fin->pts_i || !fin->pts_j)) return ISV_ERR_BAD_ARG;
   ISV_CUDA(cudaSetDevice(h->device));
   // in  = [lm_offset 2 (as int64)] [obs 6L] [pose_fwd 14] [ex 7] [se3 48] [rel 48] [rp 5] | [pose_bwd 14] [sb_bwd 18] [vb 90] [preint 467]
-  // out = [se3 48] [pg 89] [rel 48] [vb 90] [rp 13] [rank 2 x i32 = 1] [status i32 = 1]
+  // out = [se3 48] [pg 89] [rel 48] [vb 90] [rp 13] [rank 2 x i32 = 1] [status i32 = 1] [flag i32 = 1]
   const size_t n_f = 2 + 6 * L + 14 + 7 + ISV_SE3_REC + ISV_REL_REC + ISV_RP_IN_REC;
   const size_t n_b = 14 + 18 + ISV_VB_REC + ISV_PREINT_REC;
-  const size_t n_in = n_f + n_b;
-  const size_t n_out = ISV_SE3_REC + ISV_PG_REC + ISV_REL_REC + ISV_VB_REC + ISV_RP_REC + 2;
-  isv_status st = ensure_pinned(h, (n_in + n_out) * sizeof(double));
-  if (st != ISV_OK) return st;
-  st = ensure_dbuf(h, (n_in + n_out + kScratchPerWindow + 64) * sizeof(double));
-  if (st != ISV_OK) return st;
-  double* hp = (double*)h->pinned;
+  const size_t n_in = (n_f + n_b + 1) & ~(size_t)1;
+  const size_t n_out = ISV_SE3_REC + ISV_PG_REC + ISV_REL_REC + ISV_VB_REC + ISV_RP_REC + 3;
+  isv_batch_in probe;
+  memset(&probe, 0, sizeof(probe));
+  probe.n_windows = 1;
+  probe.preint = bin->preint;
+  const int mode = fused_eligible(h, &probe, ISV_RUN_BOTH) ? h->event_mode : 2;
+  isv_status st;
+  double* hp;     // host view of the block
+  double* d;      // device view
+  if (mode == 0) {
+    st = ensure_mapped(h, (n_in + n_out) * sizeof(double));
+    if (st != ISV_OK) return st;
+    hp = (double*)h->mapped;
+    d = (double*)h->mapped_dev;
+  } else {
+    st = ensure_pinned(h, (n_in + n_out) * sizeof(double));
+    if (st != ISV_OK) return st;
+    st = ensure_dbuf(h, (n_in + n_out + kScratchPerWindow + 64) * sizeof(double));
+    if (st != ISV_OK) return st;
+    hp = (double*)h->pinned;
+    d = (double*)h->dbuf;
+  }
   int64_t* off = (int64_t*)hp;
   off[0] = 0; off[1] = (int64_t)L;
+  // the kernels read x_i, y_i, inv_dep and -- unless it is 1 everywhere, which the feature tracker guarantees
+  // (src/System.cpp:346) -- z_i: components 3, 4 (pts_j) are never read, so they are not packed
   double* obs = hp + 2;
+  bool z_one = true;
   for (size_t k = 0; k < L; ++k) {
     obs[k] = fin->pts_i[3 * k];
     obs[L + k] = fin->pts_i[3 * k + 1];
-    obs[2 * L + k] = fin->pts_i[3 * k + 2];
-    obs[3 * L + k] = fin->pts_j[3 * k];
-    obs[4 * L + k] = fin->pts_j[3 * k + 1];
+    const double z = fin->pts_i[3 * k + 2];
+    obs[2 * L + k] = z;
+    z_one &= (z == 1.0);
     obs[5 * L + k] = fin->inv_dep[k];
   }
   double* q = obs + 6 * L;
@@ -782,9 +884,7 @@ isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in
   memcpy(hb + 14, bin->sb_i, 72); memcpy(hb + 23, bin->sb_j, 72);
   memcpy(hb + 32, bin->prior_vb, ISV_VB_REC * 8);
   memcpy(hb + 32 + ISV_VB_REC, bin->preint, ISV_PREINT_REC * 8);
-  double* d = (double*)h->dbuf;
   cudaStream_t s = h->stream;
-  ISV_CUDA(cudaMemcpyAsync(d, hp, n_in * sizeof(double), cudaMemcpyHostToDevice, s));
   double* dq = d + 2 + 6 * L;
   double* db = d + n_f;
   double* dout = d + n_in;
@@ -804,6 +904,7 @@ isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in
   bi.sb_bwd = db + 14;
   bi.prior_vb = db + 32;
   bi.preint = db + 32 + ISV_VB_REC;
+  bi.flags = z_one ? ISV_IN_PTS_I_Z_ONE : 0;
   isv_batch_out bo;
   memset(&bo, 0, sizeof(bo));
   bo.se3_out = dout;
@@ -813,12 +914,43 @@ isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in
   bo.rp_out = bo.vb_out + ISV_VB_REC;
   bo.rank = (int32_t*)(bo.rp_out + ISV_RP_REC);
   bo.status = (int32_t*)(bo.rp_out + ISV_RP_REC + 1);
-  ISV_CUDA(cudaMemsetAsync(bo.rank, 0, 8, s));
-  st = launch_batch(h, &bi, &bo, ISV_RUN_BOTH, s, dout + n_out);
-  if (st != ISV_OK) return st;
+  int32_t* dflag = (int32_t*)(bo.rp_out + ISV_RP_REC + 2);
   double* ho = hp + n_in;
-  ISV_CUDA(cudaMemcpyAsync(ho, dout, n_out * sizeof(double), cudaMemcpyDeviceToHost, s));
-  ISV_CUDA(cudaStreamSynchronize(s));
+  if (mode == 0) {
+    volatile int32_t* hflag = (volatile int32_t*)(ho + (n_out - 1));
+    const int32_t seq = ++h->event_seq;
+    *hflag = seq - 1;
+    __sync_synchronize();   // the packed event is in memory before the launch is submitted
+    st = launch_fused(h, &bi, &bo, s, dflag, seq);
+    if (st != ISV_OK) return st;
+    // spin on the completion word; every ~4 k polls make sure the stream has not died under us
+    for (unsigned spins = 1;; ++spins) {
+      if (*hflag == seq) break;
+      if ((spins & 0xfff) == 0) {
+        const cudaError_t e = cudaStreamQuery(s);
+        if (e == cudaSuccess) {
+          if (*hflag == seq) break;
+          return ISV_ERR_CUDA;   // the kernel ended without publishing
+        }
+        if (e != cudaErrorNotReady) { cudaGetLastError(); return ISV_ERR_CUDA; }
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    __sync_synchronize();
+  } else {
+    ISV_CUDA(cudaMemcpyAsync(d, hp, n_in * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (mode == 1) {
+      st = launch_fused(h, &bi, &bo, s, nullptr, 0);
+    } else {
+      ISV_CUDA(cudaMemsetAsync(bo.rank, 0, 8, s));
+      st = launch_batch(h, &bi, &bo, ISV_RUN_BOTH, s, dout + n_out);
+    }
+    if (st != ISV_OK) return st;
+    ISV_CUDA(cudaMemcpyAsync(ho, dout, n_out * sizeof(double), cudaMemcpyDeviceToHost, s));
+    ISV_CUDA(cudaStreamSynchronize(s));
+  }
   const double* o = ho;
   memcpy(fout->se3, o, ISV_SE3_REC * 8); o += ISV_SE3_REC;
   memcpy(fout->pg, o, ISV_PG_REC * 8); o += ISV_PG_REC;
@@ -828,6 +960,29 @@ isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in
   fout->rank = ((const int32_t*)o)[0];
   bout->rank = ((const int32_t*)o)[1];
   fout->status = bout->status = ((const int32_t*)(o + 1))[0];
+  return ISV_OK;
+}
+
+isv_status isv_test_fused_stamps(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, int64_t* stamps_dev) {
+  if (!h || !stamps_dev) return ISV_ERR_BAD_ARG;
+  isv_status st = check_batch(in, out, ISV_RUN_BOTH);
+  if (st != ISV_OK) return st;
+  if (!in->preint || in->n_windows < 1) return ISV_ERR_BAD_ARG;
+  ISV_CUDA(cudaSetDevice(h->device));
+  return launch_fused(h, in, out, h->stream, nullptr, 0, (long long*)stamps_dev);
+}
+
+isv_status isv_test_event_latency(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in* bin, isv_fwd_out* fout, isv_bwd_out* bout,
+                                  int iters, double* us) {
+  if (!h || iters < 0 || (iters > 0 && !us)) return ISV_ERR_BAD_ARG;
+  for (int i = 0; i < iters; ++i) {
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    const isv_status st = isv_marg_event(h, fin, bin, fout, bout);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (st != ISV_OK) return st;
+    us[i] = (double)(t1.tv_sec - t0.tv_sec) * 1e6 + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-3;
+  }
   return ISV_OK;
 }
 

@@ -92,12 +92,10 @@ constexpr int kFJ_W = 0, kFJ_G = 144, kFJ_JR6 = 216, kFJ_IMU = 252, kFJ_REL = 70
 
 constexpr int kJacTasks = 7;   // blockIdx.y: one short chain per (window, factor)
 
-__global__ void __launch_bounds__(128)
-marg_factor_jac_kernel(isv_batch_in in, isv_batch_out out, double* __restrict__ fj, DevCfg cfg, int task0) {
-  const int win = blockIdx.x * blockDim.x + threadIdx.x;
-  if (win >= in.n_windows) return;
-  const int task = task0 + blockIdx.y;   // forward launch: task0 = 0, gridDim.y = 4; backward: task0 = 4, gridDim.y = 3
-  double* F = fj + (size_t)win * kFJ;
+// One (window, task) chain, executed by one thread.  F = the window's factor-Jacobian record (kFJ doubles; global scratch in
+// the batch kernels, shared memory in the fused single-event kernel).  wstatus: where status bits are OR-ed (may be null).
+__device__ __forceinline__ void factor_jac_task(const isv_batch_in& in, const isv_batch_out& out, double* F, const DevCfg& cfg,
+                                                int win, int task, int32_t* wstatus) {
   if (task < 4) {
     const double* pose0 = in.pose_fwd + (size_t)win * 14;
     const double* pose1 = pose0 + 7;
@@ -187,7 +185,7 @@ marg_factor_jac_kernel(isv_batch_in in, isv_batch_out out, double* __restrict__ 
       // IMUFactor::Evaluate, tangent twin (imu_factor.h:161-265); OrderMap (:1358-1366):
       // T_V@0, VB_V@6, T_{V-1}@15, VB_{V-1}@21.  The record was zero-filled by the launcher.
       const double* pre = in.preint + (size_t)win * ISV_PREINT_REC;
-      if ((nonunit(pose_i) || nonunit(pose_j)) && out.status) atomicOr(out.status + win, ISV_W_NONUNIT_QUAT);
+      if ((nonunit(pose_i) || nonunit(pose_j)) && wstatus) atomicOr(wstatus, ISV_W_NONUNIT_QUAT);
       imu_jacobians(pose_i, sb_i, pose_j, sb_j, pre, cfg.g, F + kFJ_IMU, 1, 15, 21, 0, 6, nullptr, 0, 1, 30);
     } else if (task == 5) {
       double* o_rel = out.rel_out + (size_t)win * ISV_REL_REC;
@@ -212,6 +210,14 @@ marg_factor_jac_kernel(isv_batch_in in, isv_batch_out out, double* __restrict__ 
       for (int i = 0; i < 9; ++i) o_vb[i] = sb_j[i];   // Linear9Factor(vb): VB = para_SpeedBias[V]
     }
   }
+}
+
+__global__ void __launch_bounds__(128)
+marg_factor_jac_kernel(isv_batch_in in, isv_batch_out out, double* __restrict__ fj, DevCfg cfg, int task0) {
+  const int win = blockIdx.x * blockDim.x + threadIdx.x;
+  if (win >= in.n_windows) return;
+  const int task = task0 + blockIdx.y;   // forward launch: task0 = 0, gridDim.y = 4; backward: task0 = 4, gridDim.y = 3
+  factor_jac_task(in, out, fj + (size_t)win * kFJ, cfg, win, task, out.status ? out.status + win : nullptr);
 }
 
 // =================================================================================================
@@ -263,16 +269,14 @@ constexpr int kAccWarps = ISV_ACC_WARPS;
 #endif
 // ISO = ProjectionFactor::sqrt_info is a multiple of the identity (it always is in the reference: FOCAL_LENGTH / 1.5 * I,
 //       src/estimator.cpp:35): the weighting commutes with the direction and drops out of the per-landmark chain.
+// Body of the landmark phase for one warp: landmarks [lm0, lm0 + L) of window `win` -> the 42 Gram-triangle entries at g.
+// The batch kernel gives a warp its whole window; the fused single-event kernel splits one window over several warps.
+// K = kAccSmemPerWarp doubles of shared memory owned by the calling warp; wstatus = where status bits are OR-ed (or null).
 template <bool ZONE, bool ISO>
-__global__ void ISV_ACC_BOUNDS
-marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* wstatus, DevCfg cfg) {
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int win = blockIdx.x * kAccWarps + warp;
-  if (win >= in.n_windows) return;
-  double* K = smem + warp * kAccSmemPerWarp;  // [0]F [9]f [12]tp [15]ric [24]M = ric^T F
-  double* R = K + 34;                         // reduction staging
+__device__ __forceinline__ void forward_accum_body(const isv_batch_in& in, const DevCfg& cfg, const int win, const int lane,
+                                                   double* K, const long long lm0, const int L, double* __restrict__ g,
+                                                   int32_t* wstatus) {
+  double* R = K + 34;                         // reduction staging;  K: [0]F [9]f [12]tp [15]ric [24]M = ric^T F
   int status = 0;
 
   const double* pose0 = in.pose_fwd + (size_t)win * 14;
@@ -300,8 +304,6 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
   }
   __syncwarp();
 
-  const long long lm0 = in.lm_offset[win];
-  const int L = (int)(in.lm_offset[win + 1] - lm0);
   const long long st = in.lm_stride;
   const double s00 = cfg.ps[0], s10 = cfg.ps[1], s01 = cfg.ps[2], s11 = cfg.ps[3];
   // ric is used three times per landmark: keep it in registers; F, f, tp are broadcast LDS
@@ -435,7 +437,6 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
   // cross-lane reduction through shared memory: lane l parks its 21 partial sums in column l of a
   // [21][33] tile, then lane t adds up row t (conflict-free both ways) -- 4x fewer instructions than
   // 42 shuffle trees.  Fixed summation order: results do not depend on scheduling.
-  double* g = gram + (size_t)win * 42;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -451,20 +452,31 @@ marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* w
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) status |= __shfl_xor_sync(kFullMask, status, o);
-  if (lane == 0 && status && wstatus) atomicOr(wstatus + win, status);
+  if (lane == 0 && status && wstatus) atomicOr(wstatus, status);
 }
 
-// ---- kernel 2: everything after the landmark sums (12x12 / 6x6 algebra), one warp per window ----
-__global__ void __launch_bounds__(kThreads, ISV_FWD_TAIL_MINB)
-marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __restrict__ gram,
-                         const double* __restrict__ fj, DevCfg cfg, double* __restrict__ dbg_lamda_prior) {
+template <bool ZONE, bool ISO>
+__global__ void ISV_ACC_BOUNDS
+marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* wstatus, DevCfg cfg) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int win = blockIdx.x * kWarpsPerCta + warp;
+  const int win = blockIdx.x * kAccWarps + warp;
   if (win >= in.n_windows) return;
-  double* K = smem + warp * kFwdSmemPerWarp;  // Psi (12x6 column-major)
-  double* X = K + kFwdConst;                  // tail work
+  const long long lm0 = in.lm_offset[win];
+  const int L = (int)(in.lm_offset[win + 1] - lm0);
+  forward_accum_body<ZONE, ISO>(in, cfg, win, lane, smem + warp * kAccSmemPerWarp, lm0, L, gram + (size_t)win * 42,
+                                wstatus ? wstatus + win : nullptr);
+}
+
+// ---- kernel 2: everything after the landmark sums (12x12 / 6x6 algebra), one warp per window ----
+// Body for one warp and window.  K = kFwdSmemPerWarp doubles of shared memory owned by the warp; gw = the window's 42 Gram
+// entries, F = its factor-Jacobian record (global in the batch kernel, shared in the fused one).
+__device__ __forceinline__ void forward_tail_body(const isv_batch_in& in, const isv_batch_out& out, const DevCfg& cfg, const int win,
+                                                  const int lane, double* K, const double* __restrict__ gw,
+                                                  const double* __restrict__ F, int32_t* wstatus,
+                                                  double* __restrict__ dbg_lamda_prior) {
+  double* X = K + kFwdConst;                  // tail work;  K = Psi (12x6 column-major)
   int status = 0;
   int nonfinite = 0;
 
@@ -473,11 +485,8 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
   // every global load of this kernel is issued here, up front: the factor-Jacobian record (252 doubles, 8
   // per lane, parked in registers until the work area is free) and the Gram triangles
   double fjr[8];
-  {
-    const double* F = fj + (size_t)win * kFJ;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) fjr[t] = (32 * t + lane < 252) ? F[32 * t + lane] : 0.0;
-  }
+  for (int t = 0; t < 8; ++t) fjr[t] = (32 * t + lane < 252) ? F[32 * t + lane] : 0.0;
   // work map (doubles): S12[0] H12[144] Ye[288] Ys[324] tmp[360..432) ; then
   // Wst[288] G[432] Jr6[504] tA[612] tB[684] wk[756]
   double* S12 = X;
@@ -511,7 +520,7 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
     int i = 0;
     while ((i + 1) * (i + 2) / 2 <= t) ++i;
     const int j = t - i * (i + 1) / 2;
-    const double ve = gram[(size_t)win * 42 + t], vw = gram[(size_t)win * 42 + 21 + t];
+    const double ve = gw[t], vw = gw[21 + t];
     Ye[i + 6 * j] = ve; Ye[j + 6 * i] = ve;
     Ys[i + 6 * j] = vw; Ys[j + 6 * i] = vw;
   }
@@ -635,8 +644,20 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
   for (int o = 16; o > 0; o >>= 1) status |= __shfl_xor_sync(kFullMask, status, o);
   if (lane == 0) {
     out.rank[2 * win] = out_rank;
-    if (out.status) atomicOr(out.status + win, status);
+    if (wstatus) atomicOr(wstatus, status);
   }
+}
+
+__global__ void __launch_bounds__(kThreads, ISV_FWD_TAIL_MINB)
+marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __restrict__ gram,
+                         const double* __restrict__ fj, DevCfg cfg, double* __restrict__ dbg_lamda_prior) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int win = blockIdx.x * kWarpsPerCta + warp;
+  if (win >= in.n_windows) return;
+  forward_tail_body(in, out, cfg, win, lane, smem + warp * kFwdSmemPerWarp, gram + (size_t)win * 42, fj + (size_t)win * kFJ,
+                    out.status ? out.status + win : nullptr, dbg_lamda_prior);
 }
 
 // =================================================================================================
@@ -657,15 +678,25 @@ marg_forward_tail_kernel(isv_batch_in in, isv_batch_out out, const double* __res
 constexpr int kGld = 21;  // G rows in shared memory: element (k, c) at Gs[k * 21 + c]
 constexpr int kBwdLc = 0, kBwdHv = 272, kBwdPv = 296, kBwdGs = 344, kBwdT = 660;
 constexpr int kLcLd = 16;   // Cholesky factor of the covariance: column k at Lc[16 k + i] (16-byte aligned pairs), [256..271) = 1 / L_kk
-__global__ void __launch_bounds__(kThreads, ISV_BWD_MINB)
-marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restrict__ fj, DevCfg cfg, int vo_size,
-                     double* __restrict__ dbg_g) {
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int win = blockIdx.x * kWarpsPerCta + warp;
-  if (win >= in.n_windows) return;
-  double* S = smem + warp * kBwdSmemPerWarp;
+// Named barrier of the fused single-event kernel: the backward warp waits here (after the covariance Cholesky, which needs
+// only the pre-integration record) for the warps that evaluate the IMU / relative-pose / roll-pitch Jacobians.
+constexpr int kFusedBarBwd = 1, kFusedBarFwd = 2;
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// Body for one warp and window.  S = kBwdSmemPerWarp doubles of shared memory owned by the warp, F = the window's
+// factor-Jacobian record.  FUSED_BAR > 0: F is produced concurrently by other warps of the CTA; it is not touched before the
+// named barrier kFusedBarBwd (FUSED_BAR threads) that follows the covariance Cholesky.
+template <int FUSED_BAR>
+__device__ __forceinline__ void backward_body(const isv_batch_in& in, const isv_batch_out& out, const DevCfg& cfg, const int win,
+                                              const int lane, double* S, const double* __restrict__ F, int32_t* wstatus,
+                                              double* __restrict__ dbg_g, long long* clk = nullptr) {
+  // profiling aid of the fused kernel (isv_test_fused_stamps): cycle counter at the phase boundaries
+  int n_clk = 0;
+  auto tick = [&]() {
+    if (FUSED_BAR > 0 && clk && lane == 0) clk[n_clk] = clock64();
+    ++n_clk;
+  };
   double* Lc = S + kBwdLc;     // Cholesky factor of the covariance, column k at Lc[16 k + i]; [256..271) = 1 / L_kk
   double* hv = S + kBwdHv;     // current Householder vector (15) + tau
   double* pvt = S + kBwdPv;    // LQ: the pivot row of the current step (two buffers of 24, alternating)
@@ -676,7 +707,6 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
 
   const double* pvb = in.prior_vb + (size_t)win * ISV_VB_REC;
   const double* pre = in.preint + (size_t)win * ISV_PREINT_REC;
-  const double* F = fj + (size_t)win * kFJ;
   double* o_rel = out.rel_out + (size_t)win * ISV_REL_REC;
   double* o_vb = out.vb_out + (size_t)win * ISV_VB_REC;
   double* o_rp = out.rp_out + (size_t)win * ISV_RP_REC;
@@ -686,7 +716,8 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
   double* cov = T + 344;     // up to 9 x 9
   // [Ji | Jj | Jrp] of the recovered factors: loaded now, parked in shared memory after the Cholesky (the
   // global-load latency hides behind it)
-  const double jr0 = F[kFJ_REL + lane], jr1 = F[kFJ_REL + 32 + lane], jr2 = (lane < 20) ? F[kFJ_REL + 64 + lane] : 0.0;
+  double jr0 = 0.0, jr1 = 0.0, jr2 = 0.0;
+  if (FUSED_BAR == 0) { jr0 = F[kFJ_REL + lane]; jr1 = F[kFJ_REL + 32 + lane]; jr2 = (lane < 20) ? F[kFJ_REL + 64 + lane] : 0.0; }
 
   // ---- covariance = L L^T, one column per lane in registers (right-looking) ------------------------
   {
@@ -727,6 +758,12 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
   }
   // ---- my column: IMU rows (unweighted Jacobian from marg_factor_jac_kernel, row-major 15 x 30:
   //      coalesced) and, for the VB_{V-1} columns, the prior rows (sqrt_info column, :1372-1380) -----
+  tick();   // [0] covariance Cholesky done
+  if (FUSED_BAR > 0) {
+    named_bar_sync(kFusedBarBwd, FUSED_BAR);
+    tick();   // [1] factor Jacobians arrived
+    jr0 = F[kFJ_REL + lane]; jr1 = F[kFJ_REL + 32 + lane]; jr2 = (lane < 20) ? F[kFJ_REL + 64 + lane] : 0.0;
+  }
   const int c = lane < 30 ? lane : 29;
   double col[15], pr[9];
 #pragma unroll
@@ -792,6 +829,7 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
     }
     __syncwarp();
   }
+  tick();   // [2] whitening + 9 Householder steps done
   // rows 9-23 of columns 0..20 are G (15 x 21) with G^T G = Lamda_prior: transpose to one row per lane
   if (lane < 21) {
 #pragma unroll
@@ -879,6 +917,7 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
     (void)kFirstPair;
   }
   __syncwarp();
+  tick();   // [3] LQ done
   // L (rows of lanes 0-14, lower triangular) -> shared; solve L^T y = rhs for all 32 lanes at once:
   // lanes 0-14: rhs = e_lane (columns of L^-T, for the eigenvalue bound), lanes 15-31: rhs = (Jr Q^T)_r
   double* Ls = T + 88;  // 15 x 15 (ld 16: column k at Ls[16 k + m], 16-byte aligned pairs) + 15 reciprocal diagonals at [240..);
@@ -910,6 +949,7 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
   ninv2 = warp_sum(ninv2);
   int rank;
   const bool fast = isfinite(ninv2) && ninv2 > 0.0 && (1.0 / ninv2) > cfg.alpha;
+  tick();   // [4] back-substitution + eigenvalue bound done
   if (fast) {
     rank = 15;
     __syncwarp();
@@ -934,6 +974,7 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
       dst[e] = acc;
     }
     __syncwarp();
+    tick();   // [5] covariance blocks done
     {
       // the three sqrt-information factors at once: lanes 0-8 vb (9x9), 9-14 rel (6x6), 15-16 rp (2x2);
       // the per-group scratch overlays JU, which is dead from here on
@@ -1006,8 +1047,20 @@ marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restric
   for (int o = 16; o > 0; o >>= 1) status |= __shfl_xor_sync(kFullMask, status, o);
   if (lane == 0) {
     out.rank[2 * win + 1] = rank;
-    if (out.status) atomicOr(out.status + win, status);
+    if (wstatus) atomicOr(wstatus, status);
   }
+}
+
+__global__ void __launch_bounds__(kThreads, ISV_BWD_MINB)
+marg_backward_kernel(isv_batch_in in, isv_batch_out out, const double* __restrict__ fj, DevCfg cfg, int vo_size,
+                     double* __restrict__ dbg_g) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int win = blockIdx.x * kWarpsPerCta + warp;
+  if (win >= in.n_windows) return;
+  backward_body<0>(in, out, cfg, win, lane, smem + warp * kBwdSmemPerWarp, fj + (size_t)win * kFJ,
+                   out.status ? out.status + win : nullptr, dbg_g);
   (void)vo_size;
 }
 

@@ -69,6 +69,46 @@ def test_randomised_sweep_matches_c_oracle(backend, L, ragged, n, seed):
     assert el.max() <= TOL and np.array_equal(sub.rank, lit.rank)
 
 
+def test_fused_event_kernel_matches_c_oracle_and_batch_kernels(backend):
+    """The one-launch fused kernel (one CTA per window: marg_event_fused_kernel, the route of isv_marg_event and of small
+    device batches) on 148 distinct ragged windows -- incl. the empty window, fewer landmarks than the seven landmark warps,
+    the lane-tile edges and two L ~ 1000 windows -- against the C oracle and against the warp-per-window batch kernels:
+    same device functions, only the summation order of the landmark Gram differs."""
+    n, seed = 148, 104
+    counts = np.random.default_rng(seed).integers(0, 301, n)
+    edges = [0, 1, 2, 6, 7, 8, 31, 32, 33, 63, 64, 65, 127, 128, 129, 223, 224, 225, 896, 897, 1000, 1250]
+    counts[:len(edges)] = edges
+    batch = bench.make_batch(150, n, seed, ragged=1.0, counts=counts)
+    backend.set_tuning(capi.TUNE_FUSED_MAX_WINDOWS, 148)
+    l0 = backend.launch_count
+    out = _run_gpu(backend, batch)
+    assert backend.launch_count - l0 == 1
+    backend.set_tuning(capi.TUNE_FUSED_MAX_WINDOWS, 0)
+    try:
+        l0 = backend.launch_count
+        outb = _run_gpu(backend, batch)
+        assert backend.launch_count - l0 == 5
+    finally:
+        backend.set_tuning(capi.TUNE_FUSED_MAX_WINDOWS, 148)
+    ref = ref_c.marg_window_batch(batch, 3, 0, True)
+    err = outputs_rel_diff(out, ref, 3)
+    worst = int(np.argmax(err))
+    print(f"\nfused kernel: {n} windows, worst rel err vs C oracle {err.max():.3e} at window {worst} (L = {counts[worst]}), "
+          f"median {np.median(err):.2e}; vs batch kernels {outputs_rel_diff(out, outb, 3).max():.3e}")
+    assert np.all(np.isfinite(err)) and err.max() <= TOL
+    assert np.array_equal(out.rank, ref.rank) and not out.status.any()
+    assert outputs_rel_diff(out, outb, 3).max() <= 1e-11
+    # discrete outcomes agree exactly on both routes
+    assert np.array_equal(out.rank, outb.rank) and np.array_equal(out.status, outb.status)
+    # status bits travel through shared memory in the fused kernel: a non-unit quaternion must still be flagged
+    bad = batch.take(np.arange(4))
+    bad.pose_fwd = bad.pose_fwd.copy()
+    bad.pose_fwd[2, 0, 3:7] *= 1.001
+    ob = _run_gpu(backend, bad)
+    assert ob.status[2] & 0x08          # ISV_W_NONUNIT_QUAT
+    assert not ob.status[[0, 1, 3]].any()
+
+
 def _rot(axis, angle):
     axis = np.asarray(axis, float) / np.linalg.norm(axis)
     return O.SO3.exp(axis * angle).matrix()

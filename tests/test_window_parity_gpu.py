@@ -20,12 +20,14 @@ def _events(config_id, batch_id, L, rounds):
 
 
 @pytest.mark.parametrize("L", [150, 1, 31, 32, 33, 1000])
-def test_device_batch_matches_oracle(backend, L):
+def test_device_batch_matches_oracle(backend, kernel_route, L):
     events = _events(1, L % 7, L, 3)
     batch = pack_events(events)
     db = DeviceBatch(batch, "cuda:0")
+    l0 = backend.launch_count
     backend.marg_window_batch(db, capi.RUN_BOTH)
     backend.synchronize()
+    assert backend.launch_count - l0 == (1 if kernel_route == "fused_kernel" else 5)
     out = db.outputs()
     for w, ev in enumerate(events):
         errs = compare_event(out, w, ev)
@@ -53,13 +55,26 @@ def test_host_batch_and_single_window(backend):
                                                       batch.preint[1])
     assert status == 0 and rank == ev.bwd_out.rank
     assert np.array_equal(rel, out.rel[1]) and np.array_equal(vb, out.vb[1]) and np.array_equal(rp, out.rp[1])
-    # the whole MARGIN_OLD event in one call: bit-identical to the two separate calls
-    (se3e, pge, rke, ste), (rele, vbe, rpe, rkb, stb) = backend.marg_event(
-        (f.pose0, f.pose1, f.ex_pose, f.inv_dep, f.pts_i, f.pts_j, batch.prior_se3[1], batch.prior_rel[1], batch.prior_rp[1]),
-        (b.pose_i, b.sb_i, b.pose_j, b.sb_j, batch.prior_vb[1], batch.preint[1]))
-    assert ste == 0 and stb == 0 and rke == 6 and rkb == ev.bwd_out.rank
-    assert np.array_equal(se3e, se3) and np.array_equal(pge, pg)
-    assert np.array_equal(rele, rel) and np.array_equal(vbe, vb) and np.array_equal(rpe, rp)
+    # the whole MARGIN_OLD event in one call, on its three routes: 0 = zero-copy fused kernel (the default), 1 = fused kernel
+    # on a device mirror, 2 = the batch kernels.  Route 2 is bit-identical to the two separate calls; the fused kernel sums
+    # the landmark Gram as seven partial sums and deals the IMU Jacobian over nine lanes, i.e. agrees to rounding
+    from tests.helpers import rel_err
+    for mode in (2, 1, 0, 0):
+        backend.set_tuning(capi.TUNE_EVENT_MODE, mode)
+        (se3e, pge, rke, ste), (rele, vbe, rpe, rkb, stb) = backend.marg_event(
+            (f.pose0, f.pose1, f.ex_pose, f.inv_dep, f.pts_i, f.pts_j, batch.prior_se3[1], batch.prior_rel[1], batch.prior_rp[1]),
+            (b.pose_i, b.sb_i, b.pose_j, b.sb_j, batch.prior_vb[1], batch.preint[1]))
+        assert ste == 0 and stb == 0 and rke == 6 and rkb == ev.bwd_out.rank, mode
+        if mode == 2:
+            assert np.array_equal(se3e, se3) and np.array_equal(pge, pg)
+        else:
+            assert rel_err(se3e[12:], se3[12:]) <= 1e-12 and rel_err(pge[12:48], pg[12:48]) <= 1e-12, mode
+            assert rel_err(pge[48:84], pg[48:84]) <= 1e-12 and np.array_equal(se3e[:12], se3[:12]), mode
+        if mode == 2:
+            assert np.array_equal(rele, rel) and np.array_equal(vbe, vb) and np.array_equal(rpe, rp)
+        else:
+            assert rel_err(rele, rel) <= 1e-12 and rel_err(vbe[9:], vb[9:]) <= 1e-12 and rel_err(rpe, rp) <= 1e-12, mode
+    backend.set_tuning(capi.TUNE_EVENT_MODE, 0)
 
 
 import os
@@ -71,7 +86,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 @pytest.mark.parametrize("name", ["cfg1_L150_ragged.npz", "cfg2_L1000_literal.npz", "bench_windows_L1000.npz",
                                   "bench_windows_L150.npz", "bench_windows_L2000.npz"])
-def test_committed_golden_fixtures(backend, name):
+def test_committed_golden_fixtures(backend, kernel_route, name):
     """cfg1 incl. ragged/empty windows (L = 0, 1, 31, 32, 33, 80); cfg2 = the literal dense oracle at L = 1000."""
     batch, ref, _ = load_batch(os.path.join(GOLD, name))
     db = DeviceBatch(batch, "cuda:0")
