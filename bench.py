@@ -153,7 +153,10 @@ def make_batch(L, n_windows, seed, ragged=RAGGED, counts=None):
         P0, P1 = pose_fwd[w0:w1, 0, 0:3], pose_fwd[w0:w1, 1, 0:3]
         u, v = rng.uniform(0, IMG_W, m), rng.uniform(0, IMG_H, m)
         depth = rng.uniform(1.0, 8.0, m)
-        pts_i = np.stack([(u - CX) / FX, (v - CY) / FY, np.ones(m)], axis=1)
+        # pts_i.x / pts_i.y are cv::Point2f values widened to double in the reference (feature_tracker_simple.h:55,
+        # System.cpp:119-122): the synthetic observations are FP32-representable too
+        pts_i = np.stack([((u - CX) / FX).astype(np.float32).astype(np.float64),
+                          ((v - CY) / FY).astype(np.float32).astype(np.float64), np.ones(m)], axis=1)
         pb = (pts_i * depth[:, None]) @ ric.T + tic                          # body frame 0
         pw = np.einsum("nij,nj->ni", R0[wid], pb) + P0[wid]
         pb1 = np.einsum("nji,nj->ni", R1[wid], pw - P1[wid])                  # R1^T (pw - P1)
@@ -494,13 +497,20 @@ def measure(cx, L, n, which, steps, warmup, seed, full, e2e=True):
         #     preintegrate_kernel first) and pts_i.z == 1 promised (src/System.cpp:346): 3 of the 6 landmark components
         #     cross PCIe (pts_j is never read by the information-only marginalization, pts_i.z is the constant 1);
         # (b) ABI 1 inputs (the full records), for comparison
-        for tag, kw, lm_comp, bwd_f in (("", dict(raw_imu=True, z_one=True), 3, ("pose_bwd", "sb_bwd", "prior_vb", "imu_raw", "imu_init")),
-                                        ("_abi1", dict(), 4, ("pose_bwd", "sb_bwd", "prior_vb", "preint"))):
+        # (a') ABI 3 inputs: (a) plus pts_i.x / pts_i.y as the FP32 values the feature tracker produced (cv::Point2f in the
+        #     reference): 4 + 4 + 8 bytes per landmark
+        from is_vins_b200.backend import xy_as_f32
+        xyf_t = torch.from_numpy(xy_as_f32(batch.lm_obs)).pin_memory()
+        cx.keep.append(xyf_t)
+        raw_f = ("pose_bwd", "sb_bwd", "prior_vb", "imu_raw", "imu_init")
+        for tag, kw, lm_bytes, bwd_f in (("", dict(raw_imu=True, z_one=True, xy_f32=xyf_t.numpy()), 16, raw_f),
+                                         ("_abi2", dict(raw_imu=True, z_one=True), 24, raw_f),
+                                         ("_abi1", dict(), 32, ("pose_bwd", "sb_bwd", "prior_vb", "preint"))):
             if tag and not full:
                 continue
             h2d = 0
             if which & 1:
-                h2d += sum(getattr(batch, f).nbytes for f in fwd_f) + lm_comp * batch.n_landmarks * 8
+                h2d += sum(getattr(batch, f).nbytes for f in fwd_f) + lm_bytes * batch.n_landmarks
             if which & 2:
                 h2d += sum(getattr(batch, f).nbytes for f in bwd_f)
             for _ in range(max(1, min(warmup, 3))):
@@ -520,7 +530,7 @@ def measure(cx, L, n, which, steps, warmup, seed, full, e2e=True):
                 # the pre-integration record was rebuilt on the GPU from the raw samples)
                 from is_vins_b200.batch import outputs_rel_diff
                 r["e2e_vs_device_path_max_rel"] = float(outputs_rel_diff(hout, r["out"], which).max())
-            if cx.rank == 0 and tag:
+            if cx.rank == 0 and tag == "_abi1":
                 r["e2e_abi1_bits_equal"] = bool(all(np.array_equal(getattr(hout, f), getattr(r["out"], f)) for f in fams))
     # ---- the copy ceiling the e2e number runs under: the same byte counts as plain pinned cudaMemcpyAsync, H2D and D2H
     #      overlapped on two streams, every rank at once (what the host / PCIe can feed; tools/h2d_peak.py is the long form)
@@ -675,9 +685,9 @@ def run_cuda(args, L):
     h = measure(cx, L, n, capi.RUN_BOTH, args.steps, args.warmup, 1000 + rank, full=True)
     names = list(KERNELS)
     tl = maxr([h["ms_total"], h["e2e_ms"], h["sustained_ms"] / h["sustained_steps"], h["sustained_2nd_half_ms_per_step"],
-               h["e2e_ms_abi1"], h["copy_ceiling_ms"]] + [h["per"][k] for k in names])
-    ms_total, e2e_ms, sus_ms, sus2_ms, e2e1_ms, ceil_ms = tl[0:6]
-    per = dict(zip(names, tl[6:]))
+               h["e2e_ms_abi1"], h["copy_ceiling_ms"], h["e2e_ms_abi2"]] + [h["per"][k] for k in names])
+    ms_total, e2e_ms, sus_ms, sus2_ms, e2e1_ms, ceil_ms, e2e2_ms = tl[0:7]
+    per = dict(zip(names, tl[7:]))
     tot_lm = maxr([float(h["n_lm"])])[0]
     line = None
     if rank == 0:
@@ -719,8 +729,10 @@ def run_cuda(args, L):
             "clocks": h["clocks"],
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h["h2d"], "d2h_bytes_per_step": h["d2h"],
                     "ms_per_step": e2e_ms / args.steps, "gb_per_s": (h["h2d"] + h["d2h"]) / (e2e_ms / args.steps * 1e-3) / 1e9,
-                    "inputs": "ABI 2: raw IMU samples (12 + 7 K doubles; preintegrate_kernel runs inside the call) instead of the "
-                              "467-double pre-integration record; pts_i.z == 1 promised (ISV_IN_PTS_I_Z_ONE): 3 doubles per landmark",
+                    "inputs": "ABI 3: raw IMU samples (12 + 7 K doubles; preintegrate_kernel runs inside the call) instead of the "
+                              "467-double pre-integration record; pts_i.z == 1 promised (ISV_IN_PTS_I_Z_ONE); pts_i.x / pts_i.y as "
+                              "the FP32 values the reference's feature tracker produces (cv::Point2f, widened exactly on the GPU): "
+                              "4 + 4 + 8 bytes per landmark",
                     "max_rel_diff_vs_device_path": h.get("e2e_vs_device_path_max_rel"),
                     "copy_ceiling": {"ms_per_step": ceil_ms, "value": world * n / (ceil_ms * 1e-3), "unit": UNIT,
                                      "frac": (e2e_ms / args.steps and ceil_ms / (e2e_ms / args.steps)),
@@ -728,6 +740,9 @@ def run_cuda(args, L):
                                              "ranks at once, max over ranks: what host memory / PCIe can feed on this box (the "
                                              "aggregate saturates near 115 GB/s at 2-4 GPUs and 186 GB/s at 8: "
                                              "profiles/r02n_h2d_peak_*gpu.json)"},
+                    "abi2": {"value": world * n * args.steps / (e2e2_ms * 1e-3), "h2d_bytes_per_step": h["h2d_abi2"],
+                             "ms_per_step": e2e2_ms / args.steps,
+                             "inputs": "ABI 2: as above with pts_i.x / pts_i.y as doubles (24 bytes per landmark)"},
                     "abi1": {"value": world * n * args.steps / (e2e1_ms * 1e-3), "h2d_bytes_per_step": h["h2d_abi1"],
                              "ms_per_step": e2e1_ms / args.steps, "results_bit_equal_device_path": h.get("e2e_abi1_bits_equal"),
                              "inputs": "ABI 1: the full records (467-double pre-integration, 4 doubles per landmark)"}},

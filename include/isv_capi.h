@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define ISV_ABI_VERSION 2   /* 2: isv_batch_in grew imu_raw / imu_init / imu_count / imu_k_max / flags (zero = v1 behaviour) */
+#define ISV_ABI_VERSION 3   /* 2: isv_batch_in grew imu_raw / imu_init / imu_count / imu_k_max / flags (zero = v1 behaviour);
+                               3: ... and lm_xy_f32 (NULL = v2 behaviour) */
 
 /* ---- status codes (SURVEY.md 8b "error conventions": the reference has none -- void + assert) */
 typedef enum isv_status {
@@ -80,9 +81,13 @@ int64_t isv_launch_count(const isv_handle* h);
  *   ISV_TUNE_FUSED_MAX_WINDOWS (env ISV_FUSED_MAX, default 148): isv_marg_window_batch(ISV_RUN_BOTH) calls of at most this
  *       many windows take the one-launch fused kernel (one CTA per window); 0 = always the warp-per-window batch kernels.
  *   ISV_TUNE_EVENT_MODE (env ISV_EVENT_MODE, default 0): route of isv_marg_event -- 0 zero-copy fused kernel, 1 fused
- *       kernel on a device-side mirror (H2D, launch, D2H, stream synchronise), 2 batch kernels on the mirror.          */
+ *       kernel on a device-side mirror (H2D, launch, D2H, stream synchronise), 2 batch kernels on the mirror.
+ *   ISV_TUNE_ACC_PERSIST (env ISV_ACC_PERSIST, default 0 = one CTA per window): persistent warps per SM of the landmark
+ *       kernel for batches of >= 2368 windows -- an occupancy experiment (leave registers to the backward kernel so that
+ *       it runs beside the landmark phase), measured without gain and kept for re-measurement.                         */
 #define ISV_TUNE_FUSED_MAX_WINDOWS 1
 #define ISV_TUNE_EVENT_MODE 2
+#define ISV_TUNE_ACC_PERSIST 3
 isv_status isv_set_tuning(isv_handle* h, int knob, int value);
 
 /* ---- index maps: the bit-exact contract -------------------------------
@@ -142,6 +147,14 @@ typedef struct isv_batch_in {
   const int32_t* imu_count;      /* [n] samples used per window, or NULL = imu_k_max everywhere */
   int32_t imu_k_max;             /* samples stored per window                                   */
   int32_t flags;                 /* ISV_IN_* bits                                               */
+  /* ---- ABI 3 (NULL = ABI 2 behaviour) ---------------------------------------------------------
+   * pts_i.x / pts_i.y are FP32 values in the reference: the feature tracker stores the undistorted
+   * points as cv::Point2f (include/feature_tracker/feature_tracker_simple.h:55,
+   * src/feature_tracker/feature_tracker_simple.cpp:207) and System widens them to double
+   * (src/System.cpp:119-122).  A caller that still has the floats hands them over as they are:
+   * components 0 and 1 of lm_obs are then neither read nor copied, the kernels widen on load
+   * (exact), and a landmark costs 4 + 4 + 8 bytes of PCIe / HBM traffic instead of 24.           */
+  const float* lm_xy_f32;        /* [2][lm_stride] pts_i.x, pts_i.y as float, or NULL            */
 } isv_batch_in;
 
 /* pts_i.z == 1 for every landmark (the feature tracker normalises: src/System.cpp:346): component 2 of

@@ -24,13 +24,27 @@ def _dp(a: np.ndarray):
     return a.ctypes.data_as(capi.c_double_p)
 
 
+def xy_as_f32(lm_obs: np.ndarray) -> np.ndarray:
+    """Components 0, 1 of lm_obs (pts_i.x, pts_i.y) narrowed to FP32 [2, n_lm]; they are cv::Point2f values in the reference
+    (feature_tracker_simple.h:55, System.cpp:119-122), so the narrowing must be exact -- anything else is a caller error."""
+    xy = np.ascontiguousarray(lm_obs[0:2].astype(np.float32))
+    if not np.array_equal(xy.astype(np.float64), lm_obs[0:2]):
+        raise ValueError("xy_f32: pts_i.x / pts_i.y are not FP32-representable; pass them as doubles")
+    return xy
+
+
 class DeviceBatch:
     """A WindowBatch resident in HBM (torch CUDA tensors) plus preallocated outputs."""
 
-    def __init__(self, batch: WindowBatch, device, pinned_src: bool = False, raw_imu: bool = False, z_one: bool = False):
+    def __init__(self, batch: WindowBatch, device, pinned_src: bool = False, raw_imu: bool = False, z_one: bool = False,
+                 xy_f32: bool = False):
         """raw_imu: hand the library the raw IMU samples (imu_raw / imu_init) instead of the pre-integration record (ABI
-        2: it runs preintegrate_kernel first); z_one: promise pts_i.z == 1 (ISV_IN_PTS_I_Z_ONE)."""
+        2: it runs preintegrate_kernel first); z_one: promise pts_i.z == 1 (ISV_IN_PTS_I_Z_ONE); xy_f32: hand pts_i.x / pts_i.y
+        over as FP32 (ABI 3, isv_batch_in::lm_xy_f32 -- they ARE floats in the reference; raises if narrowing is lossy)."""
         import torch
+        self.xy_f32 = None
+        if xy_f32:
+            self.xy_f32 = torch.from_numpy(xy_as_f32(batch.lm_obs)).to(device)
         self.raw_imu, self.flags = bool(raw_imu), (capi.IN_PTS_I_Z_ONE if z_one else 0)
         if raw_imu and (batch.imu_raw is None or batch.imu_init is None):
             raise ValueError("raw_imu=True needs batch.imu_raw / batch.imu_init")
@@ -63,6 +77,8 @@ class DeviceBatch:
         if self.raw_imu:
             bi.imu_raw, bi.imu_init, bi.imu_k_max = g("imu_raw"), g("imu_init"), int(t["imu_raw"].shape[1])
         bi.flags = self.flags
+        if self.xy_f32 is not None:
+            bi.lm_xy_f32 = self.xy_f32.data_ptr()
         o = self.out
         bo = capi.isv_batch_out(o["se3"].data_ptr(), o["pg"].data_ptr(), o["rel"].data_ptr(), o["vb"].data_ptr(),
                                 o["rp"].data_ptr(), o["rank"].data_ptr(), o["status"].data_ptr())
@@ -125,7 +141,7 @@ class MargBackend:
     # ---- batched, host pointers (H2D + kernels + D2H inside the call) ---------------------------
     def marg_window_batch_host(self, batch: WindowBatch, which: int = capi.RUN_BOTH,
                                out: Optional[WindowOutputs] = None, raw_imu: bool = False,
-                               z_one: bool = False) -> WindowOutputs:
+                               z_one: bool = False, xy_f32: Optional[np.ndarray] = None) -> WindowOutputs:
         """raw_imu / z_one: see DeviceBatch (fewer bytes cross PCIe: 12 + 7 K doubles instead of the 467-double
         pre-integration record, 3 instead of 4 doubles per landmark)."""
         n = batch.n
@@ -140,6 +156,9 @@ class MargBackend:
         if raw_imu:
             bi.imu_raw, bi.imu_init, bi.imu_k_max = _p(batch.imu_raw), _p(batch.imu_init), int(batch.imu_raw.shape[1])
         bi.flags = capi.IN_PTS_I_Z_ONE if z_one else 0
+        if xy_f32 is not None:   # ABI 3: [2, n_lm] float32 from xy_as_f32(batch.lm_obs) (pin it for the e2e measurement)
+            assert xy_f32.dtype == np.float32 and xy_f32.shape == (2, batch.lm_obs.shape[1]) and xy_f32.flags.c_contiguous
+            bi.lm_xy_f32 = _p(xy_f32)
         bo = capi.isv_batch_out(_p(out.se3), _p(out.pg), _p(out.rel), _p(out.vb), _p(out.rp), _p(out.rank),
                                 _p(out.status))
         capi.check(self.lib.isv_marg_window_batch_host(self.h, C.byref(bi), C.byref(bo), which),

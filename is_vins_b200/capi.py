@@ -22,7 +22,7 @@ ACC_REC, ACC_COVREL, ACC_DISTANCE, ACC_LENGTH, ACC_VIO_INDEX, ACC_PG_INDEX, ACC_
 ACC_RI, ACC_TI, ACC_RP_VALID, ACC_RP, ACC_COVABS = 89, 98, 101, 102, 115
 RUN_FORWARD, RUN_BACKWARD, RUN_BOTH = 1, 2, 3
 RUN_FORWARD_STAGE1, RUN_FORWARD_STAGE2, RUN_FACTOR_JAC, RUN_BACKWARD_STAGE2 = 4, 8, 16, 32
-TUNE_FUSED_MAX_WINDOWS, TUNE_EVENT_MODE = 1, 2   # isv_set_tuning knobs (include/isv_capi.h)
+TUNE_FUSED_MAX_WINDOWS, TUNE_EVENT_MODE, TUNE_ACC_PERSIST = 1, 2, 3   # isv_set_tuning knobs (include/isv_capi.h)
 POSE, SB, SE3_REC, REL_REC, VB_REC, RP_IN_REC, RP_REC, PG_REC, PREINT_REC = 7, 9, 48, 48, 90, 5, 13, 89, 467
 IMU_RAW_REC = 7
 
@@ -46,7 +46,9 @@ class isv_batch_in(C.Structure):
                 ("prior_vb", C.c_void_p), ("preint", C.c_void_p),
                 # ABI 2: raw IMU samples instead of the pre-integration record, and the ISV_IN_* flags
                 ("imu_raw", C.c_void_p), ("imu_init", C.c_void_p), ("imu_count", C.c_void_p),
-                ("imu_k_max", C.c_int32), ("flags", C.c_int32)]
+                ("imu_k_max", C.c_int32), ("flags", C.c_int32),
+                # ABI 3: pts_i.x / pts_i.y as the FP32 values the feature tracker produced
+                ("lm_xy_f32", C.c_void_p)]
 
 
 class isv_batch_out(C.Structure):

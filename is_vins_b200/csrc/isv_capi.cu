@@ -43,12 +43,17 @@ struct isv_handle {
   size_t mapped_bytes;
   int32_t event_seq;     //   completion-flag sequence number
   int fused_max;         // ISV_TUNE_FUSED_MAX_WINDOWS
+  int acc_persist;       // ISV_TUNE_ACC_PERSIST: persistent landmark-kernel warps per SM (0 = one CTA per window)
+  int n_sm;
+  int32_t* counters;     // device: work counters of the persistent kernels, one 16-int slot per launching stream
   int event_mode;        // ISV_TUNE_EVENT_MODE
   char* eig;             // eigensolver scratch of the generic engine (tridiagonal + rotation log per problem), grow-only
   size_t eig_bytes;
   double* gram;          // [n][42 + kFJ] scratch handed between the kernels of one batch, grow-only:
   size_t gram_bytes;     //   landmark Gram triangles (forward stage 1 -> 2) and the factor-Jacobian records
-  cudaEvent_t jac_ev[6]; // fork / join events of launch_batch, three per launching stream
+  cudaEvent_t jac_ev[12]; // fork / join events of launch_batch, three per launching slot
+  cudaStream_t pipe[2];   // third and fourth pipeline stream of the chunked host path (slots 2, 3)
+  cudaStream_t fork[8];   // side streams of launch_batch: [2 slot] backward chain, [2 slot + 1] forward factor Jacobians
   // isv_marg_window_batch: the ~15 runtime calls of one launch_batch (fork / join over three streams) replayed as one
   // CUDA graph when the same buffers come back (a server loop re-fills the same device batch every step)
   struct BatchGraph { isv_batch_in in; isv_batch_out out; int which; cudaStream_t stream; double* gram; cudaGraphExec_t exec; int launches; };
@@ -58,6 +63,18 @@ struct isv_handle {
 };
 
 constexpr int kFusedMaxWindows = 148;   // one CTA per SM: see launch_fused
+constexpr int kAccPersistPerSm = 0;     // persistent landmark-kernel warps per SM (see marg_forward_accum_kernel): OFF by default,
+constexpr int kAccPersistMinWindows = 2368;   // measured without gain; when on, used for batches of at least this many windows
+// the landmark kernel's eight instantiations: pts_i.z == 1 promised / sqrt_info = c I / pts_i.xy as FP32
+static const void* accum_kernel_variant(bool zone, bool iso, bool xyf) {
+  static const void* const k[8] = {
+      (const void*)marg_forward_accum_kernel<false, false, false>, (const void*)marg_forward_accum_kernel<true, false, false>,
+      (const void*)marg_forward_accum_kernel<false, true, false>,  (const void*)marg_forward_accum_kernel<true, true, false>,
+      (const void*)marg_forward_accum_kernel<false, false, true>,  (const void*)marg_forward_accum_kernel<true, false, true>,
+      (const void*)marg_forward_accum_kernel<false, true, true>,   (const void*)marg_forward_accum_kernel<true, true, true>};
+  return k[(zone ? 1 : 0) | (iso ? 2 : 0) | (xyf ? 4 : 0)];
+}
+
 
 #define ISV_CUDA(call)                                                                       \
   do {                                                                                       \
@@ -130,21 +147,24 @@ isv_status isv_create(const isv_config* cfg, int device, isv_handle** out) {
   for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
   for (int i = 0; i < 4; ++i) cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
   for (int i = 0; i < 3; ++i) cudaEventCreateWithFlags(&h->aux_ev[i], cudaEventDisableTiming);
-  for (int i = 0; i < 6; ++i) cudaEventCreateWithFlags(&h->jac_ev[i], cudaEventDisableTiming);
+  for (int i = 0; i < 12; ++i) cudaEventCreateWithFlags(&h->jac_ev[i], cudaEventDisableTiming);
+  for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking);
+  for (int i = 0; i < 8; ++i) cudaStreamCreateWithFlags(&h->fork[i], cudaStreamNonBlocking);
   h->stream = h->own_stream;
   {
     const char* e = getenv("ISV_FUSED_MAX");
     h->fused_max = e ? atoi(e) : kFusedMaxWindows;
+    e = getenv("ISV_ACC_PERSIST");
+    h->acc_persist = e ? atoi(e) : kAccPersistPerSm;
+    h->n_sm = prop.multiProcessorCount;
+    if (cudaMalloc(&h->counters, 64 * sizeof(int32_t)) != cudaSuccess) { cudaGetLastError(); h->counters = nullptr; h->acc_persist = 0; }
     e = getenv("ISV_EVENT_MODE");
     h->event_mode = e ? atoi(e) : 0;
     if (h->event_mode < 0 || h->event_mode > 2) h->event_mode = 0;
   }
   {
     const int sm = (int)(kAccWarps * kAccSmemPerWarp * sizeof(double));
-    cudaFuncSetAttribute(marg_forward_accum_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    cudaFuncSetAttribute(marg_forward_accum_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    cudaFuncSetAttribute(marg_forward_accum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    cudaFuncSetAttribute(marg_forward_accum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    for (int v = 0; v < 8; ++v) cudaFuncSetAttribute(accum_kernel_variant(v & 1, v & 2, v & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
   }
   cudaFuncSetAttribute(marg_forward_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kWarpsPerCta * kFwdSmemPerWarp * sizeof(double)));
@@ -169,6 +189,7 @@ void isv_destroy(isv_handle* h) {
   if (h->eig) cudaFree(h->eig);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->mapped) cudaFreeHost(h->mapped);
+  if (h->counters) cudaFree(h->counters);
   for (int i = 0; i < 4; ++i)
     if (h->bgraph[i].exec) cudaGraphExecDestroy(h->bgraph[i].exec);
   for (int i = 0; i < 4; ++i)
@@ -177,8 +198,12 @@ void isv_destroy(isv_handle* h) {
     if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
   for (int i = 0; i < 3; ++i)
     if (h->aux_ev[i]) cudaEventDestroy(h->aux_ev[i]);
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < 12; ++i)
     if (h->jac_ev[i]) cudaEventDestroy(h->jac_ev[i]);
+  for (int i = 0; i < 2; ++i)
+    if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
+  for (int i = 0; i < 8; ++i)
+    if (h->fork[i]) cudaStreamDestroy(h->fork[i]);
   cudaStreamDestroy(h->own_stream);
   cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -205,6 +230,7 @@ isv_status isv_set_tuning(isv_handle* h, int knob, int value) {
   if (!h) return ISV_ERR_BAD_ARG;
   if (knob == ISV_TUNE_FUSED_MAX_WINDOWS && value >= 0) { h->fused_max = value; return ISV_OK; }
   if (knob == ISV_TUNE_EVENT_MODE && value >= 0 && value <= 2) { h->event_mode = value; return ISV_OK; }
+  if (knob == ISV_TUNE_ACC_PERSIST && value >= 0 && value <= 16) { h->acc_persist = h->counters ? value : 0; return ISV_OK; }
   return ISV_ERR_BAD_ARG;
 }
 
@@ -261,8 +287,27 @@ constexpr size_t kScratchPerWindow = 42 + kFJ + ISV_PREINT_REC;
 
 struct DbgStores { double* lamda_prior_fwd; double* g_bwd; };
 
+// occupancy experiments (measurement only): extra dynamic shared memory per CTA of each window kernel
+static size_t exp_smem(const char* name) {
+  const char* e = getenv(name);
+  return e ? (size_t)atol(e) : 0;
+}
+
 static isv_status launch_batch(isv_handle* h, const isv_batch_in* in_arg, const isv_batch_out* out, int which,
                                cudaStream_t stream, double* scratch, DbgStores dbg = DbgStores{nullptr, nullptr}) {
+  static const size_t x_acc = exp_smem("ISV_EXP_ACC_SMEM"), x_tail = exp_smem("ISV_EXP_TAIL_SMEM"), x_bwd = exp_smem("ISV_EXP_BWD_SMEM");
+  static const bool x_once = [] {
+    if (x_acc) {
+      const int sm = (int)(kAccWarps * kAccSmemPerWarp * sizeof(double) + x_acc);
+      for (int v = 0; v < 8; ++v) cudaFuncSetAttribute(accum_kernel_variant(v & 1, v & 2, v & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    }
+    if (x_tail) cudaFuncSetAttribute(marg_forward_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(kWarpsPerCta * kFwdSmemPerWarp * sizeof(double) + x_tail));
+    if (x_bwd) cudaFuncSetAttribute(marg_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(kWarpsPerCta * kBwdSmemPerWarp * sizeof(double) + x_bwd));
+    return true;
+  }();
+  (void)x_once;
   const int n = in_arg->n_windows;
   if (n == 0) return ISV_OK;
   if (!scratch) return ISV_ERR_BAD_ARG;
@@ -278,7 +323,15 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in_arg, const 
   const bool jac_fwd = which & (ISV_RUN_FORWARD | ISV_RUN_FACTOR_JAC);
   const bool jac_bwd = which & (ISV_RUN_BACKWARD | ISV_RUN_FACTOR_JAC);
   const bool bwd = which & (ISV_RUN_BACKWARD | ISV_RUN_BACKWARD_STAGE2);
-  if (out->status) ISV_CUDA(cudaMemsetAsync(out->status, 0, sizeof(int32_t) * (size_t)n, stream));
+  const bool stage1_ = which & (ISV_RUN_FORWARD | ISV_RUN_FORWARD_STAGE1);
+  const bool persist = stage1_ && h->acc_persist > 0 && h->counters && n >= kAccPersistMinWindows;
+  const int slot = (stream == h->copy_stream) ? 1 : (stream == h->pipe[0] ? 2 : (stream == h->pipe[1] ? 3 : 0));
+  int32_t* counter = persist ? h->counters + 16 * slot : nullptr;
+  if (out->status || persist) {
+    int32_t dummy_n = out->status ? n : 0;
+    zero_i32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out->status, dummy_n, counter, persist ? 1 : 0);
+    ++h->launches;
+  }
   const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
   // Three independent chains: [landmark kernel] on the caller's stream, [forward factor Jacobians] and
   // [backward factor Jacobians -> marg_backward_kernel] on side streams.  The factor-Jacobian launches are
@@ -287,10 +340,9 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in_arg, const 
   // the call joins the backward chain.
   const bool fork_b = (which & ISV_RUN_BACKWARD) && (which & ISV_RUN_FORWARD);
   const bool fork_f = jac_fwd && stage1;
-  const int slot = (stream == h->copy_stream) ? 1 : 0;
   cudaEvent_t* ev = h->jac_ev + 3 * slot;   // [0] fork point, [1] backward chain done, [2] forward Jacobians done
-  cudaStream_t bs = fork_b ? h->aux[slot] : stream;
-  cudaStream_t fs = fork_f ? h->aux[2 + slot] : stream;
+  cudaStream_t bs = fork_b ? h->fork[2 * slot] : stream;
+  cudaStream_t fs = fork_f ? h->fork[2 * slot + 1] : stream;
   if (fork_b || fork_f) ISV_CUDA(cudaEventRecord(ev[0], stream));
   if (fork_b) ISV_CUDA(cudaStreamWaitEvent(bs, ev[0], 0));
   if (fork_f) ISV_CUDA(cudaStreamWaitEvent(fs, ev[0], 0));
@@ -307,32 +359,41 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in_arg, const 
   }
   if (jac_bwd) {
     // the IMU Jacobian record is sparse: zero-fill it, the kernel writes the non-zero blocks
-    ISV_CUDA(cudaMemset2DAsync(fj + kFJ_IMU, kFJ * sizeof(double), 0, 450 * sizeof(double), (size_t)n, bs));
+    {
+      const long long tot = (long long)n * 450;
+      const int zgrid = (int)(tot / 1024 < 1184 ? (tot + 1023) / 1024 : 1184);   // <= 8 CTAs per SM, 4 elements per thread and pass
+      zero_rows_kernel<<<zgrid, 256, 0, bs>>>(fj + kFJ_IMU, n, 450, kFJ);
+      ++h->launches;
+    }
     marg_factor_jac_kernel<<<dim3((n + 127) / 128, 3), 128, 0, bs>>>(*in, *out, fj, h->dcfg, 4);
     ++h->launches;
   }
   if (stage1) {
     const int agrid = (n + kAccWarps - 1) / kAccWarps;
-    const size_t asm_ = kAccWarps * kAccSmemPerWarp * sizeof(double);
+    const size_t asm_ = kAccWarps * kAccSmemPerWarp * sizeof(double) + x_acc;
     const bool zone = (in->flags & ISV_IN_PTS_I_Z_ONE) != 0;
     // ProjectionFactor::sqrt_info = c I (always, in the reference: src/estimator.cpp:35) takes the leaner chain
     static const bool no_iso = getenv("ISV_NO_ISO") != nullptr;   // A/B switch for measurements
     const bool iso = !no_iso && h->dcfg.ps[1] == 0.0 && h->dcfg.ps[2] == 0.0 && h->dcfg.ps[0] == h->dcfg.ps[3];
-    if (zone && iso) marg_forward_accum_kernel<true, true><<<agrid, 32 * kAccWarps, asm_, stream>>>(*in, gram, out->status, h->dcfg);
-    else if (zone) marg_forward_accum_kernel<true, false><<<agrid, 32 * kAccWarps, asm_, stream>>>(*in, gram, out->status, h->dcfg);
-    else if (iso) marg_forward_accum_kernel<false, true><<<agrid, 32 * kAccWarps, asm_, stream>>>(*in, gram, out->status, h->dcfg);
-    else marg_forward_accum_kernel<false, false><<<agrid, 32 * kAccWarps, asm_, stream>>>(*in, gram, out->status, h->dcfg);
+    const bool xyf = in->lm_xy_f32 != nullptr;
+    const void* ak = accum_kernel_variant(zone, iso, xyf);
+    isv_batch_in a_in = *in;
+    int32_t* a_status = out->status;
+    DevCfg a_cfg = h->dcfg;
+    void* args[5] = {&a_in, &gram, &a_status, &a_cfg, &counter};
+    const int pgrid = persist ? h->acc_persist * h->n_sm / kAccWarps : agrid;
+    ISV_CUDA(cudaLaunchKernel(ak, dim3(pgrid < agrid ? pgrid : agrid), dim3(32 * kAccWarps), args, asm_, stream));
     ++h->launches;
   }
   if (bwd) {
-    marg_backward_kernel<<<grid, kThreads, kWarpsPerCta * kBwdSmemPerWarp * sizeof(double), bs>>>(*in, *out, fj, h->dcfg,
+    marg_backward_kernel<<<grid, kThreads, kWarpsPerCta * kBwdSmemPerWarp * sizeof(double) + x_bwd, bs>>>(*in, *out, fj, h->dcfg,
                                                                                                  h->cfg.vo_size, dbg.g_bwd);
     ++h->launches;
   }
   if (fork_b) ISV_CUDA(cudaEventRecord(ev[1], bs));
   if (fork_f) ISV_CUDA(cudaStreamWaitEvent(stream, ev[2], 0));
   if (stage2) {
-    marg_forward_tail_kernel<<<grid, kThreads, kWarpsPerCta * kFwdSmemPerWarp * sizeof(double), stream>>>(
+    marg_forward_tail_kernel<<<grid, kThreads, kWarpsPerCta * kFwdSmemPerWarp * sizeof(double) + x_tail, stream>>>(
         *in, *out, gram, fj, h->dcfg, dbg.lamda_prior_fwd);
     ++h->launches;
   }
@@ -347,7 +408,7 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in_arg, const 
 // fitting one CTA per SM; beyond that the warp-per-window batch kernels have the higher throughput.
 static bool fused_eligible(const isv_handle* h, const isv_batch_in* in, int which) {
   const bool iso = h->dcfg.ps[1] == 0.0 && h->dcfg.ps[2] == 0.0 && h->dcfg.ps[0] == h->dcfg.ps[3];
-  return which == ISV_RUN_BOTH && in->preint && iso && in->n_windows >= 1 && in->n_windows <= h->fused_max;
+  return which == ISV_RUN_BOTH && in->preint && !in->lm_xy_f32 && iso && in->n_windows >= 1 && in->n_windows <= h->fused_max;
 }
 static isv_status launch_fused(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, cudaStream_t stream,
                                int32_t* done_flag, int32_t done_seq, long long* stamps = nullptr) {
@@ -464,6 +525,8 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   auto carve = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
   const size_t o_lmoff = carve(fwd ? (n + 1) * sizeof(int64_t) : 0);
   const size_t o_obs = carve(fwd ? 6 * (size_t)n_lm * D : 0);
+  const bool xyf = fwd && in->lm_xy_f32;
+  const size_t o_xyf = carve(xyf ? 2 * (size_t)n_lm * sizeof(float) : 0);
   const size_t o_posef = carve(fwd ? n * 14 * D : 0);
   const size_t o_ex = carve(fwd ? (in->ex_pose_shared ? 7 : n * 7) * D : 0);
   const size_t o_pse3 = carve(fwd ? n * ISV_SE3_REC * D : 0);
@@ -501,31 +564,69 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   char* d = h->dbuf;
   // Chunked pipeline on two streams: chunk c+1's H2D overlaps chunk c's kernels and D2H (PCIe is
   // full duplex).  The caller's stream is fenced before and after with events.
-  cudaStream_t ss[2] = {h->own_stream, h->copy_stream};
+  // Four pipeline streams: every chunk is a dependent chain H2D -> kernels -> D2H, and at L ~ 150 that chain is
+  // latency- not bandwidth-bound (0.12 + 0.39 + 0.25 ms per 2368 windows, profiles/r02t_host_pipeline_trace.txt): with two
+  // streams only two chunks were ever in flight.
+  constexpr int kPipe = 4;
+  cudaStream_t ss[kPipe] = {h->own_stream, h->copy_stream, h->pipe[0], h->pipe[1]};
   if (h->stream != h->own_stream) {
     ISV_CUDA(cudaEventRecord(h->ev[0], h->stream));
-    ISV_CUDA(cudaStreamWaitEvent(ss[0], h->ev[0], 0));
-    ISV_CUDA(cudaStreamWaitEvent(ss[1], h->ev[0], 0));
+    for (int i = 0; i < kPipe; ++i) ISV_CUDA(cudaStreamWaitEvent(ss[i], h->ev[0], 0));
   } else {
     ISV_CUDA(cudaEventRecord(h->ev[0], ss[0]));
-    ISV_CUDA(cudaStreamWaitEvent(ss[1], h->ev[0], 0));
+    for (int i = 1; i < kPipe; ++i) ISV_CUDA(cudaStreamWaitEvent(ss[i], h->ev[0], 0));
   }
-  ISV_CUDA(cudaMemsetAsync(d + o_rank, 0, n * 2 * sizeof(int32_t), ss[0]));
+  zero_i32_kernel<<<(int)((2 * n + 255) / 256), 256, 0, ss[0]>>>((int32_t*)(d + o_rank), (long long)(2 * n));
+  // The per-window records cross once, one copy per array for the whole batch, ahead of the chunk loop: ~320 doubles per
+  // window that used to travel as nine copies PER CHUNK (every copy pays a fixed DMA set-up; at L = 150 they are half of the
+  // bytes).  Only the landmark components and the results are chunked.
+  auto up = [&](size_t o, const void* src, size_t bytes) {
+    return bytes ? cudaMemcpyAsync(d + o, src, bytes, cudaMemcpyHostToDevice, ss[0]) : cudaSuccess;
+  };
   if (fwd) {
-    ISV_CUDA(cudaMemcpyAsync(d + o_lmoff, in->lm_offset, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ss[0]));
-    ISV_CUDA(cudaMemcpyAsync(d + o_ex, in->ex_pose, (in->ex_pose_shared ? 7 : n * 7) * D, cudaMemcpyHostToDevice, ss[0]));
+    ISV_CUDA(up(o_lmoff, in->lm_offset, (n + 1) * sizeof(int64_t)));
+    ISV_CUDA(up(o_ex, in->ex_pose, (in->ex_pose_shared ? 7 : n * 7) * D));
+    ISV_CUDA(up(o_posef, in->pose_fwd, n * 14 * D));
+    ISV_CUDA(up(o_pse3, in->prior_se3, n * ISV_SE3_REC * D));
+    ISV_CUDA(up(o_prel, in->prior_rel, n * ISV_REL_REC * D));
+    if (in->prior_rp) ISV_CUDA(up(o_prp, in->prior_rp, n * ISV_RP_IN_REC * D));
+  }
+  if (bwd) {
+    ISV_CUDA(up(o_poseb, in->pose_bwd, n * 14 * D));
+    ISV_CUDA(up(o_sbb, in->sb_bwd, n * 18 * D));
+    ISV_CUDA(up(o_pvb, in->prior_vb, n * ISV_VB_REC * D));
+    if (!raw_imu) {
+      ISV_CUDA(up(o_pre, in->preint, n * ISV_PREINT_REC * D));
+    } else {
+      ISV_CUDA(up(o_iraw, in->imu_raw, n * K * 7 * D));
+      ISV_CUDA(up(o_iinit, in->imu_init, n * 12 * D));
+      if (in->imu_count) ISV_CUDA(up(o_icnt, in->imu_count, n * sizeof(int32_t)));
+    }
   }
   ISV_CUDA(cudaEventRecord(h->ev[1], ss[0]));
-  ISV_CUDA(cudaStreamWaitEvent(ss[1], h->ev[1], 0));
+  for (int i = 1; i < kPipe; ++i) ISV_CUDA(cudaStreamWaitEvent(ss[i], h->ev[1], 0));
   size_t n_chunks = n / 512;
   if (n_chunks < 1) n_chunks = 1;
   static const int max_chunks = getenv("ISV_HOST_CHUNKS") ? atoi(getenv("ISV_HOST_CHUNKS")) : 4;   // measured at 9472 windows: 2 / 4 / 8 / 16 chunks
                                                                                                    // -> 1.68 / 1.76 / 1.73 / 1.56 M windows/s
   if (n_chunks > (size_t)max_chunks) n_chunks = max_chunks > 0 ? max_chunks : 1;
+  // ISV_HOST_TRACE=1: timeline of the chunk pipeline (device events + host issue times), printed to stderr
+  static const bool trace = getenv("ISV_HOST_TRACE") != nullptr;
+  cudaEvent_t tev[1 + 4 * 16];
+  double thost[16][4];
+  timespec tr0;
+  const bool tr = trace && n_chunks <= 16;
+  auto host_ms = [&]() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (t.tv_sec - tr0.tv_sec) * 1e3 + (t.tv_nsec - tr0.tv_nsec) * 1e-6; };
+  if (tr) {
+    for (size_t i = 0; i < 1 + 4 * n_chunks; ++i) cudaEventCreate(&tev[i]);
+    clock_gettime(CLOCK_MONOTONIC, &tr0);
+    cudaEventRecord(tev[0], ss[0]);
+  }
   for (size_t c = 0; c < n_chunks; ++c) {
     const size_t w0 = n * c / n_chunks, w1 = n * (c + 1) / n_chunks, m = w1 - w0;
     if (m == 0) continue;
-    cudaStream_t s = ss[c & 1];
+    cudaStream_t s = ss[c % kPipe];
+    if (tr) { thost[c][0] = host_ms(); cudaEventRecord(tev[1 + 4 * c], s); }
     isv_batch_in din;
     isv_batch_out dout;
     memset(&din, 0, sizeof(din));
@@ -536,22 +637,22 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     if (fwd) {
       const int64_t a = in->lm_offset[w0], b = in->lm_offset[w1];
       // components 3,4 (pts_j) are never read by the information-only marginalization: not copied
-      static const int comps[4] = {0, 1, 5, 2};     // pts_i.z last: skipped under ISV_IN_PTS_I_Z_ONE
-      for (int ci = 0; ci < (z_one ? 3 : 4) && b > a; ++ci)
+      static const int comps[4] = {5, 2, 0, 1};     // inv_dep; pts_i.z (skipped under ISV_IN_PTS_I_Z_ONE); pts_i.x, pts_i.y
+      for (int ci = 0; ci < 4 && b > a; ++ci) {
+        if ((comps[ci] == 2 && z_one) || (comps[ci] < 2 && xyf)) continue;
         ISV_CUDA(cudaMemcpyAsync(d + o_obs + ((size_t)comps[ci] * n_lm + a) * D,
                                  in->lm_obs + (size_t)comps[ci] * in->lm_stride + a, (size_t)(b - a) * D,
                                  cudaMemcpyHostToDevice, s));
-      ISV_CUDA(cudaMemcpyAsync(d + o_posef + w0 * 14 * D, in->pose_fwd + w0 * 14, m * 14 * D, cudaMemcpyHostToDevice, s));
-      ISV_CUDA(cudaMemcpyAsync(d + o_pse3 + w0 * ISV_SE3_REC * D, in->prior_se3 + w0 * ISV_SE3_REC, m * ISV_SE3_REC * D,
-                               cudaMemcpyHostToDevice, s));
-      ISV_CUDA(cudaMemcpyAsync(d + o_prel + w0 * ISV_REL_REC * D, in->prior_rel + w0 * ISV_REL_REC, m * ISV_REL_REC * D,
-                               cudaMemcpyHostToDevice, s));
-      if (in->prior_rp)
-        ISV_CUDA(cudaMemcpyAsync(d + o_prp + w0 * ISV_RP_IN_REC * D, in->prior_rp + w0 * ISV_RP_IN_REC,
-                                 m * ISV_RP_IN_REC * D, cudaMemcpyHostToDevice, s));
+      }
+      if (xyf && b > a)   // ABI 3: the FP32 x, y of the feature tracker, 8 instead of 16 bytes per landmark
+        for (int ci = 0; ci < 2; ++ci)
+          ISV_CUDA(cudaMemcpyAsync(d + o_xyf + ((size_t)ci * n_lm + a) * sizeof(float),
+                                   in->lm_xy_f32 + (size_t)ci * in->lm_stride + a, (size_t)(b - a) * sizeof(float),
+                                   cudaMemcpyHostToDevice, s));
       din.lm_offset = (const int64_t*)(d + o_lmoff) + w0;   // absolute offsets into the whole mirror
       din.lm_obs = (const double*)(d + o_obs);
       din.lm_stride = n_lm;
+      din.lm_xy_f32 = xyf ? (const float*)(d + o_xyf) : nullptr;
       din.pose_fwd = (const double*)(d + o_posef) + w0 * 14;
       din.ex_pose = (const double*)(d + o_ex) + (in->ex_pose_shared ? 0 : w0 * 7);
       din.prior_se3 = (const double*)(d + o_pse3) + w0 * ISV_SE3_REC;
@@ -561,18 +662,7 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
       dout.pg_out = (double*)(d + o_pg) + w0 * ISV_PG_REC;
     }
     if (bwd) {
-      ISV_CUDA(cudaMemcpyAsync(d + o_poseb + w0 * 14 * D, in->pose_bwd + w0 * 14, m * 14 * D, cudaMemcpyHostToDevice, s));
-      ISV_CUDA(cudaMemcpyAsync(d + o_sbb + w0 * 18 * D, in->sb_bwd + w0 * 18, m * 18 * D, cudaMemcpyHostToDevice, s));
-      ISV_CUDA(cudaMemcpyAsync(d + o_pvb + w0 * ISV_VB_REC * D, in->prior_vb + w0 * ISV_VB_REC, m * ISV_VB_REC * D,
-                               cudaMemcpyHostToDevice, s));
-      if (!raw_imu) {
-        ISV_CUDA(cudaMemcpyAsync(d + o_pre + w0 * ISV_PREINT_REC * D, in->preint + w0 * ISV_PREINT_REC,
-                                 m * ISV_PREINT_REC * D, cudaMemcpyHostToDevice, s));
-      } else {
-        if (K) ISV_CUDA(cudaMemcpyAsync(d + o_iraw + w0 * K * 7 * D, in->imu_raw + w0 * K * 7, m * K * 7 * D, cudaMemcpyHostToDevice, s));
-        ISV_CUDA(cudaMemcpyAsync(d + o_iinit + w0 * 12 * D, in->imu_init + w0 * 12, m * 12 * D, cudaMemcpyHostToDevice, s));
-        if (in->imu_count)
-          ISV_CUDA(cudaMemcpyAsync(d + o_icnt + w0 * sizeof(int32_t), in->imu_count + w0, m * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+      if (raw_imu) {
         din.imu_raw = (const double*)(d + o_iraw) + w0 * K * 7;
         din.imu_init = (const double*)(d + o_iinit) + w0 * 12;
         din.imu_count = in->imu_count ? (const int32_t*)(d + o_icnt) + w0 : nullptr;
@@ -588,8 +678,10 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     }
     dout.rank = (int32_t*)(d + o_rank) + 2 * w0;
     dout.status = (int32_t*)(d + o_stat) + w0;
+    if (tr) { thost[c][1] = host_ms(); cudaEventRecord(tev[2 + 4 * c], s); }
     st = launch_batch(h, &din, &dout, which, s, (double*)(d + o_gram) + w0 * kScratchPerWindow);
     if (st != ISV_OK) return st;
+    if (tr) { thost[c][2] = host_ms(); cudaEventRecord(tev[3 + 4 * c], s); }
     if (fwd) {
       ISV_CUDA(cudaMemcpyAsync(out->se3_out + w0 * ISV_SE3_REC, dout.se3_out, m * ISV_SE3_REC * D, cudaMemcpyDeviceToHost, s));
       ISV_CUDA(cudaMemcpyAsync(out->pg_out + w0 * ISV_PG_REC, dout.pg_out, m * ISV_PG_REC * D, cudaMemcpyDeviceToHost, s));
@@ -602,9 +694,20 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     ISV_CUDA(cudaMemcpyAsync(out->rank + 2 * w0, dout.rank, m * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     if (out->status)
       ISV_CUDA(cudaMemcpyAsync(out->status + w0, dout.status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (tr) { thost[c][3] = host_ms(); cudaEventRecord(tev[4 + 4 * c], s); }
   }
-  ISV_CUDA(cudaStreamSynchronize(ss[0]));
-  ISV_CUDA(cudaStreamSynchronize(ss[1]));
+  for (int i = 0; i < kPipe; ++i) ISV_CUDA(cudaStreamSynchronize(ss[i]));
+  if (tr) {
+    const double t_end = host_ms();
+    for (size_t c = 0; c < n_chunks; ++c) {
+      float e[4];
+      for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&e[k], tev[0], tev[1 + 4 * c + k]);
+      fprintf(stderr, "[isv trace] chunk %zu: device ms  start %.3f | H2D done %.3f | kernels done %.3f | D2H done %.3f   ||  host issue ms  %.3f %.3f %.3f %.3f\n",
+              c, e[0], e[1], e[2], e[3], thost[c][0], thost[c][1], thost[c][2], thost[c][3]);
+    }
+    fprintf(stderr, "[isv trace] host: call returned at %.3f ms\n", t_end);
+    for (size_t i = 0; i < 1 + 4 * n_chunks; ++i) cudaEventDestroy(tev[i]);
+  }
   return ISV_OK;
 }
 

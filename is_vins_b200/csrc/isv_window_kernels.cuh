@@ -16,6 +16,8 @@
 // Both sums are SYRKs  X X^T  with X 12 x L of rank <= 6: they are accumulated as 6x6 Gram matrices
 // in registers (see "6-vector form" below).  Everything after that is 12x12 / 6x6 algebra.
 #pragma once
+#include <type_traits>
+
 #include "isv_device_math.cuh"
 #include "isv_factors.cuh"
 #include "isv_small_qr.cuh"
@@ -212,6 +214,21 @@ __device__ __forceinline__ void factor_jac_task(const isv_batch_in& in, const is
   }
 }
 
+// Zero-fill helpers of the batch launcher.  They replace cudaMemsetAsync / cudaMemset2DAsync, which the driver may hand to a
+// copy engine: inside the chunked host pipeline (isv_marg_window_batch_host) such a memset queued behind the next chunk's
+// multi-megabyte H2D copies and held the kernel chain up for up to 0.4 ms (profiles/r02t_host_pipeline_trace.txt).
+__global__ void zero_rows_kernel(double* __restrict__ base, int n_rows, int row_len, int row_stride) {
+  const long long total = (long long)n_rows * row_len;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / row_len;
+    base[r * row_stride + (i - r * row_len)] = 0.0;
+  }
+}
+__global__ void zero_i32_kernel(int32_t* __restrict__ p, long long n, int32_t* __restrict__ q = nullptr, int nq = 0) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = 0;
+  if (blockIdx.x == 0 && (int)threadIdx.x < nq) q[threadIdx.x] = 0;
+}
+
 __global__ void __launch_bounds__(128)
 marg_factor_jac_kernel(isv_batch_in in, isv_batch_out out, double* __restrict__ fj, DevCfg cfg, int task0) {
   const int win = blockIdx.x * blockDim.x + threadIdx.x;
@@ -272,7 +289,8 @@ constexpr int kAccWarps = ISV_ACC_WARPS;
 // Body of the landmark phase for one warp: landmarks [lm0, lm0 + L) of window `win` -> the 42 Gram-triangle entries at g.
 // The batch kernel gives a warp its whole window; the fused single-event kernel splits one window over several warps.
 // K = kAccSmemPerWarp doubles of shared memory owned by the calling warp; wstatus = where status bits are OR-ed (or null).
-template <bool ZONE, bool ISO>
+// XYF = pts_i.x / pts_i.y come as the FP32 values the feature tracker produced (isv_batch_in::lm_xy_f32), widened on load
+template <bool ZONE, bool ISO, bool XYF = false>
 __device__ __forceinline__ void forward_accum_body(const isv_batch_in& in, const DevCfg& cfg, const int win, const int lane,
                                                    double* K, const long long lm0, const int L, double* __restrict__ g,
                                                    int32_t* wstatus) {
@@ -380,14 +398,16 @@ __device__ __forceinline__ void forward_accum_body(const isv_batch_in& in, const
   // entries (entry e = landmarks base + 32 e + lane); an entry is refilled -- for the landmark 128 further on, i.e. two
   // steps ahead -- as soon as its values have been copied out.  The loop is unrolled over the ring, so ring indices are
   // compile-time (no register shuffling) and the loads use immediate offsets from four running pointers.
-  const double* __restrict__ qx = in.lm_obs + lm0 + lane;
-  const double* __restrict__ qy = qx + st;
-  const double* __restrict__ qz = qx + 2 * st;
-  const double* __restrict__ ql = qx + 5 * st;
-  double rx[4], ry[4], rz[4], rl[4];
+  using xy_t = typename std::conditional<XYF, float, double>::type;
+  const xy_t* __restrict__ qx = (XYF ? reinterpret_cast<const xy_t*>(in.lm_xy_f32) : reinterpret_cast<const xy_t*>(in.lm_obs)) + lm0 + lane;
+  const xy_t* __restrict__ qy = qx + st;
+  const double* __restrict__ qz = in.lm_obs + lm0 + lane + 2 * st;
+  const double* __restrict__ ql = in.lm_obs + lm0 + lane + 5 * st;
+  xy_t rx[4], ry[4];   // XYF: the ring holds the floats (8 registers less), widened when a step consumes them
+  double rz[4], rl[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    rx[e] = 0.0; ry[e] = 0.0; rz[e] = 1.0; rl[e] = 1.0;
+    rx[e] = 0; ry[e] = 0; rz[e] = 1.0; rl[e] = 1.0;
     if (32 * e + lane < L) { rx[e] = qx[32 * e]; ry[e] = qy[32 * e]; if (!ZONE) rz[e] = qz[32 * e]; rl[e] = ql[32 * e]; }
   }
   // Main loop: whole super-steps of 128 landmarks.  Every lane has work, so the body carries no predicate and no branch:
@@ -455,18 +475,33 @@ __device__ __forceinline__ void forward_accum_body(const isv_batch_in& in, const
   if (lane == 0 && status && wstatus) atomicOr(wstatus, status);
 }
 
-template <bool ZONE, bool ISO>
+// `next` != null: PERSISTENT form (ISV_TUNE_ACC_PERSIST warps per SM pull windows from a counter).  An experiment, off by
+// default: 8 one-window CTAs per SM fill the register file, so nothing runs next to the landmark phase although it leaves
+// 40 % of the FP64 pipe idle; 4 persistent warps per SM keep 70 % of the 8-warp throughput
+// (profiles/r02r_occupancy_experiment.txt) and leave half of the registers to the backward kernel's CTAs.  Measured
+// (profiles/r02u_persistent_accum_sweep.txt): the step does NOT get shorter -- 0.353 -> 0.388 ms at 4 warps per SM,
+// 0.361 at 6; landmark and backward kernel take as long side by side as one after the other, with the same
+// shared-memory carveout on every kernel and with 32 hardware queues as well.
+template <bool ZONE, bool ISO, bool XYF = false>
 __global__ void ISV_ACC_BOUNDS
-marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* wstatus, DevCfg cfg) {
+marg_forward_accum_kernel(isv_batch_in in, double* __restrict__ gram, int32_t* wstatus, DevCfg cfg, int32_t* next) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int win = blockIdx.x * kAccWarps + warp;
-  if (win >= in.n_windows) return;
-  const long long lm0 = in.lm_offset[win];
-  const int L = (int)(in.lm_offset[win + 1] - lm0);
-  forward_accum_body<ZONE, ISO>(in, cfg, win, lane, smem + warp * kAccSmemPerWarp, lm0, L, gram + (size_t)win * 42,
-                                wstatus ? wstatus + win : nullptr);
+  int win = blockIdx.x * kAccWarps + warp;
+  for (;;) {
+    if (next) {
+      if (lane == 0) win = atomicAdd(next, 1);
+      win = __shfl_sync(kFullMask, win, 0);
+    }
+    if (win >= in.n_windows) return;
+    const long long lm0 = in.lm_offset[win];
+    const int L = (int)(in.lm_offset[win + 1] - lm0);
+    forward_accum_body<ZONE, ISO, XYF>(in, cfg, win, lane, smem + warp * kAccSmemPerWarp, lm0, L, gram + (size_t)win * 42,
+                                       wstatus ? wstatus + win : nullptr);
+    if (!next) return;
+    __syncwarp();
+  }
 }
 
 // ---- kernel 2: everything after the landmark sums (12x12 / 6x6 algebra), one warp per window ----

@@ -19,7 +19,10 @@ def test_bench_batch_windows_are_distinct_ragged_and_valid():
     # no two windows share a state or an observation
     assert len(np.unique(b.pose_fwd.reshape(n, -1), axis=0)) == n
     assert len(np.unique(b.prior_se3, axis=0)) == n and len(np.unique(b.prior_vb, axis=0)) == n
-    assert len(np.unique(b.lm_obs[0])) == b.n_landmarks and len(np.unique(b.lm_obs[5])) == b.n_landmarks
+    assert len(np.unique(b.lm_obs[0:2].T, axis=0)) == b.n_landmarks and len(np.unique(b.lm_obs[5])) == b.n_landmarks
+    # pts_i.x / pts_i.y are cv::Point2f values in the reference (feature_tracker_simple.h:55): FP32-representable here too,
+    # which is what lets the e2e path ship them as floats (ABI 3) without changing a bit of the arithmetic
+    assert np.array_equal(b.lm_obs[0:2].astype(np.float32).astype(np.float64), b.lm_obs[0:2])
     # landmarks are in front of both cameras and inside a sane field of view
     assert np.all(b.lm_obs[5] > 0.1) and np.all(b.lm_obs[5] < 1.1) and np.all(b.lm_obs[2] == 1.0)
     assert np.abs(b.lm_obs[3:5]).max() < 3.0

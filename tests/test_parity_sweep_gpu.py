@@ -87,7 +87,7 @@ def test_fused_event_kernel_matches_c_oracle_and_batch_kernels(backend):
     try:
         l0 = backend.launch_count
         outb = _run_gpu(backend, batch)
-        assert backend.launch_count - l0 == 5
+        assert backend.launch_count - l0 == 7   # 2 zero-fills, 2 x factor Jacobians, landmark phase, tail, backward
     finally:
         backend.set_tuning(capi.TUNE_FUSED_MAX_WINDOWS, 148)
     ref = ref_c.marg_window_batch(batch, 3, 0, True)
@@ -281,6 +281,32 @@ def test_raw_imu_and_z_one_inputs(backend):
         assert np.array_equal(getattr(out1, f), getattr(out2, f)), f
     out3 = backend.marg_window_batch_host(b, capi.RUN_BACKWARD, raw_imu=True)
     assert np.array_equal(out3.vb, out1.vb) and np.array_equal(out3.rel, out1.rel)
+    # ABI 3: pts_i.x / pts_i.y handed over as the FP32 values they are in the reference (cv::Point2f): widened exactly on
+    # load, so every bit of the result is the one the double inputs give -- on the device path and on the host path, with
+    # the f64 components 0, 1 poisoned to prove they are not read
+    from is_vins_b200.backend import xy_as_f32
+    xyf = xy_as_f32(b.lm_obs)
+    dbx = DeviceBatch(b, "cuda:0", raw_imu=True, z_one=True, xy_f32=True)
+    dbx.t["lm_obs"][0:2].fill_(float("nan"))
+    backend.marg_window_batch(dbx, capi.RUN_BOTH)
+    backend.synchronize()
+    outx = dbx.outputs()
+    dby = DeviceBatch(b, "cuda:0", xy_f32=True)            # without the z promise: the other kernel instantiation
+    backend.marg_window_batch(dby, capi.RUN_BOTH)
+    backend.synchronize()
+    outy = dby.outputs()
+    keep = b.lm_obs[0:2].copy()
+    b.lm_obs[0:2] = np.nan
+    outh = backend.marg_window_batch_host(b, capi.RUN_BOTH, raw_imu=True, z_one=True, xy_f32=xyf)
+    b.lm_obs[0:2] = keep
+    for f in FIELDS:
+        assert np.array_equal(getattr(outx, f), getattr(out1, f)), f
+        assert np.array_equal(getattr(outh, f), getattr(out1, f)), f
+        assert np.array_equal(getattr(outy, f), getattr(out0, f)), f
+    with pytest.raises(ValueError):                        # values that are not floats are refused by the mirror
+        bad = b.lm_obs.copy()
+        bad[0, 3] += 1e-12
+        xy_as_f32(bad)
     b.lm_obs[2, 0] = 2.0                                   # the promise is spot-checked on the host path
     with pytest.raises(capi.IsvError):
         backend.marg_window_batch_host(b, capi.RUN_BOTH, z_one=True)

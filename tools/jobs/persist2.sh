@@ -1,0 +1,8 @@
+#!/bin/bash
+run() { echo "== $*"; env "$@" python bench.py --quick --steps 10 --warmup 3 --features ${FEAT:-1000} --windows 9472 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('%.0f' % d['value'], round(d['ms_per_step'],4), {k: round(v, 4) for k, v in d['kernels_ms'].items()})"; }
+for FEAT in 1000 150; do
+  export FEAT
+  for mc in 8 32; do
+  for p in 0 4; do run ISV_NO_CARVEOUT=1 ISV_ACC_PERSIST=$p CUDA_DEVICE_MAX_CONNECTIONS=$mc; run ISV_ACC_PERSIST=$p CUDA_DEVICE_MAX_CONNECTIONS=$mc; done
+  done
+done
