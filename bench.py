@@ -383,7 +383,8 @@ def measure(cx, L, n, which, steps, warmup, seed, full, e2e=True):
     from is_vins_b200.batch import WindowOutputs
     be, dev = cx.be, cx.dev
     batch = make_batch(L, n, seed)
-    db = DeviceBatch(batch, dev)
+    dev_fmt = os.environ.get("ISV_BENCH_DEVICE_INPUTS", "abi1")   # experiment switch: abi1 | zone | abi3 (z_one + xy_f32)
+    db = DeviceBatch(batch, dev, z_one=dev_fmt in ("zone", "abi3"), xy_f32=dev_fmt == "abi3")
     r = {"batch": batch, "n": n, "n_lm": batch.n_landmarks, "L": L, "which": which}
     flush = None
     if n * alg_bytes(L, which) <= 126e6:
@@ -605,6 +606,33 @@ def single_window_latency(cx, batch):
         if it >= 20:
             ts.append(time.perf_counter() - t0)
     lat["host_single_event_us"] = float(np.median(ts) * 1e6)
+    # the same call timed INSIDE the library (isv_test_event_latency: what a C++ estimator pays per MARGIN_OLD event, without
+    # the Python binding's marshalling), on its three routes: zero-copy fused kernel (default), fused kernel behind one H2D /
+    # D2H, the five batch kernels behind one H2D / D2H
+    ev = {}
+    for mode, label in ((0, "zero_copy_fused_kernel"), (1, "staged_fused_kernel"), (2, "staged_batch_kernels")):
+        be.set_tuning(capi.TUNE_EVENT_MODE, mode)
+        be.event_latency_us(args1, args2, 30)
+        us = be.event_latency_us(args1, args2, 300)
+        ev[label] = {"median": float(np.median(us)), "p99": float(np.percentile(us, 99))}
+    be.set_tuning(capi.TUNE_EVENT_MODE, 0)
+    lat["event_c_abi_us"] = ev
+    # the batch kernels on the resident window (what `device_resident_us` was before the fused kernel existed)
+    be.set_tuning(capi.TUNE_FUSED_MAX_WINDOWS, 0)
+    for _ in range(20):
+        be.marg_window_batch(d1, capi.RUN_BOTH)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(200):
+        t0 = time.perf_counter()
+        be.marg_window_batch(d1, capi.RUN_BOTH)
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    be.set_tuning(capi.TUNE_FUSED_MAX_WINDOWS, 148)
+    lat["device_resident_batch_kernels_us"] = float(np.median(ts) * 1e6)
+    lat["note"] = ("device_resident_us / host_*_us are wall times through the Python binding (~15 us of interpreter and ctypes "
+                   "overhead per call; host_single_event_us additionally ~30 us of NumPy marshalling); event_c_abi_us is the "
+                   "latency at the C ABI")
     lat["landmarks"] = int(one.n_landmarks)
     return lat
 

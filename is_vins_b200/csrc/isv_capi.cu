@@ -173,9 +173,9 @@ isv_status isv_create(const isv_config* cfg, int device, isv_handle** out) {
   cudaFuncSetAttribute(preintegrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kWarpsPerCta * kPreSmemPerWarp * sizeof(double)));
   cudaFuncSetAttribute(marg_event_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)(kEvSmemDoubles * sizeof(double)));
+                       (int)((kEvSmemDoubles + kEvStageMaxDoubles) * sizeof(double)));
   cudaFuncSetAttribute(marg_event_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)(kEvSmemDoubles * sizeof(double)));
+                       (int)((kEvSmemDoubles + kEvStageMaxDoubles) * sizeof(double)));
   *out = h;
   return ISV_OK;
 }
@@ -411,12 +411,15 @@ static bool fused_eligible(const isv_handle* h, const isv_batch_in* in, int whic
   return which == ISV_RUN_BOTH && in->preint && !in->lm_xy_f32 && iso && in->n_windows >= 1 && in->n_windows <= h->fused_max;
 }
 static isv_status launch_fused(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, cudaStream_t stream,
-                               int32_t* done_flag, int32_t done_seq, long long* stamps = nullptr) {
-  const size_t sm = kEvSmemDoubles * sizeof(double);
+                               int32_t* done_flag, int32_t done_seq, long long* stamps = nullptr, int stage_doubles = 0,
+                               int lam_comp = 5) {
+  const size_t sm = (size_t)(kEvSmemDoubles + stage_doubles) * sizeof(double);
   if (in->flags & ISV_IN_PTS_I_Z_ONE)
-    marg_event_fused_kernel<true, true><<<in->n_windows, kEvThreads, sm, stream>>>(*in, *out, h->dcfg, done_flag, done_seq, stamps);
+    marg_event_fused_kernel<true, true><<<in->n_windows, kEvThreads, sm, stream>>>(*in, *out, h->dcfg, done_flag, done_seq, stamps,
+                                                                                   stage_doubles, lam_comp);
   else
-    marg_event_fused_kernel<false, true><<<in->n_windows, kEvThreads, sm, stream>>>(*in, *out, h->dcfg, done_flag, done_seq, stamps);
+    marg_event_fused_kernel<false, true><<<in->n_windows, kEvThreads, sm, stream>>>(*in, *out, h->dcfg, done_flag, done_seq, stamps,
+                                                                                    stage_doubles, lam_comp);
   ++h->launches;
   ISV_CUDA(cudaGetLastError());
   return ISV_OK;
@@ -614,7 +617,7 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   static const bool trace = getenv("ISV_HOST_TRACE") != nullptr;
   cudaEvent_t tev[1 + 4 * 16];
   double thost[16][4];
-  timespec tr0;
+  timespec tr0 = {};
   const bool tr = trace && n_chunks <= 16;
   auto host_ms = [&]() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (t.tv_sec - tr0.tv_sec) * 1e3 + (t.tv_nsec - tr0.tv_nsec) * 1e-6; };
   if (tr) {
@@ -936,17 +939,24 @@ isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in
   const size_t L = (size_t)fin->n_landmarks;
   if (L > 0 && (!fin->inv_dep || !fin->pts_i || !fin->pts_j)) return ISV_ERR_BAD_ARG;
   ISV_CUDA(cudaSetDevice(h->device));
-  // in  = [lm_offset 2 (as int64)] [obs 6L] [pose_fwd 14] [ex 7] [se3 48] [rel 48] [rp 5] | [pose_bwd 14] [sb_bwd 18] [vb 90] [preint 467]
+  // in  = [lm_offset 2 (as int64)] [pose_fwd 14] [ex 7] [se3 48] [rel 48] [rp 5] [pose_bwd 14] [sb_bwd 18] [vb 90] [preint 467] [pad 1]
+  //       [landmark components, L doubles each]
   // out = [se3 48] [pg 89] [rel 48] [vb 90] [rp 13] [rank 2 x i32 = 1] [status i32 = 1] [flag i32 = 1]
-  const size_t n_f = 2 + 6 * L + 14 + 7 + ISV_SE3_REC + ISV_REL_REC + ISV_RP_IN_REC;
-  const size_t n_b = 14 + 18 + ISV_VB_REC + ISV_PREINT_REC;
-  const size_t n_in = (n_f + n_b + 1) & ~(size_t)1;
-  const size_t n_out = ISV_SE3_REC + ISV_PG_REC + ISV_REL_REC + ISV_VB_REC + ISV_RP_REC + 3;
+  // The fused routes (0, 1) pack the components the kernel reads next to each other -- x, y, [z,] inverse depth: 3 or 4 L
+  // doubles -- so that the whole event is one contiguous block the kernel stages with a single bulk copy; the batch-kernel
+  // route (2) keeps the ABI's six-component layout (x y z . . inverse depth).
   isv_batch_in probe;
   memset(&probe, 0, sizeof(probe));
   probe.n_windows = 1;
   probe.preint = bin->preint;
   const int mode = fused_eligible(h, &probe, ISV_RUN_BOTH) ? h->event_mode : 2;
+  bool z_one = true;
+  for (size_t k = 0; k < L; ++k) z_one &= (fin->pts_i[3 * k + 2] == 1.0);   // always, in the reference (src/System.cpp:346)
+  const size_t n_rec = 14 + 7 + ISV_SE3_REC + ISV_REL_REC + ISV_RP_IN_REC + 14 + 18 + ISV_VB_REC + ISV_PREINT_REC + 1;   // 712
+  const int lam_comp = mode == 2 ? 5 : (z_one ? 2 : 3);
+  const size_t n_obs = (size_t)(lam_comp + 1) * L;
+  const size_t n_in = (2 + n_rec + n_obs + 1) & ~(size_t)1;
+  const size_t n_out = ISV_SE3_REC + ISV_PG_REC + ISV_REL_REC + ISV_VB_REC + ISV_RP_REC + 3;
   isv_status st;
   double* hp;     // host view of the block
   double* d;      // device view
@@ -965,38 +975,35 @@ isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in
   }
   int64_t* off = (int64_t*)hp;
   off[0] = 0; off[1] = (int64_t)L;
-  // the kernels read x_i, y_i, inv_dep and -- unless it is 1 everywhere, which the feature tracker guarantees
-  // (src/System.cpp:346) -- z_i: components 3, 4 (pts_j) are never read, so they are not packed
-  double* obs = hp + 2;
-  bool z_one = true;
-  for (size_t k = 0; k < L; ++k) {
-    obs[k] = fin->pts_i[3 * k];
-    obs[L + k] = fin->pts_i[3 * k + 1];
-    const double z = fin->pts_i[3 * k + 2];
-    obs[2 * L + k] = z;
-    z_one &= (z == 1.0);
-    obs[5 * L + k] = fin->inv_dep[k];
-  }
-  double* q = obs + 6 * L;
+  double* q = hp + 2;
   memcpy(q, fin->pose0, 56); memcpy(q + 7, fin->pose1, 56); memcpy(q + 14, fin->ex_pose, 56);
   memcpy(q + 21, fin->prior_se3, ISV_SE3_REC * 8); memcpy(q + 21 + ISV_SE3_REC, fin->prior_rel, ISV_REL_REC * 8);
   double* rp = q + 21 + ISV_SE3_REC + ISV_REL_REC;
   if (fin->prior_rp) memcpy(rp, fin->prior_rp, ISV_RP_IN_REC * 8); else memset(rp, 0, ISV_RP_IN_REC * 8);
-  double* hb = hp + n_f;
+  double* hb = rp + ISV_RP_IN_REC;
   memcpy(hb, bin->pose_i, 56); memcpy(hb + 7, bin->pose_j, 56);
   memcpy(hb + 14, bin->sb_i, 72); memcpy(hb + 23, bin->sb_j, 72);
   memcpy(hb + 32, bin->prior_vb, ISV_VB_REC * 8);
   memcpy(hb + 32 + ISV_VB_REC, bin->preint, ISV_PREINT_REC * 8);
+  hb[32 + ISV_VB_REC + ISV_PREINT_REC] = 0.0;
+  // the kernels read x_i, y_i, inv_dep and -- unless it is 1 everywhere -- z_i; pts_j is never read, so it is not packed
+  double* obs = hp + 2 + n_rec;
+  for (size_t k = 0; k < L; ++k) {
+    obs[k] = fin->pts_i[3 * k];
+    obs[L + k] = fin->pts_i[3 * k + 1];
+    if (lam_comp != 2) obs[2 * L + k] = fin->pts_i[3 * k + 2];
+    obs[(size_t)lam_comp * L + k] = fin->inv_dep[k];
+  }
   cudaStream_t s = h->stream;
-  double* dq = d + 2 + 6 * L;
-  double* db = d + n_f;
+  double* dq = d + 2;
+  double* db = dq + 21 + ISV_SE3_REC + ISV_REL_REC + ISV_RP_IN_REC;
   double* dout = d + n_in;
   isv_batch_in bi;
   memset(&bi, 0, sizeof(bi));
   bi.n_windows = 1;
   bi.ex_pose_shared = 1;
   bi.lm_offset = (const int64_t*)d;
-  bi.lm_obs = d + 2;
+  bi.lm_obs = d + 2 + n_rec;
   bi.lm_stride = (int64_t)L;
   bi.pose_fwd = dq;
   bi.ex_pose = dq + 14;
@@ -1008,6 +1015,11 @@ isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in
   bi.prior_vb = db + 32;
   bi.preint = db + 32 + ISV_VB_REC;
   bi.flags = z_one ? ISV_IN_PTS_I_Z_ONE : 0;
+  // what the fused kernel stages into shared memory with one bulk copy: the whole event if it fits, else the records
+  static const bool no_stage = getenv("ISV_EVENT_NO_STAGE") != nullptr;   // A/B switch for measurements
+  int stage_doubles = (int)((2 + n_rec + n_obs + 1) & ~(size_t)1);
+  if (stage_doubles > kEvStageMaxDoubles) stage_doubles = (int)(2 + n_rec);
+  if (no_stage) stage_doubles = 0;
   isv_batch_out bo;
   memset(&bo, 0, sizeof(bo));
   bo.se3_out = dout;
@@ -1024,7 +1036,7 @@ isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in
     const int32_t seq = ++h->event_seq;
     *hflag = seq - 1;
     __sync_synchronize();   // the packed event is in memory before the launch is submitted
-    st = launch_fused(h, &bi, &bo, s, dflag, seq);
+    st = launch_fused(h, &bi, &bo, s, dflag, seq, nullptr, stage_doubles, lam_comp);
     if (st != ISV_OK) return st;
     // spin on the completion word; every ~4 k polls make sure the stream has not died under us
     for (unsigned spins = 1;; ++spins) {
@@ -1045,7 +1057,7 @@ isv_status isv_marg_event(isv_handle* h, const isv_fwd_in* fin, const isv_bwd_in
   } else {
     ISV_CUDA(cudaMemcpyAsync(d, hp, n_in * sizeof(double), cudaMemcpyHostToDevice, s));
     if (mode == 1) {
-      st = launch_fused(h, &bi, &bo, s, nullptr, 0);
+      st = launch_fused(h, &bi, &bo, s, nullptr, 0, nullptr, stage_doubles, lam_comp);
     } else {
       ISV_CUDA(cudaMemsetAsync(bo.rank, 0, 8, s));
       st = launch_batch(h, &bi, &bo, ISV_RUN_BOTH, s, dout + n_out);

@@ -39,17 +39,55 @@ constexpr int kEvPart = kEvAcc + kEvAccWarps * kAccSmemPerWarp;     // partial G
 constexpr int kEvGram = kEvPart + kEvAccWarps * 42;                 // their sum [42]
 constexpr int kEvStat = kEvGram + 42;                               // status word
 constexpr int kEvSmemDoubles = kEvStat + 2;
+static_assert(kEvSmemDoubles % 2 == 0, "the staged event block starts 16-byte aligned");
+constexpr int kEvStageMaxDoubles = (200 * 1024) / 8 - kEvSmemDoubles;   // what fits next to the work areas in one SM
 static_assert((kFJ % 2 == 0) && (kBwdSmemPerWarp % 2 == 0) && (kFwdSmemPerWarp % 2 == 0) && (kAccSmemPerWarp % 2 == 0),
               "16-byte alignment of the shared-memory map");
 
+// ---- bulk-async staging of one event's inputs (isv_marg_event) --------------------------------------------------------
+// The event block is one contiguous, 16-byte aligned region [lm_offset | records | landmark components]: one thread hands it
+// to the TMA engine as ONE cp.async.bulk (SASS UBLKCP) that completes on an mbarrier, and every chain then starts from
+// shared memory instead of paying its own first-touch round trip to HBM -- or, on the zero-copy route, over PCIe to the
+// host's pinned block (~2 us each, several per chain).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+
+// stage_doubles > 0: the first stage_doubles doubles at in.lm_offset (the packed event block of isv_marg_event) are staged
+// into shared memory behind the kernel's work areas and every input pointer inside that range is re-based onto the copy.
+// lam_comp: position of the inverse-depth component in lm_obs (5 in the ABI's layout; 2 / 3 in the packed event block).
 template <bool ZONE, bool ISO>
 __global__ void __launch_bounds__(kEvThreads, 1)
-marg_event_fused_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int32_t* done_flag, int32_t done_seq,
-                        long long* stamps) {
+marg_event_fused_kernel(isv_batch_in in_arg, isv_batch_out out, DevCfg cfg, int32_t* done_flag, int32_t done_seq,
+                        long long* stamps, int stage_doubles, int lam_comp) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int win = blockIdx.x;
+  isv_batch_in in = in_arg;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kEvStat + 1);
+  if (stage_doubles > 0 && threadIdx.x == 0) {
+    mbar_init(mbar, 1);
+    bulk_g2s(smem + kEvSmemDoubles, in_arg.lm_offset, (uint32_t)stage_doubles * 8u, mbar);
+  }
   // profiling aid (isv_test_fused_stamps): SM cycle counter at the phase boundaries of every warp of window 0
   int n_stamp = 0;
   auto stamp = [&]() {
@@ -63,6 +101,21 @@ marg_event_fused_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int32_t*
   for (int i = threadIdx.x; i < 450; i += kEvThreads) FJ[kFJ_IMU + i] = 0.0;
   if (threadIdx.x == 0) *sstat = 0;
   __syncthreads();
+  if (stage_doubles > 0) {
+    mbar_wait(mbar, 0);
+    const char* base = reinterpret_cast<const char*>(in_arg.lm_offset);
+    const char* copy = reinterpret_cast<const char*>(smem + kEvSmemDoubles);
+    const long long span = (long long)stage_doubles * 8;
+    auto rb = [&](const double* p) -> const double* {
+      const long long o = reinterpret_cast<const char*>(p) - base;
+      return (p && o >= 0 && o < span) ? reinterpret_cast<const double*>(copy + o) : p;
+    };
+    in.lm_offset = reinterpret_cast<const int64_t*>(copy);
+    in.lm_obs = rb(in.lm_obs);
+    in.pose_fwd = rb(in.pose_fwd); in.ex_pose = rb(in.ex_pose); in.prior_se3 = rb(in.prior_se3);
+    in.prior_rel = rb(in.prior_rel); in.prior_rp = rb(in.prior_rp);
+    in.pose_bwd = rb(in.pose_bwd); in.sb_bwd = rb(in.sb_bwd); in.prior_vb = rb(in.prior_vb); in.preint = rb(in.preint);
+  }
   stamp();
 
   if (warp == 0) {
@@ -95,7 +148,7 @@ marg_event_fused_kernel(isv_batch_in in, isv_batch_out out, DevCfg cfg, int32_t*
     const int b0 = min(L, a * per);
     const int cnt = min(per, L - b0);
     forward_accum_body<ZONE, ISO>(in, cfg, win, lane, smem + kEvAcc + a * kAccSmemPerWarp, lm0 + b0, cnt, smem + kEvPart + 42 * a,
-                                  sstat);
+                                  sstat, lam_comp);
     stamp();
     if (warp < kEvWarps - 1) {
       __threadfence_block();

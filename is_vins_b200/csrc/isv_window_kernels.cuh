@@ -293,7 +293,7 @@ constexpr int kAccWarps = ISV_ACC_WARPS;
 template <bool ZONE, bool ISO, bool XYF = false>
 __device__ __forceinline__ void forward_accum_body(const isv_batch_in& in, const DevCfg& cfg, const int win, const int lane,
                                                    double* K, const long long lm0, const int L, double* __restrict__ g,
-                                                   int32_t* wstatus) {
+                                                   int32_t* wstatus, const int lam_comp = 5) {
   double* R = K + 34;                         // reduction staging;  K: [0]F [9]f [12]tp [15]ric [24]M = ric^T F
   int status = 0;
 
@@ -402,7 +402,7 @@ __device__ __forceinline__ void forward_accum_body(const isv_batch_in& in, const
   const xy_t* __restrict__ qx = (XYF ? reinterpret_cast<const xy_t*>(in.lm_xy_f32) : reinterpret_cast<const xy_t*>(in.lm_obs)) + lm0 + lane;
   const xy_t* __restrict__ qy = qx + st;
   const double* __restrict__ qz = in.lm_obs + lm0 + lane + 2 * st;
-  const double* __restrict__ ql = in.lm_obs + lm0 + lane + 5 * st;
+  const double* __restrict__ ql = in.lm_obs + lm0 + lane + lam_comp * st;   // 5 in the ABI's layout; the packed event block: 2 / 3
   xy_t rx[4], ry[4];   // XYF: the ring holds the floats (8 registers less), widened when a step consumes them
   double rz[4], rl[4];
 #pragma unroll

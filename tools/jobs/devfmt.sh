@@ -1,0 +1,2 @@
+run() { echo "== $*"; env "$@" python bench.py --quick --steps 10 --warmup 3 --features ${FEAT:-1000} --windows 9472 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('%.0f' % d['value'], round(d['ms_per_step'],4), {k: round(v, 4) for k, v in d['kernels_ms'].items()})"; }
+for FEAT in 1000 150; do export FEAT; for f in abi1 zone abi3; do run ISV_BENCH_DEVICE_INPUTS=$f; done; done
