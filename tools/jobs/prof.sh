@@ -5,8 +5,8 @@ python bench.py > gpurun_out/r02x_bench.json 2> gpurun_out/r02x_bench.err || tai
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02x_bench_reference_arm.json 2>> gpurun_out/r02x_bench.err
 python tools/profile_driver.py > /dev/null 2>&1 && echo driver-ok
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02x_launches.csv python bench.py --steps 2 --warmup 1 --no-configs --no-cpu > gpurun_out/r02x_ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"marg_|preintegrate|zero_" -c 40 -f -o gpurun_out/r02x_prof python tools/profile_driver.py > gpurun_out/r02x_ncu_full.log 2>&1
+ncu --set full --clock-control none -k regex:"marg_|preintegrate|zero_" -c 40 -f -o /tmp/r02x_prof python tools/profile_driver.py > gpurun_out/r02x_ncu_full.log 2>&1
 tail -2 gpurun_out/r02x_ncu_full.log
-python tools/ncu_summary.py gpurun_out/r02x_prof.ncu-rep gpurun_out/r02x_ncu_full_summary.json > /dev/null 2>&1 && echo summary-ok
+python tools/ncu_summary.py /tmp/r02x_prof.ncu-rep gpurun_out/r02x_ncu_full_summary.json > /dev/null 2>&1 && echo summary-ok
 python tools/sass_census.py > gpurun_out/r02x_sass_census.json 2>/dev/null && echo sass-ok
-ls -la gpurun_out/r02x_prof.ncu-rep
+ls -la /tmp/r02x_prof.ncu-rep; du -sh gpurun_out
