@@ -677,7 +677,21 @@ def run_cuda(args, L):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on STDOUT: keep stdout = one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on STDOUT when the communicator is created: send fd 1 to stderr until the first
+        # collective has run, so that stdout carries the JSON line and nothing else
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device=f"cuda:{local}")
+            dist.all_reduce(warm)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     cx = Ctx()
     cx.world, cx.rank, cx.local, cx.dev = world, rank, local, f"cuda:{local}"

@@ -1,3 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --no-configs > gpurun_out/r02x_bench_2gpu.json 2> gpurun_out/r02x_bench_2gpu.err || tail -5 gpurun_out/r02x_bench_2gpu.err
-python -c "
-import json; d=json.load(open('gpurun_out/r02x_bench_2gpu.json')); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['e2e']['copy_ceiling']['ms_per_step'])"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --no-configs > gpurun_out/r02x_bench_2gpu.json 2> gpurun_out/r02x_bench_2gpu.err; echo rc=$?
+tail -c 1500 gpurun_out/r02x_bench_2gpu.err
+head -c 300 gpurun_out/r02x_bench_2gpu.json
