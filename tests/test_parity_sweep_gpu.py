@@ -109,6 +109,29 @@ def test_fused_event_kernel_matches_c_oracle_and_batch_kernels(backend):
     assert not ob.status[[0, 1, 3]].any()
 
 
+@pytest.mark.parametrize("L", [0, 5, 150, 4000])
+def test_event_call_all_routes_and_staging_limits(backend, L):
+    """isv_marg_event on its three routes against the C oracle: L = 0 (no landmark block), 5 (fewer landmarks than landmark
+    warps), 150, and 4000 (the event no longer fits the kernel's shared-memory staging area: only the records are staged by
+    the bulk copy, the landmarks are read in place)."""
+    b = bench.make_batch(max(L, 1), 1, 900 + L, ragged=0.0, counts=np.array([L]))
+    ref = ref_c.marg_window_batch(b, 3, 0, True)
+    o = b.lm_obs
+    fwd = (b.pose_fwd[0, 0], b.pose_fwd[0, 1], b.ex_pose, o[5], np.ascontiguousarray(o[0:3].T),
+           np.ascontiguousarray(np.vstack([o[3:5], np.ones((1, o.shape[1]))]).T), b.prior_se3[0], b.prior_rel[0], b.prior_rp[0])
+    bwd = (b.pose_bwd[0, 0], b.sb_bwd[0, 0], b.pose_bwd[0, 1], b.sb_bwd[0, 1], b.prior_vb[0], b.preint[0])
+    try:
+        for mode in (0, 1, 2, 0):
+            backend.set_tuning(capi.TUNE_EVENT_MODE, mode)
+            (se3, pg, rkf, stf), (rel, vb, rp, rkb, stb) = backend.marg_event(fwd, bwd)
+            out = type(ref)(se3[None], pg[None], rel[None], vb[None], rp[None], np.array([[rkf, rkb]], np.int32), np.array([stf], np.int32))
+            err = outputs_rel_diff(out, ref, 3).max()
+            assert err <= TOL, (L, mode, err)
+            assert (rkf, rkb) == (int(ref.rank[0, 0]), int(ref.rank[0, 1])) and stf == 0 and stb == 0, (L, mode)
+    finally:
+        backend.set_tuning(capi.TUNE_EVENT_MODE, 0)
+
+
 def _rot(axis, angle):
     axis = np.asarray(axis, float) / np.linalg.norm(axis)
     return O.SO3.exp(axis * angle).matrix()
