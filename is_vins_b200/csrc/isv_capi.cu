@@ -53,6 +53,8 @@ struct isv_handle {
   size_t gram_bytes;     //   landmark Gram triangles (forward stage 1 -> 2) and the factor-Jacobian records
   cudaEvent_t jac_ev[12]; // fork / join events of launch_batch, three per launching slot
   cudaStream_t pipe[2];   // third and fourth pipeline stream of the chunked host path (slots 2, 3)
+  cudaStream_t h2d_stream;   // every H2D copy of the chunked host path, in chunk order
+  cudaEvent_t chunk_ev[16];  // "chunk c is on the device"
   cudaStream_t fork[8];   // side streams of launch_batch: [2 slot] backward chain, [2 slot + 1] forward factor Jacobians
   // isv_marg_window_batch: the ~15 runtime calls of one launch_batch (fork / join over three streams) replayed as one
   // CUDA graph when the same buffers come back (a server loop re-fills the same device batch every step)
@@ -149,6 +151,8 @@ isv_status isv_create(const isv_config* cfg, int device, isv_handle** out) {
   for (int i = 0; i < 3; ++i) cudaEventCreateWithFlags(&h->aux_ev[i], cudaEventDisableTiming);
   for (int i = 0; i < 12; ++i) cudaEventCreateWithFlags(&h->jac_ev[i], cudaEventDisableTiming);
   for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&h->chunk_ev[i], cudaEventDisableTiming);
   for (int i = 0; i < 8; ++i) cudaStreamCreateWithFlags(&h->fork[i], cudaStreamNonBlocking);
   h->stream = h->own_stream;
   {
@@ -202,6 +206,9 @@ void isv_destroy(isv_handle* h) {
     if (h->jac_ev[i]) cudaEventDestroy(h->jac_ev[i]);
   for (int i = 0; i < 2; ++i)
     if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
+  if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+  for (int i = 0; i < 16; ++i)
+    if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
   for (int i = 0; i < 8; ++i)
     if (h->fork[i]) cudaStreamDestroy(h->fork[i]);
   cudaStreamDestroy(h->own_stream);
@@ -572,6 +579,11 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   // streams only two chunks were ever in flight.
   constexpr int kPipe = 4;
   cudaStream_t ss[kPipe] = {h->own_stream, h->copy_stream, h->pipe[0], h->pipe[1]};
+  // All H2D copies go through ONE stream, in chunk order (the copy engine serves them at line rate either way, but spread
+  // over the four pipeline streams it picked its own order -- chunk 3 landed before chunks 1 and 2 -- so the chunk that
+  // arrives last, whose kernels and D2H nothing overlaps, could not be chosen); chunk c's pipeline stream waits for
+  // "chunk c is on the device".
+  cudaStream_t hs = h->h2d_stream;
   if (h->stream != h->own_stream) {
     ISV_CUDA(cudaEventRecord(h->ev[0], h->stream));
     for (int i = 0; i < kPipe; ++i) ISV_CUDA(cudaStreamWaitEvent(ss[i], h->ev[0], 0));
@@ -579,12 +591,13 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     ISV_CUDA(cudaEventRecord(h->ev[0], ss[0]));
     for (int i = 1; i < kPipe; ++i) ISV_CUDA(cudaStreamWaitEvent(ss[i], h->ev[0], 0));
   }
+  ISV_CUDA(cudaStreamWaitEvent(hs, h->ev[0], 0));
   zero_i32_kernel<<<(int)((2 * n + 255) / 256), 256, 0, ss[0]>>>((int32_t*)(d + o_rank), (long long)(2 * n));
   // The per-window records cross once, one copy per array for the whole batch, ahead of the chunk loop: ~320 doubles per
   // window that used to travel as nine copies PER CHUNK (every copy pays a fixed DMA set-up; at L = 150 they are half of the
   // bytes).  Only the landmark components and the results are chunked.
   auto up = [&](size_t o, const void* src, size_t bytes) {
-    return bytes ? cudaMemcpyAsync(d + o, src, bytes, cudaMemcpyHostToDevice, ss[0]) : cudaSuccess;
+    return bytes ? cudaMemcpyAsync(d + o, src, bytes, cudaMemcpyHostToDevice, hs) : cudaSuccess;
   };
   if (fwd) {
     ISV_CUDA(up(o_lmoff, in->lm_offset, (n + 1) * sizeof(int64_t)));
@@ -606,13 +619,27 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
       if (in->imu_count) ISV_CUDA(up(o_icnt, in->imu_count, n * sizeof(int32_t)));
     }
   }
-  ISV_CUDA(cudaEventRecord(h->ev[1], ss[0]));
+  ISV_CUDA(cudaEventRecord(h->ev[1], ss[0]));      // the rank zero-fill
   for (int i = 1; i < kPipe; ++i) ISV_CUDA(cudaStreamWaitEvent(ss[i], h->ev[1], 0));
   size_t n_chunks = n / 512;
   if (n_chunks < 1) n_chunks = 1;
   static const int max_chunks = getenv("ISV_HOST_CHUNKS") ? atoi(getenv("ISV_HOST_CHUNKS")) : 4;   // measured at 9472 windows: 2 / 4 / 8 / 16 chunks
                                                                                                    // -> 1.68 / 1.76 / 1.73 / 1.56 M windows/s
   if (n_chunks > (size_t)max_chunks) n_chunks = max_chunks > 0 ? max_chunks : 1;
+  if (n_chunks > 16) n_chunks = 16;
+  // The call ends with the LAST chunk's kernels and D2H, which nothing overlaps: when the landmark stream dominates the
+  // bytes (L in the hundreds and up) the last of four chunks is the smallest (30 / 30 / 25 / 15 % of the windows: 3.71 ->
+  // 3.66 ms at L ~ 1000; at L ~ 150 the chunks are latency-bound and equal sizes are better, 1.47 vs 1.51 ms).
+  // ISV_HOST_EVEN_CHUNKS=1 forces equal chunks for A/B measurements.
+  static const bool even_env = getenv("ISV_HOST_EVEN_CHUNKS") != nullptr;
+  const bool even_chunks = even_env || (size_t)n_lm * 16 < (size_t)n * 8192;
+  auto bound = [&](size_t c) -> size_t {
+    if (n_chunks == 4 && !even_chunks && n >= 64) {
+      static const double cum[5] = {0.0, 0.30, 0.60, 0.85, 1.0};
+      return c >= 4 ? n : (size_t)(cum[c] * (double)n);
+    }
+    return n * c / n_chunks;
+  };
   // ISV_HOST_TRACE=1: timeline of the chunk pipeline (device events + host issue times), printed to stderr
   static const bool trace = getenv("ISV_HOST_TRACE") != nullptr;
   cudaEvent_t tev[1 + 4 * 16];
@@ -626,7 +653,7 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     cudaEventRecord(tev[0], ss[0]);
   }
   for (size_t c = 0; c < n_chunks; ++c) {
-    const size_t w0 = n * c / n_chunks, w1 = n * (c + 1) / n_chunks, m = w1 - w0;
+    const size_t w0 = bound(c), w1 = bound(c + 1), m = w1 - w0;
     if (m == 0) continue;
     cudaStream_t s = ss[c % kPipe];
     if (tr) { thost[c][0] = host_ms(); cudaEventRecord(tev[1 + 4 * c], s); }
@@ -645,13 +672,13 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
         if ((comps[ci] == 2 && z_one) || (comps[ci] < 2 && xyf)) continue;
         ISV_CUDA(cudaMemcpyAsync(d + o_obs + ((size_t)comps[ci] * n_lm + a) * D,
                                  in->lm_obs + (size_t)comps[ci] * in->lm_stride + a, (size_t)(b - a) * D,
-                                 cudaMemcpyHostToDevice, s));
+                                 cudaMemcpyHostToDevice, hs));
       }
       if (xyf && b > a)   // ABI 3: the FP32 x, y of the feature tracker, 8 instead of 16 bytes per landmark
         for (int ci = 0; ci < 2; ++ci)
           ISV_CUDA(cudaMemcpyAsync(d + o_xyf + ((size_t)ci * n_lm + a) * sizeof(float),
                                    in->lm_xy_f32 + (size_t)ci * in->lm_stride + a, (size_t)(b - a) * sizeof(float),
-                                   cudaMemcpyHostToDevice, s));
+                                   cudaMemcpyHostToDevice, hs));
       din.lm_offset = (const int64_t*)(d + o_lmoff) + w0;   // absolute offsets into the whole mirror
       din.lm_obs = (const double*)(d + o_obs);
       din.lm_stride = n_lm;
@@ -681,6 +708,8 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     }
     dout.rank = (int32_t*)(d + o_rank) + 2 * w0;
     dout.status = (int32_t*)(d + o_stat) + w0;
+    ISV_CUDA(cudaEventRecord(h->chunk_ev[c], hs));          // records + chunks 0 .. c are on the device
+    ISV_CUDA(cudaStreamWaitEvent(s, h->chunk_ev[c], 0));
     if (tr) { thost[c][1] = host_ms(); cudaEventRecord(tev[2 + 4 * c], s); }
     st = launch_batch(h, &din, &dout, which, s, (double*)(d + o_gram) + w0 * kScratchPerWindow);
     if (st != ISV_OK) return st;
@@ -700,6 +729,7 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     if (tr) { thost[c][3] = host_ms(); cudaEventRecord(tev[4 + 4 * c], s); }
   }
   for (int i = 0; i < kPipe; ++i) ISV_CUDA(cudaStreamSynchronize(ss[i]));
+  ISV_CUDA(cudaStreamSynchronize(hs));
   if (tr) {
     const double t_end = host_ms();
     for (size_t c = 0; c < n_chunks; ++c) {
