@@ -640,6 +640,10 @@ void isv_pose_plus_jacobian(double* jacobian);
 isv_status isv_test_psd_eig(isv_handle* h, int nb, int n, const double* A, double* G, double* lam,
                             int32_t* info);
 
+/* ---- unit-test hook: the lean reciprocal square root / reciprocal the hot chains use instead of rsqrt() and 1.0 / x
+ * (hardware seed + two Newton steps, is_vins_b200/csrc/isv_device_math.cuh): x [n] (host) -> 1 / sqrt(x), 1 / x.       */
+isv_status isv_test_fast_special(isv_handle* h, int n, const double* x, double* rsqrt_out, double* rcp_out);
+
 /* ---- measurement hook: `iters` back-to-back isv_marg_event calls of the same event, timed one by one on the host with
  * CLOCK_MONOTONIC from inside the library (i.e. the latency a C/C++ estimator sees, without a binding's marshalling).
  * us [iters] = microseconds of each call; the last call's results are left in fwd_out / bwd_out.                    */

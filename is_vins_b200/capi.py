@@ -183,6 +183,7 @@ SYMBOLS = [
     ("isv_marg_forward", C.c_int, [_H, C.POINTER(isv_fwd_in), C.POINTER(isv_fwd_out)]),
     ("isv_marg_backward", C.c_int, [_H, C.POINTER(isv_bwd_in), C.POINTER(isv_bwd_out)]),
     ("isv_marg_event", C.c_int, [_H, C.POINTER(isv_fwd_in), C.POINTER(isv_bwd_in), C.POINTER(isv_fwd_out), C.POINTER(isv_bwd_out)]),
+    ("isv_test_fast_special", C.c_int, [_H, C.c_int, c_double_p, c_double_p, c_double_p]),
     ("isv_test_fused_stamps", C.c_int, [_H, C.POINTER(isv_batch_in), C.POINTER(isv_batch_out), C.c_void_p]),
     ("isv_test_event_latency", C.c_int, [_H, C.POINTER(isv_fwd_in), C.POINTER(isv_bwd_in), C.POINTER(isv_fwd_out),
                                          C.POINTER(isv_bwd_out), C.c_int, C.POINTER(C.c_double)]),

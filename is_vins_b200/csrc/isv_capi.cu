@@ -1174,6 +1174,28 @@ __global__ void psd_eig_test_kernel(int nb, int n, const double* A, double* G, d
 }
 }  // namespace isv
 
+// ---- unit-test hook: the lean reciprocal square root / reciprocal of isv_device_math.cuh ------------------------------
+namespace isv {
+__global__ void fast_special_kernel(int n, const double* __restrict__ x, double* __restrict__ rs, double* __restrict__ rc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { rs[i] = fast_rsqrt(x[i]); rc[i] = fast_rcp(x[i]); }
+}
+}  // namespace isv
+extern "C" isv_status isv_test_fast_special(isv_handle* h, int n, const double* x, double* rsqrt_out, double* rcp_out) {
+  if (!h || n < 0 || (n > 0 && (!x || !rsqrt_out || !rcp_out))) return ISV_ERR_BAD_ARG;
+  if (n == 0) return ISV_OK;
+  ISV_CUDA(cudaSetDevice(h->device));
+  isv_status st = ensure_dbuf(h, (size_t)3 * n * sizeof(double));
+  if (st != ISV_OK) return st;
+  double* d = (double*)h->dbuf;
+  ISV_CUDA(cudaMemcpyAsync(d, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  fast_special_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, d, d + n, d + 2 * (size_t)n);
+  ISV_CUDA(cudaMemcpyAsync(rsqrt_out, d + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  ISV_CUDA(cudaMemcpyAsync(rcp_out, d + 2 * (size_t)n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  ISV_CUDA(cudaStreamSynchronize(h->stream));
+  return ISV_OK;
+}
+
 extern "C" isv_status isv_test_psd_eig(isv_handle* h, int nb, int n, const double* A, double* G, double* lam,
                                        int32_t* info) {
   if (!h || nb <= 0 || n < 1 || n > 63 || !A || !G || !lam || !info) return ISV_ERR_BAD_ARG;

@@ -32,6 +32,43 @@ struct Quat {
   double w, x, y, z;
 };
 
+// Lean reciprocal square root / reciprocal for the hot chains of the window kernels.  CUDA's rsqrt() and 1.0 / x expand to
+// ~20-25 instructions each (seed + Newton + exponent / special-case handling with a slow-path branch); ncu's source view put
+// 18 % of the backward kernel's stall samples and 17 % of its instructions on them (profiles/r02z_backward_hot_lines.txt).
+// Here: the hardware seed (MUFU.RSQ64H / MUFU.RCP64H through rsqrt.approx / rcp.approx, relative error < 2^-20) and two
+// Newton steps (error 1.5 e^2 resp. e^2 per step: below 2^-80 after two), nothing else.  Faithful to ~1 ulp for finite,
+// normal, positive arguments -- which is what the call sites guarantee (pivots checked > 0, norms of non-zero vectors);
+// zero / negative / non-finite arguments give NaN instead of the IEEE special value, and every such case is already
+// flagged (ISV_W_NOT_SPD / ISV_W_SINGULAR) or replaced by a select at the call site.  -DISV_FAST_SPECIAL=0 builds the
+// library versions back in for A/B measurements.
+#ifndef ISV_FAST_SPECIAL
+#define ISV_FAST_SPECIAL 1
+#endif
+ISV_DI double fast_rsqrt(double x) {
+#if ISV_FAST_SPECIAL
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-x * y, y, 1.0);
+  return fma(0.5 * y, e, y);
+#else
+  return rsqrt(x);
+#endif
+}
+ISV_DI double fast_rcp(double x) {
+#if ISV_FAST_SPECIAL
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+#else
+  return 1.0 / x;
+#endif
+}
+
 // Quaterniond(PS[6], PS[3], PS[4], PS[5])
 ISV_DI Quat quat_from_pose(const double* ps) { return Quat{ps[6], ps[3], ps[4], ps[5]}; }
 

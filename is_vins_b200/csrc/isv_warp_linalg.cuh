@@ -624,7 +624,7 @@ __device__ __forceinline__ int w_sqrt_info_from_cov_regs(const double* A, int ld
   for (int j = N - 1; j >= 0; --j) {
     const double d = u[j][j];
     if (!(d > 0.0)) bad = 1;
-    const double ri = rsqrt(d);
+    const double ri = fast_rsqrt(d);
     rinv[j] = ri;
 #pragma unroll
     for (int i = 0; i < j; ++i) u[i][j] *= ri;
@@ -671,7 +671,7 @@ __device__ __forceinline__ int w_llt_upper_regs(const double* M, int ld, double*
 #pragma unroll
     for (int k = 0; k < j; ++k) d = fma(-l[j][k], l[j][k], d);
     if (!(d > 0.0)) bad = 1;
-    const double ri = rsqrt(d);
+    const double ri = fast_rsqrt(d);
     l[j][j] = d * ri;
 #pragma unroll
     for (int i = j + 1; i < N; ++i) {
@@ -715,7 +715,7 @@ __device__ __forceinline__ int w_sqrt_info_multi(const double* A, int N, int c, 
     if (active && c == j) {
       const double d = a[j];
       if (!(d > 0.0)) bad = 1;
-      const double ri = rsqrt(d);
+      const double ri = fast_rsqrt(d);
       Us[N * N + j] = ri;
 #pragma unroll
       for (int i = 0; i < NMAX; ++i)
@@ -774,7 +774,7 @@ __device__ __forceinline__ int w_spd_inverse_regs(double* A, int ld, int lane) {
     for (int k = 0; k < j; ++k) d = fma(-l[j][k] * l[j][k], l[k][k], d);   // l[k][k] holds d_k
     if (!(d > 0.0)) bad = 1;
     l[j][j] = d;
-    dinv[j] = 1.0 / d;
+    dinv[j] = fast_rcp(d);
 #pragma unroll
     for (int i = j + 1; i < N; ++i) {
       double v = l[i][j];

@@ -358,7 +358,7 @@ __device__ __forceinline__ void forward_accum_body(const isv_batch_in& in, const
     const double n2 = g0 * g0 + g1 * g1;
     // ONE reciprocal square root gives both 1 / (|g| c2) and rho = 1 / c2 (the FP64 division and rsqrt are the two
     // longest instruction sequences of the chain):  r = rsqrt(n2 c2^2) ;  1 / (|g| c2) = sign(c2) r ;  rho = r^2 n2 c2
-    const double r = rsqrt(n2 * (c2 * c2));
+    const double r = rsqrt(n2 * (c2 * c2));   // (the lean fast_rsqrt costs this kernel registers: 255 + a spill, +1.7 % time)
     const bool ok = n2 > 0.0;
     double rho = (r * r) * (n2 * c2);
     double in_ = copysign(r, c2);
@@ -765,7 +765,7 @@ __device__ __forceinline__ void backward_body(const isv_batch_in& in, const isv_
       if (lane == k) {
         const double d = a[k];
         if (!(d > 0.0)) status |= ISV_W_NOT_SPD;
-        const double ri = rsqrt(d);
+        const double ri = fast_rsqrt(d);
         Lc[256 + k] = ri;
         // column k, rows k..14, stored as aligned pairs (row k - 1 of an odd k rides along: never read)
         double2* c2 = reinterpret_cast<double2*>(Lc + kLcLd * k);
@@ -833,9 +833,9 @@ __device__ __forceinline__ void backward_body(const isv_batch_in& in, const isv_
       double gamma = 0.0, w0 = 0.0;
       if (tt > 0.0) {
         const double nrm = fma(x0, x0, tt);
-        const double ab = nrm * rsqrt(nrm);            // |beta|
+        const double ab = nrm * fast_rsqrt(nrm);       // |beta|
         const double ax = fabs(x0);
-        gamma = 1.0 / (ab * (ab + ax));
+        gamma = fast_rcp(ab * (ab + ax));
         w0 = (x0 >= 0.0) ? (ax + ab) : -(ax + ab);     // x0 - beta , beta = -sign(x0) |beta|
       }
       // the reflector travels as nine 16-byte words: [0..14] tail, [15] gamma, [16] w0 ([17] unused)
@@ -927,9 +927,9 @@ __device__ __forceinline__ void backward_body(const isv_batch_in& in, const isv_
     const double tt = hx.x, x0 = hx.y;
     const bool nzt = tt > 0.0;
     const double nrm = fma(x0, x0, tt);
-    const double ab = nrm * rsqrt(nrm);              // |beta|
+    const double ab = nrm * fast_rsqrt(nrm);         // |beta|
     const double ax = fabs(x0);
-    const double gamma = nzt ? 1.0 / (ab * (ab + ax)) : 0.0;
+    const double gamma = nzt ? fast_rcp(ab * (ab + ax)) : 0.0;
     const double w0 = nzt ? ((x0 >= 0.0) ? (ax + ab) : -(ax + ab)) : 0.0;   // x0 - beta
     const double beta = nzt ? ((x0 >= 0.0) ? -ab : ab) : x0;
     double v[22];
@@ -960,7 +960,7 @@ __device__ __forceinline__ void backward_body(const isv_batch_in& in, const isv_
   if (lane < 15) {
 #pragma unroll
     for (int c = 0; c < 15; ++c) Ls[lane + 16 * c] = row[c];
-    Ls[240 + lane] = 1.0 / row[lane];
+    Ls[240 + lane] = fast_rcp(row[lane]);
   }
   __syncwarp();
   double y[16];

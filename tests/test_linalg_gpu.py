@@ -109,3 +109,23 @@ def test_sym_eig_flags_non_finite_input_and_terminates(backend):
     assert info[1, 1] <= 3 * n * n + 64
     for b in (0, 2):                                       # the neighbours of the bad problem are untouched
         assert np.abs(lam[b] - np.linalg.eigvalsh(A[b])).max() <= 1e-12 * np.abs(lam[b]).max()
+
+
+def test_fast_rsqrt_and_rcp_are_faithful(backend):
+    """The lean reciprocal square root / reciprocal of the hot chains (MUFU seed + two Newton steps instead of CUDA's rsqrt()
+    and division): within 2 ulp of the correctly rounded value over 300 decades of normal positive arguments, and exact
+    powers of two come out exact."""
+    import ctypes as C
+    from is_vins_b200 import capi
+    rng = np.random.default_rng(5)
+    x = np.concatenate([10.0 ** rng.uniform(-150, 150, 200000), rng.uniform(0.5, 2.0, 100000), 2.0 ** np.arange(-200, 201, 2.0)])
+    rs, rc = np.zeros_like(x), np.zeros_like(x)
+    dp = lambda a: a.ctypes.data_as(capi.c_double_p)
+    capi.check(backend.lib.isv_test_fast_special(backend.h, len(x), dp(x), dp(rs), dp(rc)), "isv_test_fast_special")
+    ref_rs = (1.0 / np.sqrt(x.astype(np.longdouble))).astype(np.float64)
+    ref_rc = (1.0 / x.astype(np.longdouble)).astype(np.float64)
+    ulp = lambda a, b: np.abs(a - b) / np.spacing(np.abs(b))
+    print(f"\nfast_rsqrt worst {ulp(rs, ref_rs).max():.2f} ulp, fast_rcp worst {ulp(rc, ref_rc).max():.2f} ulp")
+    assert ulp(rs, ref_rs).max() <= 2.0 and ulp(rc, ref_rc).max() <= 2.0
+    p2 = x[-201:]
+    assert np.array_equal(rs[-201:], 1.0 / np.sqrt(p2)) and np.array_equal(rc[-201:], 1.0 / p2)
