@@ -186,13 +186,18 @@ typedef struct isv_batch_out {
 #define ISV_RUN_BACKWARD_STAGE2 32
 
 /* stream-ordered, asynchronous; `which` selects MargForward / MargBackward / both.
- * Unused inputs/outputs of a skipped half may be NULL.                                          */
+ * Unused inputs/outputs of a skipped half may be NULL.
+ * Routes: ISV_RUN_BOTH on at most ISV_TUNE_FUSED_MAX_WINDOWS (148) windows with `preint` given takes ONE launch of the fused
+ * kernel (one CTA per window, is_vins_b200/csrc/isv_event_kernel.cuh); everything else the warp-per-window batch kernels
+ * (7 launches forked over three streams; replayed as one cached CUDA graph for repeated calls on up to 4736 windows).
+ * Both routes run the same device functions; results agree to rounding (the fused kernel sums the landmark Gram as seven
+ * partial sums).                                                                                  */
 isv_status isv_marg_window_batch(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out,
                                  int which);
 
-/* same call with HOST pointers in both structs: stages H2D (pinned, chunked, overlapped with
- * compute), runs the kernels, copies the outputs back and synchronises.  This is what the
- * e2e number in bench.py times.                                                                 */
+/* same call with HOST pointers in both structs: copies the per-window records once, then pipelines the landmark
+ * components (H2D, one ordered stream), the kernels and the results (D2H) in four chunks on four streams, and
+ * synchronises.  Pinned host buffers make the copies asynchronous.  This is what the e2e number in bench.py times.   */
 isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in,
                                       const isv_batch_out* out, int which);
 
