@@ -54,6 +54,7 @@ struct isv_handle {
   cudaEvent_t jac_ev[12]; // fork / join events of launch_batch, three per launching slot
   cudaStream_t pipe[2];   // third and fourth pipeline stream of the chunked host path (slots 2, 3)
   cudaStream_t h2d_stream;   // every H2D copy of the chunked host path, in chunk order
+  cudaStream_t bwd_stream;   // the backward half of the host path (it needs no landmarks: once, for the whole batch)
   cudaEvent_t chunk_ev[16];  // "chunk c is on the device"
   cudaStream_t fork[8];   // side streams of launch_batch: [2 slot] backward chain, [2 slot + 1] forward factor Jacobians
   // isv_marg_window_batch: the ~15 runtime calls of one launch_batch (fork / join over three streams) replayed as one
@@ -152,6 +153,7 @@ isv_status isv_create(const isv_config* cfg, int device, isv_handle** out) {
   for (int i = 0; i < 12; ++i) cudaEventCreateWithFlags(&h->jac_ev[i], cudaEventDisableTiming);
   for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->bwd_stream, cudaStreamNonBlocking);
   for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&h->chunk_ev[i], cudaEventDisableTiming);
   for (int i = 0; i < 8; ++i) cudaStreamCreateWithFlags(&h->fork[i], cudaStreamNonBlocking);
   h->stream = h->own_stream;
@@ -207,6 +209,7 @@ void isv_destroy(isv_handle* h) {
   for (int i = 0; i < 2; ++i)
     if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
   if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+  if (h->bwd_stream) cudaStreamDestroy(h->bwd_stream);
   for (int i = 0; i < 16; ++i)
     if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
   for (int i = 0; i < 8; ++i)
@@ -301,7 +304,8 @@ static size_t exp_smem(const char* name) {
 }
 
 static isv_status launch_batch(isv_handle* h, const isv_batch_in* in_arg, const isv_batch_out* out, int which,
-                               cudaStream_t stream, double* scratch, DbgStores dbg = DbgStores{nullptr, nullptr}) {
+                               cudaStream_t stream, double* scratch, DbgStores dbg = DbgStores{nullptr, nullptr},
+                               bool zero_status = true) {
   static const size_t x_acc = exp_smem("ISV_EXP_ACC_SMEM"), x_tail = exp_smem("ISV_EXP_TAIL_SMEM"), x_bwd = exp_smem("ISV_EXP_BWD_SMEM");
   static const bool x_once = [] {
     if (x_acc) {
@@ -334,8 +338,8 @@ static isv_status launch_batch(isv_handle* h, const isv_batch_in* in_arg, const 
   const bool persist = stage1_ && h->acc_persist > 0 && h->counters && n >= kAccPersistMinWindows;
   const int slot = (stream == h->copy_stream) ? 1 : (stream == h->pipe[0] ? 2 : (stream == h->pipe[1] ? 3 : 0));
   int32_t* counter = persist ? h->counters + 16 * slot : nullptr;
-  if (out->status || persist) {
-    int32_t dummy_n = out->status ? n : 0;
+  if ((out->status && zero_status) || persist) {
+    int32_t dummy_n = (out->status && zero_status) ? n : 0;
     zero_i32_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out->status, dummy_n, counter, persist ? 1 : 0);
     ++h->launches;
   }
@@ -569,6 +573,7 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   const size_t o_rank = carve(n * 2 * sizeof(int32_t));
   const size_t o_stat = carve(n * sizeof(int32_t));
   const size_t o_gram = carve(n * kScratchPerWindow * D);   // per-chunk slices: [w0 * kScratchPerWindow ...)
+  const size_t o_gramB = carve(bwd ? n * kScratchPerWindow * D : 0);   // the whole-batch backward call's own scratch
   st = ensure_dbuf(h, off);
   if (st != ISV_OK) return st;
   char* d = h->dbuf;
@@ -592,7 +597,9 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     for (int i = 1; i < kPipe; ++i) ISV_CUDA(cudaStreamWaitEvent(ss[i], h->ev[0], 0));
   }
   ISV_CUDA(cudaStreamWaitEvent(hs, h->ev[0], 0));
+  // rank and status are zeroed once, here: the forward chunks and the whole-batch backward call OR into the same status words
   zero_i32_kernel<<<(int)((2 * n + 255) / 256), 256, 0, ss[0]>>>((int32_t*)(d + o_rank), (long long)(2 * n));
+  zero_i32_kernel<<<(int)((n + 255) / 256), 256, 0, ss[0]>>>((int32_t*)(d + o_stat), (long long)n);
   // The per-window records cross once, one copy per array for the whole batch, ahead of the chunk loop: ~320 doubles per
   // window that used to travel as nine copies PER CHUNK (every copy pays a fixed DMA set-up; at L = 150 they are half of the
   // bytes).  Only the landmark components and the results are chunked.
@@ -619,8 +626,50 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
       if (in->imu_count) ISV_CUDA(up(o_icnt, in->imu_count, n * sizeof(int32_t)));
     }
   }
-  ISV_CUDA(cudaEventRecord(h->ev[1], ss[0]));      // the rank zero-fill
+  ISV_CUDA(cudaEventRecord(h->ev[1], ss[0]));      // the rank / status zero-fill
   for (int i = 1; i < kPipe; ++i) ISV_CUDA(cudaStreamWaitEvent(ss[i], h->ev[1], 0));
+  // ---- the backward half: MargBackward reads no landmark, only the per-window records that have just been queued -- it
+  // runs ONCE for the whole batch (whole waves instead of four latency-bound partial ones, a quarter of the launches) on
+  // its own stream, under the landmark H2D, and its three result arrays go back as three copies.  Only the forward half
+  // (landmark phase + tail) is chunked behind the landmark stream.
+  cudaStream_t sb = h->bwd_stream;
+  if (bwd) {
+    ISV_CUDA(cudaEventRecord(h->ev[2], hs));       // the records are on the device
+    ISV_CUDA(cudaStreamWaitEvent(sb, h->ev[1], 0));
+    ISV_CUDA(cudaStreamWaitEvent(sb, h->ev[2], 0));
+    isv_batch_in bin;
+    isv_batch_out bout;
+    memset(&bin, 0, sizeof(bin));
+    memset(&bout, 0, sizeof(bout));
+    bin.n_windows = (int32_t)n;
+    bin.flags = in->flags;
+    bin.pose_bwd = (const double*)(d + o_poseb);
+    bin.sb_bwd = (const double*)(d + o_sbb);
+    bin.prior_vb = (const double*)(d + o_pvb);
+    if (raw_imu) {
+      bin.imu_raw = (const double*)(d + o_iraw);
+      bin.imu_init = (const double*)(d + o_iinit);
+      bin.imu_count = in->imu_count ? (const int32_t*)(d + o_icnt) : nullptr;
+      bin.imu_k_max = in->imu_k_max;
+    } else {
+      bin.preint = (const double*)(d + o_pre);
+    }
+    bout.rel_out = (double*)(d + o_rel);
+    bout.vb_out = (double*)(d + o_vb);
+    bout.rp_out = (double*)(d + o_rp);
+    bout.rank = (int32_t*)(d + o_rank);
+    bout.status = (int32_t*)(d + o_stat);
+    st = launch_batch(h, &bin, &bout, ISV_RUN_BACKWARD, sb, (double*)(d + o_gramB), DbgStores{nullptr, nullptr}, false);
+    if (st != ISV_OK) return st;
+    ISV_CUDA(cudaEventRecord(h->ev[3], sb));       // backward kernels done: rank[.][1] and the status bits are final on their side
+    ISV_CUDA(cudaMemcpyAsync(out->rel_out, bout.rel_out, n * ISV_REL_REC * D, cudaMemcpyDeviceToHost, sb));
+    ISV_CUDA(cudaMemcpyAsync(out->vb_out, bout.vb_out, n * ISV_VB_REC * D, cudaMemcpyDeviceToHost, sb));
+    ISV_CUDA(cudaMemcpyAsync(out->rp_out, bout.rp_out, n * ISV_RP_REC * D, cudaMemcpyDeviceToHost, sb));
+    if (!fwd) {
+      ISV_CUDA(cudaMemcpyAsync(out->rank, bout.rank, n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, sb));
+      if (out->status) ISV_CUDA(cudaMemcpyAsync(out->status, bout.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, sb));
+    }
+  }
   size_t n_chunks = n / 512;
   if (n_chunks < 1) n_chunks = 1;
   static const int max_chunks = getenv("ISV_HOST_CHUNKS") ? atoi(getenv("ISV_HOST_CHUNKS")) : 4;   // measured at 9472 windows: 2 / 4 / 8 / 16 chunks
@@ -652,7 +701,7 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     clock_gettime(CLOCK_MONOTONIC, &tr0);
     cudaEventRecord(tev[0], ss[0]);
   }
-  for (size_t c = 0; c < n_chunks; ++c) {
+  for (size_t c = 0; fwd && c < n_chunks; ++c) {
     const size_t w0 = bound(c), w1 = bound(c + 1), m = w1 - w0;
     if (m == 0) continue;
     cudaStream_t s = ss[c % kPipe];
@@ -691,38 +740,20 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
       dout.se3_out = (double*)(d + o_se3) + w0 * ISV_SE3_REC;
       dout.pg_out = (double*)(d + o_pg) + w0 * ISV_PG_REC;
     }
-    if (bwd) {
-      if (raw_imu) {
-        din.imu_raw = (const double*)(d + o_iraw) + w0 * K * 7;
-        din.imu_init = (const double*)(d + o_iinit) + w0 * 12;
-        din.imu_count = in->imu_count ? (const int32_t*)(d + o_icnt) + w0 : nullptr;
-        din.imu_k_max = in->imu_k_max;
-      }
-      din.pose_bwd = (const double*)(d + o_poseb) + w0 * 14;
-      din.sb_bwd = (const double*)(d + o_sbb) + w0 * 18;
-      din.prior_vb = (const double*)(d + o_pvb) + w0 * ISV_VB_REC;
-      din.preint = raw_imu ? nullptr : (const double*)(d + o_pre) + w0 * ISV_PREINT_REC;
-      dout.rel_out = (double*)(d + o_rel) + w0 * ISV_REL_REC;
-      dout.vb_out = (double*)(d + o_vb) + w0 * ISV_VB_REC;
-      dout.rp_out = (double*)(d + o_rp) + w0 * ISV_RP_REC;
-    }
     dout.rank = (int32_t*)(d + o_rank) + 2 * w0;
     dout.status = (int32_t*)(d + o_stat) + w0;
     ISV_CUDA(cudaEventRecord(h->chunk_ev[c], hs));          // records + chunks 0 .. c are on the device
     ISV_CUDA(cudaStreamWaitEvent(s, h->chunk_ev[c], 0));
     if (tr) { thost[c][1] = host_ms(); cudaEventRecord(tev[2 + 4 * c], s); }
-    st = launch_batch(h, &din, &dout, which, s, (double*)(d + o_gram) + w0 * kScratchPerWindow);
+    st = launch_batch(h, &din, &dout, ISV_RUN_FORWARD, s, (double*)(d + o_gram) + w0 * kScratchPerWindow, DbgStores{nullptr, nullptr},
+                      false);
     if (st != ISV_OK) return st;
     if (tr) { thost[c][2] = host_ms(); cudaEventRecord(tev[3 + 4 * c], s); }
     if (fwd) {
       ISV_CUDA(cudaMemcpyAsync(out->se3_out + w0 * ISV_SE3_REC, dout.se3_out, m * ISV_SE3_REC * D, cudaMemcpyDeviceToHost, s));
       ISV_CUDA(cudaMemcpyAsync(out->pg_out + w0 * ISV_PG_REC, dout.pg_out, m * ISV_PG_REC * D, cudaMemcpyDeviceToHost, s));
     }
-    if (bwd) {
-      ISV_CUDA(cudaMemcpyAsync(out->rel_out + w0 * ISV_REL_REC, dout.rel_out, m * ISV_REL_REC * D, cudaMemcpyDeviceToHost, s));
-      ISV_CUDA(cudaMemcpyAsync(out->vb_out + w0 * ISV_VB_REC, dout.vb_out, m * ISV_VB_REC * D, cudaMemcpyDeviceToHost, s));
-      ISV_CUDA(cudaMemcpyAsync(out->rp_out + w0 * ISV_RP_REC, dout.rp_out, m * ISV_RP_REC * D, cudaMemcpyDeviceToHost, s));
-    }
+    if (bwd) ISV_CUDA(cudaStreamWaitEvent(s, h->ev[3], 0));   // rank / status of the chunk's windows carry the backward half too
     ISV_CUDA(cudaMemcpyAsync(out->rank + 2 * w0, dout.rank, m * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     if (out->status)
       ISV_CUDA(cudaMemcpyAsync(out->status + w0, dout.status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -730,6 +761,7 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   }
   for (int i = 0; i < kPipe; ++i) ISV_CUDA(cudaStreamSynchronize(ss[i]));
   ISV_CUDA(cudaStreamSynchronize(hs));
+  if (bwd) ISV_CUDA(cudaStreamSynchronize(sb));
   if (tr) {
     const double t_end = host_ms();
     for (size_t c = 0; c < n_chunks; ++c) {
