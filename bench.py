@@ -504,33 +504,51 @@ def measure(cx, L, n, which, steps, warmup, seed, full, e2e=True):
         xyf_t = torch.from_numpy(xy_as_f32(batch.lm_obs)).pin_memory()
         cx.keep.append(xyf_t)
         raw_f = ("pose_bwd", "sb_bwd", "prior_vb", "imu_raw", "imu_init")
-        for tag, kw, lm_bytes, bwd_f in (("", dict(raw_imu=True, z_one=True, xy_f32=xyf_t.numpy()), 16, raw_f),
+        # (a'') ABI 4 inputs / outputs: (a') plus every record without its structural zeros -- the sqrt_info blocks are upper
+        #     triangular, covRel symmetric: 252 instead of 319 doubles of records in, 191 instead of 289 doubles of results out
+        from is_vins_b200.batch import pack_tri_inputs, packed_outputs, unpack_outputs
+        tri = {k: (None if v is None else torch.from_numpy(v).pin_memory()) for k, v in pack_tri_inputs(batch).items()}
+        cx.keep.append(tri)
+        tri_np = {k: (None if v is None else v.numpy()) for k, v in tri.items()}
+        pout_t = {k: torch.from_numpy(getattr(packed_outputs(n), k)).pin_memory() for k in ("se3", "pg", "rel", "vb", "rp", "rank", "status")}
+        pout = WindowOutputs(*[pout_t[k].numpy() for k in ("se3", "pg", "rel", "vb", "rp", "rank", "status")])
+        tri_saved = sum(getattr(batch, f).nbytes - tri_np[f].nbytes for f in ("prior_se3", "prior_rel", "prior_rp", "prior_vb")
+                        if tri_np[f] is not None and ((f != "prior_vb" and which & 1) or (f == "prior_vb" and which & 2)))
+        d2h_tri = sum(pout_t[k].numpy().nbytes for k in ((["se3", "pg"] if which & 1 else []) + (["rel", "vb", "rp"] if which & 2 else [])
+                                                         + ["rank", "status"]))
+        for tag, kw, lm_bytes, bwd_f in (("", dict(raw_imu=True, z_one=True, xy_f32=xyf_t.numpy(), tri_in=tri_np, tri_out=True), 16, raw_f),
+                                         ("_abi3", dict(raw_imu=True, z_one=True, xy_f32=xyf_t.numpy()), 16, raw_f),
                                          ("_abi2", dict(raw_imu=True, z_one=True), 24, raw_f),
                                          ("_abi1", dict(), 32, ("pose_bwd", "sb_bwd", "prior_vb", "preint"))):
             if tag and not full:
                 continue
+            ho = pout if not tag else hout
             h2d = 0
             if which & 1:
                 h2d += sum(getattr(batch, f).nbytes for f in fwd_f) + lm_bytes * batch.n_landmarks
             if which & 2:
                 h2d += sum(getattr(batch, f).nbytes for f in bwd_f)
+            if not tag:
+                h2d -= tri_saved
             for _ in range(max(1, min(warmup, 3))):
-                be.marg_window_batch_host(batch, which, hout, **kw)
+                be.marg_window_batch_host(batch, which, ho, **kw)
             cx.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(steps):
-                be.marg_window_batch_host(batch, which, hout, **kw)   # synchronises internally after the D2H
+                be.marg_window_batch_host(batch, which, ho, **kw)   # synchronises internally after the D2H
             e1.record()
             cx.barrier()
             r["e2e_ms" + tag] = e0.elapsed_time(e1)
-            r["h2d" + tag], r["d2h"] = h2d, d2h
-            assert int(np.count_nonzero(hout.status)) == 0
+            r["h2d" + tag] = h2d
+            r["d2h" + tag] = d2h_tri if not tag else d2h
+            assert int(np.count_nonzero(ho.status)) == 0
             if cx.rank == 0 and not tag:
                 # the e2e path's results against the device path's: equal to rounding (z == 1 is folded into the arithmetic,
-                # the pre-integration record was rebuilt on the GPU from the raw samples)
+                # the pre-integration record was rebuilt on the GPU from the raw samples); the packed results are expanded
+                # here, after the timed region
                 from is_vins_b200.batch import outputs_rel_diff
-                r["e2e_vs_device_path_max_rel"] = float(outputs_rel_diff(hout, r["out"], which).max())
+                r["e2e_vs_device_path_max_rel"] = float(outputs_rel_diff(unpack_outputs(pout), r["out"], which).max())
             if cx.rank == 0 and tag == "_abi1":
                 r["e2e_abi1_bits_equal"] = bool(all(np.array_equal(getattr(hout, f), getattr(r["out"], f)) for f in fams))
     # ---- the copy ceiling the e2e number runs under: the same byte counts as plain pinned cudaMemcpyAsync, H2D and D2H
@@ -727,9 +745,9 @@ def run_cuda(args, L):
     h = measure(cx, L, n, capi.RUN_BOTH, args.steps, args.warmup, 1000 + rank, full=True)
     names = list(KERNELS)
     tl = maxr([h["ms_total"], h["e2e_ms"], h["sustained_ms"] / h["sustained_steps"], h["sustained_2nd_half_ms_per_step"],
-               h["e2e_ms_abi1"], h["copy_ceiling_ms"], h["e2e_ms_abi2"]] + [h["per"][k] for k in names])
-    ms_total, e2e_ms, sus_ms, sus2_ms, e2e1_ms, ceil_ms, e2e2_ms = tl[0:7]
-    per = dict(zip(names, tl[7:]))
+               h["e2e_ms_abi1"], h["copy_ceiling_ms"], h["e2e_ms_abi2"], h["e2e_ms_abi3"]] + [h["per"][k] for k in names])
+    ms_total, e2e_ms, sus_ms, sus2_ms, e2e1_ms, ceil_ms, e2e2_ms, e2e3_ms = tl[0:8]
+    per = dict(zip(names, tl[8:]))
     tot_lm = maxr([float(h["n_lm"])])[0]
     line = None
     if rank == 0:
@@ -771,7 +789,10 @@ def run_cuda(args, L):
             "clocks": h["clocks"],
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h["h2d"], "d2h_bytes_per_step": h["d2h"],
                     "ms_per_step": e2e_ms / args.steps, "gb_per_s": (h["h2d"] + h["d2h"]) / (e2e_ms / args.steps * 1e-3) / 1e9,
-                    "inputs": "ABI 3: raw IMU samples (12 + 7 K doubles; preintegrate_kernel runs inside the call) instead of the "
+                    "inputs": "ABI 4 = ABI 3 + every record without its structural zeros, in and out (upper-triangular sqrt_info "
+                              "blocks as 21 / 45 / 3 numbers, the symmetric covRel as 21: 252 instead of 319 doubles of records per "
+                              "window in, 191 instead of 289 doubles of results out; expanded / compacted on the device).  "
+                              "ABI 3: raw IMU samples (12 + 7 K doubles; preintegrate_kernel runs inside the call) instead of the "
                               "467-double pre-integration record; pts_i.z == 1 promised (ISV_IN_PTS_I_Z_ONE); pts_i.x / pts_i.y as "
                               "the FP32 values the reference's feature tracker produces (cv::Point2f, widened exactly on the GPU): "
                               "4 + 4 + 8 bytes per landmark",
@@ -782,6 +803,9 @@ def run_cuda(args, L):
                                              "ranks at once, max over ranks: what host memory / PCIe can feed on this box (the "
                                              "aggregate saturates near 115 GB/s at 2-4 GPUs and 186 GB/s at 8: "
                                              "profiles/r02n_h2d_peak_*gpu.json)"},
+                    "abi3": {"value": world * n * args.steps / (e2e3_ms * 1e-3), "h2d_bytes_per_step": h["h2d_abi3"],
+                             "d2h_bytes_per_step": h["d2h_abi3"], "ms_per_step": e2e3_ms / args.steps,
+                             "inputs": "ABI 3: as above with the full (square) records in and out"},
                     "abi2": {"value": world * n * args.steps / (e2e2_ms * 1e-3), "h2d_bytes_per_step": h["h2d_abi2"],
                              "ms_per_step": e2e2_ms / args.steps,
                              "inputs": "ABI 2: as above with pts_i.x / pts_i.y as doubles (24 bytes per landmark)"},

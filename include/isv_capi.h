@@ -28,8 +28,9 @@
 extern "C" {
 #endif
 
-#define ISV_ABI_VERSION 3   /* 2: isv_batch_in grew imu_raw / imu_init / imu_count / imu_k_max / flags (zero = v1 behaviour);
-                               3: ... and lm_xy_f32 (NULL = v2 behaviour) */
+#define ISV_ABI_VERSION 4   /* 2: isv_batch_in grew imu_raw / imu_init / imu_count / imu_k_max / flags (zero = v1 behaviour);
+                               3: ... and lm_xy_f32 (NULL = v2 behaviour);
+                               4: flags ISV_IN_TRI_RECORDS / ISV_OUT_TRI_RECORDS on the host-pointer entry point */
 
 /* ---- status codes (SURVEY.md 8b "error conventions": the reference has none -- void + assert) */
 typedef enum isv_status {
@@ -160,6 +161,24 @@ typedef struct isv_batch_in {
 /* pts_i.z == 1 for every landmark (the feature tracker normalises: src/System.cpp:346): component 2 of
  * lm_obs is neither read by the kernels nor copied by the host entry point (which spot-checks it). */
 #define ISV_IN_PTS_I_Z_ONE 1
+/* ABI 4, host-pointer entry point only (isv_marg_window_batch_host): the records cross PCIe WITHOUT their structural zeros.
+ * Every sqrt_info in the path is upper triangular (it is an `LLT(...).matrixL().transpose()`, src/estimator.cpp:1349,
+ * :1500-1516, include/factor/*.h) and covRel is symmetric, so a 6 x 6 block is 21 numbers, a 9 x 9 block 45, a 2 x 2 block 3.
+ *   ISV_IN_TRI_RECORDS   the prior records arrive packed: prior_se3 / prior_rel [n][33] = t | delta_t 3, R 9 (column-major),
+ *                        upper triangle of sqrt_info column by column 21; prior_vb [n][54] = VB 9 + 45; prior_rp [n][4] =
+ *                        valid + 3.  (319 -> 252 doubles per window together with the other records.)
+ *   ISV_OUT_TRI_RECORDS  the results are delivered packed: se3_out / rel_out [n][33]; pg_out [n][59] = delta_t 3, delta_R 9,
+ *                        sqrt_info 21, covRel (upper triangle) 21, distance, covAbs 4; vb_out [n][54]; rp_out [n][12] =
+ *                        R 9 + 3.  (289 -> 191 doubles per window.)
+ * The kernels keep working on the full records in HBM; two small kernels expand / compact them on the device.        */
+#define ISV_IN_TRI_RECORDS 2
+#define ISV_OUT_TRI_RECORDS 4
+#define ISV_SE3_TRI_REC 33
+#define ISV_REL_TRI_REC 33
+#define ISV_VB_TRI_REC 54
+#define ISV_RP_IN_TRI_REC 4
+#define ISV_PG_TRI_REC 59
+#define ISV_RP_TRI_REC 12
 
 typedef struct isv_batch_out {
   double* se3_out;               /* [n][48]  forwardPosePriorEdgeToAdd                          */

@@ -141,10 +141,14 @@ class MargBackend:
     # ---- batched, host pointers (H2D + kernels + D2H inside the call) ---------------------------
     def marg_window_batch_host(self, batch: WindowBatch, which: int = capi.RUN_BOTH,
                                out: Optional[WindowOutputs] = None, raw_imu: bool = False,
-                               z_one: bool = False, xy_f32: Optional[np.ndarray] = None) -> WindowOutputs:
+                               z_one: bool = False, xy_f32: Optional[np.ndarray] = None,
+                               tri_in: Optional[Dict[str, Optional[np.ndarray]]] = None, tri_out: bool = False) -> WindowOutputs:
         """raw_imu / z_one: see DeviceBatch (fewer bytes cross PCIe: 12 + 7 K doubles instead of the 467-double
         pre-integration record, 3 instead of 4 doubles per landmark)."""
         n = batch.n
+        if out is None and tri_out:
+            from .batch import packed_outputs
+            out = packed_outputs(n)
         if out is None:
             out = WindowOutputs(np.zeros((n, capi.SE3_REC)), np.zeros((n, capi.PG_REC)), np.zeros((n, capi.REL_REC)),
                                 np.zeros((n, capi.VB_REC)), np.zeros((n, capi.RP_REC)),
@@ -155,7 +159,11 @@ class MargBackend:
                                _p(batch.prior_vb), None if raw_imu else _p(batch.preint))
         if raw_imu:
             bi.imu_raw, bi.imu_init, bi.imu_k_max = _p(batch.imu_raw), _p(batch.imu_init), int(batch.imu_raw.shape[1])
-        bi.flags = capi.IN_PTS_I_Z_ONE if z_one else 0
+        bi.flags = (capi.IN_PTS_I_Z_ONE if z_one else 0) | (capi.OUT_TRI_RECORDS if tri_out else 0)
+        if tri_in is not None:   # ABI 4: batch.pack_tri_inputs(batch) -- the prior records without their structural zeros
+            bi.flags |= capi.IN_TRI_RECORDS
+            bi.prior_se3, bi.prior_rel, bi.prior_vb = _p(tri_in["prior_se3"]), _p(tri_in["prior_rel"]), _p(tri_in["prior_vb"])
+            bi.prior_rp = _p(tri_in["prior_rp"])
         if xy_f32 is not None:   # ABI 3: [2, n_lm] float32 from xy_as_f32(batch.lm_obs) (pin it for the e2e measurement)
             assert xy_f32.dtype == np.float32 and xy_f32.shape == (2, batch.lm_obs.shape[1]) and xy_f32.flags.c_contiguous
             bi.lm_xy_f32 = _p(xy_f32)

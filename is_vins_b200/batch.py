@@ -32,6 +32,55 @@ def rp_in_record(valid: bool, sqrt_info=None) -> np.ndarray:
     return r
 
 
+# ---- ABI 4: records without their structural zeros (include/isv_capi.h ISV_IN_TRI_RECORDS / ISV_OUT_TRI_RECORDS) ----------
+# A record = segments that are copied (kind 0) or N x N column-major blocks whose upper triangle travels column by column.
+TRI_LAYOUTS = {"se3": [(0, 12), (1, 6)], "rel": [(0, 12), (1, 6)], "vb": [(0, 9), (1, 9)], "rp_in": [(0, 1), (1, 2)],
+               "pg": [(0, 12), (1, 6), (1, 6), (0, 5)], "rp": [(0, 9), (1, 2)]}
+
+
+def _tri_index(layout):
+    """(full index of every packed element, full length): the gather map full -> packed."""
+    idx, fo = [], 0
+    for kind, N in layout:
+        if kind == 0:
+            idx += list(range(fo, fo + N))
+            fo += N
+        else:
+            idx += [fo + i + N * j for j in range(N) for i in range(j + 1)]
+            fo += N * N
+    return np.asarray(idx, np.int64), fo
+
+
+def pack_tri(records: np.ndarray, family: str) -> np.ndarray:
+    """[n, full] records -> [n, packed] (upper triangles only); raises if a strict lower triangle of a sqrt_info is not zero."""
+    idx, fl = _tri_index(TRI_LAYOUTS[family])
+    records = np.asarray(records, float)
+    assert records.shape[1] == fl
+    mask = np.ones(fl, bool)
+    mask[idx] = False
+    if family != "pg" and np.any(records[:, mask] != 0.0):
+        raise ValueError(f"pack_tri({family}): a strict lower triangle is not zero")
+    return np.ascontiguousarray(records[:, idx])
+
+
+def unpack_tri(packed: np.ndarray, family: str, symmetric_blocks: Sequence[int] = ()) -> np.ndarray:
+    """[n, packed] -> [n, full] with zero strict lower triangles; blocks listed in symmetric_blocks (segment numbers) are
+    mirrored instead (covRel of the pose-graph record: segment 2)."""
+    layout = TRI_LAYOUTS[family]
+    idx, fl = _tri_index(layout)
+    packed = np.asarray(packed, float)
+    full = np.zeros((packed.shape[0], fl))
+    full[:, idx] = packed
+    fo = 0
+    for sno, (kind, N) in enumerate(layout):
+        if kind == 1 and sno in symmetric_blocks:
+            up = full[:, fo:fo + N * N].reshape(-1, N, N).copy()   # [n][j][i] (column-major): only i <= j is filled
+            dg = up * np.eye(N)
+            full[:, fo:fo + N * N] = (up + up.transpose(0, 2, 1) - dg).reshape(-1, N * N)
+        fo += N * N if kind else N
+    return full
+
+
 @dataclass
 class WindowBatch:
     """Inputs of n independent MARGIN_OLD events (MargForward + MargBackward)."""
@@ -219,3 +268,23 @@ def outputs_rel_diff(a: WindowOutputs, b: WindowOutputs, which: int = 3) -> np.n
             r = np.linalg.norm(y[:, lo:hi], axis=1)
             worst = np.maximum(worst, np.where(r > 0, d / np.where(r > 0, r, 1.0), d))
     return worst
+
+
+def pack_tri_inputs(batch: "WindowBatch") -> Dict[str, Optional[np.ndarray]]:
+    """The four prior-record arrays of a batch in the ABI 4 packed form (ISV_IN_TRI_RECORDS)."""
+    return {"prior_se3": pack_tri(batch.prior_se3, "se3"), "prior_rel": pack_tri(batch.prior_rel, "rel"),
+            "prior_rp": None if batch.prior_rp is None else pack_tri(batch.prior_rp, "rp_in"),
+            "prior_vb": pack_tri(batch.prior_vb, "vb")}
+
+
+def packed_outputs(n: int) -> "WindowOutputs":
+    """Result buffers of the ABI 4 packed form (ISV_OUT_TRI_RECORDS): 191 instead of 289 doubles per window."""
+    return WindowOutputs(np.zeros((n, capi.SE3_TRI_REC)), np.zeros((n, capi.PG_TRI_REC)), np.zeros((n, capi.REL_TRI_REC)),
+                         np.zeros((n, capi.VB_TRI_REC)), np.zeros((n, capi.RP_TRI_REC)), np.zeros((n, 2), np.int32),
+                         np.zeros((n,), np.int32))
+
+
+def unpack_outputs(o: "WindowOutputs") -> "WindowOutputs":
+    """Packed results -> the full records (strict lower triangles of the sqrt_info blocks zero, covRel mirrored)."""
+    return WindowOutputs(unpack_tri(o.se3, "se3"), unpack_tri(o.pg, "pg", symmetric_blocks=(2,)), unpack_tri(o.rel, "rel"),
+                         unpack_tri(o.vb, "vb"), unpack_tri(o.rp, "rp"), o.rank, o.status)

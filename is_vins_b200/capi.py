@@ -16,7 +16,8 @@ ISV_OK, ISV_ERR_BAD_ARG, ISV_ERR_CUDA, ISV_ERR_ALLOC = 0, 1, 2, 3
 W_NOT_SPD, W_RANK_DEFICIENT, W_NONFINITE, W_NONUNIT_QUAT, W_EIG_NOCONV, W_SINGULAR = 1, 2, 4, 8, 16, 32
 W_BAD_INDEX = 64
 W_DIAG_COUPLED = 128
-IN_PTS_I_Z_ONE = 1
+IN_PTS_I_Z_ONE, IN_TRI_RECORDS, OUT_TRI_RECORDS = 1, 2, 4   # isv_batch_in::flags (the TRI bits: host-pointer entry point only)
+SE3_TRI_REC, REL_TRI_REC, VB_TRI_REC, RP_IN_TRI_REC, PG_TRI_REC, RP_TRI_REC = 33, 33, 54, 4, 59, 12
 IMU_JAC_REC, YAW_REC = 480, 4
 ACC_REC, ACC_COVREL, ACC_DISTANCE, ACC_LENGTH, ACC_VIO_INDEX, ACC_PG_INDEX, ACC_TS = 119, 48, 84, 85, 86, 87, 88
 ACC_RI, ACC_TI, ACC_RP_VALID, ACC_RP, ACC_COVABS = 89, 98, 101, 102, 115

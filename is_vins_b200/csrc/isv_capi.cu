@@ -68,6 +68,21 @@ struct isv_handle {
 constexpr int kFusedMaxWindows = 148;   // one CTA per SM: see launch_fused
 constexpr int kAccPersistPerSm = 0;     // persistent landmark-kernel warps per SM (see marg_forward_accum_kernel): OFF by default,
 constexpr int kAccPersistMinWindows = 2368;   // measured without gain; when on, used for batches of at least this many windows
+// ABI 4 record layouts (include/isv_capi.h ISV_IN_TRI_RECORDS / ISV_OUT_TRI_RECORDS)
+static const TriLayout kTriSe3 = {2, {0, 1, 0, 0}, {12, 6, 0, 0}};       // 48 <-> 33 (also the RelativePoseFactor record)
+static const TriLayout kTriVb = {2, {0, 1, 0, 0}, {9, 9, 0, 0}};         // 90 <-> 54
+static const TriLayout kTriRpIn = {2, {0, 1, 0, 0}, {1, 2, 0, 0}};       // 5 <-> 4
+static const TriLayout kTriPg = {4, {0, 1, 1, 0}, {12, 6, 6, 5}};        // 89 <-> 59
+static const TriLayout kTriRpOut = {2, {0, 1, 0, 0}, {9, 2, 0, 0}};      // 13 <-> 12
+template <bool PACK>
+static void tri_launch(isv_handle* h, cudaStream_t s, size_t n, const double* src, double* dst, const TriLayout& lay) {
+  if (n == 0) return;
+  const long long total = (long long)n * tri_full_len(lay);
+  const int grid = (int)(total / 256 + 1 < 1184 ? total / 256 + 1 : 1184);
+  tri_records_kernel<PACK><<<grid, 256, 0, s>>>((long long)n, src, dst, lay);
+  ++h->launches;
+}
+
 // the landmark kernel's eight instantiations: pts_i.z == 1 promised / sqrt_info = c I / pts_i.xy as FP32
 static const void* accum_kernel_variant(bool zone, bool iso, bool xyf) {
   static const void* const k[8] = {
@@ -270,7 +285,7 @@ int isv_order_map_backward(int V, int32_t* out) {
 }
 
 // ---- batched device entry point ---------------------------------------------------------------
-static isv_status check_batch(const isv_batch_in* in, const isv_batch_out* out, int which) {
+static isv_status check_batch(const isv_batch_in* in, const isv_batch_out* out, int which, bool allow_tri = false) {
   constexpr int kAll = ISV_RUN_BOTH | ISV_RUN_FORWARD_STAGE1 | ISV_RUN_FORWARD_STAGE2 | ISV_RUN_FACTOR_JAC | ISV_RUN_BACKWARD_STAGE2;
   if (!in || !out || in->n_windows < 0 || (which & ~kAll) || which == 0) return ISV_ERR_BAD_ARG;
   if (!out->rank) return ISV_ERR_BAD_ARG;
@@ -280,7 +295,7 @@ static isv_status check_batch(const isv_batch_in* in, const isv_batch_out* out, 
       return ISV_ERR_BAD_ARG;
     if (!in->lm_obs && in->lm_stride != 0) return ISV_ERR_BAD_ARG;
   }
-  if (in->flags & ~ISV_IN_PTS_I_Z_ONE) return ISV_ERR_BAD_ARG;
+  if (in->flags & ~(ISV_IN_PTS_I_Z_ONE | (allow_tri ? (ISV_IN_TRI_RECORDS | ISV_OUT_TRI_RECORDS) : 0))) return ISV_ERR_BAD_ARG;
   if (which & (ISV_RUN_BACKWARD | ISV_RUN_BACKWARD_STAGE2 | ISV_RUN_FACTOR_JAC)) {
     if (!in->pose_bwd || !in->sb_bwd || !in->prior_vb || !out->rel_out || !out->vb_out || !out->rp_out)
       return ISV_ERR_BAD_ARG;
@@ -525,7 +540,7 @@ static isv_status ensure_dbuf(isv_handle* h, size_t bytes) {
 isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, const isv_batch_out* out, int which) {
   if (!h) return ISV_ERR_BAD_ARG;
   if (which & ~ISV_RUN_BOTH) return ISV_ERR_BAD_ARG;   // the stage flags are device-path profiling aids
-  isv_status st = check_batch(in, out, which);
+  isv_status st = check_batch(in, out, which, true);
   if (st != ISV_OK) return st;
   const size_t n = (size_t)in->n_windows;
   if (n == 0) return ISV_OK;
@@ -574,6 +589,13 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   const size_t o_stat = carve(n * sizeof(int32_t));
   const size_t o_gram = carve(n * kScratchPerWindow * D);   // per-chunk slices: [w0 * kScratchPerWindow ...)
   const size_t o_gramB = carve(bwd ? n * kScratchPerWindow * D : 0);   // the whole-batch backward call's own scratch
+  const bool tri_in = (in->flags & ISV_IN_TRI_RECORDS) != 0, tri_out = (in->flags & ISV_OUT_TRI_RECORDS) != 0;
+  const size_t p_se3 = carve(tri_in && fwd ? n * ISV_SE3_TRI_REC * D : 0), p_rel = carve(tri_in && fwd ? n * ISV_REL_TRI_REC * D : 0);
+  const size_t p_rp = carve(tri_in && fwd && in->prior_rp ? n * ISV_RP_IN_TRI_REC * D : 0), p_vb = carve(tri_in && bwd ? n * ISV_VB_TRI_REC * D : 0);
+  const size_t q_se3 = carve(tri_out && fwd ? n * ISV_SE3_TRI_REC * D : 0), q_pg = carve(tri_out && fwd ? n * ISV_PG_TRI_REC * D : 0);
+  const size_t q_rel = carve(tri_out && bwd ? n * ISV_REL_TRI_REC * D : 0), q_vb = carve(tri_out && bwd ? n * ISV_VB_TRI_REC * D : 0);
+  const size_t q_rp = carve(tri_out && bwd ? n * ISV_RP_TRI_REC * D : 0);
+  const int kflags = in->flags & ISV_IN_PTS_I_Z_ONE;   // what the kernels know about
   st = ensure_dbuf(h, off);
   if (st != ISV_OK) return st;
   char* d = h->dbuf;
@@ -610,20 +632,17 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     ISV_CUDA(up(o_lmoff, in->lm_offset, (n + 1) * sizeof(int64_t)));
     ISV_CUDA(up(o_ex, in->ex_pose, (in->ex_pose_shared ? 7 : n * 7) * D));
     ISV_CUDA(up(o_posef, in->pose_fwd, n * 14 * D));
-    ISV_CUDA(up(o_pse3, in->prior_se3, n * ISV_SE3_REC * D));
-    ISV_CUDA(up(o_prel, in->prior_rel, n * ISV_REL_REC * D));
-    if (in->prior_rp) ISV_CUDA(up(o_prp, in->prior_rp, n * ISV_RP_IN_REC * D));
-  }
-  if (bwd) {
-    ISV_CUDA(up(o_poseb, in->pose_bwd, n * 14 * D));
-    ISV_CUDA(up(o_sbb, in->sb_bwd, n * 18 * D));
-    ISV_CUDA(up(o_pvb, in->prior_vb, n * ISV_VB_REC * D));
-    if (!raw_imu) {
-      ISV_CUDA(up(o_pre, in->preint, n * ISV_PREINT_REC * D));
-    } else {
-      ISV_CUDA(up(o_iraw, in->imu_raw, n * K * 7 * D));
-      ISV_CUDA(up(o_iinit, in->imu_init, n * 12 * D));
-      if (in->imu_count) ISV_CUDA(up(o_icnt, in->imu_count, n * sizeof(int32_t)));
+    if (!tri_in) {
+      ISV_CUDA(up(o_pse3, in->prior_se3, n * ISV_SE3_REC * D));
+      ISV_CUDA(up(o_prel, in->prior_rel, n * ISV_REL_REC * D));
+      if (in->prior_rp) ISV_CUDA(up(o_prp, in->prior_rp, n * ISV_RP_IN_REC * D));
+    } else {   // ABI 4: packed records up, expanded on the device (on the H2D stream: a few microseconds between two copies)
+      ISV_CUDA(up(p_se3, in->prior_se3, n * ISV_SE3_TRI_REC * D));
+      ISV_CUDA(up(p_rel, in->prior_rel, n * ISV_REL_TRI_REC * D));
+      if (in->prior_rp) ISV_CUDA(up(p_rp, in->prior_rp, n * ISV_RP_IN_TRI_REC * D));
+      tri_launch<false>(h, hs, n, (const double*)(d + p_se3), (double*)(d + o_pse3), kTriSe3);
+      tri_launch<false>(h, hs, n, (const double*)(d + p_rel), (double*)(d + o_prel), kTriSe3);
+      if (in->prior_rp) tri_launch<false>(h, hs, n, (const double*)(d + p_rp), (double*)(d + o_prp), kTriRpIn);
     }
   }
   ISV_CUDA(cudaEventRecord(h->ev[1], ss[0]));      // the rank / status zero-fill
@@ -633,41 +652,79 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
   // its own stream, under the landmark H2D, and its three result arrays go back as three copies.  Only the forward half
   // (landmark phase + tail) is chunked behind the landmark stream.
   cudaStream_t sb = h->bwd_stream;
-  if (bwd) {
-    ISV_CUDA(cudaEventRecord(h->ev[2], hs));       // the records are on the device
-    ISV_CUDA(cudaStreamWaitEvent(sb, h->ev[1], 0));
-    ISV_CUDA(cudaStreamWaitEvent(sb, h->ev[2], 0));
+  // (When only the backward half is wanted nothing hides it, so it is pipelined itself: four sub-batches, each with its own
+  // record copies, on the four pipeline streams.)
+  const size_t nb = bwd ? ((!fwd && n >= 2048) ? 4 : 1) : 0;
+  for (size_t k = 0; k < nb; ++k) {
+    const size_t w0 = n * k / nb, w1 = n * (k + 1) / nb, m = w1 - w0;
+    if (m == 0) continue;
+    cudaStream_t sk = nb == 1 ? sb : ss[k % kPipe];
+    auto upr = [&](size_t o, const void* src, size_t rec_bytes) {   // rows [w0, w1) of a per-window array
+      return cudaMemcpyAsync(d + o + w0 * rec_bytes, (const char*)src + w0 * rec_bytes, m * rec_bytes, cudaMemcpyHostToDevice, hs);
+    };
+    ISV_CUDA(upr(o_poseb, in->pose_bwd, 14 * D));
+    ISV_CUDA(upr(o_sbb, in->sb_bwd, 18 * D));
+    if (!tri_in) {
+      ISV_CUDA(upr(o_pvb, in->prior_vb, ISV_VB_REC * D));
+    } else {
+      ISV_CUDA(upr(p_vb, in->prior_vb, ISV_VB_TRI_REC * D));
+      tri_launch<false>(h, hs, m, (const double*)(d + p_vb) + w0 * ISV_VB_TRI_REC, (double*)(d + o_pvb) + w0 * ISV_VB_REC, kTriVb);
+    }
+    if (!raw_imu) {
+      ISV_CUDA(upr(o_pre, in->preint, ISV_PREINT_REC * D));
+    } else {
+      if (K) ISV_CUDA(upr(o_iraw, in->imu_raw, K * 7 * D));
+      ISV_CUDA(upr(o_iinit, in->imu_init, 12 * D));
+      if (in->imu_count) ISV_CUDA(upr(o_icnt, in->imu_count, sizeof(int32_t)));
+    }
+    cudaEvent_t ev_rec = h->chunk_ev[12 + k];      // "the records of sub-batch k are on the device"
+    ISV_CUDA(cudaEventRecord(ev_rec, hs));
+    ISV_CUDA(cudaStreamWaitEvent(sk, h->ev[1], 0));
+    ISV_CUDA(cudaStreamWaitEvent(sk, ev_rec, 0));
     isv_batch_in bin;
     isv_batch_out bout;
     memset(&bin, 0, sizeof(bin));
     memset(&bout, 0, sizeof(bout));
-    bin.n_windows = (int32_t)n;
-    bin.flags = in->flags;
-    bin.pose_bwd = (const double*)(d + o_poseb);
-    bin.sb_bwd = (const double*)(d + o_sbb);
-    bin.prior_vb = (const double*)(d + o_pvb);
+    bin.n_windows = (int32_t)m;
+    bin.flags = kflags;
+    bin.pose_bwd = (const double*)(d + o_poseb) + w0 * 14;
+    bin.sb_bwd = (const double*)(d + o_sbb) + w0 * 18;
+    bin.prior_vb = (const double*)(d + o_pvb) + w0 * ISV_VB_REC;
     if (raw_imu) {
-      bin.imu_raw = (const double*)(d + o_iraw);
-      bin.imu_init = (const double*)(d + o_iinit);
-      bin.imu_count = in->imu_count ? (const int32_t*)(d + o_icnt) : nullptr;
+      bin.imu_raw = (const double*)(d + o_iraw) + w0 * K * 7;
+      bin.imu_init = (const double*)(d + o_iinit) + w0 * 12;
+      bin.imu_count = in->imu_count ? (const int32_t*)(d + o_icnt) + w0 : nullptr;
       bin.imu_k_max = in->imu_k_max;
     } else {
-      bin.preint = (const double*)(d + o_pre);
+      bin.preint = (const double*)(d + o_pre) + w0 * ISV_PREINT_REC;
     }
-    bout.rel_out = (double*)(d + o_rel);
-    bout.vb_out = (double*)(d + o_vb);
-    bout.rp_out = (double*)(d + o_rp);
-    bout.rank = (int32_t*)(d + o_rank);
-    bout.status = (int32_t*)(d + o_stat);
-    st = launch_batch(h, &bin, &bout, ISV_RUN_BACKWARD, sb, (double*)(d + o_gramB), DbgStores{nullptr, nullptr}, false);
+    bout.rel_out = (double*)(d + o_rel) + w0 * ISV_REL_REC;
+    bout.vb_out = (double*)(d + o_vb) + w0 * ISV_VB_REC;
+    bout.rp_out = (double*)(d + o_rp) + w0 * ISV_RP_REC;
+    bout.rank = (int32_t*)(d + o_rank) + 2 * w0;
+    bout.status = (int32_t*)(d + o_stat) + w0;
+    st = launch_batch(h, &bin, &bout, ISV_RUN_BACKWARD, sk, (double*)(d + o_gramB) + w0 * kScratchPerWindow, DbgStores{nullptr, nullptr},
+                      false);
     if (st != ISV_OK) return st;
-    ISV_CUDA(cudaEventRecord(h->ev[3], sb));       // backward kernels done: rank[.][1] and the status bits are final on their side
-    ISV_CUDA(cudaMemcpyAsync(out->rel_out, bout.rel_out, n * ISV_REL_REC * D, cudaMemcpyDeviceToHost, sb));
-    ISV_CUDA(cudaMemcpyAsync(out->vb_out, bout.vb_out, n * ISV_VB_REC * D, cudaMemcpyDeviceToHost, sb));
-    ISV_CUDA(cudaMemcpyAsync(out->rp_out, bout.rp_out, n * ISV_RP_REC * D, cudaMemcpyDeviceToHost, sb));
+    if (nb == 1) ISV_CUDA(cudaEventRecord(h->ev[3], sk));   // backward kernels done: rank[.][1] and its status bits are final
+    if (!tri_out) {
+      ISV_CUDA(cudaMemcpyAsync(out->rel_out + w0 * ISV_REL_REC, bout.rel_out, m * ISV_REL_REC * D, cudaMemcpyDeviceToHost, sk));
+      ISV_CUDA(cudaMemcpyAsync(out->vb_out + w0 * ISV_VB_REC, bout.vb_out, m * ISV_VB_REC * D, cudaMemcpyDeviceToHost, sk));
+      ISV_CUDA(cudaMemcpyAsync(out->rp_out + w0 * ISV_RP_REC, bout.rp_out, m * ISV_RP_REC * D, cudaMemcpyDeviceToHost, sk));
+    } else {   // ABI 4: compacted on the device, 99 instead of 151 doubles per window on the way back
+      double* qr = (double*)(d + q_rel) + w0 * ISV_REL_TRI_REC;
+      double* qv = (double*)(d + q_vb) + w0 * ISV_VB_TRI_REC;
+      double* qp = (double*)(d + q_rp) + w0 * ISV_RP_TRI_REC;
+      tri_launch<true>(h, sk, m, bout.rel_out, qr, kTriSe3);
+      tri_launch<true>(h, sk, m, bout.vb_out, qv, kTriVb);
+      tri_launch<true>(h, sk, m, bout.rp_out, qp, kTriRpOut);
+      ISV_CUDA(cudaMemcpyAsync(out->rel_out + w0 * ISV_REL_TRI_REC, qr, m * ISV_REL_TRI_REC * D, cudaMemcpyDeviceToHost, sk));
+      ISV_CUDA(cudaMemcpyAsync(out->vb_out + w0 * ISV_VB_TRI_REC, qv, m * ISV_VB_TRI_REC * D, cudaMemcpyDeviceToHost, sk));
+      ISV_CUDA(cudaMemcpyAsync(out->rp_out + w0 * ISV_RP_TRI_REC, qp, m * ISV_RP_TRI_REC * D, cudaMemcpyDeviceToHost, sk));
+    }
     if (!fwd) {
-      ISV_CUDA(cudaMemcpyAsync(out->rank, bout.rank, n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, sb));
-      if (out->status) ISV_CUDA(cudaMemcpyAsync(out->status, bout.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, sb));
+      ISV_CUDA(cudaMemcpyAsync(out->rank + 2 * w0, bout.rank, m * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, sk));
+      if (out->status) ISV_CUDA(cudaMemcpyAsync(out->status + w0, bout.status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, sk));
     }
   }
   size_t n_chunks = n / 512;
@@ -712,7 +769,7 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
     memset(&dout, 0, sizeof(dout));
     din.n_windows = (int32_t)m;
     din.ex_pose_shared = in->ex_pose_shared;
-    din.flags = in->flags;
+    din.flags = kflags;
     if (fwd) {
       const int64_t a = in->lm_offset[w0], b = in->lm_offset[w1];
       // components 3,4 (pts_j) are never read by the information-only marginalization: not copied
@@ -749,9 +806,16 @@ isv_status isv_marg_window_batch_host(isv_handle* h, const isv_batch_in* in, con
                       false);
     if (st != ISV_OK) return st;
     if (tr) { thost[c][2] = host_ms(); cudaEventRecord(tev[3 + 4 * c], s); }
-    if (fwd) {
+    if (fwd && !tri_out) {
       ISV_CUDA(cudaMemcpyAsync(out->se3_out + w0 * ISV_SE3_REC, dout.se3_out, m * ISV_SE3_REC * D, cudaMemcpyDeviceToHost, s));
       ISV_CUDA(cudaMemcpyAsync(out->pg_out + w0 * ISV_PG_REC, dout.pg_out, m * ISV_PG_REC * D, cudaMemcpyDeviceToHost, s));
+    } else if (fwd) {
+      double* qs = (double*)(d + q_se3) + w0 * ISV_SE3_TRI_REC;
+      double* qp = (double*)(d + q_pg) + w0 * ISV_PG_TRI_REC;
+      tri_launch<true>(h, s, m, dout.se3_out, qs, kTriSe3);
+      tri_launch<true>(h, s, m, dout.pg_out, qp, kTriPg);
+      ISV_CUDA(cudaMemcpyAsync(out->se3_out + w0 * ISV_SE3_TRI_REC, qs, m * ISV_SE3_TRI_REC * D, cudaMemcpyDeviceToHost, s));
+      ISV_CUDA(cudaMemcpyAsync(out->pg_out + w0 * ISV_PG_TRI_REC, qp, m * ISV_PG_TRI_REC * D, cudaMemcpyDeviceToHost, s));
     }
     if (bwd) ISV_CUDA(cudaStreamWaitEvent(s, h->ev[3], 0));   // rank / status of the chunk's windows carry the backward half too
     ISV_CUDA(cudaMemcpyAsync(out->rank + 2 * w0, dout.rank, m * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));

@@ -229,6 +229,35 @@ __global__ void zero_i32_kernel(int32_t* __restrict__ p, long long n, int32_t* _
   if (blockIdx.x == 0 && (int)threadIdx.x < nq) q[threadIdx.x] = 0;
 }
 
+// ABI 4 (host path): records without their structural zeros.  A record is up to four segments, each either copied or an
+// N x N column-major block whose upper triangle travels (column by column: (0,0), (0,1), (1,1), (0,2), ...).
+// PACK = false: packed -> full (strict lower triangle = 0); PACK = true: full -> packed.  One thread per full element.
+struct TriLayout { int nseg; int kind[4]; int len[4]; };   // kind 0: copy `len` doubles; kind 1: upper triangle of a len x len block
+__host__ __device__ inline int tri_full_len(const TriLayout& L) { int t = 0; for (int s = 0; s < L.nseg; ++s) t += L.kind[s] ? L.len[s] * L.len[s] : L.len[s]; return t; }
+__host__ __device__ inline int tri_packed_len(const TriLayout& L) { int t = 0; for (int s = 0; s < L.nseg; ++s) t += L.kind[s] ? L.len[s] * (L.len[s] + 1) / 2 : L.len[s]; return t; }
+template <bool PACK>
+__global__ void tri_records_kernel(long long n, const double* __restrict__ src, double* __restrict__ dst, TriLayout lay) {
+  const int fl = tri_full_len(lay), pl = tri_packed_len(lay);
+  const long long total = n * fl;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long w = idx / fl;
+    int e = (int)(idx - w * fl), fo = 0, po = 0, pe = -1;
+    for (int s = 0; s < lay.nseg; ++s) {
+      const int N = lay.len[s];
+      const int fs = lay.kind[s] ? N * N : N, ps = lay.kind[s] ? N * (N + 1) / 2 : N;
+      if (e < fo + fs) {
+        const int r = e - fo;
+        if (!lay.kind[s]) pe = po + r;
+        else { const int i = r % N, j = r / N; pe = (i <= j) ? po + j * (j + 1) / 2 + i : -1; }
+        break;
+      }
+      fo += fs; po += ps;
+    }
+    if (PACK) { if (pe >= 0) dst[w * pl + pe] = src[idx]; }
+    else dst[idx] = pe >= 0 ? src[w * pl + pe] : 0.0;
+  }
+}
+
 __global__ void __launch_bounds__(128)
 marg_factor_jac_kernel(isv_batch_in in, isv_batch_out out, double* __restrict__ fj, DevCfg cfg, int task0) {
   const int win = blockIdx.x * blockDim.x + threadIdx.x;

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"libisv_b200.so does not export {name}"
     bound = {s[0] for s in capi.SYMBOLS}
     assert declared == bound, (declared ^ bound)
-    assert lib.isv_abi_version() == 3
+    assert lib.isv_abi_version() == 4
 
 
 def test_default_config_matches_euroc_yaml():

@@ -326,6 +326,31 @@ def test_raw_imu_and_z_one_inputs(backend):
         assert np.array_equal(getattr(outx, f), getattr(out1, f)), f
         assert np.array_equal(getattr(outh, f), getattr(out1, f)), f
         assert np.array_equal(getattr(outy, f), getattr(out0, f)), f
+    # ABI 4: the prior records in and the recovered factors out WITHOUT their structural zeros (upper-triangular sqrt_info
+    # blocks as 21 / 45 / 3 numbers, the symmetric covRel as 21): expanded / compacted on the device around the same kernels,
+    # so after unpacking every bit is the one the full records give
+    from is_vins_b200.batch import pack_tri_inputs, unpack_outputs
+    tri = pack_tri_inputs(b)
+    assert tri["prior_se3"].shape[1] == capi.SE3_TRI_REC and tri["prior_vb"].shape[1] == capi.VB_TRI_REC
+    outp = backend.marg_window_batch_host(b, capi.RUN_BOTH, raw_imu=True, z_one=True, xy_f32=xyf, tri_in=tri, tri_out=True)
+    assert outp.pg.shape[1] == capi.PG_TRI_REC and outp.rp.shape[1] == capi.RP_TRI_REC
+    outu = unpack_outputs(outp)
+    for f in FIELDS:
+        if f == "pg":   # covRel = rpOmega^-1 is symmetric to rounding only: the packed form carries its upper triangle
+            assert np.array_equal(outu.pg[:, :48], out1.pg[:, :48]) and np.array_equal(outu.pg[:, 84:], out1.pg[:, 84:])
+            up = np.triu(np.ones((6, 6), bool)).flatten(order="F")
+            assert np.array_equal(outu.pg[:, 48:84][:, up], out1.pg[:, 48:84][:, up])
+            assert np.abs(outu.pg[:, 48:84] - out1.pg[:, 48:84]).max() <= 1e-12 * np.abs(out1.pg[:, 48:84]).max()
+        else:
+            assert np.array_equal(getattr(outu, f), getattr(out1, f)), f
+    outq = unpack_outputs(backend.marg_window_batch_host(b, capi.RUN_BACKWARD, tri_in=tri, tri_out=True))   # record-IMU inputs
+    assert np.array_equal(outq.rel, out0.rel) and np.array_equal(outq.vb, out0.vb) and np.array_equal(outq.rp, out0.rp)
+    outf = unpack_outputs(backend.marg_window_batch_host(b, capi.RUN_FORWARD, tri_out=True))                # full records in
+    assert np.array_equal(outf.se3, out0.se3) and np.array_equal(outf.pg[:, :48], out0.pg[:, :48])
+    dbt = DeviceBatch(b, "cuda:0")
+    dbt.flags = capi.IN_TRI_RECORDS                        # the packed forms belong to the host-pointer entry point only
+    with pytest.raises(capi.IsvError):
+        backend.marg_window_batch(dbt, capi.RUN_BOTH)
     with pytest.raises(ValueError):                        # values that are not floats are refused by the mirror
         bad = b.lm_obs.copy()
         bad[0, 3] += 1e-12

@@ -37,13 +37,20 @@ def main():
     ht["status"] = torch.zeros((n,), dtype=torch.int32).pin_memory()
     hout = WindowOutputs(*[ht[k].numpy() for k in ("se3", "pg", "rel", "vb", "rp", "rank", "status")])
     res = {"L": L, "n": n, "chunks": os.environ.get("ISV_HOST_CHUNKS", "default")}
-    for tag, kw in (("abi3", dict(raw_imu=True, z_one=True, xy_f32=xyf.numpy())), ("abi2", dict(raw_imu=True, z_one=True)), ("abi1", dict())):
+    from is_vins_b200.batch import pack_tri_inputs, packed_outputs
+    tri_t = {k: (None if v is None else torch.from_numpy(v).pin_memory()) for k, v in pack_tri_inputs(b).items()}
+    tri = {k: (None if v is None else v.numpy()) for k, v in tri_t.items()}
+    pt = {k: torch.from_numpy(getattr(packed_outputs(n), k)).pin_memory() for k in ("se3", "pg", "rel", "vb", "rp", "rank", "status")}
+    pout = WindowOutputs(*[pt[k].numpy() for k in ("se3", "pg", "rel", "vb", "rp", "rank", "status")])
+    for tag, kw in (("abi4", dict(raw_imu=True, z_one=True, xy_f32=xyf.numpy(), tri_in=tri, tri_out=True)),
+                    ("abi3", dict(raw_imu=True, z_one=True, xy_f32=xyf.numpy())), ("abi2", dict(raw_imu=True, z_one=True)), ("abi1", dict())):
+        ho = pout if tag == "abi4" else hout
         for _ in range(3):
-            be.marg_window_batch_host(b, capi.RUN_BOTH, hout, **kw)
+            be.marg_window_batch_host(b, capi.RUN_BOTH, ho, **kw)
         ts = []
         for _ in range(10):
             t0 = time.perf_counter()
-            be.marg_window_batch_host(b, capi.RUN_BOTH, hout, **kw)
+            be.marg_window_batch_host(b, capi.RUN_BOTH, ho, **kw)
             ts.append(time.perf_counter() - t0)
         res[tag + "_ms"] = round(float(np.median(ts)) * 1e3, 3)
     print(json.dumps(res))
