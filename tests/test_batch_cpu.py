@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -70,3 +71,44 @@ def test_window_sharding_world_size_2_gloo():
     assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == b.n     # shards tile [0, n)
     assert all(r[3] == 2.0 for r in res)                                      # max over ranks
     assert all(r[4] == b.n and r[5] == b.n_landmarks for r in res)            # nothing lost or duplicated
+
+
+def test_tri_record_packing_round_trips_and_matches_the_header():
+    """ABI 4 (ISV_IN_TRI_RECORDS / ISV_OUT_TRI_RECORDS): the Python reference packing -- record sizes equal the header's,
+    pack -> unpack is the identity on records whose sqrt_info blocks are upper triangular (covRel symmetric), and a non-zero
+    strict lower triangle is refused."""
+    import os
+    import re
+    from is_vins_b200 import capi
+    from is_vins_b200.batch import TRI_LAYOUTS, _tri_index, pack_tri, unpack_tri
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "isv_capi.h")).read()
+    want = {k: int(v) for k, v in re.findall(r"#define (ISV_\w+_TRI_REC) (\d+)", hdr)}
+    assert want == {"ISV_SE3_TRI_REC": capi.SE3_TRI_REC, "ISV_REL_TRI_REC": capi.REL_TRI_REC, "ISV_VB_TRI_REC": capi.VB_TRI_REC,
+                    "ISV_RP_IN_TRI_REC": capi.RP_IN_TRI_REC, "ISV_PG_TRI_REC": capi.PG_TRI_REC, "ISV_RP_TRI_REC": capi.RP_TRI_REC}
+    sizes = {"se3": (capi.SE3_REC, capi.SE3_TRI_REC), "rel": (capi.REL_REC, capi.REL_TRI_REC), "vb": (capi.VB_REC, capi.VB_TRI_REC),
+             "rp_in": (capi.RP_IN_REC, capi.RP_IN_TRI_REC), "pg": (capi.PG_REC, capi.PG_TRI_REC), "rp": (capi.RP_REC, capi.RP_TRI_REC)}
+    rng = np.random.default_rng(3)
+    for fam, (full, packed) in sizes.items():
+        idx, fl = _tri_index(TRI_LAYOUTS[fam])
+        assert fl == full and len(idx) == packed and len(set(idx.tolist())) == packed
+        rec = np.zeros((7, full))
+        fo = 0
+        for sno, (kind, N) in enumerate(TRI_LAYOUTS[fam]):
+            if kind == 0:
+                rec[:, fo:fo + N] = rng.normal(size=(7, N))
+                fo += N
+            else:
+                for w in range(7):
+                    M = np.triu(rng.normal(size=(N, N)))
+                    if fam == "pg" and sno == 2:
+                        M = M + M.T                      # covRel: symmetric
+                    rec[w, fo:fo + N * N] = M.flatten(order="F")
+                fo += N * N
+        p = pack_tri(rec, fam)
+        assert p.shape == (7, packed)
+        back = unpack_tri(p, fam, symmetric_blocks=(2,) if fam == "pg" else ())
+        assert np.array_equal(back, rec), fam
+    bad = np.zeros((1, capi.SE3_REC))
+    bad[0, 12 + 1] = 1.0                                  # element (1, 0) of the column-major sqrt_info: strict lower triangle
+    with pytest.raises(ValueError):
+        pack_tri(bad, "se3")
