@@ -516,19 +516,25 @@ def measure(cx, L, n, which, steps, warmup, seed, full, e2e=True):
                         if tri_np[f] is not None and ((f != "prior_vb" and which & 1) or (f == "prior_vb" and which & 2)))
         d2h_tri = sum(pout_t[k].numpy().nbytes for k in ((["se3", "pg"] if which & 1 else []) + (["rel", "vb", "rp"] if which & 2 else [])
                                                          + ["rank", "status"]))
-        for tag, kw, lm_bytes, bwd_f in (("", dict(raw_imu=True, z_one=True, xy_f32=xyf_t.numpy(), tri_in=tri_np, tri_out=True), 16, raw_f),
-                                         ("_abi3", dict(raw_imu=True, z_one=True, xy_f32=xyf_t.numpy()), 16, raw_f),
+        # the packed records pay from a few thousand windows on (the two expand / compact kernels add ~0.05 ms of latency to
+        # a call: 0.74 vs 0.70 ms at 4096 windows of L ~ 150, 1.29 vs 1.43 ms at 9472): smaller batches take ABI 3
+        use_tri = n >= 8192
+        r["e2e_abi"] = 4 if use_tri else 3
+        abi3_kw = dict(raw_imu=True, z_one=True, xy_f32=xyf_t.numpy())
+        for tag, kw, lm_bytes, bwd_f in (("", dict(abi3_kw, tri_in=tri_np, tri_out=True) if use_tri else abi3_kw, 16, raw_f),
+                                         ("_abi3", abi3_kw, 16, raw_f),
                                          ("_abi2", dict(raw_imu=True, z_one=True), 24, raw_f),
                                          ("_abi1", dict(), 32, ("pose_bwd", "sb_bwd", "prior_vb", "preint"))):
             if tag and not full:
                 continue
-            ho = pout if not tag else hout
+            packed = use_tri and not tag
+            ho = pout if packed else hout
             h2d = 0
             if which & 1:
                 h2d += sum(getattr(batch, f).nbytes for f in fwd_f) + lm_bytes * batch.n_landmarks
             if which & 2:
                 h2d += sum(getattr(batch, f).nbytes for f in bwd_f)
-            if not tag:
+            if packed:
                 h2d -= tri_saved
             for _ in range(max(1, min(warmup, 3))):
                 be.marg_window_batch_host(batch, which, ho, **kw)
@@ -541,14 +547,14 @@ def measure(cx, L, n, which, steps, warmup, seed, full, e2e=True):
             cx.barrier()
             r["e2e_ms" + tag] = e0.elapsed_time(e1)
             r["h2d" + tag] = h2d
-            r["d2h" + tag] = d2h_tri if not tag else d2h
+            r["d2h" + tag] = d2h_tri if packed else d2h
             assert int(np.count_nonzero(ho.status)) == 0
             if cx.rank == 0 and not tag:
                 # the e2e path's results against the device path's: equal to rounding (z == 1 is folded into the arithmetic,
                 # the pre-integration record was rebuilt on the GPU from the raw samples); the packed results are expanded
                 # here, after the timed region
                 from is_vins_b200.batch import outputs_rel_diff
-                r["e2e_vs_device_path_max_rel"] = float(outputs_rel_diff(unpack_outputs(pout), r["out"], which).max())
+                r["e2e_vs_device_path_max_rel"] = float(outputs_rel_diff(unpack_outputs(pout) if packed else hout, r["out"], which).max())
             if cx.rank == 0 and tag == "_abi1":
                 r["e2e_abi1_bits_equal"] = bool(all(np.array_equal(getattr(hout, f), getattr(r["out"], f)) for f in fams))
     # ---- the copy ceiling the e2e number runs under: the same byte counts as plain pinned cudaMemcpyAsync, H2D and D2H
@@ -789,6 +795,7 @@ def run_cuda(args, L):
             "clocks": h["clocks"],
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h["h2d"], "d2h_bytes_per_step": h["d2h"],
                     "ms_per_step": e2e_ms / args.steps, "gb_per_s": (h["h2d"] + h["d2h"]) / (e2e_ms / args.steps * 1e-3) / 1e9,
+                    "input_abi": h.get("e2e_abi"),
                     "inputs": "ABI 4 = ABI 3 + every record without its structural zeros, in and out (upper-triangular sqrt_info "
                               "blocks as 21 / 45 / 3 numbers, the symmetric covRel as 21: 252 instead of 319 doubles of records per "
                               "window in, 191 instead of 289 doubles of results out; expanded / compacted on the device).  "
@@ -858,7 +865,7 @@ def run_cuda(args, L):
                      "value": world * nc * args.steps / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c / args.steps,
                      "latency_us_per_window": ms_c / args.steps * 1e3 / nc,
                      "e2e": {"value": world * nc * args.steps / (e2e_c * 1e-3), "unit": UNIT, "h2d_bytes_per_step": r["h2d"],
-                             "d2h_bytes_per_step": r["d2h"], "ms_per_step": e2e_c / args.steps},
+                             "d2h_bytes_per_step": r["d2h"], "ms_per_step": e2e_c / args.steps, "input_abi": r.get("e2e_abi")},
                      "gpu_launches": r["launches"],
                      "parity": parity_check(r["batch"], r["out"], which, 32, 2 if Lc <= 1000 else 0, threads)}
                 if cpu_legs:
