@@ -98,6 +98,20 @@ def test_committed_golden_fixtures(backend, kernel_route, name):
     assert not out.status.any()
 
 
+@pytest.mark.parametrize("name", ["cfg1_L150_ragged.npz", "bench_windows_L1000.npz"])
+def test_golden_fixtures_through_the_packed_host_path(backend, name):
+    """ABI 4 on the committed fixtures (incl. the ragged / empty windows and whatever prior_rp they carry): packed prior
+    records in, packed results out through isv_marg_window_batch_host, expanded on the host and compared with the oracle."""
+    from is_vins_b200.batch import pack_tri_inputs, unpack_outputs
+    batch, ref, _ = load_batch(os.path.join(GOLD, name))
+    out = unpack_outputs(backend.marg_window_batch_host(batch, capi.RUN_BOTH, tri_in=pack_tri_inputs(batch), tri_out=True))
+    errs = compare_outputs(out, ref)
+    assert max(errs.values()) <= TOL, errs
+    assert np.array_equal(out.rank, ref.rank) and not out.status.any()
+    full = backend.marg_window_batch_host(batch, capi.RUN_BOTH)
+    assert np.array_equal(out.se3, full.se3) and np.array_equal(out.vb, full.vb) and np.array_equal(out.rel, full.rel)
+
+
 def test_backward_only_config3(backend):
     """BASELINE configs[2] maps to MargBackward alone: forward outputs untouched."""
     batch, ref, _ = load_batch(os.path.join(GOLD, "cfg1_L150_ragged.npz"))
